@@ -1,0 +1,161 @@
+/*
+ * prlib_cuda.h -- C-ABI of libprlib_cuda, the B200 (sm_100a) implementation of PRLib's
+ * local-statistics + Otsu binarization path.
+ *
+ * The reference has no FFI layer: its "operator API" for this path is six C++ free functions
+ * (namespace prl, cv::Mat in / cv::Mat out).  Each entry point below names the reference
+ * interface (file:line under the PRLib tree) whose body it replaces.  The cv::Mat-facing shim
+ * that keeps the reference signatures lives in prlib_b200/shim/ and calls only this header.
+ *
+ * Conventions
+ *   - plain pointers and sizes, no C++/torch types; every function returns int:
+ *     PRL_OK (0) or a negative PRL_E_* code; nothing throws, nothing calls back.
+ *   - `step` / `*_step` are row pitches in BYTES (cv::Mat::step).  Host-pointer entry points
+ *     accept pageable or pinned memory; `*_dev` entry points take device pointers that are
+ *     already resident in HBM and run asynchronously on the context's stream.
+ *   - there is NO CPU fallback: without a usable CUDA device every call fails with PRL_E_CUDA.
+ *   - a context owns one device, one stream (or borrows one), scratch planes and staging
+ *     buffers; a context must not be used from two host threads at once (use one per thread).
+ */
+#ifndef PRLIB_CUDA_H
+#define PRLIB_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRL_OK              0
+#define PRL_E_INVALID      (-1)  /* empty image, NULL pointer, bad window (reference: std::invalid_argument) */
+#define PRL_E_EMPTY_ROI    (-2)  /* min(rows, cols) <= window for WJ/NICK/Feng (reference: cv::Exception) */
+#define PRL_E_CUDA         (-3)  /* CUDA runtime / launch failure, or no device */
+#define PRL_E_NOMEM        (-4)  /* device or pinned-host allocation failed */
+#define PRL_E_UNSUPPORTED  (-5)  /* shape outside what the kernels handle (e.g. padded width > 65536) */
+
+/* local-statistics methods */
+enum {
+    PRL_SAUVOLA    = 0,  /* prl::binarizeSauvola     binarizeSauvola.h:43-47,    binarizeSauvola.cpp:32-135    */
+    PRL_NIBLACK    = 1,  /* prl::binarizeNiblack     binarizeNiblack.h:43-47,    binarizeNiblack.cpp:32-127    */
+    PRL_WOLFJOLION = 2,  /* prl::binarizeWolfJolion  binarizeWolfJolion.h:43-47, binarizeWolfJolion.cpp:33-148 */
+    PRL_NICK       = 3,  /* prl::binarizeNICK        binarizeNICK.h:43-47,       binarizeNICK.cpp:33-144       */
+    PRL_FENG       = 4   /* prl::binarizeFeng        binarizeFeng.h:46-53,       binarizeFeng.cpp:31-164       */
+};
+
+typedef struct prl_cuda_ctx prl_cuda_ctx;
+
+/* ---- context ------------------------------------------------------------------------- */
+int         prl_cuda_device_count(void);
+int         prl_cuda_create(int device, prl_cuda_ctx** out);
+void        prl_cuda_destroy(prl_cuda_ctx* ctx);
+const char* prl_cuda_last_error(const prl_cuda_ctx* ctx);   /* ctx may be NULL: last create() error */
+/* Borrow an externally owned cudaStream_t (e.g. torch's current stream) for all later calls;
+ * NULL restores the context's own stream. */
+int         prl_cuda_set_stream(prl_cuda_ctx* ctx, void* cuda_stream);
+int         prl_cuda_synchronize(prl_cuda_ctx* ctx);
+/* Upper bound (bytes) for the S/Q scratch planes of one in-flight chunk of pages (default 48 GiB,
+ * clipped to 70 % of free HBM at first use). */
+int         prl_cuda_set_workspace_limit(prl_cuda_ctx* ctx, size_t bytes);
+
+/* Geometry of the reference's processingRect (binarizeSauvola.cpp:57,66; binarizeWolfJolion.cpp:58,69):
+ * Sauvola/Niblack -> (rows+2h-w) x (cols+2h-w); WJ/NICK/Feng -> (rows-w) x (cols-w), with
+ * w = min(window, rows, cols), h = w/2.  Returns PRL_E_INVALID for a bad window, PRL_E_EMPTY_ROI
+ * when the rect is empty. */
+int prl_cuda_output_shape(int method, int rows, int cols, int window, int* out_rows, int* out_cols);
+
+/* ---- kernel 1: replicate-pad + integral images ----------------------------------------
+ * Replaces cv::copyMakeBorder + cv::integral(CV_64F) + Rect(1,1,..) crop,
+ * binarizeSauvola.cpp:65-77 (same block in Niblack:65-77, WolfJolion:71-85, NICK:71-85, Feng:68-82).
+ * sum / sqsum: (rows+2*pad) x (cols+2*pad) INCLUSIVE prefix sums, contiguous int64 (exact). */
+int prl_cuda_integral_u8(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step,
+                         int pad, int64_t* sum, int64_t* sqsum);
+
+/* ---- kernels 1+2: the five local-statistics binarizers --------------------------------
+ * params: Sauvola/Niblack/WJ/NICK {k}; Feng {alpha1, k1, k2, gamma} (always pass 4 doubles).
+ * src is single-channel u8 (see prl_cuda_bgr2gray for the cvtColor front step).
+ * dst receives out_rows x out_cols u8 0/255 (cv::compare CMP_GT), after the optional
+ * morphology tail (morph_iters > 0: dilate xN then erode xN; < 0: erode then dilate;
+ * binarizeSauvola.cpp:125-134). */
+int prl_cuda_binarize_local(prl_cuda_ctx* ctx, int method, const uint8_t* src, int rows, int cols,
+                            size_t step, int window, const double* params, int morph_iters,
+                            uint8_t* dst, size_t dst_step, int* out_rows, int* out_cols);
+
+/* Parity hook: the u8 threshold surface T8 = saturate_cast<uchar>(cvRound(T))
+ * (thresholdsValues.convertTo(CV_8UC1), binarizeSauvola.cpp:119).  aux (may be NULL) receives
+ * {I_min, s_max} as used by Wolf-Jolion / Feng (binarizeWolfJolion.cpp:115-119). */
+int prl_cuda_threshold_map(prl_cuda_ctx* ctx, int method, const uint8_t* src, int rows, int cols,
+                           size_t step, int window, const double* params, uint8_t* t8,
+                           size_t t8_step, int* out_rows, int* out_cols, double* aux);
+
+/* cv::cvtColor(BGR2GRAY / BGRA2GRAY) front step (binarizeSauvola.cpp:49-52), OpenCV 4.x 8-bit
+ * fixed point: (B*3735 + G*19235 + R*9798 + 16384) >> 15.  channels = 3 or 4. */
+int prl_cuda_bgr2gray(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step,
+                      int channels, uint8_t* dst, size_t dst_step);
+
+/* Morphology tail alone (cv::dilate / cv::erode with the default 3x3 element, n iterations,
+ * border ignored), binarizeSauvola.cpp:125-134. */
+int prl_cuda_morph(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step,
+                   int morph_iters, uint8_t* dst, size_t dst_step);
+
+/* ---- kernel 3: Otsu -------------------------------------------------------------------
+ * cv::threshold(src, dst, 128, maxval, THRESH_BINARY|THRESH_OTSU): call sites
+ * src/deskew/deskew.cpp:224, src/removeLines.cpp:45, src/imageLibCommon.cpp:295-296. */
+int prl_cuda_otsu_threshold(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step, int* thr);
+int prl_cuda_otsu_global(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step,
+                         double maxval, uint8_t* dst, size_t dst_step, int* thr);
+/* Per-rectangle Otsu loop of prl::binarizeLocalOtsu, binarizeLocalOtsu.cpp:138-162:
+ * dst = 255; for each rect (x,y,w,h): dst(rect) = 0 where (src > otsu(rect) ? maxval : 0) ^ 255 != 0.
+ * thr_out (may be NULL) receives the n_rects thresholds. */
+int prl_cuda_otsu_rects(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step,
+                        const int32_t* xywh, int n_rects, double maxval, uint8_t* dst, size_t dst_step,
+                        int32_t* thr_out);
+/* Same loop with rects := the regular tile_w x tile_h grid (edge tiles clipped): BASELINE config 4. */
+int prl_cuda_otsu_tiles(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step,
+                        int tile_w, int tile_h, double maxval, uint8_t* dst, size_t dst_step);
+
+/* ---- device-resident batch entry points (inputs already in HBM; asynchronous) ----------
+ * Pages are n_pages images of rows x cols u8 at d_src + p*src_page_stride, row pitch src_step
+ * (bytes).  Masks go to d_dst + p*dst_page_stride, row pitch dst_step; they are out_rows x
+ * out_cols (prl_cuda_output_shape).  Pitches that are multiples of 16 bytes get the vector path. */
+int prl_cuda_binarize_local_batch_dev(prl_cuda_ctx* ctx, int method, const uint8_t* d_src, int n_pages,
+                                      int rows, int cols, size_t src_step, size_t src_page_stride,
+                                      int window, const double* params, int morph_iters,
+                                      uint8_t* d_dst, size_t dst_step, size_t dst_page_stride);
+/* Kernel 1 alone over a batch; planes are (rows+2*pad) rows of plane_pitch int64 ELEMENTS. */
+int prl_cuda_integral_u8_batch_dev(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int rows, int cols,
+                                   size_t src_step, size_t src_page_stride, int pad,
+                                   int64_t* d_sum, int64_t* d_sqsum, size_t plane_pitch, size_t plane_page_stride);
+int prl_cuda_otsu_global_batch_dev(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int rows, int cols,
+                                   size_t src_step, size_t src_page_stride, double maxval,
+                                   uint8_t* d_dst, size_t dst_step, size_t dst_page_stride, int32_t* d_thr);
+int prl_cuda_otsu_tiles_batch_dev(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int rows, int cols,
+                                  size_t src_step, size_t src_page_stride, int tile_w, int tile_h, double maxval,
+                                  uint8_t* d_dst, size_t dst_step, size_t dst_page_stride);
+/* synthpage-v2 generator (bit-identical to oracle/prl_oracle.py:synth_page). */
+int prl_cuda_synth_pages_dev(prl_cuda_ctx* ctx, uint8_t* d_dst, int n_pages, int rows, int cols,
+                             size_t step, size_t page_stride, uint32_t seed, uint32_t first_page);
+
+/* ---- host batch + page dispatcher -------------------------------------------------------
+ * n_pages contiguous rows x cols u8 pages in host memory -> n_pages contiguous out_rows x
+ * out_cols masks.  Pages are sharded in contiguous ranges over `devices` (one host thread, one
+ * context and a 3-deep pinned staging ring per device; no collective).  devices == NULL or
+ * n_dev <= 0 means "every visible device". */
+int prl_cuda_binarize_batch(const int* devices, int n_dev, int method, const uint8_t* pages, int n_pages,
+                            int rows, int cols, int window, const double* params, int morph_iters,
+                            uint8_t* masks);
+
+/* ---- instrumentation ---------------------------------------------------------------------
+ * With timing enabled every kernel launch is bracketed by CUDA events on the launching stream.
+ * prl_cuda_timing_get sums them per kernel family ("integral", "threshold", "smax", "morph",
+ * "otsu_hist", "otsu_search", "otsu_apply", "otsu_tiles", "synth", "bgr2gray", "band_carry");
+ * it synchronizes the stream. */
+int  prl_cuda_timing_enable(prl_cuda_ctx* ctx, int on);
+int  prl_cuda_timing_reset(prl_cuda_ctx* ctx);
+int  prl_cuda_timing_get(prl_cuda_ctx* ctx, const char* family, double* total_ms, long long* launches);
+long long prl_cuda_launch_count(const prl_cuda_ctx* ctx);   /* kernels launched since create/reset */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRLIB_CUDA_H */

@@ -1,0 +1,108 @@
+"""prl::binarize* mirrored on the host side: same names, parameters, defaults and error behaviour
+as the reference headers, bodies replaced by calls into libprlib_cuda (no CPU fallback).
+
+  prl::binarizeSauvola     src/binarizations/binarizeSauvola.h:43-47
+  prl::binarizeNiblack     src/binarizations/binarizeNiblack.h:43-47
+  prl::binarizeWolfJolion  src/binarizations/binarizeWolfJolion.h:43-47
+  prl::binarizeNICK        src/binarizations/binarizeNICK.h:43-47
+  prl::binarizeFeng        src/binarizations/binarizeFeng.h:46-53
+  prl::binarizeLocalOtsu   src/binarizations/binarizeLocalOtsu.h:50-57  (per-rectangle core only: the
+                           Canny/contour front-end stays with the caller)
+
+cv::Mat in / cv::Mat out becomes numpy in / numpy out.  std::invalid_argument -> ValueError;
+cv::Exception (empty processingRect) -> PrlCudaError(PRL_E_EMPTY_ROI).  The C++ reference also
+overwrites its input Mat with the padded gray image; `padded_gray()` returns that side effect for
+callers that relied on it (the C++ shim in prlib_b200/shim reproduces it in place).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import capi
+from .context import Context, default_context
+
+
+def _gray(image, ctx: Context) -> np.ndarray:
+    im = np.asarray(image)
+    if im.size == 0:
+        raise ValueError("Input image for binarization is empty")       # binarizeSauvola.cpp:38-41
+    if im.ndim == 3 and im.shape[2] != 1:
+        return ctx.bgr2gray(im)                                           # cvtColor(BGR2GRAY) :49-52
+    return im
+
+
+def _check_window(window: int):
+    if not (window > 1 and window % 2 == 1):                             # :43-47
+        raise ValueError("Window size must satisfy the following condition: "
+                         "( (windowSize > 1) && ((windowSize % 2) == 1) ) ")
+
+
+def _local(image, method, window, params, morph, device):
+    im = np.asarray(image)
+    if im.size == 0:
+        raise ValueError("Input image for binarization is empty")
+    _check_window(window)                      # argument errors come first, as in the reference
+    ctx = default_context(device)
+    return ctx.binarize_local(_gray(im, ctx), method, window, params, morph)
+
+
+def binarizeSauvola(imageInput, windowSize: int = 101, thresholdCoefficient: float = 0.01,
+                    morphIterationCount: int = 2, device: int = 0) -> np.ndarray:
+    return _local(imageInput, capi.SAUVOLA, windowSize, (thresholdCoefficient,), morphIterationCount, device)
+
+
+def binarizeNiblack(imageInput, windowSize: int = 101, thresholdCoefficient: float = 0.01,
+                    morphIterationCount: int = 2, device: int = 0) -> np.ndarray:
+    return _local(imageInput, capi.NIBLACK, windowSize, (thresholdCoefficient,), morphIterationCount, device)
+
+
+def binarizeWolfJolion(imageInput, windowSize: int = 101, thresholdCoefficient: float = 0.01,
+                       morphIterationCount: int = 2, device: int = 0) -> np.ndarray:
+    return _local(imageInput, capi.WOLFJOLION, windowSize, (thresholdCoefficient,), morphIterationCount, device)
+
+
+def binarizeNICK(imageInput, windowSize: int = 21, thresholdCoefficient: float = -0.01,
+                 morphIterationCount: int = 0, device: int = 0) -> np.ndarray:
+    return _local(imageInput, capi.NICK, windowSize, (thresholdCoefficient,), morphIterationCount, device)
+
+
+def binarizeFeng(imageInput, windowSize: int = 21, thresholdCoefficient_alpha1: float = 0.75,
+                 thresholdCoefficient_k1: float = 0.2, thresholdCoefficient_k2: float = 0.03,
+                 thresholdCoefficient_gamma: float = 2.0, morphIterationCount: int = 2, device: int = 0) -> np.ndarray:
+    return _local(imageInput, capi.FENG, windowSize,
+                  (thresholdCoefficient_alpha1, thresholdCoefficient_k1, thresholdCoefficient_k2,
+                   thresholdCoefficient_gamma), morphIterationCount, device)
+
+
+def padded_gray(imageInput, windowSize: int, device: int = 0) -> np.ndarray:
+    """What the reference leaves in `imageInput` after a local-statistics call: the gray image
+    replicate-padded by w/2 (binarizeSauvola.cpp:49-52, :65)."""
+    ctx = default_context(device)
+    g = _gray(imageInput, ctx)
+    w = min(windowSize, min(g.shape[0], g.shape[1]))
+    return np.pad(g, w // 2, mode="edge")
+
+
+def otsuThreshold(image, maxValue: float = 255.0, device: int = 0):
+    """cv::threshold(src, dst, 128, maxValue, THRESH_BINARY|THRESH_OTSU) -> (thr, dst)
+    (src/deskew/deskew.cpp:224, src/removeLines.cpp:45, src/imageLibCommon.cpp:295-296)."""
+    ctx = default_context(device)
+    return ctx.otsu_global(_gray(image, ctx), maxValue)
+
+
+def binarizeLocalOtsuRects(image, rects, maxValue: float = 255.0, device: int = 0) -> np.ndarray:
+    """The per-contour-rectangle loop of prl::binarizeLocalOtsu (binarizeLocalOtsu.cpp:138-162);
+    `rects` are the cv::boundingRect(x, y, w, h) of the caller's contours."""
+    if not (0 <= maxValue <= 255):                                        # binarizeLocalOtsu.cpp:52-55
+        raise ValueError("Max value must be in range [0; 255]")
+    ctx = default_context(device)
+    return ctx.otsu_rects(_gray(image, ctx), rects, maxValue)
+
+
+def binarizeLocalOtsuTiles(image, tileWidth: int = 64, tileHeight: int = 64, maxValue: float = 255.0,
+                           device: int = 0) -> np.ndarray:
+    """Same loop with rects := the regular tile grid (BASELINE.json config 4)."""
+    if not (0 <= maxValue <= 255):
+        raise ValueError("Max value must be in range [0; 255]")
+    ctx = default_context(device)
+    return ctx.otsu_tiles(_gray(image, ctx), tileWidth, tileHeight, maxValue)

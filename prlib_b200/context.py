@@ -1,0 +1,253 @@
+"""Host-side handle on a libprlib_cuda context (one device, one stream, scratch planes)."""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import capi
+from .capi import PrlCudaError
+
+_FAMILIES = ("integral", "threshold", "smax", "morph", "otsu_hist", "otsu_search", "otsu_apply", "otsu_tiles",
+             "synth", "bgr2gray", "band_carry")
+
+
+def _params4(params) -> "C.Array":
+    arr = (C.c_double * 4)(0.0, 0.0, 0.0, 0.0)
+    for i, v in enumerate(np.atleast_1d(np.asarray(params, dtype=np.float64)).tolist()[:4]):
+        arr[i] = v
+    return arr
+
+
+def _as_u8_2d(a, name="image") -> np.ndarray:
+    a = np.asarray(a)
+    if a.dtype != np.uint8:
+        raise TypeError(f"{name} must be uint8")
+    if a.ndim == 3 and a.shape[2] == 1:
+        a = a[:, :, 0]
+    if a.ndim != 2:
+        raise ValueError(f"{name} must be a single-channel 2-D array")
+    if a.strides[1] != 1 or a.strides[0] < a.shape[1]:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+class Context:
+    """Owns one prl_cuda_ctx.  Not thread-safe: use one Context per host thread."""
+
+    def __init__(self, device: int = 0):
+        self._L = capi.load()
+        h = C.c_void_p()
+        rc = self._L.prl_cuda_create(int(device), C.byref(h))
+        if rc != capi.PRL_OK:
+            raise PrlCudaError(rc, (self._L.prl_cuda_last_error(None) or b"").decode())
+        self._h = h
+        self.device = int(device)
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.prl_cuda_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != capi.PRL_OK:
+            msg = (self._L.prl_cuda_last_error(self._h) or b"").decode()
+            if rc == capi.PRL_E_INVALID:
+                raise ValueError(msg)          # the reference throws std::invalid_argument here
+            raise PrlCudaError(rc, msg)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self._L.prl_cuda_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        self._check(self._L.prl_cuda_synchronize(self._h))
+
+    def set_workspace_limit(self, nbytes: int):
+        self._check(self._L.prl_cuda_set_workspace_limit(self._h, int(nbytes)))
+
+    def timing_enable(self, on: bool = True):
+        self._check(self._L.prl_cuda_timing_enable(self._h, int(on)))
+
+    def timing_reset(self):
+        self._check(self._L.prl_cuda_timing_reset(self._h))
+
+    def timing(self) -> dict:
+        out = {}
+        for fam in _FAMILIES:
+            ms, n = C.c_double(), C.c_longlong()
+            self._check(self._L.prl_cuda_timing_get(self._h, fam.encode(), C.byref(ms), C.byref(n)))
+            if n.value:
+                out[fam] = {"ms": ms.value, "launches": n.value}
+        return out
+
+    def launch_count(self) -> int:
+        return int(self._L.prl_cuda_launch_count(self._h))
+
+    # -- host-pointer entry points -------------------------------------------------------------
+    def integral(self, gray, pad: int):
+        g = _as_u8_2d(gray)
+        r, c = g.shape
+        S = np.empty((r + 2 * pad, c + 2 * pad), np.int64)
+        Q = np.empty_like(S)
+        self._check(self._L.prl_cuda_integral_u8(self._h, g.ctypes.data, r, c, g.strides[0], int(pad),
+                                                 S.ctypes.data, Q.ctypes.data))
+        return S, Q
+
+    def output_shape(self, method: int, rows: int, cols: int, window: int):
+        orow, ocol = C.c_int(), C.c_int()
+        rc = self._L.prl_cuda_output_shape(method, rows, cols, window, C.byref(orow), C.byref(ocol))
+        return rc, orow.value, ocol.value
+
+    def binarize_local(self, gray, method: int, window: int, params, morph_iters: int = 0):
+        g = _as_u8_2d(gray)
+        r, c = g.shape
+        rc, orow, ocol = self.output_shape(method, r, c, window)
+        out = np.empty((max(orow, 0), max(ocol, 0)), np.uint8)
+        a, b = C.c_int(), C.c_int()
+        self._check(self._L.prl_cuda_binarize_local(self._h, method, g.ctypes.data, r, c, g.strides[0], int(window),
+                                                    _params4(params), int(morph_iters), out.ctypes.data,
+                                                    max(ocol, 1), C.byref(a), C.byref(b)))
+        return out
+
+    def threshold_map(self, gray, method: int, window: int, params):
+        g = _as_u8_2d(gray)
+        r, c = g.shape
+        rc, orow, ocol = self.output_shape(method, r, c, window)
+        out = np.empty((max(orow, 0), max(ocol, 0)), np.uint8)
+        a, b = C.c_int(), C.c_int()
+        aux = (C.c_double * 2)()
+        self._check(self._L.prl_cuda_threshold_map(self._h, method, g.ctypes.data, r, c, g.strides[0], int(window),
+                                                   _params4(params), out.ctypes.data, max(ocol, 1), C.byref(a),
+                                                   C.byref(b), aux))
+        return out, {"imin": aux[0], "smax": aux[1]}
+
+    def bgr2gray(self, image):
+        im = np.asarray(image)
+        if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] not in (3, 4):
+            raise ValueError("expected an HxWx3 or HxWx4 uint8 image")
+        im = np.ascontiguousarray(im)
+        r, c, ch = im.shape
+        out = np.empty((r, c), np.uint8)
+        self._check(self._L.prl_cuda_bgr2gray(self._h, im.ctypes.data, r, c, im.strides[0], ch, out.ctypes.data, c))
+        return out
+
+    def morph(self, mask, iters: int):
+        m = _as_u8_2d(mask, "mask")
+        r, c = m.shape
+        out = np.empty((r, c), np.uint8)
+        self._check(self._L.prl_cuda_morph(self._h, m.ctypes.data, r, c, m.strides[0], int(iters), out.ctypes.data, c))
+        return out
+
+    def otsu_threshold(self, gray) -> int:
+        g = _as_u8_2d(gray)
+        t = C.c_int()
+        self._check(self._L.prl_cuda_otsu_threshold(self._h, g.ctypes.data, g.shape[0], g.shape[1], g.strides[0], C.byref(t)))
+        return t.value
+
+    def otsu_global(self, gray, maxval: float = 255.0):
+        g = _as_u8_2d(gray)
+        out = np.empty(g.shape, np.uint8)
+        t = C.c_int()
+        self._check(self._L.prl_cuda_otsu_global(self._h, g.ctypes.data, g.shape[0], g.shape[1], g.strides[0],
+                                                 float(maxval), out.ctypes.data, g.shape[1], C.byref(t)))
+        return t.value, out
+
+    def otsu_rects(self, gray, rects, maxval: float = 255.0, return_thresholds: bool = False):
+        g = _as_u8_2d(gray)
+        xywh = np.ascontiguousarray(np.asarray(rects, np.int32).reshape(-1, 4))
+        out = np.empty(g.shape, np.uint8)
+        thr = np.zeros(max(len(xywh), 1), np.int32)
+        self._check(self._L.prl_cuda_otsu_rects(self._h, g.ctypes.data, g.shape[0], g.shape[1], g.strides[0],
+                                                xywh.ctypes.data if len(xywh) else None, len(xywh), float(maxval),
+                                                out.ctypes.data, g.shape[1], thr.ctypes.data))
+        return (out, thr[:len(xywh)]) if return_thresholds else out
+
+    def otsu_tiles(self, gray, tile_w: int = 64, tile_h: int = 64, maxval: float = 255.0):
+        g = _as_u8_2d(gray)
+        out = np.empty(g.shape, np.uint8)
+        self._check(self._L.prl_cuda_otsu_tiles(self._h, g.ctypes.data, g.shape[0], g.shape[1], g.strides[0],
+                                                int(tile_w), int(tile_h), float(maxval), out.ctypes.data, g.shape[1]))
+        return out
+
+    # -- device-pointer entry points (raw addresses: torch .data_ptr() or cudaMalloc) ----------
+    def binarize_local_batch_dev(self, method, d_src, n_pages, rows, cols, src_step, src_page_stride, window, params,
+                                 morph_iters, d_dst, dst_step, dst_page_stride):
+        self._check(self._L.prl_cuda_binarize_local_batch_dev(self._h, method, d_src, n_pages, rows, cols, src_step,
+                                                              src_page_stride, window, _params4(params), morph_iters,
+                                                              d_dst, dst_step, dst_page_stride))
+
+    def integral_batch_dev(self, d_src, n_pages, rows, cols, src_step, src_page_stride, pad, d_sum, d_sqsum,
+                           plane_pitch, plane_page_stride):
+        self._check(self._L.prl_cuda_integral_u8_batch_dev(self._h, d_src, n_pages, rows, cols, src_step, src_page_stride,
+                                                           pad, d_sum, d_sqsum, plane_pitch, plane_page_stride))
+
+    def otsu_global_batch_dev(self, d_src, n_pages, rows, cols, src_step, src_page_stride, maxval, d_dst, dst_step,
+                              dst_page_stride, d_thr):
+        self._check(self._L.prl_cuda_otsu_global_batch_dev(self._h, d_src, n_pages, rows, cols, src_step, src_page_stride,
+                                                           float(maxval), d_dst, dst_step, dst_page_stride, d_thr))
+
+    def otsu_tiles_batch_dev(self, d_src, n_pages, rows, cols, src_step, src_page_stride, tile_w, tile_h, maxval,
+                             d_dst, dst_step, dst_page_stride):
+        self._check(self._L.prl_cuda_otsu_tiles_batch_dev(self._h, d_src, n_pages, rows, cols, src_step, src_page_stride,
+                                                          tile_w, tile_h, float(maxval), d_dst, dst_step, dst_page_stride))
+
+    def synth_pages_dev(self, d_dst, n_pages, rows, cols, step, page_stride, seed=2024, first_page=0):
+        self._check(self._L.prl_cuda_synth_pages_dev(self._h, d_dst, n_pages, rows, cols, step, page_stride, seed, first_page))
+
+
+_tls = threading.local()
+
+
+def default_context(device: int = 0) -> Context:
+    """Per-thread, per-device lazily created context used by the prl-style free functions."""
+    d = getattr(_tls, "ctxs", None)
+    if d is None:
+        d = _tls.ctxs = {}
+    if device not in d:
+        d[device] = Context(device)
+    return d[device]
+
+
+def binarize_batch(pages: np.ndarray, method: int, window: int, params, morph_iters: int = 0, devices=None,
+                   out: np.ndarray | None = None) -> np.ndarray:
+    """Host batch + page dispatcher (prl_cuda_binarize_batch): (N, rows, cols) u8 -> (N, out_rows, out_cols)."""
+    L = capi.load()
+    pages = np.asarray(pages)
+    if pages.dtype != np.uint8 or pages.ndim != 3 or not pages.flags.c_contiguous:
+        raise ValueError("pages must be a C-contiguous (N, rows, cols) uint8 array")
+    n, r, c = pages.shape
+    orow, ocol = C.c_int(), C.c_int()
+    rc = L.prl_cuda_output_shape(method, r, c, window, C.byref(orow), C.byref(ocol))
+    if rc == capi.PRL_E_INVALID:
+        raise ValueError("empty image or window not (>1 and odd)")
+    if rc != capi.PRL_OK:
+        raise PrlCudaError(rc, "empty processingRect: min(rows, cols) <= windowSize")
+    if out is None:
+        out = np.empty((n, orow.value, ocol.value), np.uint8)
+    elif out.shape != (n, orow.value, ocol.value) or out.dtype != np.uint8 or not out.flags.c_contiguous:
+        raise ValueError("out has the wrong shape/dtype")
+    devs = None
+    nd = 0
+    if devices is not None:
+        nd = len(devices)
+        devs = (C.c_int * nd)(*devices)
+    rc = L.prl_cuda_binarize_batch(devs, nd, method, pages.ctypes.data, n, r, c, int(window), _params4(params),
+                                   int(morph_iters), out.ctypes.data)
+    if rc != capi.PRL_OK:
+        msg = (L.prl_cuda_last_error(None) or b"").decode()
+        if rc == capi.PRL_E_INVALID:
+            raise ValueError(msg)
+        raise PrlCudaError(rc, msg)
+    return out

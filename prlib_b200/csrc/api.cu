@@ -1,0 +1,684 @@
+// api.cu -- the C-ABI of libprlib_cuda (include/prlib_cuda.h): context, host-pointer drop-in entry
+// points, device-resident batch entry points, and the pinned-memory batch loader + page dispatcher.
+#include "common.cuh"
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <thread>
+#include <mutex>
+#include <memory>
+#include <algorithm>
+
+static thread_local std::string g_create_err;
+
+// ------------------------------------------------------------------------------------------------
+// plumbing
+// ------------------------------------------------------------------------------------------------
+int prl_set_err(prl_cuda_ctx* ctx, int code, const char* what, cudaError_t ce)
+{
+    std::string m = what ? what : "";
+    if (ce != cudaSuccess) { m += ": "; m += cudaGetErrorString(ce); }
+    if (ctx) ctx->err = m; else g_create_err = m;
+    return code;
+}
+
+int prl_ensure(prl_cuda_ctx* ctx, void** ptr, size_t* have, size_t need)
+{
+    if (need <= *have && *ptr) return PRL_OK;
+    if (*ptr) {
+        // earlier launches on this stream may still read the old buffer
+        PRL_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(*ptr); *ptr = nullptr; *have = 0;
+    }
+    if (need == 0) need = 256;
+    cudaError_t e = cudaMalloc(ptr, need);
+    if (e != cudaSuccess) { *ptr = nullptr; return prl_set_err(ctx, PRL_E_NOMEM, "cudaMalloc", e); }
+    *have = need;
+    return PRL_OK;
+}
+
+int prl_ensure_pinned(prl_cuda_ctx* ctx, size_t need)
+{
+    if (need <= ctx->h_pin_bytes && ctx->h_pin) return PRL_OK;
+    if (ctx->h_pin) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->h_pin); ctx->h_pin = nullptr; ctx->h_pin_bytes = 0; }
+    cudaError_t e = cudaMallocHost((void**)&ctx->h_pin, need);
+    if (e != cudaSuccess) { ctx->h_pin = nullptr; return prl_set_err(ctx, PRL_E_NOMEM, "cudaMallocHost", e); }
+    ctx->h_pin_bytes = need;
+    return PRL_OK;
+}
+
+void prl_launch_begin(prl_cuda_ctx* ctx, int family)
+{
+    ctx->launches++;
+    if (!ctx->timing) return;
+    prl_timing_rec r; r.family = family;
+    cudaEvent_t ev[2];
+    for (int i = 0; i < 2; ++i) {
+        if (!ctx->event_pool.empty()) { ev[i] = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+        else cudaEventCreate(&ev[i]);
+    }
+    r.a = ev[0]; r.b = ev[1];
+    cudaEventRecord(r.a, ctx->stream);
+    ctx->recs.push_back(r);
+}
+
+void prl_launch_end(prl_cuda_ctx* ctx)
+{
+    if (!ctx->timing || ctx->recs.empty()) return;
+    cudaEventRecord(ctx->recs.back().b, ctx->stream);
+}
+
+static void timing_collect(prl_cuda_ctx* ctx)
+{
+    if (ctx->recs.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& r : ctx->recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            auto& t = ctx->totals[r.family];
+            t.first += ms; t.second += 1;
+        }
+        ctx->event_pool.push_back(r.a); ctx->event_pool.push_back(r.b);
+    }
+    ctx->recs.clear();
+}
+
+static const char* kFamilyNames[FAM_COUNT] = {"integral", "threshold", "smax", "morph", "otsu_hist", "otsu_search",
+                                              "otsu_apply", "otsu_tiles", "synth", "bgr2gray", "band_carry"};
+
+int prl_make_geom(int method, int rows, int cols, int window, prl_geom* g)
+{
+    if (rows <= 0 || cols <= 0) return PRL_E_INVALID;                       // imageInput.empty()  binarizeSauvola.cpp:38-41
+    if (!((window > 1) && ((window % 2) == 1))) return PRL_E_INVALID;       // binarizeSauvola.cpp:43-47
+    if (method < PRL_SAUVOLA || method > PRL_FENG) return PRL_E_INVALID;
+    g->rows = rows; g->cols = cols;
+    g->w = std::min(window, std::min(cols, rows));                          // :57
+    g->h = g->w / 2; g->d = g->w - 1;
+    g->Hp = rows + 2 * g->h; g->Wp = cols + 2 * g->h;                       // copyMakeBorder :65
+    if (method == PRL_SAUVOLA || method == PRL_NIBLACK) {                   // rect after padding :66
+        g->out_cols = g->Wp - g->w; g->out_rows = g->Hp - g->w;
+    } else {                                                                // rect before padding (WolfJolion.cpp:69)
+        g->out_cols = cols - g->w; g->out_rows = rows - g->w;
+    }
+    g->pitch = prl_plane_pitch(g->Wp);
+    if (g->out_cols <= 0 || g->out_rows <= 0) return PRL_E_EMPTY_ROI;
+    return PRL_OK;
+}
+
+static inline size_t round16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+extern "C" int prl_cuda_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int prl_cuda_create(int device, prl_cuda_ctx** out)
+{
+    if (!out) return PRL_E_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return prl_set_err(nullptr, PRL_E_CUDA, "no CUDA device available (libprlib_cuda has no CPU fallback)", e);
+    }
+    if (device < 0 || device >= n) return prl_set_err(nullptr, PRL_E_INVALID, "bad device index");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return prl_set_err(nullptr, PRL_E_CUDA, "cudaSetDevice", e);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return prl_set_err(nullptr, PRL_E_CUDA, "cudaGetDeviceProperties", e);
+    if (prop.major != 10) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "device %d is sm_%d%d; libprlib_cuda is built for sm_100a only", device, prop.major, prop.minor);
+        return prl_set_err(nullptr, PRL_E_CUDA, buf);
+    }
+    prl_cuda_ctx* c = new prl_cuda_ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return prl_set_err(nullptr, PRL_E_CUDA, "cudaStreamCreate", e); }
+    c->stream = c->own_stream;
+    *out = c;
+    return PRL_OK;
+}
+
+extern "C" void prl_cuda_destroy(prl_cuda_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto& ev : c->event_pool) cudaEventDestroy(ev);
+    cudaFree(c->planes); cudaFree(c->carry); cudaFree(c->colsum); cudaFree(c->scalars);
+    cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_tmp); cudaFree(c->d_misc);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+extern "C" const char* prl_cuda_last_error(const prl_cuda_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int prl_cuda_set_stream(prl_cuda_ctx* c, void* s)
+{
+    if (!c) return PRL_E_INVALID;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return PRL_OK;
+}
+
+extern "C" int prl_cuda_synchronize(prl_cuda_ctx* c)
+{
+    if (!c) return PRL_E_INVALID;
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return PRL_OK;
+}
+
+extern "C" int prl_cuda_set_workspace_limit(prl_cuda_ctx* c, size_t bytes)
+{
+    if (!c || bytes == 0) return PRL_E_INVALID;
+    c->workspace_limit = bytes;
+    return PRL_OK;
+}
+
+extern "C" int prl_cuda_output_shape(int method, int rows, int cols, int window, int* out_rows, int* out_cols)
+{
+    prl_geom g;
+    int rc = prl_make_geom(method, rows, cols, window, &g);
+    if (rc == PRL_E_INVALID) return rc;
+    if (out_rows) *out_rows = g.out_rows;
+    if (out_cols) *out_cols = g.out_cols;
+    return rc;
+}
+
+extern "C" int prl_cuda_timing_enable(prl_cuda_ctx* c, int on) { if (!c) return PRL_E_INVALID; timing_collect(c); c->timing = on != 0; return PRL_OK; }
+extern "C" int prl_cuda_timing_reset(prl_cuda_ctx* c)
+{
+    if (!c) return PRL_E_INVALID;
+    timing_collect(c); c->totals.clear(); c->launches = 0;
+    return PRL_OK;
+}
+extern "C" int prl_cuda_timing_get(prl_cuda_ctx* c, const char* family, double* total_ms, long long* launches)
+{
+    if (!c || !family) return PRL_E_INVALID;
+    cudaSetDevice(c->device);
+    timing_collect(c);
+    for (int f = 0; f < FAM_COUNT; ++f)
+        if (strcmp(family, kFamilyNames[f]) == 0) {
+            auto it = c->totals.find(f);
+            if (total_ms) *total_ms = it == c->totals.end() ? 0.0 : it->second.first;
+            if (launches) *launches = it == c->totals.end() ? 0 : it->second.second;
+            return PRL_OK;
+        }
+    return prl_set_err(c, PRL_E_INVALID, "unknown kernel family");
+}
+extern "C" long long prl_cuda_launch_count(const prl_cuda_ctx* c) { return c ? c->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// device-resident batch entry points
+// ------------------------------------------------------------------------------------------------
+static size_t planes_budget(prl_cuda_ctx* c)
+{
+    size_t lim = c->workspace_limit;
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
+        size_t avail = fr + c->planes_bytes;          // what we already hold counts as available to us
+        lim = std::min(lim, (size_t)(avail * 0.7));
+    }
+    return lim;
+}
+
+// mode 0: masks (+morph), mode 1: T8 maps
+static int local_batch_dev(prl_cuda_ctx* c, int method, int mode, const uint8_t* d_src, int n_pages, int rows, int cols,
+                           size_t src_step, size_t src_page_stride, int window, const double* params, int morph_iters,
+                           uint8_t* d_dst, size_t dst_step, size_t dst_page_stride)
+{
+    if (!c || !d_src || !d_dst || !params || n_pages <= 0) return prl_set_err(c, PRL_E_INVALID, "null pointer or empty batch");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    prl_geom g;
+    int rc = prl_make_geom(method, rows, cols, window, &g);
+    if (rc) return prl_set_err(c, rc, rc == PRL_E_EMPTY_ROI ? "empty processingRect: min(rows, cols) <= windowSize"
+                                                             : "empty image or window not (>1 and odd)");
+    if ((size_t)g.out_cols > dst_step) return prl_set_err(c, PRL_E_INVALID, "dst_step smaller than out_cols");
+
+    const size_t plane_elems = (size_t)g.Hp * g.pitch;          // one plane of one page
+    const size_t per_page = 2 * plane_elems * sizeof(int64_t);
+    size_t budget = planes_budget(c);
+    int chunk = (int)std::min<size_t>((size_t)n_pages, std::max<size_t>(1, budget / per_page));
+    if ((size_t)chunk * per_page > c->planes_bytes || !c->planes) {
+        rc = prl_ensure(c, (void**)&c->planes, &c->planes_bytes, (size_t)chunk * per_page);
+        if (rc) return rc;
+    }
+    rc = prl_ensure(c, &c->scalars, &c->scalars_bytes, (size_t)n_pages * 16);
+    if (rc) return rc;
+    uint32_t* d_imin = (uint32_t*)c->scalars;
+    long long* d_smax = (long long*)((uint8_t*)c->scalars + (size_t)n_pages * 8);
+
+    size_t tmp_step = round16((size_t)g.out_cols);
+    if (morph_iters != 0 && mode == 0) {
+        rc = prl_ensure(c, (void**)&c->d_tmp, &c->d_tmp_bytes, (size_t)chunk * g.out_rows * tmp_step);
+        if (rc) return rc;
+    }
+
+    int64_t* S = c->planes;
+    int64_t* Q = c->planes + (size_t)chunk * plane_elems;
+    for (int p0 = 0; p0 < n_pages; p0 += chunk) {
+        const int np = std::min(chunk, n_pages - p0);
+        const uint8_t* src = d_src + (size_t)p0 * src_page_stride;
+        uint8_t* dst = d_dst + (size_t)p0 * dst_page_stride;
+        rc = prl_k_integral(c, src, np, rows, cols, src_step, src_page_stride, g.h, S, Q, g.pitch, plane_elems, d_imin + p0);
+        if (rc) return rc;
+        rc = prl_k_threshold(c, method, mode, src, np, g, src_step, src_page_stride, S, Q, plane_elems, params,
+                             d_imin + p0, d_smax + p0, dst, dst_step, dst_page_stride);
+        if (rc) return rc;
+        if (morph_iters != 0 && mode == 0) {
+            rc = prl_k_morph(c, dst, c->d_tmp, np, g.out_rows, g.out_cols, dst_step, dst_page_stride, tmp_step,
+                             (size_t)g.out_rows * tmp_step, morph_iters);
+            if (rc) return rc;
+        }
+    }
+    return PRL_OK;
+}
+
+extern "C" int prl_cuda_binarize_local_batch_dev(prl_cuda_ctx* c, int method, const uint8_t* d_src, int n_pages,
+                                                 int rows, int cols, size_t src_step, size_t src_page_stride,
+                                                 int window, const double* params, int morph_iters,
+                                                 uint8_t* d_dst, size_t dst_step, size_t dst_page_stride)
+{
+    return local_batch_dev(c, method, 0, d_src, n_pages, rows, cols, src_step, src_page_stride, window, params,
+                           morph_iters, d_dst, dst_step, dst_page_stride);
+}
+
+extern "C" int prl_cuda_integral_u8_batch_dev(prl_cuda_ctx* c, const uint8_t* d_src, int n_pages, int rows, int cols,
+                                              size_t src_step, size_t src_page_stride, int pad,
+                                              int64_t* d_sum, int64_t* d_sqsum, size_t plane_pitch, size_t plane_page_stride)
+{
+    if (!c || !d_src || !d_sum || !d_sqsum || n_pages <= 0 || rows <= 0 || cols <= 0 || pad < 0)
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    if (plane_pitch < (size_t)(cols + 2 * pad) + ((cols + 2 * pad) & 1) || (plane_pitch & 1))
+        return prl_set_err(c, PRL_E_INVALID, "plane_pitch must be even and >= padded width rounded up to even");
+    if ((((uintptr_t)d_sum) | ((uintptr_t)d_sqsum)) & 15 || (plane_page_stride & 1))
+        return prl_set_err(c, PRL_E_INVALID, "planes must be 16-byte aligned");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    return prl_k_integral(c, d_src, n_pages, rows, cols, src_step, src_page_stride, pad, d_sum, d_sqsum, plane_pitch,
+                          plane_page_stride, nullptr);
+}
+
+extern "C" int prl_cuda_otsu_global_batch_dev(prl_cuda_ctx* c, const uint8_t* d_src, int n_pages, int rows, int cols,
+                                              size_t src_step, size_t src_page_stride, double maxval,
+                                              uint8_t* d_dst, size_t dst_step, size_t dst_page_stride, int32_t* d_thr)
+{
+    if (!c || !d_src || !d_dst || !d_thr || n_pages <= 0 || rows <= 0 || cols <= 0) return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    return prl_k_otsu_global(c, d_src, n_pages, rows, cols, src_step, src_page_stride, maxval, d_dst, dst_step,
+                             dst_page_stride, d_thr, true);
+}
+
+extern "C" int prl_cuda_otsu_tiles_batch_dev(prl_cuda_ctx* c, const uint8_t* d_src, int n_pages, int rows, int cols,
+                                             size_t src_step, size_t src_page_stride, int tile_w, int tile_h, double maxval,
+                                             uint8_t* d_dst, size_t dst_step, size_t dst_page_stride)
+{
+    if (!c || !d_src || !d_dst || n_pages <= 0 || rows <= 0 || cols <= 0 || tile_w <= 0 || tile_h <= 0)
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    if ((long long)tile_w * tile_h > 0x7fffffffLL) return prl_set_err(c, PRL_E_UNSUPPORTED, "tile too large");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    return prl_k_otsu_tiles(c, d_src, n_pages, rows, cols, src_step, src_page_stride, tile_w, tile_h, maxval, d_dst,
+                            dst_step, dst_page_stride);
+}
+
+extern "C" int prl_cuda_synth_pages_dev(prl_cuda_ctx* c, uint8_t* d_dst, int n_pages, int rows, int cols,
+                                        size_t step, size_t page_stride, uint32_t seed, uint32_t first_page)
+{
+    if (!c || !d_dst || n_pages <= 0 || rows <= 0 || cols <= 0) return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    return prl_k_synth(c, d_dst, n_pages, rows, cols, step, page_stride, seed, first_page);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-pointer (drop-in) entry points: stage -> kernels -> stage back, synchronous
+// ------------------------------------------------------------------------------------------------
+static int stage_in(prl_cuda_ctx* c, const uint8_t* src, int rows, size_t width_bytes, size_t step, size_t* dstep)
+{
+    *dstep = round16(width_bytes);
+    int rc = prl_ensure(c, (void**)&c->d_in, &c->d_in_bytes, *dstep * rows);
+    if (rc) return rc;
+    PRL_CUDA_TRY(c, cudaMemcpy2DAsync(c->d_in, *dstep, src, step, width_bytes, rows, cudaMemcpyHostToDevice, c->stream));
+    return PRL_OK;
+}
+
+static int local_host(prl_cuda_ctx* c, int method, int mode, const uint8_t* src, int rows, int cols, size_t step,
+                      int window, const double* params, int morph_iters, uint8_t* dst, size_t dst_step,
+                      int* out_rows, int* out_cols, double* aux)
+{
+    if (!c) return PRL_E_INVALID;
+    if (!src || !dst || !params) return prl_set_err(c, PRL_E_INVALID, "null pointer");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    prl_geom g;
+    int rc = prl_make_geom(method, rows, cols, window, &g);
+    if (rc) return prl_set_err(c, rc, rc == PRL_E_EMPTY_ROI ? "empty processingRect: min(rows, cols) <= windowSize"
+                                                             : "empty image or window not (>1 and odd)");
+    if (step < (size_t)cols || dst_step < (size_t)g.out_cols) return prl_set_err(c, PRL_E_INVALID, "step smaller than row width");
+    size_t in_step;
+    rc = stage_in(c, src, rows, cols, step, &in_step); if (rc) return rc;
+    const size_t o_step = round16(g.out_cols);
+    rc = prl_ensure(c, (void**)&c->d_out, &c->d_out_bytes, o_step * g.out_rows); if (rc) return rc;
+    rc = local_batch_dev(c, method, mode, c->d_in, 1, rows, cols, in_step, in_step * rows, window, params, morph_iters,
+                         c->d_out, o_step, o_step * g.out_rows);
+    if (rc) return rc;
+    PRL_CUDA_TRY(c, cudaMemcpy2DAsync(dst, dst_step, c->d_out, o_step, g.out_cols, g.out_rows, cudaMemcpyDeviceToHost, c->stream));
+    if (aux) {
+        uint32_t imin = 0; long long smax = 0;
+        PRL_CUDA_TRY(c, cudaMemcpyAsync(&imin, c->scalars, 4, cudaMemcpyDeviceToHost, c->stream));
+        PRL_CUDA_TRY(c, cudaMemcpyAsync(&smax, (uint8_t*)c->scalars + 8, 8, cudaMemcpyDeviceToHost, c->stream));
+        PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        aux[0] = (double)imin;
+        double s; memcpy(&s, &smax, 8); aux[1] = (method == PRL_WOLFJOLION) ? s : NAN;
+    }
+    PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (out_rows) *out_rows = g.out_rows;
+    if (out_cols) *out_cols = g.out_cols;
+    return PRL_OK;
+}
+
+extern "C" int prl_cuda_binarize_local(prl_cuda_ctx* c, int method, const uint8_t* src, int rows, int cols,
+                                       size_t step, int window, const double* params, int morph_iters,
+                                       uint8_t* dst, size_t dst_step, int* out_rows, int* out_cols)
+{
+    return local_host(c, method, 0, src, rows, cols, step, window, params, morph_iters, dst, dst_step, out_rows, out_cols, nullptr);
+}
+
+extern "C" int prl_cuda_threshold_map(prl_cuda_ctx* c, int method, const uint8_t* src, int rows, int cols,
+                                      size_t step, int window, const double* params, uint8_t* t8,
+                                      size_t t8_step, int* out_rows, int* out_cols, double* aux)
+{
+    return local_host(c, method, 1, src, rows, cols, step, window, params, 0, t8, t8_step, out_rows, out_cols, aux);
+}
+
+extern "C" int prl_cuda_integral_u8(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step,
+                                    int pad, int64_t* sum, int64_t* sqsum)
+{
+    if (!c) return PRL_E_INVALID;
+    if (!src || !sum || !sqsum || rows <= 0 || cols <= 0 || pad < 0 || step < (size_t)cols)
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    const int Hp = rows + 2 * pad, Wp = cols + 2 * pad;
+    const size_t pitch = prl_plane_pitch(Wp), plane = (size_t)Hp * pitch;
+    size_t in_step;
+    int rc = stage_in(c, src, rows, cols, step, &in_step); if (rc) return rc;
+    rc = prl_ensure(c, (void**)&c->planes, &c->planes_bytes, 2 * plane * sizeof(int64_t)); if (rc) return rc;
+    rc = prl_k_integral(c, c->d_in, 1, rows, cols, in_step, in_step * rows, pad, c->planes, c->planes + plane, pitch, plane, nullptr);
+    if (rc) return rc;
+    PRL_CUDA_TRY(c, cudaMemcpy2DAsync(sum, (size_t)Wp * 8, c->planes, pitch * 8, (size_t)Wp * 8, Hp, cudaMemcpyDeviceToHost, c->stream));
+    PRL_CUDA_TRY(c, cudaMemcpy2DAsync(sqsum, (size_t)Wp * 8, c->planes + plane, pitch * 8, (size_t)Wp * 8, Hp, cudaMemcpyDeviceToHost, c->stream));
+    PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return PRL_OK;
+}
+
+extern "C" int prl_cuda_bgr2gray(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step,
+                                 int channels, uint8_t* dst, size_t dst_step)
+{
+    if (!c) return PRL_E_INVALID;
+    if (!src || !dst || rows <= 0 || cols <= 0 || (channels != 3 && channels != 4) || step < (size_t)cols * channels ||
+        dst_step < (size_t)cols)
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    size_t in_step;
+    int rc = stage_in(c, src, rows, (size_t)cols * channels, step, &in_step); if (rc) return rc;
+    const size_t o_step = round16(cols);
+    rc = prl_ensure(c, (void**)&c->d_out, &c->d_out_bytes, o_step * rows); if (rc) return rc;
+    rc = prl_k_bgr2gray(c, c->d_in, rows, cols, in_step, channels, c->d_out, o_step); if (rc) return rc;
+    PRL_CUDA_TRY(c, cudaMemcpy2DAsync(dst, dst_step, c->d_out, o_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
+    PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return PRL_OK;
+}
+
+extern "C" int prl_cuda_morph(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step,
+                              int morph_iters, uint8_t* dst, size_t dst_step)
+{
+    if (!c) return PRL_E_INVALID;
+    if (!src || !dst || rows <= 0 || cols <= 0 || step < (size_t)cols || dst_step < (size_t)cols)
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    size_t in_step;
+    int rc = stage_in(c, src, rows, cols, step, &in_step); if (rc) return rc;
+    rc = prl_ensure(c, (void**)&c->d_tmp, &c->d_tmp_bytes, in_step * rows); if (rc) return rc;
+    rc = prl_k_morph(c, c->d_in, c->d_tmp, 1, rows, cols, in_step, in_step * rows, in_step, in_step * rows, morph_iters);
+    if (rc) return rc;
+    PRL_CUDA_TRY(c, cudaMemcpy2DAsync(dst, dst_step, c->d_in, in_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
+    PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return PRL_OK;
+}
+
+static int otsu_host(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step, double maxval,
+                     uint8_t* dst, size_t dst_step, int* thr, bool apply)
+{
+    if (!c) return PRL_E_INVALID;
+    if (!src || rows <= 0 || cols <= 0 || step < (size_t)cols || (apply && (!dst || dst_step < (size_t)cols)))
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    size_t in_step;
+    int rc = stage_in(c, src, rows, cols, step, &in_step); if (rc) return rc;
+    const size_t o_step = round16(cols);
+    rc = prl_ensure(c, (void**)&c->d_out, &c->d_out_bytes, o_step * rows); if (rc) return rc;
+    rc = prl_ensure(c, &c->scalars, &c->scalars_bytes, 64); if (rc) return rc;
+    int32_t* d_thr = (int32_t*)c->scalars;
+    rc = prl_k_otsu_global(c, c->d_in, 1, rows, cols, in_step, in_step * rows, maxval, c->d_out, o_step, o_step * rows, d_thr, apply);
+    if (rc) return rc;
+    int32_t t = 0;
+    PRL_CUDA_TRY(c, cudaMemcpyAsync(&t, d_thr, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (apply)
+        PRL_CUDA_TRY(c, cudaMemcpy2DAsync(dst, dst_step, c->d_out, o_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
+    PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (thr) *thr = t;
+    return PRL_OK;
+}
+
+extern "C" int prl_cuda_otsu_threshold(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step, int* thr)
+{
+    return otsu_host(c, src, rows, cols, step, 255.0, nullptr, 0, thr, false);
+}
+
+extern "C" int prl_cuda_otsu_global(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step,
+                                    double maxval, uint8_t* dst, size_t dst_step, int* thr)
+{
+    return otsu_host(c, src, rows, cols, step, maxval, dst, dst_step, thr, true);
+}
+
+extern "C" int prl_cuda_otsu_rects(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step,
+                                   const int32_t* xywh, int n_rects, double maxval, uint8_t* dst, size_t dst_step,
+                                   int32_t* thr_out)
+{
+    if (!c) return PRL_E_INVALID;
+    if (!src || !dst || rows <= 0 || cols <= 0 || step < (size_t)cols || dst_step < (size_t)cols || n_rects < 0 ||
+        (n_rects > 0 && !xywh))
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    for (int r = 0; r < n_rects; ++r) {   // cv::Mat::operator()(Rect) asserts the ROI is inside the image
+        const int32_t* q = xywh + 4 * r;
+        if (q[2] <= 0 || q[3] <= 0 || q[0] < 0 || q[1] < 0 || (long long)q[0] + q[2] > cols || (long long)q[1] + q[3] > rows)
+            return prl_set_err(c, PRL_E_INVALID, "rectangle outside the image");
+    }
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    size_t in_step;
+    int rc = stage_in(c, src, rows, cols, step, &in_step); if (rc) return rc;
+    const size_t o_step = round16(cols);
+    rc = prl_ensure(c, (void**)&c->d_out, &c->d_out_bytes, o_step * rows); if (rc) return rc;
+    const size_t rl = (size_t)std::max(1, n_rects) * 16;
+    rc = prl_ensure(c, (void**)&c->d_tmp, &c->d_tmp_bytes, rl + (size_t)std::max(1, n_rects) * 4); if (rc) return rc;
+    int32_t* d_rects = (int32_t*)c->d_tmp;
+    int32_t* d_thr = (int32_t*)(c->d_tmp + rl);
+    if (n_rects) PRL_CUDA_TRY(c, cudaMemcpyAsync(d_rects, xywh, (size_t)n_rects * 16, cudaMemcpyHostToDevice, c->stream));
+    rc = prl_k_otsu_rects(c, c->d_in, rows, cols, in_step, d_rects, n_rects, maxval, c->d_out, o_step, d_thr);
+    if (rc) return rc;
+    PRL_CUDA_TRY(c, cudaMemcpy2DAsync(dst, dst_step, c->d_out, o_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
+    if (thr_out && n_rects)
+        PRL_CUDA_TRY(c, cudaMemcpyAsync(thr_out, d_thr, (size_t)n_rects * 4, cudaMemcpyDeviceToHost, c->stream));
+    PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return PRL_OK;
+}
+
+extern "C" int prl_cuda_otsu_tiles(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step,
+                                   int tile_w, int tile_h, double maxval, uint8_t* dst, size_t dst_step)
+{
+    if (!c) return PRL_E_INVALID;
+    if (!src || !dst || rows <= 0 || cols <= 0 || step < (size_t)cols || dst_step < (size_t)cols || tile_w <= 0 || tile_h <= 0)
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    size_t in_step;
+    int rc = stage_in(c, src, rows, cols, step, &in_step); if (rc) return rc;
+    const size_t o_step = round16(cols);
+    rc = prl_ensure(c, (void**)&c->d_out, &c->d_out_bytes, o_step * rows); if (rc) return rc;
+    rc = prl_cuda_otsu_tiles_batch_dev(c, c->d_in, 1, rows, cols, in_step, in_step * rows, tile_w, tile_h, maxval,
+                                       c->d_out, o_step, o_step * rows);
+    if (rc) return rc;
+    PRL_CUDA_TRY(c, cudaMemcpy2DAsync(dst, dst_step, c->d_out, o_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
+    PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return PRL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host batch: pinned-memory loader + page dispatcher (one host thread per device, no collective)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct DeviceWorker {
+    prl_cuda_ctx* ctx = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    static constexpr int NBUF = 3;
+    uint8_t* d_in[NBUF] = {nullptr, nullptr, nullptr};
+    uint8_t* d_out[NBUF] = {nullptr, nullptr, nullptr};
+    size_t in_bytes = 0, out_bytes = 0;
+    cudaEvent_t ev_in[NBUF], ev_comp[NBUF], ev_out[NBUF];
+    bool events = false;
+    ~DeviceWorker()
+    {
+        if (!ctx) return;
+        cudaSetDevice(ctx->device);
+        for (int i = 0; i < NBUF; ++i) { cudaFree(d_in[i]); cudaFree(d_out[i]); }
+        if (events) for (int i = 0; i < NBUF; ++i) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_comp[i]); cudaEventDestroy(ev_out[i]); }
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_out) cudaStreamDestroy(s_out);
+        prl_cuda_destroy(ctx);
+    }
+};
+
+std::mutex g_workers_mu;
+// cached per device across calls; leaked on purpose (no CUDA calls from static destructors at exit)
+auto& g_workers = *new std::map<int, std::unique_ptr<DeviceWorker>>();
+
+DeviceWorker* get_worker(int device, std::string* err)
+{
+    std::lock_guard<std::mutex> lk(g_workers_mu);
+    auto it = g_workers.find(device);
+    if (it != g_workers.end()) return it->second.get();
+    std::unique_ptr<DeviceWorker> w(new DeviceWorker());
+    int rc = prl_cuda_create(device, &w->ctx);
+    if (rc) { *err = prl_cuda_last_error(nullptr); w->ctx = nullptr; return nullptr; }
+    cudaStreamCreateWithFlags(&w->s_in, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&w->s_out, cudaStreamNonBlocking);
+    for (int i = 0; i < DeviceWorker::NBUF; ++i) {
+        cudaEventCreateWithFlags(&w->ev_in[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&w->ev_comp[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&w->ev_out[i], cudaEventDisableTiming);
+    }
+    w->events = true;
+    DeviceWorker* p = w.get();
+    g_workers[device] = std::move(w);
+    return p;
+}
+
+// pages [p0, p1) of the batch on one device: 3-slot ring, H2D / kernels / D2H on three streams
+int run_shard(DeviceWorker* w, int method, const uint8_t* pages, int p0, int p1, int rows, int cols, int window,
+              const double* params, int morph_iters, uint8_t* masks, const prl_geom& g, std::string* err)
+{
+    prl_cuda_ctx* c = w->ctx;
+#define SHARD_TRY(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { *err = std::string(#call) + ": " + cudaGetErrorString(_e); return PRL_E_CUDA; } } while (0)
+    SHARD_TRY(cudaSetDevice(c->device));
+    const size_t in_step = round16(cols), o_step = round16(g.out_cols);
+    const size_t in_page = in_step * rows, out_page = o_step * g.out_rows;
+    const size_t host_in_page = (size_t)rows * cols, host_out_page = (size_t)g.out_rows * g.out_cols;
+    // chunk: about 128 MiB of input per slot, at least 1 page
+    int chunk = (int)std::max<size_t>(1, ((size_t)128 << 20) / in_page);
+    chunk = std::min(chunk, std::max(1, (p1 - p0 + 2) / 3));
+    if (in_page * chunk > w->in_bytes || out_page * chunk > w->out_bytes) {
+        SHARD_TRY(cudaDeviceSynchronize());
+        for (int i = 0; i < DeviceWorker::NBUF; ++i) {
+            cudaFree(w->d_in[i]); cudaFree(w->d_out[i]); w->d_in[i] = w->d_out[i] = nullptr;
+        }
+        w->in_bytes = in_page * chunk; w->out_bytes = out_page * chunk;
+        for (int i = 0; i < DeviceWorker::NBUF; ++i) {
+            SHARD_TRY(cudaMalloc((void**)&w->d_in[i], w->in_bytes));
+            SHARD_TRY(cudaMalloc((void**)&w->d_out[i], w->out_bytes));
+        }
+    }
+    int it = 0;
+    for (int p = p0; p < p1; p += chunk, ++it) {
+        const int np = std::min(chunk, p1 - p);
+        const int slot = it % DeviceWorker::NBUF;
+        if (it >= DeviceWorker::NBUF) {
+            SHARD_TRY(cudaStreamWaitEvent(w->s_in, w->ev_comp[slot], 0));     // d_in[slot] consumed
+            SHARD_TRY(cudaStreamWaitEvent(c->stream, w->ev_out[slot], 0));    // d_out[slot] drained
+        }
+        SHARD_TRY(cudaMemcpy2DAsync(w->d_in[slot], in_step, pages + (size_t)p * host_in_page, cols, cols,
+                                    (size_t)rows * np, cudaMemcpyHostToDevice, w->s_in));
+        SHARD_TRY(cudaEventRecord(w->ev_in[slot], w->s_in));
+        SHARD_TRY(cudaStreamWaitEvent(c->stream, w->ev_in[slot], 0));
+        int rc = prl_cuda_binarize_local_batch_dev(c, method, w->d_in[slot], np, rows, cols, in_step, in_page, window,
+                                                   params, morph_iters, w->d_out[slot], o_step, out_page);
+        if (rc) { *err = c->err; return rc; }
+        SHARD_TRY(cudaEventRecord(w->ev_comp[slot], c->stream));
+        SHARD_TRY(cudaStreamWaitEvent(w->s_out, w->ev_comp[slot], 0));
+        SHARD_TRY(cudaMemcpy2DAsync(masks + (size_t)p * host_out_page, g.out_cols, w->d_out[slot], o_step, g.out_cols,
+                                    (size_t)g.out_rows * np, cudaMemcpyDeviceToHost, w->s_out));
+        SHARD_TRY(cudaEventRecord(w->ev_out[slot], w->s_out));
+    }
+    SHARD_TRY(cudaStreamSynchronize(w->s_out));
+    SHARD_TRY(cudaStreamSynchronize(c->stream));
+    SHARD_TRY(cudaStreamSynchronize(w->s_in));
+#undef SHARD_TRY
+    return PRL_OK;
+}
+
+}  // namespace
+
+extern "C" int prl_cuda_binarize_batch(const int* devices, int n_dev, int method, const uint8_t* pages, int n_pages,
+                                       int rows, int cols, int window, const double* params, int morph_iters,
+                                       uint8_t* masks)
+{
+    if (!pages || !masks || !params || n_pages <= 0) return prl_set_err(nullptr, PRL_E_INVALID, "null pointer or empty batch");
+    prl_geom g;
+    int rc = prl_make_geom(method, rows, cols, window, &g);
+    if (rc) return prl_set_err(nullptr, rc, "bad geometry / window");
+    std::vector<int> devs;
+    if (!devices || n_dev <= 0) { int n = prl_cuda_device_count(); for (int i = 0; i < n; ++i) devs.push_back(i); }
+    else devs.assign(devices, devices + n_dev);
+    if (devs.empty()) return prl_set_err(nullptr, PRL_E_CUDA, "no CUDA device available (libprlib_cuda has no CPU fallback)");
+    const int G = (int)devs.size();
+    std::vector<int> rcs(G, PRL_OK);
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> threads;
+    for (int gi = 0; gi < G; ++gi) {
+        // contiguous page ranges: device gi <- pages [gi*N/G, (gi+1)*N/G)
+        const int p0 = (int)((long long)gi * n_pages / G), p1 = (int)((long long)(gi + 1) * n_pages / G);
+        if (p1 <= p0) continue;
+        auto job = [&, gi, p0, p1]() {
+            DeviceWorker* w = get_worker(devs[gi], &errs[gi]);
+            if (!w) { rcs[gi] = PRL_E_CUDA; return; }
+            rcs[gi] = run_shard(w, method, pages, p0, p1, rows, cols, window, params, morph_iters, masks, g, &errs[gi]);
+        };
+        if (G == 1) job(); else threads.emplace_back(job);
+    }
+    for (auto& t : threads) t.join();
+    for (int gi = 0; gi < G; ++gi)
+        if (rcs[gi]) {
+            char buf[64]; snprintf(buf, sizeof buf, "device %d: ", devs[gi]);
+            return prl_set_err(nullptr, rcs[gi], (std::string(buf) + errs[gi]).c_str());
+        }
+    return PRL_OK;
+}

@@ -1,0 +1,105 @@
+// common.cuh -- context, error plumbing and launch instrumentation shared by libprlib_cuda.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/prlib_cuda.h"
+
+#define PRL_NUM_SMS_FALLBACK 148
+
+// Layout of the integral planes in HBM: rows of `pitch` int64 elements, pitch a multiple of 16
+// elements (128 B) so every row starts on a cache-line boundary and 16-byte vector accesses at
+// even columns are aligned.
+static inline size_t prl_plane_pitch(int padded_cols) { return ((size_t)padded_cols + 15) & ~(size_t)15; }
+
+struct prl_timing_rec { cudaEvent_t a, b; int family; };
+
+struct prl_cuda_ctx {
+    int device = 0;
+    int num_sms = PRL_NUM_SMS_FALLBACK;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;      // the stream every launch goes to (own or borrowed)
+    std::string err;
+
+    // scratch: integral planes S and Q for the in-flight chunk of pages
+    int64_t* planes = nullptr;  size_t planes_bytes = 0;
+    size_t workspace_limit = (size_t)48 << 30;
+    // band carries (latency mode), per-page scalars {imin (u32), smax (i64 bit pattern)}
+    void* carry = nullptr;      size_t carry_bytes = 0;
+    void* colsum = nullptr;     size_t colsum_bytes = 0;
+    void* scalars = nullptr;    size_t scalars_bytes = 0;
+    // device staging for host-pointer entry points
+    uint8_t* d_in = nullptr;    size_t d_in_bytes = 0;
+    uint8_t* d_out = nullptr;   size_t d_out_bytes = 0;
+    uint8_t* d_tmp = nullptr;   size_t d_tmp_bytes = 0;
+    void* d_misc = nullptr;     size_t d_misc_bytes = 0;   // histograms, thresholds, rect lists
+    // pinned host staging
+    uint8_t* h_pin = nullptr;   size_t h_pin_bytes = 0;
+
+    // instrumentation
+    bool timing = false;
+    long long launches = 0;
+    std::vector<prl_timing_rec> recs;
+    std::vector<cudaEvent_t> event_pool;
+    std::map<int, std::pair<double, long long>> totals;
+};
+
+enum prl_family {
+    FAM_INTEGRAL = 0, FAM_THRESHOLD, FAM_SMAX, FAM_MORPH, FAM_OTSU_HIST, FAM_OTSU_SEARCH,
+    FAM_OTSU_APPLY, FAM_OTSU_TILES, FAM_SYNTH, FAM_BGR2GRAY, FAM_BAND_CARRY, FAM_COUNT
+};
+
+int  prl_set_err(prl_cuda_ctx* ctx, int code, const char* what, cudaError_t ce = cudaSuccess);
+int  prl_ensure(prl_cuda_ctx* ctx, void** ptr, size_t* have, size_t need);          // device scratch
+int  prl_ensure_pinned(prl_cuda_ctx* ctx, size_t need);
+void prl_launch_begin(prl_cuda_ctx* ctx, int family);
+void prl_launch_end(prl_cuda_ctx* ctx);
+
+#define PRL_CUDA_TRY(ctx, call)                                                        \
+    do { cudaError_t _e = (call);                                                      \
+         if (_e != cudaSuccess) return prl_set_err((ctx), PRL_E_CUDA, #call, _e); } while (0)
+
+// RAII bracket: counts the launch and, when timing is on, records events around it.
+struct prl_launch_scope {
+    prl_cuda_ctx* c;
+    prl_launch_scope(prl_cuda_ctx* ctx, int family) : c(ctx) { prl_launch_begin(c, family); }
+    ~prl_launch_scope() { prl_launch_end(c); }
+};
+
+// ---- kernel launchers (defined in the .cu files; all asynchronous on ctx->stream) --------
+struct prl_geom {
+    int rows, cols;        // source page
+    int w, h, d;           // clamped window, w/2, w-1
+    int Hp, Wp;            // padded size
+    int out_rows, out_cols;
+    size_t pitch;          // plane pitch in int64 elements
+};
+int prl_make_geom(int method, int rows, int cols, int window, prl_geom* g);
+
+int prl_k_integral(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int rows, int cols, size_t src_step,
+                   size_t src_page_stride, int pad, int64_t* d_S, int64_t* d_Q, size_t pitch,
+                   size_t plane_page_stride, uint32_t* d_imin /*per page or null*/);
+struct prl_thr_params { double kw, nkw, p0, p1, p2; };
+int prl_k_threshold(prl_cuda_ctx* ctx, int method, int mode /*0 mask, 1 T8*/, const uint8_t* d_src, int n_pages,
+                    const prl_geom& g, size_t src_step, size_t src_page_stride, const int64_t* d_S,
+                    const int64_t* d_Q, size_t plane_page_stride, const double* params,
+                    const uint32_t* d_imin, long long* d_smax, uint8_t* d_dst, size_t dst_step,
+                    size_t dst_page_stride);
+int prl_k_morph(prl_cuda_ctx* ctx, uint8_t* d_mask, uint8_t* d_tmp, int n_pages, int rows, int cols, size_t step,
+                size_t page_stride, size_t tmp_step, size_t tmp_page_stride, int iters);
+int prl_k_bgr2gray(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, int channels,
+                   uint8_t* d_dst, size_t dst_step);
+int prl_k_synth(prl_cuda_ctx* ctx, uint8_t* d_dst, int n_pages, int rows, int cols, size_t step,
+                size_t page_stride, uint32_t seed, uint32_t first_page);
+int prl_k_otsu_global(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int rows, int cols, size_t src_step,
+                      size_t src_page_stride, double maxval, uint8_t* d_dst, size_t dst_step,
+                      size_t dst_page_stride, int32_t* d_thr /*n_pages*/, bool apply);
+int prl_k_otsu_rects(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t src_step,
+                     const int32_t* d_xywh, int n_rects, double maxval, uint8_t* d_dst, size_t dst_step,
+                     int32_t* d_thr);
+int prl_k_otsu_tiles(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int rows, int cols, size_t src_step,
+                     size_t src_page_stride, int tile_w, int tile_h, double maxval, uint8_t* d_dst,
+                     size_t dst_step, size_t dst_page_stride);
