@@ -51,12 +51,18 @@ int         prl_cuda_create(int device, prl_cuda_ctx** out);
 void        prl_cuda_destroy(prl_cuda_ctx* ctx);
 const char* prl_cuda_last_error(const prl_cuda_ctx* ctx);   /* ctx may be NULL: last create() error */
 /* Borrow an externally owned cudaStream_t (e.g. torch's current stream) for all later calls;
- * NULL restores the context's own stream. */
+ * NULL restores the context's own stream; pass cudaStreamLegacy ((void*)0x1) for the legacy
+ * default stream. */
 int         prl_cuda_set_stream(prl_cuda_ctx* ctx, void* cuda_stream);
 int         prl_cuda_synchronize(prl_cuda_ctx* ctx);
 /* Upper bound (bytes) for the S/Q scratch planes of one in-flight chunk of pages (default 48 GiB,
  * clipped to 70 % of free HBM at first use). */
 int         prl_cuda_set_workspace_limit(prl_cuda_ctx* ctx, size_t bytes);
+/* Validation switches (masks and planes are bit-identical either way; only the speed differs):
+ *   "exact_threshold" != 0 : kernel 2 evaluates the reference's FP64 formula for EVERY pixel instead
+ *                            of only for the pixels its exact-integer/FP32 decision cannot settle;
+ *   "disable_tma"     != 0 : kernel 1 uses its generic byte-load kernel instead of the TMA-staged one. */
+int         prl_cuda_set_option(prl_cuda_ctx* ctx, const char* name, long long value);
 
 /* Geometry of the reference's processingRect (binarizeSauvola.cpp:57,66; binarizeWolfJolion.cpp:58,69):
  * Sauvola/Niblack -> (rows+2h-w) x (cols+2h-w); WJ/NICK/Feng -> (rows-w) x (cols-w), with

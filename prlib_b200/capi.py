@@ -25,6 +25,7 @@ SIGNATURES = {
     "prl_cuda_set_stream": (C.c_int, [_ctx, C.c_void_p]),
     "prl_cuda_synchronize": (C.c_int, [_ctx]),
     "prl_cuda_set_workspace_limit": (C.c_int, [_ctx, C.c_size_t]),
+    "prl_cuda_set_option": (C.c_int, [_ctx, C.c_char_p, C.c_longlong]),
     "prl_cuda_output_shape": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _intp, _intp]),
     "prl_cuda_integral_u8": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),
     "prl_cuda_binarize_local": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, _f64p, C.c_int,

@@ -69,13 +69,23 @@ class Context:
         return self._h
 
     def set_stream(self, cuda_stream: int | None):
-        self._check(self._L.prl_cuda_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        """Borrow a cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream); None gives the
+        context its own stream back.  Handle 0 (torch's default stream) is passed as cudaStreamLegacy."""
+        if cuda_stream is None:
+            h = 0
+        else:
+            h = int(cuda_stream) or 1          # cudaStreamLegacy == (cudaStream_t)0x1
+        self._check(self._L.prl_cuda_set_stream(self._h, C.c_void_p(h)))
 
     def synchronize(self):
         self._check(self._L.prl_cuda_synchronize(self._h))
 
     def set_workspace_limit(self, nbytes: int):
         self._check(self._L.prl_cuda_set_workspace_limit(self._h, int(nbytes)))
+
+    def set_option(self, name: str, value: int):
+        """Validation switches: "exact_threshold", "disable_tma" (results are identical, speed differs)."""
+        self._check(self._L.prl_cuda_set_option(self._h, name.encode(), int(value)))
 
     def timing_enable(self, on: bool = True):
         self._check(self._L.prl_cuda_timing_enable(self._h, int(on)))

@@ -188,6 +188,15 @@ extern "C" int prl_cuda_set_workspace_limit(prl_cuda_ctx* c, size_t bytes)
     return PRL_OK;
 }
 
+extern "C" int prl_cuda_set_option(prl_cuda_ctx* c, const char* name, long long value)
+{
+    if (!c || !name) return PRL_E_INVALID;
+    if (strcmp(name, "exact_threshold") == 0) c->force_exact = value != 0;
+    else if (strcmp(name, "disable_tma") == 0) c->no_tma = value != 0;
+    else return prl_set_err(c, PRL_E_INVALID, "unknown option");
+    return PRL_OK;
+}
+
 extern "C" int prl_cuda_output_shape(int method, int rows, int cols, int window, int* out_rows, int* out_cols)
 {
     prl_geom g;
@@ -224,15 +233,18 @@ extern "C" long long prl_cuda_launch_count(const prl_cuda_ctx* c) { return c ? c
 // ------------------------------------------------------------------------------------------------
 // device-resident batch entry points
 // ------------------------------------------------------------------------------------------------
-static size_t planes_budget(prl_cuda_ctx* c)
+// Bytes the S/Q planes of one in-flight chunk may take.  cudaMemGetInfo is only consulted when the
+// planes have to grow (it takes the driver's allocator lock and was seen to stall for tens of ms).
+static size_t planes_budget(prl_cuda_ctx* c, size_t want)
 {
+    if (want <= c->planes_bytes && c->planes) return c->planes_bytes;
     size_t lim = c->workspace_limit;
     size_t fr = 0, tot = 0;
     if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
         size_t avail = fr + c->planes_bytes;          // what we already hold counts as available to us
         lim = std::min(lim, (size_t)(avail * 0.7));
     }
-    return lim;
+    return std::max(lim, c->planes_bytes);
 }
 
 // mode 0: masks (+morph), mode 1: T8 maps
@@ -250,7 +262,7 @@ static int local_batch_dev(prl_cuda_ctx* c, int method, int mode, const uint8_t*
 
     const size_t plane_elems = (size_t)g.Hp * g.pitch;          // one plane of one page
     const size_t per_page = 2 * plane_elems * sizeof(int64_t);
-    size_t budget = planes_budget(c);
+    const size_t budget = std::min(planes_budget(c, (size_t)n_pages * per_page), c->workspace_limit);
     int chunk = (int)std::min<size_t>((size_t)n_pages, std::max<size_t>(1, budget / per_page));
     if ((size_t)chunk * per_page > c->planes_bytes || !c->planes) {
         rc = prl_ensure(c, (void**)&c->planes, &c->planes_bytes, (size_t)chunk * per_page);

@@ -39,6 +39,9 @@ struct prl_cuda_ctx {
     // pinned host staging
     uint8_t* h_pin = nullptr;   size_t h_pin_bytes = 0;
 
+    bool force_exact = false;   // validation: kernel 2 runs the literal FP64 path for every pixel
+    bool no_tma = false;        // validation: kernel 1 uses the generic (non-TMA) kernel
+
     // instrumentation
     bool timing = false;
     long long launches = 0;

@@ -6,27 +6,34 @@
 // Feng), plus cv::minMaxLoc(image) of binarizeWolfJolion.cpp:115-116 / binarizeFeng.cpp:111-112
 // (page minimum, fused: the kernel sees every pixel anyway).
 //
-// Decomposition (HBM-bound: 1 byte read, 16 bytes written per padded pixel):
-//   * one CTA owns one page (or one row band of it) over its FULL padded width; warp k owns the
-//     256 padded columns [256k, 256k+256) as 4 sub-segments of 64 columns, lane l holding the
-//     column pair (64j + 2l, 64j + 2l + 1) -> every S/Q store is one 16-byte word per lane and
-//     512 contiguous bytes per warp instruction (full 128-B lines, no partial sectors);
-//   * row direction: lane-local pair sums -> 5-step __shfl_up warp scan per sub-segment ->
-//     sub-segment carries by shuffle broadcast -> cross-warp row offsets through a double-
-//     buffered shared-memory table, ONE __syncthreads per chunk of R rows (row prefixes fit u32:
-//     255^2 * 65536 < 2^32);
-//   * column direction: each lane keeps the running int64 column sums of its 8 columns x 2
-//     planes in registers while the CTA walks down the rows -- the row prefix never touches
-//     memory, each S/Q element is written exactly once;
-//   * the next chunk's pixels are loaded (register prefetch) before the current chunk's scan.
-// Latency mode (few pages): the page is cut into row bands; two small kernels produce each
-// band's top carry (column sums of the bands above, row-scanned) so the bands run concurrently.
+// HBM-bound: 1 byte read, 16 bytes written per padded pixel.  Decomposition:
+//   * one CTA owns one page (or one band of source rows) over its FULL padded width; warp k owns
+//     the 256 padded columns [256k, 256k+256) as 2 sub-segments of 128 columns, lane l holding the
+//     4 adjacent columns 128j + 4l .. +3 -> every S/Q store is one 32-byte STG.256 per lane, 1 KB
+//     contiguous per warp instruction (full lines, no partial sectors);
+//   * the u8 rows are staged by TMA (cp.async.bulk.tensor, one 272-byte x R box per warp and chunk
+//     of R source rows, 3-stage mbarrier ring per warp, no registers held across the latency).  TMA
+//     needs a 16-byte aligned box origin, so the box starts at the aligned byte below the strip's
+//     first padded column (272 = 256 + 16 bytes, described as 136 u16 elements because a box
+//     dimension is limited to 256 elements) and lanes undo the residual shift with one funnel shift
+//     of two aligned shared-memory words; TMA zero-fills outside the image and the two edge warps
+//     substitute the replicated border pixel;
+//   * row direction: lane-local prefix of 4 pixels -> 5-step __shfl_up warp scan per sub-segment ->
+//     cross-warp row offsets through a double-buffered shared table, ONE __syncthreads per chunk
+//     (row prefixes fit u32: 255^2 * 65536 < 2^32);
+//   * column direction: each lane keeps the running int64 column sums of its 8 columns x 2 planes
+//     in registers while the CTA walks down the rows; the replicated top/bottom border rows are
+//     emitted by re-accumulating the same row prefix, so each S/Q element is written exactly once
+//     and the row prefix never touches memory.
+// Latency mode (few pages): the page is cut into bands of source rows; two small kernels produce
+// each band's top carry (weighted column sums of the rows above, row-scanned) so bands run
+// concurrently.  integral_generic_kernel is the any-alignment / any-pitch fallback (no TMA).
 #include "common.cuh"
+#include <cuda.h>
 
 namespace {
 
 constexpr int kWarpCols = 256;   // padded columns per warp
-constexpr int kSub = 4;          // sub-segments of 64 columns
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
 {
@@ -42,20 +49,240 @@ __device__ __forceinline__ void st_v2_s64(int64_t* p, int64_t a, int64_t b)
 {
     asm volatile("st.global.v2.s64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
+__device__ __forceinline__ void st_v4_s64(int64_t* p, long long a, long long b, long long c, long long d)
+{
+    asm volatile("st.global.v4.s64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
 
+// ---- mbarrier / TMA primitives ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA kernel.  Band b covers source rows [b*rows_per_band, ...); it emits padded row y+pad for each
+// of its source rows, plus the `pad` replicated rows above row 0 / below row rows-1.
+// J = sub-segments of 128 columns per warp (1: 128 columns/warp, 16 accumulator registers/plane-pair
+// fewer -> twice the resident warps for pages up to 4096 columns; 2: 256 columns/warp for wide pages).
+// ------------------------------------------------------------------------------------------------
+template <int J> __host__ __device__ constexpr int box_bytes() { return 128 * J + 16; }   // 16-byte aligned origin
+template <int J, int R> __host__ __device__ constexpr int stage_bytes() { return (R * box_bytes<J>() + 127) / 128 * 128; }
+
+template <int MAXW, int MINB, int J, int R, int NS>
+__global__ void __launch_bounds__(MAXW * 32, MINB)
+integral_tma_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int cols, int pad, int64_t* __restrict__ S,
+                    int64_t* __restrict__ Q, size_t pitch, size_t page_stride, int rows_per_band,
+                    const int64_t* __restrict__ carry, uint32_t* __restrict__ imin)
+{
+    constexpr int WC = 128 * J;                  // padded columns per warp
+    constexpr int BOX = box_bytes<J>();
+    constexpr int STAGE = stage_bytes<J, R>();
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ uint2 tot[2][R][MAXW];
+    __shared__ uint64_t bars[MAXW][NS];
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int page = blockIdx.y, band = blockIdx.x, bands = gridDim.x;
+    const int y0 = band * rows_per_band;
+    const int y1 = min(y0 + rows_per_band, rows);
+
+    S += (size_t)page * page_stride;
+    Q += (size_t)page * page_stride;
+
+    uint8_t* slot = smem_raw + (size_t)wid * (NS * STAGE);               // this warp's ring
+    const int X0 = wid * WC;
+    const int Xl = X0 + 4 * lane;                                        // + 128 j
+    // Box origin (source byte column, multiple of 16).  Normally the aligned byte below the strip's
+    // first source column; a strip lying entirely in the right replicate border is moved left so
+    // that it still contains the last image column.
+    int xb = (X0 - pad) & ~15;
+    const bool all_right = X0 - pad >= cols;                             // every column replicates column cols-1
+    const bool all_left = X0 + WC <= pad;                                // every column replicates column 0
+    if (all_right) xb = (cols - 1) & ~15;
+    if (all_left) xb = 0;
+    const int sh = X0 - pad - xb;                                        // strip column 0 sits `sh` bytes into the box
+    const bool edge = (X0 < pad) || (X0 + WC > pad + cols);              // strip touches a replicated column
+    const int lcol = -xb;                                                // box offset of source column 0 (valid when X0 < pad)
+    const int rcol = cols - 1 - xb;                                      // box offset of source column cols-1
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) mbar_init(&bars[wid][s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    bool st[J];
+    long long accS[J][4], accQ[J][4];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        st[j] = Xl + 128 * j < (int)pitch;                               // pitch % 4 == 0
+#pragma unroll
+        for (int i = 0; i < 4; ++i) accS[j][i] = accQ[j][i] = 0;
+        if (carry != nullptr && band > 0 && st[j]) {
+            const long long* c = reinterpret_cast<const long long*>(carry) + ((size_t)page * bands + band) * 2 * pitch + Xl + 128 * j;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { accS[j][i] = c[i]; accQ[j][i] = c[pitch + i]; }
+        }
+    }
+
+    const int n_chunks = (y1 - y0 + R - 1) / R;
+    // (the descriptor address must be the kernel-parameter address itself: no lambda / local copy)
+#define PRL_ISSUE_TMA(c_)                                                                               \
+    do {                                                                                                \
+        const int s_ = (c_) % NS;                                                                       \
+        mbar_expect_tx(&bars[wid][s_], R * BOX);                                                        \
+        tma_load_3d(slot + (size_t)s_ * STAGE, &tmap, xb / 2, y0 + (c_) * R, page, &bars[wid][s_]);     \
+    } while (0)
+    if (lane == 0)
+        for (int c = 0; c < NS - 1 && c < n_chunks; ++c) PRL_ISSUE_TMA(c);
+
+    // 4 pixels of chunk row r, sub-segment j, with the replicated border substituted
+    auto fetch = [&](const uint8_t* row, int j) -> uint32_t {
+        uint32_t w;
+        if (all_right) {
+            w = row[rcol] * 0x01010101u;
+        } else if (all_left) {
+            w = row[0] * 0x01010101u;
+        } else {
+            const int b = sh + 128 * j + 4 * lane;
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(row + (b & ~3));
+            w = wp[0];
+            if (sh & 3) w = __funnelshift_r(w, wp[1], 8 * (sh & 3));
+            if (edge) {
+                const int x = Xl + 128 * j - pad;      // source column of byte 0
+                const uint32_t lv = (X0 < pad) ? row[lcol] : 0u, rv = (rcol >= 0 && rcol < BOX) ? row[rcol] : 0u;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int xi = x + i;
+                    if (xi < 0) w = (w & ~(0xffu << (8 * i))) | (lv << (8 * i));
+                    else if (xi >= cols) w = (w & ~(0xffu << (8 * i))) | (rv << (8 * i));
+                }
+            }
+        }
+        return w;
+    };
+
+    uint32_t mn4 = 0xffffffffu;
+    int buf_sel = 0;
+    for (int c = 0; c < n_chunks; ++c, buf_sel ^= 1) {
+        __syncwarp();                                         // every lane is done with slot (c-1) % NS
+        if (lane == 0 && c + NS - 1 < n_chunks) PRL_ISSUE_TMA(c + NS - 1);
+        mbar_wait(&bars[wid][c % NS], (uint32_t)((c / NS) & 1));
+        const uint8_t* buf = slot + (size_t)(c % NS) * STAGE;
+        const int yc = y0 + c * R;
+
+        // sweep 1: this warp's row totals
+#pragma unroll 2
+        for (int r = 0; r < R; ++r) {
+            uint32_t s = 0, q = 0;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const uint32_t w = fetch(buf + r * BOX, j);
+                if (yc + r < y1) mn4 = __vminu4(mn4, w);
+                const uint32_t p0 = w & 0xff, p1 = (w >> 8) & 0xff, p2 = (w >> 16) & 0xff, p3 = w >> 24;
+                s += (p0 + p1) + (p2 + p3);
+                q += (p0 * p0 + p1 * p1) + (p2 * p2 + p3 * p3);
+            }
+            s = __reduce_add_sync(0xffffffffu, s);
+            q = __reduce_add_sync(0xffffffffu, q);
+            if (lane == 0) tot[buf_sel][r][wid] = make_uint2(s, q);
+        }
+        __syncthreads();
+
+        // sweep 2: scans, column accumulation, stores
+#pragma unroll 2
+        for (int r = 0; r < R; ++r) {
+            const int y = yc + r;
+            if (y < y1) {
+                const uint2 t = (lane < wid) ? tot[buf_sel][r][lane] : make_uint2(0u, 0u);
+                uint32_t off_s = __reduce_add_sync(0xffffffffu, t.x);
+                uint32_t off_q = __reduce_add_sync(0xffffffffu, t.y);
+                uint32_t rs[J][4], rq[J][4];
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const uint32_t w = fetch(buf + r * BOX, j);
+                    const uint32_t p0 = w & 0xff, p1 = (w >> 8) & 0xff, p2 = (w >> 16) & 0xff, p3 = w >> 24;
+                    const uint32_t a1 = p0 + p1, a2 = a1 + p2, a3 = a2 + p3;
+                    const uint32_t b0 = p0 * p0, b1 = b0 + p1 * p1, b2 = b1 + p2 * p2, b3 = b2 + p3 * p3;
+                    const uint32_t is = warp_incl_scan(a3, lane), iq = warp_incl_scan(b3, lane);
+                    const uint32_t es = off_s + is - a3, eq = off_q + iq - b3;   // exclusive base of this lane
+                    rs[j][0] = es + p0; rs[j][1] = es + a1; rs[j][2] = es + a2; rs[j][3] = es + a3;
+                    rq[j][0] = eq + b0; rq[j][1] = eq + b1; rq[j][2] = eq + b2; rq[j][3] = eq + b3;
+                    if (J > 1) {
+                        off_s += __shfl_sync(0xffffffffu, is, 31);
+                        off_q += __shfl_sync(0xffffffffu, iq, 31);
+                    }
+                }
+                // source row y -> padded rows: row 0 also feeds the `pad` rows above it, row rows-1 the rows below
+                int Y = y + pad, rep = 1;
+                if (y == 0) { Y = 0; rep += pad; }
+                if (y == rows - 1) rep += pad;
+                for (int k = 0; k < rep; ++k, ++Y) {
+                    int64_t* Srow = S + (size_t)Y * pitch + Xl;
+                    int64_t* Qrow = Q + (size_t)Y * pitch + Xl;
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { accS[j][i] += (long long)rs[j][i]; accQ[j][i] += (long long)rq[j][i]; }
+                        if (st[j]) {
+                            st_v4_s64(Srow + 128 * j, accS[j][0], accS[j][1], accS[j][2], accS[j][3]);
+                            st_v4_s64(Qrow + 128 * j, accQ[j][0], accQ[j][1], accQ[j][2], accQ[j][3]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    if (imin != nullptr) {
+        uint32_t m = min(min(mn4 & 0xff, (mn4 >> 8) & 0xff), min((mn4 >> 16) & 0xff, mn4 >> 24));
+        m = __reduce_min_sync(0xffffffffu, m);
+        if (lane == 0 && y1 > y0) atomicMin(imin + page, m);
+    }
+#undef PRL_ISSUE_TMA
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic kernel (no TMA, any alignment / pitch): 2 columns per lane x 4 sub-segments of 64 columns,
+// 16-byte stores, pixels fetched with clamped byte loads.  Same band convention as the TMA kernel.
+// ------------------------------------------------------------------------------------------------
 template <int MAXW, int R>
 __global__ void __launch_bounds__(MAXW * 32)
-integral_scan_kernel(const uint8_t* __restrict__ src, size_t src_step, size_t src_page_stride, int rows, int cols,
-                     int pad, int64_t* __restrict__ S, int64_t* __restrict__ Q, size_t pitch, size_t page_stride,
-                     int rows_per_band, const int64_t* __restrict__ carry, uint32_t* __restrict__ imin)
+integral_generic_kernel(const uint8_t* __restrict__ src, size_t src_step, size_t src_page_stride, int rows, int cols,
+                        int pad, int64_t* __restrict__ S, int64_t* __restrict__ Q, size_t pitch, size_t page_stride,
+                        int rows_per_band, const int64_t* __restrict__ carry, uint32_t* __restrict__ imin, int vec_ok)
 {
+    constexpr int kSub = 4;
     __shared__ uint2 tot[2][R][MAXW];
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int page = blockIdx.y, band = blockIdx.x, bands = gridDim.x;
-    const int Hp = rows + 2 * pad, Wp = cols + 2 * pad;
-    const int Y0 = band * rows_per_band;
-    const int Y1 = min(Y0 + rows_per_band, Hp);
+    const int Wp = cols + 2 * pad;
+    const int y0 = band * rows_per_band;
+    const int y1 = min(y0 + rows_per_band, rows);
 
     src += (size_t)page * src_page_stride;
     S += (size_t)page * page_stride;
@@ -77,114 +304,107 @@ integral_scan_kernel(const uint8_t* __restrict__ src, size_t src_step, size_t sr
 #pragma unroll
     for (int j = 0; j < kSub; ++j) {
         accS[j][0] = accS[j][1] = accQ[j][0] = accQ[j][1] = 0;
-        if (carry != nullptr && band > 0 && ok[j][0]) {
-            const int64_t* c = carry + ((size_t)page * bands + band) * 2 * pitch + Xb + 64 * j;
-            longlong2 cs = *reinterpret_cast<const longlong2*>(c);
-            longlong2 cq = *reinterpret_cast<const longlong2*>(c + pitch);
-            accS[j][0] = cs.x; accS[j][1] = cs.y; accQ[j][0] = cq.x; accQ[j][1] = cq.y;
+        if (carry != nullptr && band > 0) {
+            const long long* c = reinterpret_cast<const long long*>(carry) + ((size_t)page * bands + band) * 2 * pitch + Xb + 64 * j;
+            if (ok[j][0]) { accS[j][0] = c[0]; accQ[j][0] = c[pitch]; }
+            if (ok[j][1]) { accS[j][1] = c[1]; accQ[j][1] = c[pitch + 1]; }
         }
     }
 
     uint32_t mn = 255u;
-    uint32_t cur[R][kSub], nxt[R][kSub];
-
-    auto load_chunk = [&](uint32_t (&px)[R][kSub], int Yc) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int Y = Yc + r;
-            const uint8_t* rowp = src + (size_t)min(max(Y - pad, 0), rows - 1) * src_step;
-            const bool rv = Y < Y1;
-#pragma unroll
-            for (int j = 0; j < kSub; ++j) {
-                uint32_t v0 = (rv && ok[j][0]) ? (uint32_t)__ldg(rowp + xs[j][0]) : 0u;
-                uint32_t v1 = (rv && ok[j][1]) ? (uint32_t)__ldg(rowp + xs[j][1]) : 0u;
-                px[r][j] = v0 | (v1 << 16);
-            }
-        }
-    };
-
-    load_chunk(cur, Y0);
     int buf = 0;
-    for (int Yc = Y0; Yc < Y1; Yc += R, buf ^= 1) {
-        // sweep 1: this warp's row totals for the chunk
+    for (int yc = y0; yc < y1; yc += R, buf ^= 1) {
+        uint32_t px[R][kSub];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
+            const int y = min(yc + r, rows - 1);
+            const uint8_t* rowp = src + (size_t)y * src_step;
+            const bool rvld = yc + r < y1;
             uint32_t s = 0, q = 0;
 #pragma unroll
             for (int j = 0; j < kSub; ++j) {
-                uint32_t v0 = cur[r][j] & 0xffffu, v1 = cur[r][j] >> 16;
+                const uint32_t v0 = (rvld && ok[j][0]) ? (uint32_t)__ldg(rowp + xs[j][0]) : 0u;
+                const uint32_t v1 = (rvld && ok[j][1]) ? (uint32_t)__ldg(rowp + xs[j][1]) : 0u;
+                px[r][j] = v0 | (v1 << 16);
                 s += v0 + v1;
                 q += v0 * v0 + v1 * v1;
-                if (ok[j][0] && Yc + r < Y1) mn = min(mn, v0);
-                if (ok[j][1] && Yc + r < Y1) mn = min(mn, v1);
+                if (rvld && ok[j][0]) mn = min(mn, v0);
+                if (rvld && ok[j][1]) mn = min(mn, v1);
             }
             s = __reduce_add_sync(0xffffffffu, s);
             q = __reduce_add_sync(0xffffffffu, q);
             if (lane == 0) tot[buf][r][wid] = make_uint2(s, q);
         }
-        // prefetch the next chunk while this one is scanned
-        if (Yc + R < Y1) load_chunk(nxt, Yc + R);
         __syncthreads();
-
-        // sweep 2: scans, column accumulation, stores
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int Y = Yc + r;
-            if (Y < Y1) {
-                uint2 t = (lane < wid) ? tot[buf][r][lane] : make_uint2(0u, 0u);
+            const int y = yc + r;
+            if (y < y1) {
+                const uint2 t = (lane < wid) ? tot[buf][r][lane] : make_uint2(0u, 0u);
                 uint32_t off_s = __reduce_add_sync(0xffffffffu, t.x);
                 uint32_t off_q = __reduce_add_sync(0xffffffffu, t.y);
-                int64_t* Srow = S + (size_t)Y * pitch + Xb;
-                int64_t* Qrow = Q + (size_t)Y * pitch + Xb;
+                uint32_t r0s[kSub], r1s[kSub], r0q[kSub], r1q[kSub];
 #pragma unroll
                 for (int j = 0; j < kSub; ++j) {
-                    const uint32_t v0 = cur[r][j] & 0xffffu, v1 = cur[r][j] >> 16;
+                    const uint32_t v0 = px[r][j] & 0xffffu, v1 = px[r][j] >> 16;
                     const uint32_t v1q = v1 * v1;
                     const uint32_t is = warp_incl_scan(v0 + v1, lane);
                     const uint32_t iq = warp_incl_scan(v0 * v0 + v1q, lane);
-                    const uint32_t r1s = off_s + is, r1q = off_q + iq;
-                    accS[j][0] += (long long)(r1s - v1);
-                    accS[j][1] += (long long)r1s;
-                    accQ[j][0] += (long long)(r1q - v1q);
-                    accQ[j][1] += (long long)r1q;
-                    if (ok[j][0]) {
-                        st_v2_s64(Srow + 64 * j, accS[j][0], accS[j][1]);
-                        st_v2_s64(Qrow + 64 * j, accQ[j][0], accQ[j][1]);
-                    }
+                    r1s[j] = off_s + is; r0s[j] = r1s[j] - v1;
+                    r1q[j] = off_q + iq; r0q[j] = r1q[j] - v1q;
                     off_s += __shfl_sync(0xffffffffu, is, 31);
                     off_q += __shfl_sync(0xffffffffu, iq, 31);
                 }
+                int Y = y + pad, rep = 1;
+                if (y == 0) { Y = 0; rep += pad; }
+                if (y == rows - 1) rep += pad;
+                for (int k = 0; k < rep; ++k, ++Y) {
+                    int64_t* Srow = S + (size_t)Y * pitch + Xb;
+                    int64_t* Qrow = Q + (size_t)Y * pitch + Xb;
+#pragma unroll
+                    for (int j = 0; j < kSub; ++j) {
+                        accS[j][0] += (long long)r0s[j]; accS[j][1] += (long long)r1s[j];
+                        accQ[j][0] += (long long)r0q[j]; accQ[j][1] += (long long)r1q[j];
+                        if (vec_ok && ok[j][0] && Xb + 64 * j + 1 < (int)pitch) {
+                            st_v2_s64(Srow + 64 * j, accS[j][0], accS[j][1]);
+                            st_v2_s64(Qrow + 64 * j, accQ[j][0], accQ[j][1]);
+                        } else {
+                            if (ok[j][0]) { Srow[64 * j] = accS[j][0]; Qrow[64 * j] = accQ[j][0]; }
+                            if (ok[j][1]) { Srow[64 * j + 1] = accS[j][1]; Qrow[64 * j + 1] = accQ[j][1]; }
+                        }
+                    }
+                }
             }
         }
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int j = 0; j < kSub; ++j) cur[r][j] = nxt[r][j];
     }
 
     if (imin != nullptr) {
         mn = __reduce_min_sync(0xffffffffu, mn);
-        if (lane == 0) atomicMin(imin + page, mn);
+        if (lane == 0 && y1 > y0) atomicMin(imin + page, mn);
     }
 }
 
-// ---- latency mode: per-band column sums, then row-scanned carries --------------------------
-// colsum[page][band][plane][X] = sum over the band's padded rows of P[Y][X] (plane 0) / P^2 (plane 1)
+// ---- latency mode: weighted per-band column sums, then row-scanned carries -------------------
+// colsum[page][band][plane][X] = sum over the band's source rows y of mult(y) * P(y, X), where
+// mult counts the replicated copies (row 0 and row rows-1 appear pad+1 times in the padded image).
 __global__ void __launch_bounds__(256)
 band_colsum_kernel(const uint8_t* __restrict__ src, size_t src_step, size_t src_page_stride, int rows, int cols,
                    int pad, int rows_per_band, unsigned long long* __restrict__ colsum, size_t pitch)
 {
     const int page = blockIdx.y, band = blockIdx.x, bands = gridDim.x;
-    const int Hp = rows + 2 * pad, Wp = cols + 2 * pad;
-    const int Y0 = band * rows_per_band, Y1 = min(Y0 + rows_per_band, Hp);
+    const int Wp = cols + 2 * pad;
+    const int y0 = band * rows_per_band, y1 = min(y0 + rows_per_band, rows);
     src += (size_t)page * src_page_stride;
     unsigned long long* out = colsum + ((size_t)page * bands + band) * 2 * pitch;
     for (int X = threadIdx.x; X < Wp; X += blockDim.x) {
         const int x = min(max(X - pad, 0), cols - 1);
         unsigned long long s = 0, q = 0;
-        for (int Y = Y0; Y < Y1; ++Y) {
-            unsigned int p = __ldg(src + (size_t)min(max(Y - pad, 0), rows - 1) * src_step + x);
-            s += p; q += p * p;
+        for (int y = y0; y < y1; ++y) {
+            const unsigned long long p = __ldg(src + (size_t)y * src_step + x);
+            unsigned long long mult = 1;
+            if (y == 0) mult += pad;
+            if (y == rows - 1) mult += pad;
+            s += mult * p; q += mult * p * p;
         }
         out[X] = s;
         out[pitch + X] = q;
@@ -192,7 +412,7 @@ band_colsum_kernel(const uint8_t* __restrict__ src, size_t src_step, size_t src_
 }
 
 // carry[page][band][plane][X] = sum_{b' < band} sum_{X' <= X} colsum[page][b'][plane][X']
-//                             = S[Y0(band) - 1][X]   (the integral row just above the band)
+//                             = the integral row just above the band's first emitted padded row
 __global__ void __launch_bounds__(1024)
 band_carry_kernel(const unsigned long long* __restrict__ colsum, long long* __restrict__ carry, int Wp, size_t pitch)
 {
@@ -233,33 +453,90 @@ band_carry_kernel(const unsigned long long* __restrict__ colsum, long long* __re
     }
 }
 
-}  // namespace
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+encode_tiled_fn get_encode_tiled()
+{
+    static encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = (encode_tiled_fn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
 
 // Number of row bands a page is cut into: 1 when the batch alone fills the machine.
-static int choose_bands(const prl_cuda_ctx* ctx, int n_pages, int Hp)
+int choose_bands(const prl_cuda_ctx* ctx, int n_pages, int rows, int ctas_per_sm)
 {
-    const int want = 2 * ctx->num_sms;
-    if (n_pages >= want / 2 + want / 4) return 1;
+    const int want = ctas_per_sm * ctx->num_sms;
+    if (n_pages >= want - want / 4) return 1;   // >= 1.5 pages per SM: the batch alone fills the machine
     int bands = (want + n_pages - 1) / n_pages;
-    int max_bands = Hp / 32; if (max_bands < 1) max_bands = 1;
+    int max_bands = rows / 32; if (max_bands < 1) max_bands = 1;
     if (bands > max_bands) bands = max_bands;
     if (bands > 64) bands = 64;
     return bands < 1 ? 1 : bands;
 }
 
+template <int MAXW, int MINB, int J, int R, int NS>
+int launch_tma(prl_cuda_ctx* ctx, encode_tiled_fn enc, dim3 grid, int nwarps, const uint8_t* d_src, int n_pages,
+               size_t src_step, size_t src_page_stride, int rows, int cols, int pad, int64_t* d_S, int64_t* d_Q,
+               size_t pitch, size_t plane_page_stride, int rpb, const int64_t* d_carry, uint32_t* d_imin, bool* launched)
+{
+    *launched = false;
+    CUtensorMap tmap;
+    // rows described as src_step/2 u16 elements: a (128J+16)-byte box row is <= 136 elements (<= 256 allowed)
+    const cuuint64_t gdim[3] = {(cuuint64_t)(src_step / 2), (cuuint64_t)rows, (cuuint64_t)n_pages};
+    const cuuint64_t gstr[2] = {(cuuint64_t)src_step, (cuuint64_t)(n_pages > 1 ? src_page_stride : src_step * rows)};
+    const cuuint32_t box[3] = {(cuuint32_t)(box_bytes<J>() / 2), R, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, (void*)d_src, gdim, gstr, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return PRL_OK;     // caller falls back to the generic kernel
+    const size_t smem = (size_t)nwarps * NS * stage_bytes<J, R>();
+    auto kfn = integral_tma_kernel<MAXW, MINB, J, R, NS>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        PRL_CUDA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    kfn<<<grid, nwarps * 32, smem, ctx->stream>>>(tmap, rows, cols, pad, d_S, d_Q, pitch, plane_page_stride, rpb, d_carry, d_imin);
+    *launched = true;
+    return PRL_OK;
+}
+
+}  // namespace
+
 int prl_k_integral(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int rows, int cols, size_t src_step,
                    size_t src_page_stride, int pad, int64_t* d_S, int64_t* d_Q, size_t pitch,
                    size_t plane_page_stride, uint32_t* d_imin)
 {
-    const int Hp = rows + 2 * pad, Wp = cols + 2 * pad;
-    const int nwarps = (Wp + kWarpCols - 1) / kWarpCols;
-    if (nwarps > 32) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "padded width > 8192 columns is not supported yet");
+    const int Wp = cols + 2 * pad;
+    if (Wp > 8192) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "padded width > 8192 columns is not supported yet");
     if (n_pages > 65535) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "more than 65535 pages per launch");
-    constexpr int R = 4;
-    int bands = choose_bands(ctx, n_pages, Hp);
-    int rpb = (Hp + bands - 1) / bands;
+
+    // TMA path: 16-byte aligned source rows, 32-byte aligned planes, pitch % 4 == 0
+    encode_tiled_fn enc = get_encode_tiled();
+    const bool tma_ok = enc != nullptr && !ctx->no_tma && (((uintptr_t)d_src | src_step | src_page_stride) & 15) == 0 &&
+                        ((((uintptr_t)d_S) | ((uintptr_t)d_Q)) & 31) == 0 && (pitch & 3) == 0 && (plane_page_stride & 3) == 0;
+    const bool vec_ok = ((((uintptr_t)d_S) | ((uintptr_t)d_Q)) & 15) == 0 && (pitch & 1) == 0 && (plane_page_stride & 1) == 0;
+    const bool narrow = tma_ok && Wp <= 24 * 128;        // 128 columns per warp, up to 24 warps, 2 CTAs per SM
+
+    constexpr int R = 8;
+    int bands = choose_bands(ctx, n_pages, rows, 2);
+    int rpb = (rows + bands - 1) / bands;
     rpb = (rpb + R - 1) / R * R;
-    bands = (Hp + rpb - 1) / rpb;
+    bands = (rows + rpb - 1) / rpb;
 
     if (d_imin) PRL_CUDA_TRY(ctx, cudaMemsetAsync(d_imin, 0xff, sizeof(uint32_t) * n_pages, ctx->stream));
 
@@ -280,16 +557,35 @@ int prl_k_integral(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int row
         }
         d_carry = (const int64_t*)ctx->carry;
     }
-    {
-        prl_launch_scope ls(ctx, FAM_INTEGRAL);
-        dim3 grid(bands, n_pages);
-        if (nwarps <= 16)
-            integral_scan_kernel<16, R><<<grid, nwarps * 32, 0, ctx->stream>>>(
-                d_src, src_step, src_page_stride, rows, cols, pad, d_S, d_Q, pitch, plane_page_stride, rpb, d_carry, d_imin);
-        else
-            integral_scan_kernel<32, R><<<grid, nwarps * 32, 0, ctx->stream>>>(
-                d_src, src_step, src_page_stride, rows, cols, pad, d_S, d_Q, pitch, plane_page_stride, rpb, d_carry, d_imin);
+
+    prl_launch_scope ls(ctx, FAM_INTEGRAL);
+    dim3 grid(bands, n_pages);
+    if (tma_ok) {
+        bool launched = false;
+        int rc;
+        if (narrow) {
+            const int nw = (Wp + 127) / 128;
+            rc = launch_tma<24, 2, 1, R, 3>(ctx, enc, grid, nw, d_src, n_pages, src_step, src_page_stride, rows, cols, pad, d_S, d_Q,
+                                            pitch, plane_page_stride, rpb, d_carry, d_imin, &launched);
+        } else {
+            const int nw = (Wp + 255) / 256;
+            rc = launch_tma<32, 1, 2, R, 3>(ctx, enc, grid, nw, d_src, n_pages, src_step, src_page_stride, rows, cols, pad, d_S, d_Q,
+                                            pitch, plane_page_stride, rpb, d_carry, d_imin, &launched);
+        }
+        if (rc) return rc;
+        if (launched) {
+            PRL_CUDA_TRY(ctx, cudaGetLastError());
+            return PRL_OK;
+        }
+        // the driver rejected the tensor map (e.g. stride limits): fall through to the generic kernel
     }
+    const int nwarps = (Wp + kWarpCols - 1) / kWarpCols;
+    if (nwarps <= 16)
+        integral_generic_kernel<16, 4><<<grid, nwarps * 32, 0, ctx->stream>>>(
+            d_src, src_step, src_page_stride, rows, cols, pad, d_S, d_Q, pitch, plane_page_stride, rpb, d_carry, d_imin, vec_ok);
+    else
+        integral_generic_kernel<32, 4><<<grid, nwarps * 32, 0, ctx->stream>>>(
+            d_src, src_step, src_page_stride, rows, cols, pad, d_S, d_Q, pitch, plane_page_stride, rpb, d_carry, d_imin, vec_ok);
     PRL_CUDA_TRY(ctx, cudaGetLastError());
     return PRL_OK;
 }

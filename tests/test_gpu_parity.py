@@ -63,6 +63,15 @@ def test_integral_ragged_shapes(ctx, shape):
         assert np.array_equal(S, Sw) and np.array_equal(Q, Qw)
 
 
+def test_integral_borders_wider_than_a_warp_strip(ctx):
+    rng = np.random.default_rng(21)
+    for shape, pad in (((40, 50), 150), ((33, 300), 130), ((20, 700), 260), ((25, 1), 140), ((9, 2600), 200)):
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        S, Q = ctx.integral(img, pad)
+        Sw, Qw = CO.integrals_int64(img, pad)
+        assert np.array_equal(S, Sw) and np.array_equal(Q, Qw), (shape, pad)
+
+
 def test_integral_saturated_large_needs_64_bit(ctx):
     img = np.full((3000, 3000), 255, np.uint8)     # S exceeds 2^31, Q exceeds 2^32
     S, Q = ctx.integral(img, 0)
@@ -210,6 +219,42 @@ def test_random_shapes_all_methods(ctx):
             assert assert_mask_parity(got, img, m, w, p) == 0, (i, m, w, rows, cols)
 
 
+def test_fast_decision_path_equals_literal_fp64_path(ctx, noise_page, real_crops):
+    """Kernel 2 decides most pixels from exact integer window sums + an FP32 estimate and runs the
+    reference's FP64 formula only within a proven margin of the rounding boundary; forcing the FP64
+    formula for every pixel must give byte-identical masks (and both must equal the oracle)."""
+    rng = np.random.default_rng(77)
+    ramp = (np.add.outer(np.arange(300), np.arange(420)) % 256).astype(np.uint8)
+    flat = np.repeat(np.arange(256, dtype=np.uint8), 3)[None, :].repeat(64, 0)            # every gray level, flat columns
+    sparse = np.zeros((200, 260), np.uint8); sparse[rng.integers(0, 200, 40), rng.integers(0, 260, 40)] = rng.integers(1, 256, 40)
+    border = real_crops["real_0018"].copy(); border[:, :60] = 0; border[:50, :] = 0          # scanner-style black border
+    images = [noise_page, ramp, flat, sparse, border, real_crops["real_0037"]]
+    cases = [(0, 15, (0.2,)), (0, 101, (0.01,)), (0, 15, (-3.0,)), (1, 15, (-0.2,)), (1, 31, (2.5,)), (2, 15, (0.5,)),
+             (2, 41, (0.01,)), (3, 15, (-0.1,)), (3, 51, (0.7,)), (4, 21, (0.75, 0.2, 0.03, 2.0)), (4, 15, (0.2, 0.2, 0.9, 2.0))]
+    for img in images:
+        for m, w, p in cases:
+            if min(img.shape) <= w:
+                continue
+            fast = ctx.binarize_local(img, m, w, p, 0)
+            ctx.set_option("exact_threshold", 1)
+            exact = ctx.binarize_local(img, m, w, p, 0)
+            ctx.set_option("exact_threshold", 0)
+            assert np.array_equal(fast, exact), (m, w, p, img.shape)
+            assert assert_mask_parity(fast, img, m, w, p) == 0, (m, w, p, img.shape)
+
+
+def test_integral_generic_kernel_equals_tma_kernel(ctx, noise_page):
+    a4 = CO.synth_page(5, 900, 2480)
+    for img, pad in ((noise_page, 7), (a4, 7), (a4, 50), (noise_page[:, :333], 10)):
+        S1, Q1 = ctx.integral(img, pad)
+        ctx.set_option("disable_tma", 1)
+        S2, Q2 = ctx.integral(img, pad)
+        ctx.set_option("disable_tma", 0)
+        Sw, Qw = CO.integrals_int64(np.ascontiguousarray(img), pad)
+        assert np.array_equal(S1, Sw) and np.array_equal(Q1, Qw)
+        assert np.array_equal(S2, Sw) and np.array_equal(Q2, Qw)
+
+
 # ---- Otsu ------------------------------------------------------------------------------------
 def test_otsu_global_golden_and_cv(ctx, golden, noise_page, real_crops):
     a4 = CO.synth_page(0)
@@ -240,6 +285,18 @@ def test_otsu_thresholds_exact_on_adversarial_tiles(ctx):
         else:
             t = np.full((13, 17), int(rng.integers(0, 256)), np.uint8)
         assert ctx.otsu_threshold(t) == O.otsu_threshold_cv(t), i
+
+
+def test_otsu_exact_ties(ctx):
+    rng = np.random.default_rng(123)
+    for k in range(60):
+        n = int(rng.integers(3, 18))
+        a = rng.integers(0, 128, n)
+        vals = np.concatenate([a, 255 - a]).astype(np.uint8)
+        if k % 2:
+            vals = np.concatenate([vals, [127, 128]]).astype(np.uint8)
+        t = vals.reshape(1, -1).copy()
+        assert ctx.otsu_threshold(t) == O.otsu_threshold_cv(t), k
 
 
 def test_otsu_tiles_golden(ctx, golden, noise_page):

@@ -153,6 +153,25 @@ def test_otsu_recurrence_matches_opencv():
         assert CO.otsu_from_hist(hist) == want
 
 
+def test_otsu_exact_ties_follow_opencv_cpp_not_ipp():
+    """Symmetric histograms make sigma(t) == sigma(254 - t) exactly: the winner is decided by the
+    rounding of the literal FP64 recurrence.  OpenCV's C++ code (IPP off) is the target."""
+    rng = np.random.default_rng(123)
+    for k in range(200):
+        n = int(rng.integers(3, 18))
+        a = rng.integers(0, 128, n)
+        vals = np.concatenate([a, 255 - a]).astype(np.uint8)
+        if k % 2:
+            vals = np.concatenate([vals, [127, 128]]).astype(np.uint8)
+        t = vals.reshape(1, -1).copy()
+        want = O.otsu_threshold_cv(t)
+        hist = np.bincount(t.ravel(), minlength=256)
+        assert O.otsu_threshold_from_hist(hist) == want
+        assert CO.otsu_from_hist(hist) == want
+    noise = np.random.default_rng(0).integers(0, 256, (512, 640), dtype=np.uint8)
+    assert np.array_equal(O.otsu_tiles(noise, 7, 5), CO.otsu_rects(noise, O.tile_rects(512, 640, 7, 5)))
+
+
 def test_otsu_global_and_tiles_golden(golden):
     a4 = CO.synth_page(0)
     e = golden["images"]["a4_p0"]
