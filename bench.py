@@ -213,7 +213,8 @@ def run_ours(args):
     step_in = (COLS + 15) // 16 * 16
     step_out = (g["out_cols"] + 15) // 16 * 16
     ctx = prlib_b200.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)        # a real (non-legacy) stream: kernels, events and timing all live on it
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
     # synthetic pages, generated on the device (page index = global page id: rank shards are contiguous)

@@ -202,9 +202,8 @@ integral_tma_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int cols
             for (int j = 0; j < J; ++j) {
                 const uint32_t w = fetch(buf + r * BOX, j);
                 if (yc + r < y1) mn4 = __vminu4(mn4, w);
-                const uint32_t p0 = w & 0xff, p1 = (w >> 8) & 0xff, p2 = (w >> 16) & 0xff, p3 = w >> 24;
-                s += (p0 + p1) + (p2 + p3);
-                q += (p0 * p0 + p1 * p1) + (p2 * p2 + p3 * p3);
+                s = __dp4a(w, 0x01010101u, s);       // sum of the 4 bytes
+                q = __dp4a(w, w, q);                 // sum of their squares
             }
             s = __reduce_add_sync(0xffffffffu, s);
             q = __reduce_add_sync(0xffffffffu, q);
@@ -224,12 +223,14 @@ integral_tma_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int cols
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
                     const uint32_t w = fetch(buf + r * BOX, j);
-                    const uint32_t p0 = w & 0xff, p1 = (w >> 8) & 0xff, p2 = (w >> 16) & 0xff, p3 = w >> 24;
-                    const uint32_t a1 = p0 + p1, a2 = a1 + p2, a3 = a2 + p3;
-                    const uint32_t b0 = p0 * p0, b1 = b0 + p1 * p1, b2 = b1 + p2 * p2, b3 = b2 + p3 * p3;
+                    // lane-local inclusive prefixes of the 4 bytes / their squares: one dp4a each
+                    const uint32_t a0 = w & 0xffu, a1 = __dp4a(w, 0x00000101u, 0u), a2 = __dp4a(w, 0x00010101u, 0u),
+                                   a3 = __dp4a(w, 0x01010101u, 0u);
+                    const uint32_t b0 = a0 * a0, b1 = __dp4a(w, w & 0x0000ffffu, 0u), b2 = __dp4a(w, w & 0x00ffffffu, 0u),
+                                   b3 = __dp4a(w, w, 0u);
                     const uint32_t is = warp_incl_scan(a3, lane), iq = warp_incl_scan(b3, lane);
                     const uint32_t es = off_s + is - a3, eq = off_q + iq - b3;   // exclusive base of this lane
-                    rs[j][0] = es + p0; rs[j][1] = es + a1; rs[j][2] = es + a2; rs[j][3] = es + a3;
+                    rs[j][0] = es + a0; rs[j][1] = es + a1; rs[j][2] = es + a2; rs[j][3] = es + a3;
                     rq[j][0] = eq + b0; rq[j][1] = eq + b1; rq[j][2] = eq + b2; rq[j][3] = eq + b3;
                     if (J > 1) {
                         off_s += __shfl_sync(0xffffffffu, is, 31);
@@ -563,7 +564,11 @@ int prl_k_integral(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int row
     if (tma_ok) {
         bool launched = false;
         int rc;
-        if (narrow) {
+        if (narrow && Wp <= 20 * 128) {
+            const int nw = (Wp + 127) / 128;          // A4-class widths: 51 registers available at 2 CTAs/SM
+            rc = launch_tma<20, 2, 1, R, 3>(ctx, enc, grid, nw, d_src, n_pages, src_step, src_page_stride, rows, cols, pad, d_S, d_Q,
+                                            pitch, plane_page_stride, rpb, d_carry, d_imin, &launched);
+        } else if (narrow) {
             const int nw = (Wp + 127) / 128;
             rc = launch_tma<24, 2, 1, R, 3>(ctx, enc, grid, nw, d_src, n_pages, src_step, src_page_stride, rows, cols, pad, d_S, d_Q,
                                             pitch, plane_page_stride, rpb, d_carry, d_imin, &launched);

@@ -97,17 +97,36 @@ __device__ __forceinline__ double thr_value(double m, double s, const ThrArgs& A
 
 // The reference arithmetic for one output pixel, taps read as scalars (any alignment).
 template <int METHOD>
-__device__ __noinline__ int exact_t8_at(const ThrArgs& A, const int64_t* __restrict__ S, const int64_t* __restrict__ Q,
-                                        int y, int x, double imin, double coeff)
+__device__ __forceinline__ double thr_value_p(double m, double s, double p0, double p1, double p2, double imin, double coeff)
 {
-    const long long* s0 = reinterpret_cast<const long long*>(S) + (size_t)y * A.pitch + x;
-    const long long* s1 = reinterpret_cast<const long long*>(S) + (size_t)(y + A.d) * A.pitch + x;
-    const long long* q0 = reinterpret_cast<const long long*>(Q) + (size_t)y * A.pitch + x;
-    const long long* q1 = reinterpret_cast<const long long*>(Q) + (size_t)(y + A.d) * A.pitch + x;
-    const double m = tap4(A.kw, A.nkw, __ldg(s0), __ldg(s0 + A.d), __ldg(s1), __ldg(s1 + A.d));
-    const double q = tap4(A.kw, A.nkw, __ldg(q0), __ldg(q0 + A.d), __ldg(q1), __ldg(q1 + A.d));
+    if (METHOD == PRL_SAUVOLA) {
+        return __dmul_rn(m, __dadd_rn(__dmul_rn(s, p1), p2));
+    } else if (METHOD == PRL_NIBLACK) {
+        return __dadd_rn(m, __dmul_rn(p0, s));
+    } else if (METHOD == PRL_WOLFJOLION) {
+        double dd = __dadd_rn(__dmul_rn(s, coeff), -p0);
+        dd = __dmul_rn(dd, __dadd_rn(m, -imin));
+        return __dadd_rn(m, dd);
+    } else if (METHOD == PRL_NICK) {
+        double C = __dsqrt_rn(__dadd_rn(__dmul_rn(m, m), __dmul_rn(s, s)));
+        return __dadd_rn(m, __dmul_rn(C, p0));
+    } else {
+        if (!(s == s) || s == 0.0) return __longlong_as_double(0x7ff8000000000000LL);
+        double c3 = __dadd_rn(__dmul_rn(p2, imin), -imin);
+        return __dadd_rn(__dmul_rn(p1, m), c3);
+    }
+}
+
+// (scalars by value: a reference to the kernel-parameter struct would force a per-thread stack copy)
+template <int METHOD>
+__device__ __noinline__ int exact_t8_at(const long long* __restrict__ s0, const long long* __restrict__ q0, size_t drow,
+                                        int d, double kw, double p0, double p1, double p2, double imin, double coeff)
+{
+    const double nkw = -kw;
+    const double m = tap4(kw, nkw, __ldg(s0), __ldg(s0 + d), __ldg(s0 + drow), __ldg(s0 + drow + d));
+    const double q = tap4(kw, nkw, __ldg(q0), __ldg(q0 + d), __ldg(q0 + drow), __ldg(q0 + drow + d));
     const double s = __dsqrt_rn(__dadd_rn(q, -__dmul_rn(m, m)));
-    return to_u8(thr_value<METHOD>(m, s, A, imin, coeff));
+    return to_u8(thr_value_p<METHOD>(m, s, p0, p1, p2, imin, coeff));
 }
 
 constexpr int kTR = 4;   // output rows per CTA (exact kernel)
@@ -265,10 +284,13 @@ threshold_fast_kernel(const ThrArgs A, const FastArgs F)
 
     int buf = 0;
     for (int y = y_begin; y < y_end; y += kFR, buf ^= 1) {
-        // ---- vertical differences of the low words -> shared memory
+        // ---- vertical differences of the low words -> shared memory (own copy stays in registers)
+        unsigned int dsr[kFR][4], dqr[kFR][4];
 #pragma unroll
         for (int r = 0; r < kFR; ++r) {
-            unsigned int ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
+            unsigned int (&ds)[4] = dsr[r];
+            unsigned int (&dq)[4] = dqr[r];
+            ds[0] = ds[1] = ds[2] = ds[3] = 0; dq[0] = dq[1] = dq[2] = dq[3] = 0;
             if (in_plane && y + r < y_end) {
                 long long a0, a1, a2, a3, b0, b1, b2, b3;
                 ldg256(S + (size_t)(y + r) * A.pitch + x, a0, a1, a2, a3);
@@ -292,8 +314,8 @@ threshold_fast_kernel(const ThrArgs A, const FastArgs F)
                 if (yy >= y_end) break;
                 const unsigned int* ls = &sD[buf][r][0][4 * threadIdx.x];
                 const unsigned int* lq = &sD[buf][r][1][4 * threadIdx.x];
-                const uint4 s_l = *reinterpret_cast<const uint4*>(ls);
-                const uint4 q_l = *reinterpret_cast<const uint4*>(lq);
+                const uint4 s_l = make_uint4(dsr[r][0], dsr[r][1], dsr[r][2], dsr[r][3]);
+                const uint4 q_l = make_uint4(dqr[r][0], dqr[r][1], dqr[r][2], dqr[r][3]);
                 const uint2 s_r0 = *reinterpret_cast<const uint2*>(ls + A.d);       // d even -> 8-byte aligned
                 const uint2 s_r1 = *reinterpret_cast<const uint2*>(ls + A.d + 2);
                 const uint2 q_r0 = *reinterpret_cast<const uint2*>(lq + A.d);
@@ -314,15 +336,30 @@ threshold_fast_kernel(const ThrArgs A, const FastArgs F)
                     int o;
                     if (!fast_decide<METHOD>(sw[i], qw[i], p, F, iminf, coefff, mu, o)) {
                         if (x + i < A.out_cols) {
-                            const int t8 = exact_t8_at<METHOD>(A, S, Q, yy, x + i, imin, coeff);
+                            const size_t e0 = (size_t)yy * A.pitch + x + i;
+                            const int t8 = exact_t8_at<METHOD>(reinterpret_cast<const long long*>(S) + e0,
+                                                               reinterpret_cast<const long long*>(Q) + e0, (size_t)A.d * A.pitch,
+                                                               A.d, A.kw, A.p0, A.p1, A.p2, imin, coeff);
                             o = (int)p > t8 ? 255 : 0;
                         } else o = 0;
                     }
                     o4 |= (unsigned int)o << (8 * i);
                 }
+                // dst may be dense (pitch == out_cols, odd): store with whatever alignment the row has
                 uint8_t* orow = dst + (size_t)yy * A.dst_step + x;
-                if (full4) *reinterpret_cast<unsigned int*>(orow) = o4;
-                else for (int i = 0; i < 4; ++i) if (x + i < A.out_cols) orow[i] = (uint8_t)(o4 >> (8 * i));
+                const unsigned int al = (unsigned int)(uintptr_t)orow & 3u;
+                if (!full4) {
+                    for (int i = 0; i < 4; ++i) if (x + i < A.out_cols) orow[i] = (uint8_t)(o4 >> (8 * i));
+                } else if (al == 0) {
+                    *reinterpret_cast<unsigned int*>(orow) = o4;
+                } else if (al == 2) {
+                    *reinterpret_cast<unsigned short*>(orow) = (unsigned short)o4;
+                    *reinterpret_cast<unsigned short*>(orow + 2) = (unsigned short)(o4 >> 16);
+                } else {
+                    orow[0] = (uint8_t)o4;
+                    *reinterpret_cast<unsigned short*>(orow + 1) = (unsigned short)(o4 >> 8);
+                    orow[3] = (uint8_t)(o4 >> 24);
+                }
             }
         }
     }
@@ -437,7 +474,7 @@ int prl_k_threshold(prl_cuda_ctx* ctx, int method, int mode, const uint8_t* d_sr
 
     // fast path eligibility: mask output, even tap distance < 256, window sums < 2^32, 4/32-byte aligned buffers
     FastArgs F;
-    const bool aligned = ((src_step | src_page_stride | dst_step | dst_page_stride | (uintptr_t)d_src | (uintptr_t)d_dst) & 3) == 0 &&
+    const bool aligned = ((src_step | src_page_stride | (uintptr_t)d_src) & 3) == 0 &&
                          ((((uintptr_t)d_S) | ((uintptr_t)d_Q)) & 31) == 0 && (plane_page_stride & 3) == 0 && (g.pitch & 3) == 0;
     const bool fast = mode == 0 && !ctx->force_exact && (g.d & 1) == 0 && g.d <= 254 && aligned &&
                       fast_margins(method, params, g, &F);
