@@ -1,0 +1,145 @@
+// prl_binarize_cuda.cpp -- host shim: prl::binarize*(cv::Mat&, cv::Mat&, ...) over the C-ABI of
+// libprlib_cuda.  Everything numerical happens on the GPU; this file only validates, converts the
+// Mat headers to pointers/strides and reproduces the reference's observable side effects.
+#include "prl_binarize_cuda.h"
+
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/prlib_cuda.h"
+
+namespace
+{
+// one context per host thread (the reference functions are re-entrant; so are these)
+struct ThreadCtx {
+    prl_cuda_ctx* ctx = nullptr;
+    ~ThreadCtx() { prl_cuda_destroy(ctx); }
+};
+
+prl_cuda_ctx* context()
+{
+    static thread_local ThreadCtx t;
+    if (!t.ctx) {
+        int rc = prl_cuda_create(0, &t.ctx);
+        if (rc != PRL_OK)
+            throw std::runtime_error(std::string("libprlib_cuda: ") + prl_cuda_last_error(nullptr));
+    }
+    return t.ctx;
+}
+
+void check(prl_cuda_ctx* c, int rc)
+{
+    if (rc == PRL_OK) return;
+    const std::string msg = prl_cuda_last_error(c);
+    if (rc == PRL_E_INVALID) throw std::invalid_argument(msg);
+    if (rc == PRL_E_EMPTY_ROI) throw cv::Exception(msg);      // cv::Mat::operator()(Rect) would assert
+    throw std::runtime_error("libprlib_cuda: " + msg);
+}
+
+// gray, continuous copy of the input (GPU cvtColor for 3/4-channel images)
+cv::Mat toGray(prl_cuda_ctx* c, const cv::Mat& in)
+{
+    if (in.channels() == 1) return in;
+    cv::Mat gray(in.rows, in.cols, CV_8UC1);
+    check(c, prl_cuda_bgr2gray(c, in.data, in.rows, in.cols, in.step, in.channels(), gray.data, gray.step));
+    return gray;
+}
+
+// what the reference leaves in `imageInput`: copyMakeBorder(gray, h, h, h, h, BORDER_REPLICATE)
+cv::Mat padReplicate(const cv::Mat& g, int h)
+{
+    cv::Mat p(g.rows + 2 * h, g.cols + 2 * h, CV_8UC1);
+    for (int Y = 0; Y < p.rows; ++Y) {
+        int y = Y - h; y = y < 0 ? 0 : (y >= g.rows ? g.rows - 1 : y);
+        unsigned char* d = p.ptr(Y);
+        const unsigned char* s = g.ptr(y);
+        std::memset(d, s[0], (size_t)h);
+        std::memcpy(d + h, s, (size_t)g.cols);
+        std::memset(d + h + g.cols, s[g.cols - 1], (size_t)h);
+    }
+    return p;
+}
+
+void runLocal(int method, cv::Mat& imageInput, cv::Mat& outputImage, int windowSize, const double params[4], int morph)
+{
+    if (imageInput.empty())
+        throw std::invalid_argument("Input image for binarization is empty");
+    if (!((windowSize > 1) && ((windowSize % 2) == 1)))
+        throw std::invalid_argument("Window size must satisfy the following condition: "
+                                    "( (windowSize > 1) && ((windowSize % 2) == 1) ) ");
+    prl_cuda_ctx* c = context();
+    cv::Mat gray = toGray(c, imageInput);
+    int orows = 0, ocols = 0;
+    check(c, prl_cuda_output_shape(method, gray.rows, gray.cols, windowSize, &orows, &ocols));
+    cv::Mat out(orows, ocols, CV_8UC1);
+    check(c, prl_cuda_binarize_local(c, method, gray.data, gray.rows, gray.cols, gray.step, windowSize, params, morph,
+                                     out.data, out.step, &orows, &ocols));
+#ifndef PRL_CUDA_NO_INPUT_SIDE_EFFECT
+    const int w = windowSize < gray.rows ? (windowSize < gray.cols ? windowSize : gray.cols)
+                                         : (gray.rows < gray.cols ? gray.rows : gray.cols);
+    imageInput = padReplicate(gray, w / 2);
+#endif
+    outputImage = out;
+}
+}  // namespace
+
+void prl::binarizeSauvola(cv::Mat& imageInput, cv::Mat& outputImage, int windowSize, double thresholdCoefficient,
+                          int morphIterationCount)
+{
+    const double p[4] = {thresholdCoefficient, 0, 0, 0};
+    runLocal(PRL_SAUVOLA, imageInput, outputImage, windowSize, p, morphIterationCount);
+}
+
+void prl::binarizeNiblack(cv::Mat& imageInput, cv::Mat& outputImage, int windowSize, double thresholdCoefficient,
+                          int morphIterationCount)
+{
+    const double p[4] = {thresholdCoefficient, 0, 0, 0};
+    runLocal(PRL_NIBLACK, imageInput, outputImage, windowSize, p, morphIterationCount);
+}
+
+void prl::binarizeWolfJolion(cv::Mat& imageInput, cv::Mat& outputImage, int windowSize, double thresholdCoefficient,
+                             int morphIterationCount)
+{
+    const double p[4] = {thresholdCoefficient, 0, 0, 0};
+    runLocal(PRL_WOLFJOLION, imageInput, outputImage, windowSize, p, morphIterationCount);
+}
+
+void prl::binarizeNICK(cv::Mat& imageInput, cv::Mat& outputImage, int windowSize, double thresholdCoefficient,
+                       int morphIterationCount)
+{
+    const double p[4] = {thresholdCoefficient, 0, 0, 0};
+    runLocal(PRL_NICK, imageInput, outputImage, windowSize, p, morphIterationCount);
+}
+
+void prl::binarizeFeng(cv::Mat& imageInput, cv::Mat& outputImage, int windowSize, double thresholdCoefficient_alpha1,
+                       double thresholdCoefficient_k1, double thresholdCoefficient_k2, double thresholdCoefficient_gamma,
+                       int morphIterationCount)
+{
+    const double p[4] = {thresholdCoefficient_alpha1, thresholdCoefficient_k1, thresholdCoefficient_k2,
+                         thresholdCoefficient_gamma};
+    runLocal(PRL_FENG, imageInput, outputImage, windowSize, p, morphIterationCount);
+}
+
+void prl::binarizeLocalOtsuRects(const cv::Mat& gray, const std::vector<int>& xywh, cv::Mat& binarized, double maxValue)
+{
+    if (gray.empty()) throw std::invalid_argument("Input image for binarization is empty");
+    if (!(maxValue >= 0 && maxValue <= 255)) throw std::invalid_argument("Max value must be in range [0; 255]");
+    if (gray.channels() != 1 || xywh.size() % 4 != 0) throw std::invalid_argument("expected a gray image and x,y,w,h quadruples");
+    prl_cuda_ctx* c = context();
+    cv::Mat out(gray.rows, gray.cols, CV_8UC1);
+    check(c, prl_cuda_otsu_rects(c, gray.data, gray.rows, gray.cols, gray.step, xywh.empty() ? nullptr : xywh.data(),
+                                 (int)(xywh.size() / 4), maxValue, out.data, out.step, nullptr));
+    binarized = out;
+}
+
+double prl::thresholdOtsu(const cv::Mat& src, cv::Mat& dst, double maxValue)
+{
+    if (src.empty() || src.channels() != 1) throw std::invalid_argument("expected a non-empty gray image");
+    prl_cuda_ctx* c = context();
+    cv::Mat out(src.rows, src.cols, CV_8UC1);
+    int thr = 0;
+    check(c, prl_cuda_otsu_global(c, src.data, src.rows, src.cols, src.step, maxValue, out.data, out.step, &thr));
+    dst = out;
+    return (double)thr;
+}

@@ -1,0 +1,43 @@
+// prl_binarize_cuda.h -- the reference's cv::Mat-in / cv::Mat-out binarize* entry points, bodies
+// replaced by libprlib_cuda (include/prlib_cuda.h).  Signatures, default arguments and thrown
+// exception types are those of the reference headers:
+//   binarizeSauvola.h:43-47, binarizeNiblack.h:43-47, binarizeWolfJolion.h:43-47,
+//   binarizeNICK.h:43-47, binarizeFeng.h:46-53, binarizeLocalOtsu.h:50-57 (rect-loop core only).
+// A caller that includes the reference's own headers links against this translation unit instead of
+// src/binarizations/binarize{Sauvola,Niblack,WolfJolion,NICK,Feng}.cpp and sees no difference:
+//   * std::invalid_argument for an empty image or a window that is not (>1 and odd);
+//   * cv::Exception when the processing rectangle is empty (WJ/NICK/Feng on min(rows,cols) <= window);
+//   * the INPUT Mat is left holding the replicate-padded grayscale image, as the reference leaves it
+//     (binarizeSauvola.cpp:49-52, :65) -- define PRL_CUDA_NO_INPUT_SIDE_EFFECT to skip that copy.
+// There is no CPU fallback: any CUDA failure surfaces as std::runtime_error.
+#ifndef PRL_BINARIZE_CUDA_H
+#define PRL_BINARIZE_CUDA_H
+
+#include <opencv2/core/core.hpp>
+#include <vector>
+
+namespace prl
+{
+CV_EXPORTS void binarizeSauvola(cv::Mat& imageInput, cv::Mat& outputImage, int windowSize = 101,
+                                double thresholdCoefficient = 0.01, int morphIterationCount = 2);
+CV_EXPORTS void binarizeNiblack(cv::Mat& imageInput, cv::Mat& outputImage, int windowSize = 101,
+                                double thresholdCoefficient = 0.01, int morphIterationCount = 2);
+CV_EXPORTS void binarizeWolfJolion(cv::Mat& imageInput, cv::Mat& outputImage, int windowSize = 101,
+                                   double thresholdCoefficient = 0.01, int morphIterationCount = 2);
+CV_EXPORTS void binarizeNICK(cv::Mat& imageInput, cv::Mat& outputImage, int windowSize = 21,
+                             double thresholdCoefficient = -0.01, int morphIterationCount = 0);
+CV_EXPORTS void binarizeFeng(cv::Mat& imageInput, cv::Mat& outputImage, int windowSize = 21,
+                             double thresholdCoefficient_alpha1 = 0.75, double thresholdCoefficient_k1 = 0.2,
+                             double thresholdCoefficient_k2 = 0.03, double thresholdCoefficient_gamma = 2.0,
+                             int morphIterationCount = 2);
+
+// The per-contour-rectangle Otsu loop of prl::binarizeLocalOtsu (binarizeLocalOtsu.cpp:138-162):
+// `gray` is imageToProc, xywh holds cv::boundingRect(contour) as x, y, width, height quadruples.
+CV_EXPORTS void binarizeLocalOtsuRects(const cv::Mat& gray, const std::vector<int>& xywh, cv::Mat& binarized,
+                                       double maxValue = 255);
+// cv::threshold(src, dst, 128, maxValue, THRESH_BINARY | THRESH_OTSU) (deskew.cpp:224, removeLines.cpp:45);
+// returns the threshold like cv::threshold does.
+CV_EXPORTS double thresholdOtsu(const cv::Mat& src, cv::Mat& dst, double maxValue = 255);
+}  // namespace prl
+
+#endif  // PRL_BINARIZE_CUDA_H

@@ -1,0 +1,63 @@
+// Minimal stand-in for <opencv2/core/core.hpp> -- TEST INFRASTRUCTURE ONLY.
+// This image has no OpenCV C++ SDK, so the cv::Mat-facing shim (prlib_b200/shim) is compiled and
+// exercised against this header: just enough of cv::Mat / cv::Exception for the shim's needs
+// (8-bit matrices, reference-counted storage, create / clone / assignment).  With a real OpenCV
+// installation the shim compiles unchanged against the real headers.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+
+#define CV_EXPORTS
+#define CV_CN_SHIFT 3
+#define CV_8U 0
+#define CV_MAKETYPE(depth, cn) ((depth) + (((cn)-1) << CV_CN_SHIFT))
+#define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
+#define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
+#define CV_8UC4 CV_MAKETYPE(CV_8U, 4)
+
+namespace cv {
+
+class Exception : public std::runtime_error {
+public:
+    explicit Exception(const std::string& m) : std::runtime_error(m) {}
+};
+
+class Mat {
+public:
+    int rows = 0, cols = 0;
+    unsigned char* data = nullptr;
+    size_t step = 0;
+
+    Mat() {}
+    Mat(int r, int c, int type) { create(r, c, type); }
+    void create(int r, int c, int type)
+    {
+        if (r == rows && c == cols && type == type_ && data && step == (size_t)c * channels()) return;
+        rows = r; cols = c; type_ = type;
+        step = (size_t)c * channels();
+        buf_ = std::shared_ptr<unsigned char>(new unsigned char[step * (r > 0 ? r : 1) + 1], std::default_delete<unsigned char[]>());
+        data = buf_.get();
+    }
+    bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+    int type() const { return type_; }
+    int depth() const { return type_ & 7; }
+    int channels() const { return (type_ >> CV_CN_SHIFT) + 1; }
+    bool isContinuous() const { return step == (size_t)cols * channels(); }
+    unsigned char* ptr(int y = 0) { return data + (size_t)y * step; }
+    const unsigned char* ptr(int y = 0) const { return data + (size_t)y * step; }
+    Mat clone() const
+    {
+        Mat m(rows, cols, type_);
+        for (int y = 0; y < rows; ++y) std::memcpy(m.ptr(y), ptr(y), (size_t)cols * channels());
+        return m;
+    }
+
+private:
+    int type_ = CV_8UC1;
+    std::shared_ptr<unsigned char> buf_;
+};
+
+}  // namespace cv
