@@ -297,12 +297,15 @@ static int local_batch_dev(prl_cuda_ctx* c, int method, int mode, const uint8_t*
         uint8_t* dst = d_dst + (size_t)p0 * dst_page_stride;
         rc = prl_k_integral(c, src, np, rows, cols, src_step, src_page_stride, g.h, S, Q, g.pitch, plane_elems, d_imin + p0);
         if (rc) return rc;
+        const bool with_morph = morph_iters != 0 && mode == 0;
+        // with a morphology tail kernel 2 writes the raw mask into the scratch and the tail writes the final one
         rc = prl_k_threshold(c, method, mode, src, np, g, src_step, src_page_stride, S, Q, plane_elems, params,
-                             d_imin + p0, d_smax + p0, dst, dst_step, dst_page_stride);
+                             d_imin + p0, d_smax + p0, with_morph ? c->d_tmp : dst, with_morph ? tmp_step : dst_step,
+                             with_morph ? (size_t)g.out_rows * tmp_step : dst_page_stride);
         if (rc) return rc;
-        if (morph_iters != 0 && mode == 0) {
-            rc = prl_k_morph(c, dst, c->d_tmp, np, g.out_rows, g.out_cols, dst_step, dst_page_stride, tmp_step,
-                             (size_t)g.out_rows * tmp_step, morph_iters);
+        if (with_morph) {
+            rc = prl_k_morph(c, c->d_tmp, dst, np, g.out_rows, g.out_cols, tmp_step, (size_t)g.out_rows * tmp_step,
+                             dst_step, dst_page_stride, morph_iters);
             if (rc) return rc;
         }
     }
@@ -474,7 +477,7 @@ extern "C" int prl_cuda_morph(prl_cuda_ctx* c, const uint8_t* src, int rows, int
     rc = prl_ensure(c, (void**)&c->d_tmp, &c->d_tmp_bytes, in_step * rows); if (rc) return rc;
     rc = prl_k_morph(c, c->d_in, c->d_tmp, 1, rows, cols, in_step, in_step * rows, in_step, in_step * rows, morph_iters);
     if (rc) return rc;
-    PRL_CUDA_TRY(c, cudaMemcpy2DAsync(dst, dst_step, c->d_in, in_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
+    PRL_CUDA_TRY(c, cudaMemcpy2DAsync(dst, dst_step, c->d_tmp, in_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
     PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return PRL_OK;
 }

@@ -91,8 +91,8 @@ int prl_k_threshold(prl_cuda_ctx* ctx, int method, int mode /*0 mask, 1 T8*/, co
                     const int64_t* d_Q, size_t plane_page_stride, const double* params,
                     const uint32_t* d_imin, long long* d_smax, uint8_t* d_dst, size_t dst_step,
                     size_t dst_page_stride);
-int prl_k_morph(prl_cuda_ctx* ctx, uint8_t* d_mask, uint8_t* d_tmp, int n_pages, int rows, int cols, size_t step,
-                size_t page_stride, size_t tmp_step, size_t tmp_page_stride, int iters);
+int prl_k_morph(prl_cuda_ctx* ctx, uint8_t* d_in, uint8_t* d_out, int n_pages, int rows, int cols, size_t in_step,
+                size_t in_page_stride, size_t out_step, size_t out_page_stride, int iters);
 int prl_k_bgr2gray(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, int channels,
                    uint8_t* d_dst, size_t dst_step);
 int prl_k_synth(prl_cuda_ctx* ctx, uint8_t* d_dst, int n_pages, int rows, int cols, size_t step,

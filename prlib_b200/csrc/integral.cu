@@ -392,24 +392,53 @@ __global__ void __launch_bounds__(256)
 band_colsum_kernel(const uint8_t* __restrict__ src, size_t src_step, size_t src_page_stride, int rows, int cols,
                    int pad, int rows_per_band, unsigned long long* __restrict__ colsum, size_t pitch)
 {
-    const int page = blockIdx.y, band = blockIdx.x, bands = gridDim.x;
+    // grid (column tiles of 1024, bands, pages); each thread owns 4 adjacent padded columns
+    const int page = blockIdx.z, band = blockIdx.y, bands = gridDim.y;
     const int Wp = cols + 2 * pad;
     const int y0 = band * rows_per_band, y1 = min(y0 + rows_per_band, rows);
+    const int X = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (X >= Wp) return;
     src += (size_t)page * src_page_stride;
-    unsigned long long* out = colsum + ((size_t)page * bands + band) * 2 * pitch;
-    for (int X = threadIdx.x; X < Wp; X += blockDim.x) {
-        const int x = min(max(X - pad, 0), cols - 1);
-        unsigned long long s = 0, q = 0;
-        for (int y = y0; y < y1; ++y) {
-            const unsigned long long p = __ldg(src + (size_t)y * src_step + x);
-            unsigned long long mult = 1;
-            if (y == 0) mult += pad;
-            if (y == rows - 1) mult += pad;
-            s += mult * p; q += mult * p * p;
+    int xs[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xs[i] = min(max(X + i - pad, 0), cols - 1);
+    unsigned int s[4] = {0, 0, 0, 0};
+    unsigned long long q[4] = {0, 0, 0, 0};
+    unsigned long long sb[4] = {0, 0, 0, 0};      // replicated border rows carry a multiplicity > 1
+    int y = y0;
+    for (; y + 4 <= y1; y += 4) {
+        unsigned int p[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) p[r][i] = __ldg(src + (size_t)(y + r) * src_step + xs[i]);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int yy = y + r;
+            unsigned int mult = 1;
+            if (yy == 0) mult += pad;
+            if (yy == rows - 1) mult += pad;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (mult == 1) { s[i] += p[r][i]; q[i] += p[r][i] * p[r][i]; }
+                else { sb[i] += (unsigned long long)mult * p[r][i]; q[i] += (unsigned long long)mult * p[r][i] * p[r][i]; }
+            }
         }
-        out[X] = s;
-        out[pitch + X] = q;
     }
+    for (; y < y1; ++y) {
+        unsigned long long mult = 1;
+        if (y == 0) mult += pad;
+        if (y == rows - 1) mult += pad;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const unsigned long long p = __ldg(src + (size_t)y * src_step + xs[i]);
+            sb[i] += mult * p; q[i] += mult * p * p;
+        }
+    }
+    unsigned long long* out = colsum + ((size_t)page * bands + band) * 2 * pitch;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (X + i < Wp) { out[X + i] = sb[i] + s[i]; out[pitch + X + i] = q[i]; }
 }
 
 // carry[page][band][plane][X] = sum_{b' < band} sum_{X' <= X} colsum[page][b'][plane][X']
@@ -548,7 +577,7 @@ int prl_k_integral(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int row
         rc = prl_ensure(ctx, &ctx->carry, &ctx->carry_bytes, need); if (rc) return rc;
         {
             prl_launch_scope ls(ctx, FAM_BAND_CARRY);
-            band_colsum_kernel<<<dim3(bands, n_pages), 256, 0, ctx->stream>>>(
+            band_colsum_kernel<<<dim3((Wp + 1023) / 1024, bands, n_pages), 256, 0, ctx->stream>>>(
                 d_src, src_step, src_page_stride, rows, cols, pad, rpb, (unsigned long long*)ctx->colsum, pitch);
         }
         {

@@ -3,13 +3,168 @@
 // Replaces cv::dilate / cv::erode with the default 3x3 element and `n` iterations
 // (binarizeSauvola.cpp:125-134, binarizeNiblack.cpp:115-127, binarizeWolfJolion.cpp:138-147,
 // binarizeNICK.cpp:134-143, binarizeFeng.cpp:151-163).  n iterations of a 3x3 rectangle are one
-// (2n+1)x(2n+1) rectangle; pixels outside the image are ignored (morphologyDefaultBorderValue),
-// so each pass is a separable running max / min clipped to the image.
+// (2n+1)x(2n+1) rectangle; pixels outside the image are ignored (morphologyDefaultBorderValue), i.e.
+// they act as 0 for a dilation and as 255 for an erosion.
+//
+// morph_fused_kernel does the whole closing (or opening) in ONE pass over HBM (1 byte read + 1 byte
+// written per pixel): a CTA stages its tile plus a 2n halo in shared memory and runs the four
+// separable passes (row max, column max, row min, column min) there, 4 pixels per thread with the
+// byte-SIMD __vmaxu4 / __vminu4 and funnel shifts for the horizontal taps.  morph_pass_kernel is the
+// generic one-pass-per-launch fallback for n > 8.
 #include "common.cuh"
 
 namespace {
 
-// one separable pass: horizontal (DIR 0) or vertical (DIR 1) max (IS_MAX) / min over [-n, n]
+constexpr int kSWw = 64;                      // staged tile: 64 words (256 bytes) wide ...
+constexpr int kSW = kSWw * 4;
+constexpr int kSH = 64;                       // ... and 64 rows high, halo included
+constexpr int kMaxN = 8;                      // fused kernel handles n <= 8
+
+template <bool IS_MAX> __device__ __forceinline__ uint32_t vop(uint32_t a, uint32_t b) { return IS_MAX ? __vmaxu4(a, b) : __vminu4(a, b); }
+
+// horizontal (2n+1) max/min, rows [r0, r1), word columns [c0, c1): warp w takes rows w, w+8, ..; lanes take words
+template <bool IS_MAX, int NMAX>
+__device__ __forceinline__ void hpass(const uint32_t* in, uint32_t* out, int n, int r0, int r1, int c0, int c1)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int r = r0 + wid; r < r1; r += 8) {
+        const uint32_t* row = in + r * kSWw;
+        for (int c = c0 + lane; c < c1; c += 32) {
+            // neighbours outside the staged row only feed bytes nobody consumes (see the halo bookkeeping below)
+            const uint32_t w0 = row[c];
+            const uint32_t wm1 = c > 0 ? row[c - 1] : w0, wp1 = c < kSWw - 1 ? row[c + 1] : w0;
+            uint32_t wm2 = w0, wp2 = w0;
+            if (NMAX > 4) { if (c > 1) wm2 = row[c - 2]; if (c < kSWw - 2) wp2 = row[c + 2]; }
+            uint32_t acc = w0;
+#pragma unroll
+            for (int k = 1; k <= NMAX; ++k) {
+                if (k <= n) {
+                    uint32_t left, right;     // pixels x-k and x+k
+                    if (k < 4) { left = __funnelshift_r(wm1, w0, 32 - 8 * k); right = __funnelshift_r(w0, wp1, 8 * k); }
+                    else if (k == 4) { left = wm1; right = wp1; }
+                    else if (k < 8) { left = __funnelshift_r(wm2, wm1, 32 - 8 * (k - 4)); right = __funnelshift_r(wp1, wp2, 8 * (k - 4)); }
+                    else { left = wm2; right = wp2; }
+                    acc = vop<IS_MAX>(acc, vop<IS_MAX>(left, right));
+                }
+            }
+            out[r * kSWw + c] = acc;
+        }
+    }
+}
+
+// vertical (2n+1) max/min, rows [r0, r1), word columns [c0, c1)
+template <bool IS_MAX>
+__device__ __forceinline__ void vpass(const uint32_t* in, uint32_t* out, int n, int r0, int r1, int c0, int c1)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int r = r0 + wid; r < r1; r += 8)
+        for (int c = c0 + lane; c < c1; c += 32) {
+            uint32_t acc = in[r * kSWw + c];
+            for (int k = 1; k <= n; ++k) acc = vop<IS_MAX>(acc, vop<IS_MAX>(in[(r - k) * kSWw + c], in[(r + k) * kSWw + c]));
+            out[r * kSWw + c] = acc;
+        }
+}
+
+// 4 bytes at `p` (any alignment, all four inside the row)
+__device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t* p)
+{
+    const uint32_t sh = (uint32_t)(uintptr_t)p & 3u;
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(p - sh);
+    uint32_t w = __ldg(a);
+    if (sh) w = __funnelshift_r(w, __ldg(a + 1), 8 * sh);
+    return w;
+}
+
+// CLOSE = true: dilate then erode (morph_iters > 0); false: erode then dilate (morph_iters < 0).
+// HALO = 2 * (largest n served) rounded to a multiple of 4: 4 (n <= 2), 8 (n <= 4), 16 (n <= 8).
+// Output tile: (256 - 2 HALO) x (64 - 2 HALO) pixels.
+template <bool CLOSE, int HALO>
+__global__ void __launch_bounds__(256)
+morph_fused_kernel(const uint8_t* __restrict__ src, size_t src_step, size_t src_page_stride, uint8_t* __restrict__ dst,
+                   size_t dst_step, size_t dst_page_stride, int rows, int cols, int n)
+{
+    constexpr int TW = kSW - 2 * HALO, TH = kSH - 2 * HALO, NMAX = HALO / 2, HW = HALO / 4;
+    __shared__ uint32_t bufA[kSH * kSWw], bufB[kSH * kSWw];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+    src += (size_t)blockIdx.z * src_page_stride;
+    dst += (size_t)blockIdx.z * dst_page_stride;
+    const uint32_t first_fill = CLOSE ? 0u : 255u, second_fill = CLOSE ? 255u : 0u;
+
+    // stage tile + halo; pixels outside the image take the neutral value of the first operator
+    for (int r = wid; r < kSH; r += 8) {
+        const int y = ty0 - HALO + r;
+        for (int c = lane; c < kSWw; c += 32) {
+            const int x = tx0 - HALO + 4 * c;
+            uint32_t w = first_fill * 0x01010101u;
+            if (y >= 0 && y < rows && x + 3 >= 0 && x < cols) {
+                const uint8_t* p = src + (size_t)y * src_step + x;
+                if (x >= 0 && x + 7 < cols) w = ld_u32_unaligned(p);     // (+7: the aligned pair may reach 3 bytes further)
+                else {
+                    w = 0;
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t v = (x + k >= 0 && x + k < cols) ? (uint32_t)p[k] : first_fill;
+                        w |= v << (8 * k);
+                    }
+                }
+            }
+            bufA[r * kSWw + c] = w;
+        }
+    }
+    __syncthreads();
+    // Halo bookkeeping (bytes in x, rows in y; HALO >= 2n): outputs [HALO, S-HALO) need the first operator's
+    // result on [HALO-n, S-HALO+n), which needs the input on [HALO-2n, S-HALO+2n) -- all staged.  Every pass is
+    // run over whole words / all rows it can; results outside those ranges are garbage that nothing reads.
+    // pass 1 (rows)
+    hpass<CLOSE, NMAX>(bufA, bufB, n, 0, kSH, 0, kSWw);
+    __syncthreads();
+    // pass 2 (columns)
+    vpass<CLOSE>(bufB, bufA, n, n, kSH - n, 0, kSWw);
+    __syncthreads();
+    // the second operator ignores what lies outside the image, whatever the first one produced there
+    for (int r = wid; r < kSH; r += 8) {
+        const int y = ty0 - HALO + r;
+        for (int c = lane; c < kSWw; c += 32) {
+            const int x = tx0 - HALO + 4 * c;
+            if (y < 0 || y >= rows || x + 3 < 0 || x >= cols) bufA[r * kSWw + c] = second_fill * 0x01010101u;
+            else if (x < 0 || x + 3 >= cols) {
+                uint32_t w = bufA[r * kSWw + c];
+                for (int k = 0; k < 4; ++k)
+                    if (x + k < 0 || x + k >= cols) w = (w & ~(0xffu << (8 * k))) | (second_fill << (8 * k));
+                bufA[r * kSWw + c] = w;
+            }
+        }
+    }
+    __syncthreads();
+    // pass 3 (rows)
+    hpass<!CLOSE, NMAX>(bufA, bufB, n, n, kSH - n, 0, kSWw);
+    __syncthreads();
+    // pass 4 (columns) straight to global: staged rows [HALO, HALO + TH), words [HW, HW + TW/4)
+    for (int r = HALO + wid; r < HALO + TH; r += 8) {
+        const int y = ty0 + (r - HALO);
+        if (y >= rows) break;
+        for (int c = HW + lane; c < HW + TW / 4; c += 32) {
+            const int x = tx0 + 4 * (c - HW);
+            if (x >= cols) break;
+            uint32_t acc = bufB[r * kSWw + c];
+            for (int k = 1; k <= n; ++k) acc = vop<!CLOSE>(acc, vop<!CLOSE>(bufB[(r - k) * kSWw + c], bufB[(r + k) * kSWw + c]));
+            uint8_t* o = dst + (size_t)y * dst_step + x;
+            if (x + 3 < cols && ((uintptr_t)o & 3) == 0) *reinterpret_cast<uint32_t*>(o) = acc;
+            else for (int k = 0; k < 4; ++k) if (x + k < cols) o[k] = (uint8_t)(acc >> (8 * k));
+        }
+    }
+}
+
+template <bool CLOSE, int HALO>
+void launch_fused(prl_cuda_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int n_pages, int rows, int cols, size_t in_step,
+                  size_t in_page_stride, size_t out_step, size_t out_page_stride, int n)
+{
+    constexpr int TW = kSW - 2 * HALO, TH = kSH - 2 * HALO;
+    dim3 grid((cols + TW - 1) / TW, (rows + TH - 1) / TH, n_pages);
+    morph_fused_kernel<CLOSE, HALO><<<grid, 256, 0, ctx->stream>>>(d_in, in_step, in_page_stride, d_out, out_step, out_page_stride, rows, cols, n);
+}
+
+// ---- generic fallback: one separable pass per launch -----------------------------------------
 template <int DIR, bool IS_MAX>
 __global__ void __launch_bounds__(256)
 morph_pass_kernel(const uint8_t* __restrict__ src, size_t src_step, size_t src_page_stride,
@@ -51,20 +206,41 @@ void morph_op(prl_cuda_ctx* ctx, uint8_t* d_mask, uint8_t* d_tmp, int n_pages, i
 
 }  // namespace
 
-// In place on d_mask; d_tmp is a same-shaped scratch.
-int prl_k_morph(prl_cuda_ctx* ctx, uint8_t* d_mask, uint8_t* d_tmp, int n_pages, int rows, int cols, size_t step,
-                size_t page_stride, size_t tmp_step, size_t tmp_page_stride, int iters)
+// Out of place: reads d_in, writes d_out (d_in is clobbered by the n > 8 fallback).
+int prl_k_morph(prl_cuda_ctx* ctx, uint8_t* d_in, uint8_t* d_out, int n_pages, int rows, int cols, size_t in_step,
+                size_t in_page_stride, size_t out_step, size_t out_page_stride, int iters)
 {
-    if (iters == 0) return PRL_OK;
-    if (rows > 65535 || n_pages > 65535) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "grid too large");
+    if (n_pages > 65535 || rows > 65535) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "grid too large");
+    if (iters == 0) {
+        for (int p = 0; p < n_pages; ++p)
+            PRL_CUDA_TRY(ctx, cudaMemcpy2DAsync(d_out + (size_t)p * out_page_stride, out_step, d_in + (size_t)p * in_page_stride, in_step,
+                                                cols, rows, cudaMemcpyDeviceToDevice, ctx->stream));
+        return PRL_OK;
+    }
     const int n = iters > 0 ? iters : -iters;
-    if (iters > 0) {   // closing: dilate then erode
-        morph_op<true>(ctx, d_mask, d_tmp, n_pages, rows, cols, step, page_stride, tmp_step, tmp_page_stride, n);
-        morph_op<false>(ctx, d_mask, d_tmp, n_pages, rows, cols, step, page_stride, tmp_step, tmp_page_stride, n);
-    } else {           // opening: erode then dilate
-        morph_op<false>(ctx, d_mask, d_tmp, n_pages, rows, cols, step, page_stride, tmp_step, tmp_page_stride, n);
-        morph_op<true>(ctx, d_mask, d_tmp, n_pages, rows, cols, step, page_stride, tmp_step, tmp_page_stride, n);
+    if (n <= kMaxN) {
+        prl_launch_scope ls(ctx, FAM_MORPH);
+        const bool close = iters > 0;
+        if (n <= 2) { if (close) launch_fused<true, 4>(ctx, d_in, d_out, n_pages, rows, cols, in_step, in_page_stride, out_step, out_page_stride, n);
+                      else launch_fused<false, 4>(ctx, d_in, d_out, n_pages, rows, cols, in_step, in_page_stride, out_step, out_page_stride, n); }
+        else if (n <= 4) { if (close) launch_fused<true, 8>(ctx, d_in, d_out, n_pages, rows, cols, in_step, in_page_stride, out_step, out_page_stride, n);
+                           else launch_fused<false, 8>(ctx, d_in, d_out, n_pages, rows, cols, in_step, in_page_stride, out_step, out_page_stride, n); }
+        else { if (close) launch_fused<true, 16>(ctx, d_in, d_out, n_pages, rows, cols, in_step, in_page_stride, out_step, out_page_stride, n);
+               else launch_fused<false, 16>(ctx, d_in, d_out, n_pages, rows, cols, in_step, in_page_stride, out_step, out_page_stride, n); }
+        PRL_CUDA_TRY(ctx, cudaGetLastError());
+        return PRL_OK;
+    }
+    // fallback: four single passes ping-ponging d_in <-> d_out, then one copy
+    if (iters > 0) {
+        morph_op<true>(ctx, d_in, d_out, n_pages, rows, cols, in_step, in_page_stride, out_step, out_page_stride, n);
+        morph_op<false>(ctx, d_in, d_out, n_pages, rows, cols, in_step, in_page_stride, out_step, out_page_stride, n);
+    } else {
+        morph_op<false>(ctx, d_in, d_out, n_pages, rows, cols, in_step, in_page_stride, out_step, out_page_stride, n);
+        morph_op<true>(ctx, d_in, d_out, n_pages, rows, cols, in_step, in_page_stride, out_step, out_page_stride, n);
     }
     PRL_CUDA_TRY(ctx, cudaGetLastError());
+    for (int p = 0; p < n_pages; ++p)
+        PRL_CUDA_TRY(ctx, cudaMemcpy2DAsync(d_out + (size_t)p * out_page_stride, out_step, d_in + (size_t)p * in_page_stride, in_step,
+                                            cols, rows, cudaMemcpyDeviceToDevice, ctx->stream));
     return PRL_OK;
 }
