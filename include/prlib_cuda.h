@@ -61,7 +61,9 @@ int         prl_cuda_set_workspace_limit(prl_cuda_ctx* ctx, size_t bytes);
 /* Validation switches (masks and planes are bit-identical either way; only the speed differs):
  *   "exact_threshold" != 0 : kernel 2 evaluates the reference's FP64 formula for EVERY pixel instead
  *                            of only for the pixels its exact-integer/FP32 decision cannot settle;
- *   "disable_tma"     != 0 : kernel 1 uses its generic byte-load kernel instead of the TMA-staged one. */
+ *   "disable_tma"     != 0 : kernel 1 uses its generic byte-load kernel instead of the TMA-staged one;
+ *   "disable_fused"   != 0 : big batches with small windows keep the int64 integral planes in HBM (kernel 1 +
+ *                            kernel 2) instead of the fused strip kernel that never materialises them. */
 int         prl_cuda_set_option(prl_cuda_ctx* ctx, const char* name, long long value);
 
 /* Geometry of the reference's processingRect (binarizeSauvola.cpp:57,66; binarizeWolfJolion.cpp:58,69):
@@ -154,7 +156,7 @@ int prl_cuda_binarize_batch(const int* devices, int n_dev, int method, const uin
 /* ---- instrumentation ---------------------------------------------------------------------
  * With timing enabled every kernel launch is bracketed by CUDA events on the launching stream.
  * prl_cuda_timing_get sums them per kernel family ("integral", "threshold", "smax", "morph",
- * "otsu_hist", "otsu_search", "otsu_apply", "otsu_tiles", "synth", "bgr2gray", "band_carry");
+ * "otsu_hist", "otsu_search", "otsu_apply", "otsu_tiles", "synth", "bgr2gray", "band_carry", "fused", "fused_pre");
  * it synchronizes the stream. */
 int  prl_cuda_timing_enable(prl_cuda_ctx* ctx, int on);
 int  prl_cuda_timing_reset(prl_cuda_ctx* ctx);

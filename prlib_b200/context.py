@@ -10,7 +10,7 @@ from . import capi
 from .capi import PrlCudaError
 
 _FAMILIES = ("integral", "threshold", "smax", "morph", "otsu_hist", "otsu_search", "otsu_apply", "otsu_tiles",
-             "synth", "bgr2gray", "band_carry")
+             "synth", "bgr2gray", "band_carry", "fused", "fused_pre")
 
 
 def _params4(params) -> "C.Array":

@@ -85,7 +85,7 @@ static void timing_collect(prl_cuda_ctx* ctx)
 }
 
 static const char* kFamilyNames[FAM_COUNT] = {"integral", "threshold", "smax", "morph", "otsu_hist", "otsu_search",
-                                              "otsu_apply", "otsu_tiles", "synth", "bgr2gray", "band_carry"};
+                                              "otsu_apply", "otsu_tiles", "synth", "bgr2gray", "band_carry", "fused", "fused_pre"};
 
 int prl_make_geom(int method, int rows, int cols, int window, prl_geom* g)
 {
@@ -203,6 +203,7 @@ extern "C" int prl_cuda_set_option(prl_cuda_ctx* c, const char* name, long long 
     if (!c || !name) return PRL_E_INVALID;
     if (strcmp(name, "exact_threshold") == 0) c->force_exact = value != 0;
     else if (strcmp(name, "disable_tma") == 0) c->no_tma = value != 0;
+    else if (strcmp(name, "disable_fused") == 0) c->no_fused = value != 0;
     else return prl_set_err(c, PRL_E_INVALID, "unknown option");
     return PRL_OK;
 }
@@ -269,6 +270,26 @@ static int local_batch_dev(prl_cuda_ctx* c, int method, int mode, const uint8_t*
     if (rc) return prl_set_err(c, rc, rc == PRL_E_EMPTY_ROI ? "empty processingRect: min(rows, cols) <= windowSize"
                                                              : "empty image or window not (>1 and odd)");
     if ((size_t)g.out_cols > dst_step) return prl_set_err(c, PRL_E_INVALID, "dst_step smaller than out_cols");
+
+    rc = prl_ensure(c, &c->scalars, &c->scalars_bytes, (size_t)n_pages * 16);
+    if (rc) return rc;
+    // small windows, big batches: the fused path (planes never reach HBM)
+    if (mode == 0 && prl_fused_eligible(c, method, n_pages, g, params)) {
+        uint32_t* imin = (uint32_t*)c->scalars;
+        const bool with_morph = morph_iters != 0;
+        size_t t_step = round16((size_t)g.out_cols);
+        if (with_morph) {
+            rc = prl_ensure(c, (void**)&c->d_tmp, &c->d_tmp_bytes, (size_t)n_pages * g.out_rows * t_step);
+            if (rc) return rc;
+        }
+        rc = prl_k_fused(c, method, d_src, n_pages, g, src_step, src_page_stride, params, imin, with_morph ? c->d_tmp : d_dst,
+                         with_morph ? t_step : dst_step, with_morph ? (size_t)g.out_rows * t_step : dst_page_stride);
+        if (rc) return rc;
+        if (with_morph)
+            rc = prl_k_morph(c, c->d_tmp, d_dst, n_pages, g.out_rows, g.out_cols, t_step, (size_t)g.out_rows * t_step, dst_step,
+                             dst_page_stride, morph_iters);
+        return rc;
+    }
 
     const size_t plane_elems = (size_t)g.Hp * g.pitch;          // one plane of one page
     const size_t per_page = 2 * plane_elems * sizeof(int64_t);

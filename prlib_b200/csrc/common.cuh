@@ -41,6 +41,7 @@ struct prl_cuda_ctx {
 
     bool force_exact = false;   // validation: kernel 2 runs the literal FP64 path for every pixel
     bool no_tma = false;        // validation: kernel 1 uses the generic (non-TMA) kernel
+    bool no_fused = false;      // keep the integral planes in HBM even where the fused small-window path applies
 
     // instrumentation
     bool timing = false;
@@ -52,7 +53,7 @@ struct prl_cuda_ctx {
 
 enum prl_family {
     FAM_INTEGRAL = 0, FAM_THRESHOLD, FAM_SMAX, FAM_MORPH, FAM_OTSU_HIST, FAM_OTSU_SEARCH,
-    FAM_OTSU_APPLY, FAM_OTSU_TILES, FAM_SYNTH, FAM_BGR2GRAY, FAM_BAND_CARRY, FAM_COUNT
+    FAM_OTSU_APPLY, FAM_OTSU_TILES, FAM_SYNTH, FAM_BGR2GRAY, FAM_BAND_CARRY, FAM_FUSED, FAM_FUSED_PRE, FAM_COUNT
 };
 
 int  prl_set_err(prl_cuda_ctx* ctx, int code, const char* what, cudaError_t ce = cudaSuccess);
@@ -91,6 +92,10 @@ int prl_k_threshold(prl_cuda_ctx* ctx, int method, int mode /*0 mask, 1 T8*/, co
                     const int64_t* d_Q, size_t plane_page_stride, const double* params,
                     const uint32_t* d_imin, long long* d_smax, uint8_t* d_dst, size_t dst_step,
                     size_t dst_page_stride);
+bool prl_fused_eligible(const prl_cuda_ctx* ctx, int method, int n_pages, const prl_geom& g, const double* params);
+int prl_k_fused(prl_cuda_ctx* ctx, int method, const uint8_t* d_src, int n_pages, const prl_geom& g, size_t src_step,
+                size_t src_page_stride, const double* params, uint32_t* d_imin, uint8_t* d_dst, size_t dst_step,
+                size_t dst_page_stride);
 int prl_k_morph(prl_cuda_ctx* ctx, uint8_t* d_in, uint8_t* d_out, int n_pages, int rows, int cols, size_t in_step,
                 size_t in_page_stride, size_t out_step, size_t out_page_stride, int iters);
 int prl_k_bgr2gray(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, int channels,

@@ -1,0 +1,172 @@
+// decide.cuh -- the per-pixel decision shared by kernel 2 (threshold.cu) and the fused small-window kernel
+// (fused.cu): exact integer window sums -> FP32 estimate of T -> decided unless within a proven margin of the
+// rounding boundary, in which case the reference's FP64 formula is evaluated literally from the int64 taps.
+#pragma once
+#include "common.cuh"
+#include <cmath>
+
+namespace {
+
+struct FastArgs {
+    float kwf, inv_w2f;          // 1/w^2 as float
+    float c0, c1, c2;            // method constants in FP32
+    float mu0, mu1;              // decision margin: mu = mu0 + mu1*|coeff|  (mu1 only for Wolf-Jolion)
+    float n_floor;               // fast path only when N >= n_floor  (s* >= s_floor)
+    unsigned int w2;             // w*w
+    int rows_per_cta;
+};
+
+__device__ __forceinline__ int to_u8(double T)
+{
+    // cvRound == cvtsd2si: NaN and anything outside int32 become INT_MIN -> saturates to 0
+    if (!(T > 0.0) || T >= 2147483647.5) return 0;
+    if (T >= 255.5) return 255;
+    return __double2int_rn(T);
+}
+
+// exact int64 -> double for 0 <= v < 2^52 without the (quarter-rate) I2F.F64.S64
+__device__ __forceinline__ double i2d(long long v)
+{
+    return __dadd_rn(__longlong_as_double(v | 0x4330000000000000LL), -4503599627370496.0);
+}
+
+__device__ __forceinline__ double tap4(double kw, double nkw, long long a, long long b, long long c, long long d)
+{
+    double r = __dmul_rn(kw, i2d(a));
+    r = __dadd_rn(r, __dmul_rn(nkw, i2d(b)));
+    r = __dadd_rn(r, __dmul_rn(nkw, i2d(c)));
+    r = __dadd_rn(r, __dmul_rn(kw, i2d(d)));
+    return r;
+}
+
+// The reference's FP64 threshold formulas (binarizeSauvola.cpp:115-118, binarizeNiblack.cpp:108,
+// binarizeWolfJolion.cpp:128-130, binarizeNICK.cpp:121-126, binarizeFeng.cpp:118-142), operation order kept.
+template <int METHOD>
+__device__ __forceinline__ double thr_value_p(double m, double s, double p0, double p1, double p2, double imin, double coeff)
+{
+    if (METHOD == PRL_SAUVOLA) {
+        return __dmul_rn(m, __dadd_rn(__dmul_rn(s, p1), p2));
+    } else if (METHOD == PRL_NIBLACK) {
+        return __dadd_rn(m, __dmul_rn(p0, s));
+    } else if (METHOD == PRL_WOLFJOLION) {
+        double dd = __dadd_rn(__dmul_rn(s, coeff), -p0);
+        dd = __dmul_rn(dd, __dadd_rn(m, -imin));
+        return __dadd_rn(m, dd);
+    } else if (METHOD == PRL_NICK) {
+        double C = __dsqrt_rn(__dadd_rn(__dmul_rn(m, m), __dmul_rn(s, s)));
+        return __dadd_rn(m, __dmul_rn(C, p0));
+    } else {
+        if (!(s == s) || s == 0.0) return __longlong_as_double(0x7ff8000000000000LL);
+        double c3 = __dadd_rn(__dmul_rn(p2, imin), -imin);
+        return __dadd_rn(__dmul_rn(p1, m), c3);
+    }
+}
+
+// (scalars by value: a reference to the kernel-parameter struct would force a per-thread stack copy)
+template <int METHOD>
+__device__ __noinline__ int exact_t8_at(const long long* __restrict__ s0, const long long* __restrict__ q0, size_t drow,
+                                        int d, double kw, double p0, double p1, double p2, double imin, double coeff)
+{
+    const double nkw = -kw;
+    const double m = tap4(kw, nkw, __ldg(s0), __ldg(s0 + d), __ldg(s0 + drow), __ldg(s0 + drow + d));
+    const double q = tap4(kw, nkw, __ldg(q0), __ldg(q0 + d), __ldg(q0 + drow), __ldg(q0 + drow + d));
+    const double s = __dsqrt_rn(__dadd_rn(q, -__dmul_rn(m, m)));
+    return to_u8(thr_value_p<METHOD>(m, s, p0, p1, p2, imin, coeff));
+}
+
+// the reference arithmetic from the eight integral taps
+template <int METHOD>
+__device__ __forceinline__ int exact_t8_from_taps(long long sa, long long sb, long long sc, long long sd, long long qa,
+                                                  long long qb, long long qc, long long qd, double kw, double p0,
+                                                  double p1, double p2, double imin, double coeff)
+{
+    const double nkw = -kw;
+    const double m = tap4(kw, nkw, sa, sb, sc, sd);
+    const double q = tap4(kw, nkw, qa, qb, qc, qd);
+    const double s = __dsqrt_rn(__dadd_rn(q, -__dmul_rn(m, m)));
+    return to_u8(thr_value_p<METHOD>(m, s, p0, p1, p2, imin, coeff));
+}
+
+// FP32 estimate of T from the exact window sums; returns false when the pixel must take the exact path
+template <int METHOD>
+__device__ __forceinline__ bool fast_decide(unsigned int sw, unsigned int qw, unsigned int p, const FastArgs& F,
+                                            float iminf, float coefff, float mu, int& out)
+{
+    if (qw == 0u) { out = 0; return true; }            // all-zero window => p == 0 => (0 > T8) is false
+    const unsigned long long N = (unsigned long long)F.w2 * qw - (unsigned long long)sw * sw;   // exact, >= 0
+    const float fn = (float)N;
+    const float m = (float)sw * F.kwf;
+    const float s = sqrtf(fn) * F.inv_w2f;
+    float T;
+    if (METHOD == PRL_SAUVOLA) T = m * fmaf(s, F.c1, F.c2);
+    else if (METHOD == PRL_NIBLACK) T = fmaf(F.c0, s, m);
+    else if (METHOD == PRL_WOLFJOLION) T = fmaf(fmaf(s, coefff, -F.c0), m - iminf, m);
+    else if (METHOD == PRL_NICK) T = fmaf(F.c0, sqrtf(fmaf(m, m, s * s)), m);
+    else T = fmaf(F.c1, m, fmaf(F.c2, iminf, -iminf));
+    const float g = ((float)p - 0.5f) - fmaxf(T, 0.0f);
+    const bool ok = fn >= F.n_floor;
+    if (ok && g > mu) { out = 255; return true; }
+    if (ok && g < -mu) { out = 0; return true; }
+    return false;                                       // near the rounding boundary, ill-conditioned, or NaN
+}
+
+// Host-side error analysis for the fast path: returns false when the margin is too large to be useful.
+//   reference FP64 error (vs exact real arithmetic), u = 2^-53:
+//     dm_ref <= 16 u kw Smax,  dq_ref <= 16 u kw Qmax,  dv_ref <= dq_ref + 2*255*dm_ref + u*2*255^2
+//     ds_ref <= dv_ref / s_floor + u*128          (fast path requires s* >= s_floor)
+//   FP32 estimate error (exact integer inputs), e = 2^-24:
+//     dm_est <= 3 e 255,  ds_est <= 4 e 128
+//   |dT| <= A dm + B ds + 8 e (Tmax + 512), A/B = sup |dT/dm|, |dT/ds| over m in [0,255], s in [0,128]
+inline bool fast_margins(int method, const double* params, const prl_geom& g, FastArgs* F)
+{
+    const double u = 1.1102230246251565e-16, e = 5.9604644775390625e-08;
+    const double w2 = (double)g.w * g.w, kw = 1.0 / w2;
+    const double area = (double)g.Hp * (double)g.Wp;
+    const double Smax = 255.0 * area, Qmax = 65025.0 * area;
+    const double s_floor = 0.25;
+    const double dm_ref = 16 * u * kw * Smax, dq_ref = 16 * u * kw * Qmax;
+    const double dv_ref = dq_ref + 510.0 * dm_ref + u * 2 * 65025.0;
+    if (!(dv_ref < 0.25 * s_floor * s_floor)) return false;
+    const double ds_ref = dv_ref / s_floor + u * 128;
+    const double dm = dm_ref + 3 * e * 255, ds = ds_ref + 4 * e * 128;
+    double Acoef, Bcoef, Tmax, mu1 = 0.0;
+    const double k = params[0];
+    switch (method) {
+    case PRL_SAUVOLA: {
+        const double c1 = k * (1.0 / 128.0), c2 = 1.0 - k;
+        Acoef = fabs(c2) + 128 * fabs(c1); Bcoef = 255 * fabs(c1); Tmax = 255 * Acoef;
+        F->c0 = (float)k; F->c1 = (float)c1; F->c2 = (float)c2; break;
+    }
+    case PRL_NIBLACK:
+        Acoef = 1; Bcoef = fabs(k); Tmax = 255 + 128 * fabs(k);
+        F->c0 = (float)k; F->c1 = F->c2 = 0; break;
+    case PRL_NICK:
+        Acoef = 1 + fabs(k); Bcoef = fabs(k); Tmax = 255 + fabs(k) * 286;
+        F->c0 = (float)k; F->c1 = F->c2 = 0; break;
+    case PRL_WOLFJOLION:
+        // T = m + (s*coeff - k)(m - imin), |coeff| = |k|/smax known only on the device:
+        // dT/dm = 1 + s*coeff - k -> |.| <= 1 + |k| + 128|coeff|;  dT/ds = coeff (m - imin) -> <= 255 |coeff|
+        // the FP32 rounding of coeff itself adds e*|coeff|*128*255
+        Acoef = 1 + fabs(k); Bcoef = 0; Tmax = 255 * (1 + fabs(k));
+        mu1 = 4 * (128 * dm + 255 * ds + e * 128 * 255 + 8 * e * 128 * 255);
+        F->c0 = (float)k; F->c1 = F->c2 = 0; break;
+    default: {   // Feng: T = p1*m + (k2*imin - imin)
+        const double p1 = 1.0 + (1.0 - params[0]), k2 = params[2];
+        Acoef = fabs(p1); Bcoef = 0; Tmax = 255 * fabs(p1) + 255 * (fabs(k2) + 1);
+        F->c0 = 0; F->c1 = (float)p1; F->c2 = (float)k2; break;
+    }
+    }
+    if (!(Tmax < 1e6)) return false;
+    const double mu0 = 4 * (Acoef * dm + Bcoef * ds + 8 * e * (Tmax + 512));
+    if (!(mu0 < 0.2)) return false;
+    F->mu0 = (float)(mu0 < 2e-3 ? 2e-3 : mu0);
+    F->mu1 = (float)mu1;
+    F->kwf = (float)kw; F->inv_w2f = (float)kw;
+    F->w2 = (unsigned int)(g.w * g.w);
+    const double nf = s_floor * w2;
+    F->n_floor = (float)(nf * nf * 1.0001);
+    return true;
+}
+
+
+}  // namespace

@@ -67,6 +67,58 @@ def test_batch_dev_large_batch_single_band_path(ctx, golden):
     ctx.set_stream(None)
 
 
+@pytest.mark.parametrize("method,window,params", [(0, 15, (0.2,)), (1, 15, (-0.2,)), (3, 15, (-0.1,)), (4, 15, (0.75, 0.2, 0.03, 2.0)),
+                                                  (0, 21, (0.34,)), (3, 31, (-0.2,)), (0, 3, (0.2,)), (1, 9, (0.7,))])
+def test_fused_small_window_path_equals_planes_path_and_oracle(ctx, method, window, params):
+    """Big batch + small window -> the fused strip kernel (integral planes never reach HBM).  It must give the
+    masks of kernel 1 + kernel 2 byte for byte, and those of the oracle, including on adversarial pages."""
+    n, rows, cols = 150, 260, 1000
+    rng = np.random.default_rng(window * 100 + method)
+    host = np.stack([CO.synth_page(p, rows, cols) for p in range(n)])
+    host[3] = rng.integers(0, 256, (rows, cols), dtype=np.uint8)                       # noise
+    host[4] = (np.add.outer(np.arange(rows), np.arange(cols)) % 256).astype(np.uint8)  # ramp
+    host[5] = 0                                                                        # all black
+    host[6] = 255                                                                      # saturated
+    host[7][:, :90] = 0; host[7][:40, :] = 0                                           # scanner-style black border
+    host[8] = (rng.integers(0, 2, (rows, cols)) * 255).astype(np.uint8)                # pure black / white
+    sparse = np.zeros((rows, cols), np.uint8); sparse[rng.integers(0, rows, 60), rng.integers(0, cols, 60)] = rng.integers(1, 256, 60)
+    host[9] = sparse
+    step = cols + 8                                                                     # pitch != width, 4-aligned
+    buf = torch.zeros((n, rows, step), dtype=torch.uint8, device="cuda:0")
+    buf[:, :, :cols] = torch.from_numpy(host).to("cuda:0")
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    rc, orow, ocol = ctx.output_shape(method, rows, cols, window)
+    outs = []
+    for fused_off in (0, 1):
+        ctx.set_option("disable_fused", fused_off)
+        out = torch.zeros((n, orow, ocol), dtype=torch.uint8, device="cuda:0")              # dense, odd pitch
+        ctx.timing_reset(); ctx.timing_enable(True)
+        ctx.binarize_local_batch_dev(method, buf.data_ptr(), n, rows, cols, step, rows * step, window, params, 0,
+                                     out.data_ptr(), ocol, orow * ocol)
+        torch.cuda.synchronize()
+        fam = ctx.timing(); ctx.timing_enable(False)
+        assert ("fused" in fam) == (fused_off == 0), fam                                 # the intended path really ran
+        outs.append(out.cpu().numpy())
+    ctx.set_option("disable_fused", 0)
+    assert np.array_equal(outs[0], outs[1])
+    for p in list(range(12)) + [77, 149]:
+        assert np.array_equal(outs[0][p], CO.binarize_local(host[p], method, window, params, 0)), p
+    ctx.set_stream(None)
+
+
+def test_fused_path_with_morphology_tail(ctx):
+    n, rows, cols = 140, 300, 1000
+    buf, step = _dev_pages(ctx, n, rows, cols, first=20)
+    rc, orow, ocol = ctx.output_shape(0, rows, cols, 15)
+    out = torch.zeros((n, orow, ocol), dtype=torch.uint8, device="cuda:0")
+    ctx.binarize_local_batch_dev(0, buf.data_ptr(), n, rows, cols, step, rows * step, 15, (0.2,), 2, out.data_ptr(), ocol, orow * ocol)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    for p in (0, 70, 139):
+        assert np.array_equal(got[p], CO.binarize_local(CO.synth_page(20 + p, rows, cols), 0, 15, (0.2,), 2)), p
+    ctx.set_stream(None)
+
+
 def test_batch_dev_workspace_chunking_is_invisible(ctx):
     n, rows, cols = 9, 600, 800
     buf, step = _dev_pages(ctx, n, rows, cols, first=3)
