@@ -62,8 +62,8 @@ int         prl_cuda_set_workspace_limit(prl_cuda_ctx* ctx, size_t bytes);
  *   "exact_threshold" != 0 : kernel 2 evaluates the reference's FP64 formula for EVERY pixel instead
  *                            of only for the pixels its exact-integer/FP32 decision cannot settle;
  *   "disable_tma"     != 0 : kernel 1 uses its generic byte-load kernel instead of the TMA-staged one;
- *   "disable_fused"   != 0 : big batches with small windows keep the int64 integral planes in HBM (kernel 1 +
- *                            kernel 2) instead of the fused strip kernel that never materialises them. */
+ *   "enable_fused"    != 0 : windows <= 31 (Sauvola/Niblack/NICK/Feng) run the fused strip kernel that never
+ *                            materialises the int64 integral planes in HBM (experimental: correct, not yet faster). */
 int         prl_cuda_set_option(prl_cuda_ctx* ctx, const char* name, long long value);
 
 /* Geometry of the reference's processingRect (binarizeSauvola.cpp:57,66; binarizeWolfJolion.cpp:58,69):

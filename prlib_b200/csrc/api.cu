@@ -203,7 +203,7 @@ extern "C" int prl_cuda_set_option(prl_cuda_ctx* c, const char* name, long long 
     if (!c || !name) return PRL_E_INVALID;
     if (strcmp(name, "exact_threshold") == 0) c->force_exact = value != 0;
     else if (strcmp(name, "disable_tma") == 0) c->no_tma = value != 0;
-    else if (strcmp(name, "disable_fused") == 0) c->no_fused = value != 0;
+    else if (strcmp(name, "enable_fused") == 0) c->use_fused = value != 0;
     else return prl_set_err(c, PRL_E_INVALID, "unknown option");
     return PRL_OK;
 }

@@ -41,7 +41,7 @@ struct prl_cuda_ctx {
 
     bool force_exact = false;   // validation: kernel 2 runs the literal FP64 path for every pixel
     bool no_tma = false;        // validation: kernel 1 uses the generic (non-TMA) kernel
-    bool no_fused = false;      // keep the integral planes in HBM even where the fused small-window path applies
+    bool use_fused = false;     // opt-in: fused small-window strip kernel (integral planes never reach HBM)
 
     // instrumentation
     bool timing = false;

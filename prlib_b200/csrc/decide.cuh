@@ -12,6 +12,7 @@ struct FastArgs {
     float c0, c1, c2;            // method constants in FP32
     float mu0, mu1;              // decision margin: mu = mu0 + mu1*|coeff|  (mu1 only for Wolf-Jolion)
     float n_floor;               // fast path only when N >= n_floor  (s* >= s_floor)
+    float q_floor;               // q_win >= q_floor implies N >= n_floor (used by the variance-free pre-test)
     unsigned int w2;             // w*w
     int rows_per_cta;
 };
@@ -88,14 +89,32 @@ __device__ __forceinline__ int exact_t8_from_taps(long long sa, long long sb, lo
 }
 
 // FP32 estimate of T from the exact window sums; returns false when the pixel must take the exact path
-template <int METHOD>
+// PRE: also try the variance-free bounds first (pays off where the decision arithmetic dominates: the fused
+// kernel and Sauvola in kernel 2; measured slower for Niblack / NICK in kernel 2)
+template <int METHOD, bool PRE>
 __device__ __forceinline__ bool fast_decide(unsigned int sw, unsigned int qw, unsigned int p, const FastArgs& F,
                                             float iminf, float coefff, float mu, int& out)
 {
     if (qw == 0u) { out = 0; return true; }            // all-zero window => p == 0 => (0 > T8) is false
+    const float m = (float)sw * F.kwf;
+    const float pm = (float)p - 0.5f;
+    if (PRE && (METHOD == PRL_SAUVOLA || METHOD == PRL_NIBLACK || METHOD == PRL_NICK)) {
+        // T is monotone in s and 0 <= s <= 128: with T(m, 0) and T(m, 128) as bounds most pixels (flat background,
+        // solid ink) are settled without the variance.  Sound only where the full test would not send the pixel
+        // to the exact path for conditioning (s >= s_floor), which q_win >= q_floor guarantees cheaply:
+        // N = w^2 Q - S^2 >= w^2 Q - (w-1)^2 Q = (2w-1) Q  (Cauchy-Schwarz over the (w-1)^2 window).
+        float t0, t1;
+        if (METHOD == PRL_SAUVOLA) { t0 = m * F.c2; t1 = m * fmaf(128.0f, F.c1, F.c2); }
+        else if (METHOD == PRL_NIBLACK) { t0 = m; t1 = fmaf(F.c0, 128.0f, m); }
+        else { t0 = fmaf(F.c0, m, m); t1 = fmaf(F.c0, sqrtf(fmaf(m, m, 16384.0f)), m); }   // NICK: sqrt(m^2+s^2) in [m, sqrt(m^2+128^2)]
+        const float tlo = fmaxf(fminf(t0, t1), 0.0f), thi = fmaxf(fmaxf(t0, t1), 0.0f);
+        if ((float)qw >= F.q_floor) {
+            if (pm - thi > mu) { out = 255; return true; }
+            if (pm - tlo < -mu) { out = 0; return true; }
+        }
+    }
     const unsigned long long N = (unsigned long long)F.w2 * qw - (unsigned long long)sw * sw;   // exact, >= 0
     const float fn = (float)N;
-    const float m = (float)sw * F.kwf;
     const float s = sqrtf(fn) * F.inv_w2f;
     float T;
     if (METHOD == PRL_SAUVOLA) T = m * fmaf(s, F.c1, F.c2);
@@ -103,7 +122,7 @@ __device__ __forceinline__ bool fast_decide(unsigned int sw, unsigned int qw, un
     else if (METHOD == PRL_WOLFJOLION) T = fmaf(fmaf(s, coefff, -F.c0), m - iminf, m);
     else if (METHOD == PRL_NICK) T = fmaf(F.c0, sqrtf(fmaf(m, m, s * s)), m);
     else T = fmaf(F.c1, m, fmaf(F.c2, iminf, -iminf));
-    const float g = ((float)p - 0.5f) - fmaxf(T, 0.0f);
+    const float g = pm - fmaxf(T, 0.0f);
     const bool ok = fn >= F.n_floor;
     if (ok && g > mu) { out = 255; return true; }
     if (ok && g < -mu) { out = 0; return true; }
@@ -165,6 +184,7 @@ inline bool fast_margins(int method, const double* params, const prl_geom& g, Fa
     F->w2 = (unsigned int)(g.w * g.w);
     const double nf = s_floor * w2;
     F->n_floor = (float)(nf * nf * 1.0001);
+    F->q_floor = (float)(nf * nf * 1.001 / (2.0 * g.w - 1.0));
     return true;
 }
 

@@ -125,13 +125,25 @@ local_fused_kernel(const FusedArgs A, const FastArgs F)
     // lane's padded columns X = x0 + 4*lane + i  <->  source columns xs0 + i
     const int xs0 = x0 + 4 * lane - pad;
     const bool interior = (x0 >= pad) && (x0 + kFW - pad + 8 < A.cols);
-    auto fetch = [&](int y) -> uint32_t {
+    // raw fetch of one source row: two aligned words (interior) or four clamped bytes packed (edge strips);
+    // the funnel shift is applied only when the row is consumed, PF rows later, so the loads stay in flight
+    auto fetch = [&](int y, uint32_t& lo, uint32_t& hi) {
         const uint8_t* row = src + (size_t)y * A.src_step;
-        if (interior) return ldg_u32_unaligned(row + xs0);
-        uint32_t w = 0;
+        if (interior) {
+            const uint8_t* p = row + xs0;
+            const uint32_t* a = reinterpret_cast<const uint32_t*>(p - ((uintptr_t)p & 3u));
+            lo = __ldg(a); hi = __ldg(a + 1);
+        } else {
+            uint32_t w = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) w |= (uint32_t)__ldg(row + min(max(xs0 + i, 0), A.cols - 1)) << (8 * i);
-        return w;
+            for (int i = 0; i < 4; ++i) w |= (uint32_t)__ldg(row + min(max(xs0 + i, 0), A.cols - 1)) << (8 * i);
+            lo = w; hi = 0;
+        }
+    };
+    auto combine = [&](int y, uint32_t lo, uint32_t hi) -> uint32_t {
+        if (!interior) return lo;
+        const uint32_t sh = (uint32_t)(uintptr_t)(src + (size_t)y * A.src_step + xs0) & 3u;
+        return sh ? __funnelshift_r(lo, hi, 8 * sh) : lo;
     };
 
     // which of this lane's 4 outputs exist
@@ -142,10 +154,15 @@ local_fused_kernel(const FusedArgs A, const FastArgs F)
     uint32_t accS[4] = {0, 0, 0, 0}, accQ[4] = {0, 0, 0, 0};
     uint32_t qhi = 0;                                   // 4 packed 8-bit carry counters: high words of the local Q sums
     int Y = 0;                                          // next padded row to emit
-    uint32_t w_next = fetch(0);
+    constexpr int PF = 4;                               // rows of prefetch distance
+    uint32_t plo[PF], phi[PF];
+#pragma unroll
+    for (int k = 0; k < PF; ++k) { plo[k] = phi[k] = 0; if (k < A.rows) fetch(k, plo[k], phi[k]); }
     for (int y = 0; y < A.rows; ++y) {
-        const uint32_t w = w_next;
-        if (y + 1 < A.rows) w_next = fetch(y + 1);
+        const uint32_t w = combine(y, plo[0], phi[0]);
+#pragma unroll
+        for (int k = 0; k + 1 < PF; ++k) { plo[k] = plo[k + 1]; phi[k] = phi[k + 1]; }
+        if (y + PF < A.rows) fetch(y + PF, plo[PF - 1], phi[PF - 1]);
         // strip-local row prefix of this source row (u32)
         const uint32_t a0 = w & 0xffu, a1 = __dp4a(w, 0x00000101u, 0u), a2 = __dp4a(w, 0x00010101u, 0u), a3 = __dp4a(w, 0x01010101u, 0u);
         const uint32_t b0 = a0 * a0, b1 = __dp4a(w, w & 0x0000ffffu, 0u), b2 = __dp4a(w, w & 0x00ffffffu, 0u), b3 = __dp4a(w, w, 0u);
@@ -200,7 +217,7 @@ local_fused_kernel(const FusedArgs A, const FastArgs F)
                 const uint32_t qw = (qD[i] - accQ[i]) - (qB[i] - qA[i]);
                 const uint32_t p = (p4 >> (8 * i)) & 0xffu;
                 int o;
-                if (!fast_decide<METHOD>(sw, qw, p, F, iminf, 0.f, mu, o)) {
+                if (!fast_decide<METHOD, true>(sw, qw, p, F, iminf, 0.f, mu, o)) {
                     o = 0;
                     if (xo + i < A.out_cols) {
                         // true int64 taps = strip-local + L.  The local S fits 32 bits; the local Q is 40 bits: low
@@ -259,7 +276,7 @@ int launch_fused_t(prl_cuda_ctx* ctx, const FusedArgs& A, const FastArgs& F)
 template <int METHOD>
 int launch_fused_m(prl_cuda_ctx* ctx, const FusedArgs& A, const FastArgs& F)
 {
-    if (A.d + 1 <= 16) return launch_fused_t<METHOD, 16, 4>(ctx, A, F);
+    if (A.d + 1 <= 16) return launch_fused_t<METHOD, 16, 2>(ctx, A, F);
     return launch_fused_t<METHOD, 32, 2>(ctx, A, F);
 }
 
@@ -268,13 +285,13 @@ int launch_fused_m(prl_cuda_ctx* ctx, const FusedArgs& A, const FastArgs& F)
 // Can this call take the fused path?  (mask output only; Wolf-Jolion needs s_max first -> planes path)
 bool prl_fused_eligible(const prl_cuda_ctx* ctx, int method, int n_pages, const prl_geom& g, const double* params)
 {
-    if (ctx->no_fused || ctx->force_exact) return false;
+    if (!ctx->use_fused || ctx->force_exact) return false;   // opt-in: see DESIGN.md section 4 (F2)
     if (method == PRL_WOLFJOLION) return false;
     if ((g.d & 1) || g.d + 1 > 32 || g.d < 2) return false;
     if (g.Hp > 100000) return false;                       // 8-bit carry counters of the local Q high words
     const int ow = (kFW - g.d) & ~3;
     const int ns = (g.out_cols + ow - 1) / ow;
-    if ((long long)ns * n_pages < 8LL * ctx->num_sms) return false;   // too few strips to fill the machine: planes path
+    (void)n_pages;
     FastArgs F;
     return fast_margins(method, params, g, &F);
 }

@@ -246,7 +246,7 @@ threshold_fast_kernel(const ThrArgs A, const FastArgs F)
                 for (int i = 0; i < 4; ++i) {
                     const unsigned int p = (p4 >> (8 * i)) & 0xffu;
                     int o;
-                    if (!fast_decide<METHOD>(sw[i], qw[i], p, F, iminf, coefff, mu, o)) {
+                    if (!fast_decide<METHOD, METHOD == PRL_SAUVOLA>(sw[i], qw[i], p, F, iminf, coefff, mu, o)) {
                         if (x + i < A.out_cols) {
                             const size_t e0 = (size_t)yy * A.pitch + x + i;
                             const int t8 = exact_t8_at<METHOD>(reinterpret_cast<const long long*>(S) + e0,
@@ -287,6 +287,143 @@ void launch_exact(prl_cuda_ctx* ctx, int mode, const ThrArgs& A, dim3 grid)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Wolf-Jolion s_max (cv::minMaxLoc(localDevianceValues), binarizeWolfJolion.cpp:118-119) without running
+// the FP64 formula on every pixel.  s_ref = sqrt(fl(q_ref - m_ref^2)) and |fl(q_ref - m_ref^2) - N/w^4| <= dv
+// (the reference's own rounding, bounded on the host), with N = w^2 Q_win - S_win^2 the EXACT integer
+// variance numerator.  sqrt is monotone, so the pixel that attains s_max has N >= N_max - 2 dv w^4:
+//   pass A (nmax_fast_kernel): exact N for every pixel in integer arithmetic -> N_max per page and per tile;
+//   pass B (smax_candidates_kernel): only tiles whose maximum reaches N_max - margin are revisited, and only
+//   their pixels within the margin evaluate the literal FP64 s; the maximum over those is s_max, bit-exact.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFT)
+nmax_fast_kernel(const ThrArgs A, const FastArgs F, unsigned long long* __restrict__ nmax_page,
+                 unsigned long long* __restrict__ nmax_tile)
+{
+    __shared__ __align__(16) unsigned int sD[2][kFR][2][kFC];
+    __shared__ unsigned long long wmax[kFT / 32];
+    const int page = blockIdx.z;
+    const int oc = (kFC - A.d) & ~3;
+    const int X0 = blockIdx.x * oc;
+    const int x = X0 + 4 * threadIdx.x;
+    const int y_begin = blockIdx.y * F.rows_per_cta;
+    const int y_end = min(y_begin + F.rows_per_cta, A.out_rows);
+    const int64_t* S = A.S + (size_t)page * A.plane_page_stride;
+    const int64_t* Q = A.Q + (size_t)page * A.plane_page_stride;
+    const bool in_plane = x < (int)A.pitch;
+    const bool has_out = (4 * threadIdx.x + 3 + A.d < kFC) && (4 * (int)threadIdx.x < oc) && x < A.out_cols;
+    unsigned long long best = 0;
+    int buf = 0;
+    for (int y = y_begin; y < y_end; y += kFR, buf ^= 1) {
+        unsigned int dsr[kFR][4], dqr[kFR][4];
+#pragma unroll
+        for (int r = 0; r < kFR; ++r) {
+            unsigned int (&ds)[4] = dsr[r];
+            unsigned int (&dq)[4] = dqr[r];
+            ds[0] = ds[1] = ds[2] = ds[3] = 0; dq[0] = dq[1] = dq[2] = dq[3] = 0;
+            if (in_plane && y + r < y_end) {
+                long long a0, a1, a2, a3, b0, b1, b2, b3;
+                ldg256(S + (size_t)(y + r) * A.pitch + x, a0, a1, a2, a3);
+                ldg256(S + (size_t)(y + r + A.d) * A.pitch + x, b0, b1, b2, b3);
+                ds[0] = (unsigned int)b0 - (unsigned int)a0; ds[1] = (unsigned int)b1 - (unsigned int)a1;
+                ds[2] = (unsigned int)b2 - (unsigned int)a2; ds[3] = (unsigned int)b3 - (unsigned int)a3;
+                ldg256(Q + (size_t)(y + r) * A.pitch + x, a0, a1, a2, a3);
+                ldg256(Q + (size_t)(y + r + A.d) * A.pitch + x, b0, b1, b2, b3);
+                dq[0] = (unsigned int)b0 - (unsigned int)a0; dq[1] = (unsigned int)b1 - (unsigned int)a1;
+                dq[2] = (unsigned int)b2 - (unsigned int)a2; dq[3] = (unsigned int)b3 - (unsigned int)a3;
+            }
+            *reinterpret_cast<uint4*>(&sD[buf][r][0][4 * threadIdx.x]) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
+            *reinterpret_cast<uint4*>(&sD[buf][r][1][4 * threadIdx.x]) = make_uint4(dq[0], dq[1], dq[2], dq[3]);
+        }
+        __syncthreads();
+        if (has_out) {
+#pragma unroll
+            for (int r = 0; r < kFR; ++r) {
+                if (y + r >= y_end) break;
+                const unsigned int* ls = &sD[buf][r][0][4 * threadIdx.x];
+                const unsigned int* lq = &sD[buf][r][1][4 * threadIdx.x];
+                const uint2 s_r0 = *reinterpret_cast<const uint2*>(ls + A.d), s_r1 = *reinterpret_cast<const uint2*>(ls + A.d + 2);
+                const uint2 q_r0 = *reinterpret_cast<const uint2*>(lq + A.d), q_r1 = *reinterpret_cast<const uint2*>(lq + A.d + 2);
+                const unsigned int sw[4] = {s_r0.x - dsr[r][0], s_r0.y - dsr[r][1], s_r1.x - dsr[r][2], s_r1.y - dsr[r][3]};
+                const unsigned int qw[4] = {q_r0.x - dqr[r][0], q_r0.y - dqr[r][1], q_r1.x - dqr[r][2], q_r1.y - dqr[r][3]};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (x + i < A.out_cols) {
+                        const unsigned long long N = (unsigned long long)F.w2 * qw[i] - (unsigned long long)sw[i] * sw[i];
+                        best = N > best ? N : best;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+        best = t > best ? t : best;
+    }
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < kFT / 32; ++k) best = wmax[k] > best ? wmax[k] : best;
+        nmax_tile[((size_t)page * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = best;
+        atomicMax(nmax_page + page, best);
+    }
+}
+
+// One CTA revisits up to 16 consecutive tiles of pass A (same tile geometry: oc columns x rows_per_cta rows).
+__global__ void __launch_bounds__(128)
+smax_candidates_kernel(const ThrArgs A, const FastArgs F, const unsigned long long* __restrict__ nmax_page,
+                       const unsigned long long* __restrict__ nmax_tile, int tiles_x, int tiles_y,
+                       unsigned long long margin)
+{
+    __shared__ long long wmax[4];
+    const int page = blockIdx.y;
+    const unsigned long long nmax = nmax_page[page];
+    const unsigned long long lo = nmax > margin ? nmax - margin : 0ull;
+    const int oc = (kFC - A.d) & ~3;
+    const long long* S = reinterpret_cast<const long long*>(A.S) + (size_t)page * A.plane_page_stride;
+    const long long* Q = reinterpret_cast<const long long*>(A.Q) + (size_t)page * A.plane_page_stride;
+    long long best = (long long)0xfff0000000000000LL;   // -inf
+    const int tiles = tiles_x * tiles_y;
+    for (int t = blockIdx.x * 16; t < min(tiles, blockIdx.x * 16 + 16); ++t) {
+        if (nmax_tile[(size_t)page * tiles + t] < lo) continue;             // uniform across the CTA
+        const int tx = t % tiles_x, ty = t / tiles_x;
+        const int x_begin = tx * oc, x_end = min(x_begin + oc, A.out_cols);
+        const int y_begin = ty * F.rows_per_cta, y_end = min(y_begin + F.rows_per_cta, A.out_rows);
+        const int w = x_end - x_begin, n = w * (y_end - y_begin);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int y = y_begin + i / w, x = x_begin + i % w;
+            const long long* s0 = S + (size_t)y * A.pitch + x;
+            const long long* q0 = Q + (size_t)y * A.pitch + x;
+            const size_t dr = (size_t)A.d * A.pitch;
+            const long long sa = __ldg(s0), sb = __ldg(s0 + A.d), sc = __ldg(s0 + dr), sd = __ldg(s0 + dr + A.d);
+            const long long qa = __ldg(q0), qb = __ldg(q0 + A.d), qc = __ldg(q0 + dr), qd = __ldg(q0 + dr + A.d);
+            const unsigned long long sw = (unsigned long long)((sd - sc) - (sb - sa));
+            const unsigned long long qw = (unsigned long long)((qd - qc) - (qb - qa));
+            const unsigned long long N = (unsigned long long)F.w2 * qw - sw * sw;
+            if (N < lo) continue;
+            const double m = tap4(A.kw, A.nkw, sa, sb, sc, sd);
+            const double q = tap4(A.kw, A.nkw, qa, qb, qc, qd);
+            const double sdev = __dsqrt_rn(__dadd_rn(q, -__dmul_rn(m, m)));
+            if (sdev == sdev) {                                              // NaN never wins (cv::minMaxLoc)
+                const long long bits = __double_as_longlong(sdev);
+                best = bits > best ? bits : best;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long t = __shfl_xor_sync(0xffffffffu, best, o);
+        best = t > best ? t : best;
+    }
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 4; ++k) best = wmax[k] > best ? wmax[k] : best;
+        if (best != (long long)0xfff0000000000000LL) atomicMax(A.smax + page, best);
+    }
+}
+
 __global__ void init_smax_kernel(long long* smax, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -317,21 +454,47 @@ int prl_k_threshold(prl_cuda_ctx* ctx, int method, int mode, const uint8_t* d_sr
     dim3 grid((g.out_cols + 511) / 512, (g.out_rows + kTR - 1) / kTR, n_pages);
     if (n_pages > 65535 || grid.y > 65535) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "grid too large");
 
+    // fast path eligibility: mask output, even tap distance < 256, window sums < 2^32, 4/32-byte aligned buffers
+    FastArgs F;
+    const bool aligned = ((src_step | src_page_stride | (uintptr_t)d_src) & 3) == 0 &&
+                         ((((uintptr_t)d_S) | ((uintptr_t)d_Q)) & 31) == 0 && (plane_page_stride & 3) == 0 && (g.pitch & 3) == 0;
+    const bool fast_ok = !ctx->force_exact && (g.d & 1) == 0 && g.d <= 254 && aligned && fast_margins(method, params, g, &F);
+    const int rpc = 4;   // rows per CTA of the fast kernels, see below
+    F.rows_per_cta = rpc;
+
     if (method == PRL_WOLFJOLION) {
         {
             prl_launch_scope ls(ctx, FAM_SMAX);
             init_smax_kernel<<<(n_pages + 255) / 256, 256, 0, ctx->stream>>>(d_smax, n_pages);
         }
-        prl_launch_scope ls(ctx, FAM_SMAX);
-        launch_exact<PRL_WOLFJOLION>(ctx, 2, A, grid);
+        if (fast_ok) {
+            const int oc = (kFC - g.d) & ~3;
+            const int tiles_x = (g.out_cols + oc - 1) / oc, tiles_y = (g.out_rows + rpc - 1) / rpc;
+            const size_t need = ((size_t)n_pages + (size_t)n_pages * tiles_x * tiles_y) * sizeof(unsigned long long);
+            int rc = prl_ensure(ctx, &ctx->d_misc, &ctx->d_misc_bytes, need); if (rc) return rc;
+            unsigned long long* nmax_page = (unsigned long long*)ctx->d_misc;
+            unsigned long long* nmax_tile = nmax_page + n_pages;
+            PRL_CUDA_TRY(ctx, cudaMemsetAsync(nmax_page, 0, sizeof(unsigned long long) * n_pages, ctx->stream));
+            // |fl(q_ref - m_ref^2) - N/w^4| <= dv (same bound as fast_margins) -> candidates have N >= N_max - 2 dv w^4
+            const double u = 1.1102230246251565e-16, w2 = (double)g.w * g.w, area = (double)g.Hp * (double)g.Wp;
+            const double dv = 16 * u / w2 * 65025.0 * area + 510.0 * (16 * u / w2 * 255.0 * area) + u * 2 * 65025.0;
+            const unsigned long long margin = (unsigned long long)(2.0 * dv * w2 * w2) + 2;
+            {
+                prl_launch_scope ls(ctx, FAM_SMAX);
+                nmax_fast_kernel<<<dim3(tiles_x, tiles_y, n_pages), kFT, 0, ctx->stream>>>(A, F, nmax_page, nmax_tile);
+            }
+            {
+                prl_launch_scope ls(ctx, FAM_SMAX);
+                smax_candidates_kernel<<<dim3((tiles_x * tiles_y + 15) / 16, n_pages), 128, 0, ctx->stream>>>(
+                    A, F, nmax_page, nmax_tile, tiles_x, tiles_y, margin);
+            }
+        } else {
+            prl_launch_scope ls(ctx, FAM_SMAX);
+            launch_exact<PRL_WOLFJOLION>(ctx, 2, A, grid);
+        }
     }
 
-    // fast path eligibility: mask output, even tap distance < 256, window sums < 2^32, 4/32-byte aligned buffers
-    FastArgs F;
-    const bool aligned = ((src_step | src_page_stride | (uintptr_t)d_src) & 3) == 0 &&
-                         ((((uintptr_t)d_S) | ((uintptr_t)d_Q)) & 31) == 0 && (plane_page_stride & 3) == 0 && (g.pitch & 3) == 0;
-    const bool fast = mode == 0 && !ctx->force_exact && (g.d & 1) == 0 && g.d <= 254 && aligned &&
-                      fast_margins(method, params, g, &F);
+    const bool fast = mode == 0 && fast_ok;
     prl_launch_scope ls(ctx, FAM_THRESHOLD);
     if (fast) {
         const int oc = (kFC - g.d) & ~3;
@@ -339,8 +502,6 @@ int prl_k_threshold(prl_cuda_ctx* ctx, int method, int mode, const uint8_t* d_sr
         // top row of y); the second fetch must hit L2, so the CTAs in flight have to cover a compact
         // set of rows: short tiles issued in raster order keep the live set at ~(in-flight rows + d)
         // rows of one or two pages (tens of MB), tall tiles thrash the 126 MB L2 (measured: 2x DRAM reads).
-        int rpc = 4;
-        F.rows_per_cta = rpc;
         dim3 fg((g.out_cols + oc - 1) / oc, (g.out_rows + rpc - 1) / rpc, n_pages);
         switch (method) {
         case PRL_SAUVOLA:    threshold_fast_kernel<PRL_SAUVOLA><<<fg, kFT, 0, ctx->stream>>>(A, F); break;

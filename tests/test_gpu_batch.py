@@ -90,7 +90,7 @@ def test_fused_small_window_path_equals_planes_path_and_oracle(ctx, method, wind
     rc, orow, ocol = ctx.output_shape(method, rows, cols, window)
     outs = []
     for fused_off in (0, 1):
-        ctx.set_option("disable_fused", fused_off)
+        ctx.set_option("enable_fused", 1 - fused_off)
         out = torch.zeros((n, orow, ocol), dtype=torch.uint8, device="cuda:0")              # dense, odd pitch
         ctx.timing_reset(); ctx.timing_enable(True)
         ctx.binarize_local_batch_dev(method, buf.data_ptr(), n, rows, cols, step, rows * step, window, params, 0,
@@ -99,7 +99,7 @@ def test_fused_small_window_path_equals_planes_path_and_oracle(ctx, method, wind
         fam = ctx.timing(); ctx.timing_enable(False)
         assert ("fused" in fam) == (fused_off == 0), fam                                 # the intended path really ran
         outs.append(out.cpu().numpy())
-    ctx.set_option("disable_fused", 0)
+    ctx.set_option("enable_fused", 0)
     assert np.array_equal(outs[0], outs[1])
     for p in list(range(12)) + [77, 149]:
         assert np.array_equal(outs[0][p], CO.binarize_local(host[p], method, window, params, 0)), p
@@ -111,8 +111,10 @@ def test_fused_path_with_morphology_tail(ctx):
     buf, step = _dev_pages(ctx, n, rows, cols, first=20)
     rc, orow, ocol = ctx.output_shape(0, rows, cols, 15)
     out = torch.zeros((n, orow, ocol), dtype=torch.uint8, device="cuda:0")
+    ctx.set_option("enable_fused", 1)
     ctx.binarize_local_batch_dev(0, buf.data_ptr(), n, rows, cols, step, rows * step, 15, (0.2,), 2, out.data_ptr(), ocol, orow * ocol)
     torch.cuda.synchronize()
+    ctx.set_option("enable_fused", 0)
     got = out.cpu().numpy()
     for p in (0, 70, 139):
         assert np.array_equal(got[p], CO.binarize_local(CO.synth_page(20 + p, rows, cols), 0, 15, (0.2,), 2)), p
