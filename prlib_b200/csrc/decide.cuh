@@ -115,7 +115,7 @@ __device__ __forceinline__ bool fast_decide(unsigned int sw, unsigned int qw, un
     }
     const unsigned long long N = (unsigned long long)F.w2 * qw - (unsigned long long)sw * sw;   // exact, >= 0
     const float fn = (float)N;
-    const float s = sqrtf(fn) * F.inv_w2f;
+    const float s = (fn * rsqrtf(fn)) * F.inv_w2f;     // sqrt via MUFU.RSQ (2 ulp, covered by the margin); fn == 0 gives NaN -> exact path
     float T;
     if (METHOD == PRL_SAUVOLA) T = m * fmaf(s, F.c1, F.c2);
     else if (METHOD == PRL_NIBLACK) T = fmaf(F.c0, s, m);
@@ -134,7 +134,7 @@ __device__ __forceinline__ bool fast_decide(unsigned int sw, unsigned int qw, un
 //     dm_ref <= 16 u kw Smax,  dq_ref <= 16 u kw Qmax,  dv_ref <= dq_ref + 2*255*dm_ref + u*2*255^2
 //     ds_ref <= dv_ref / s_floor + u*128          (fast path requires s* >= s_floor)
 //   FP32 estimate error (exact integer inputs), e = 2^-24:
-//     dm_est <= 3 e 255,  ds_est <= 4 e 128
+//     dm_est <= 3 e 255,  ds_est <= 8 e 128   (N -> float, MUFU.RSQ at 2 ulp, two products)
 //   |dT| <= A dm + B ds + 8 e (Tmax + 512), A/B = sup |dT/dm|, |dT/ds| over m in [0,255], s in [0,128]
 inline bool fast_margins(int method, const double* params, const prl_geom& g, FastArgs* F)
 {
@@ -147,7 +147,7 @@ inline bool fast_margins(int method, const double* params, const prl_geom& g, Fa
     const double dv_ref = dq_ref + 510.0 * dm_ref + u * 2 * 65025.0;
     if (!(dv_ref < 0.25 * s_floor * s_floor)) return false;
     const double ds_ref = dv_ref / s_floor + u * 128;
-    const double dm = dm_ref + 3 * e * 255, ds = ds_ref + 4 * e * 128;
+    const double dm = dm_ref + 3 * e * 255, ds = ds_ref + 8 * e * 128;   // ds: int->float, rsqrt (2 ulp), two products
     double Acoef, Bcoef, Tmax, mu1 = 0.0;
     const double k = params[0];
     switch (method) {

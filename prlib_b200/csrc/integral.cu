@@ -30,6 +30,7 @@
 // concurrently.  integral_generic_kernel is the any-alignment / any-pitch fallback (no TMA).
 #include "common.cuh"
 #include <cuda.h>
+#include <algorithm>
 
 namespace {
 
@@ -94,16 +95,20 @@ template <int MAXW, int MINB, int J, int R, int NS>
 __global__ void __launch_bounds__(MAXW * 32, MINB)
 integral_tma_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int cols, int pad, int64_t* __restrict__ S,
                     int64_t* __restrict__ Q, size_t pitch, size_t page_stride, int rows_per_band,
-                    const int64_t* __restrict__ carry, uint32_t* __restrict__ imin)
+                    const int64_t* __restrict__ carry, uint32_t* __restrict__ imin, int col0,
+                    uint2* __restrict__ rowoff, int has_in, int has_out)
 {
+    // Wide pages are covered by several launches ("column passes") of at most MAXW strips each: pass p starts at
+    // padded column col0 and takes, per source row, the row prefix accumulated by the passes to its left from
+    // rowoff[page][y] (has_in), and leaves its own running total there for the next pass (has_out).
     constexpr int WC = 128 * J;                  // padded columns per warp
     constexpr int BOX = box_bytes<J>();
     constexpr int STAGE = stage_bytes<J, R>();
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    __shared__ uint2 tot[2][R][MAXW];
+    __shared__ uint2 tot[2][R][MAXW + 1];          // entry 0: incoming row offset, entry 1 + w: total of warp w
     __shared__ uint64_t bars[MAXW][NS];
 
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int page = blockIdx.y, band = blockIdx.x, bands = gridDim.x;
     const int y0 = band * rows_per_band;
     const int y1 = min(y0 + rows_per_band, rows);
@@ -112,7 +117,7 @@ integral_tma_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int cols
     Q += (size_t)page * page_stride;
 
     uint8_t* slot = smem_raw + (size_t)wid * (NS * STAGE);               // this warp's ring
-    const int X0 = wid * WC;
+    const int X0 = col0 + wid * WC;
     const int Xl = X0 + 4 * lane;                                        // + 128 j
     // Box origin (source byte column, multiple of 16).  Normally the aligned byte below the strip's
     // first source column; a strip lying entirely in the right replicate border is moved left so
@@ -187,12 +192,20 @@ integral_tma_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int cols
 
     uint32_t mn4 = 0xffffffffu;
     int buf_sel = 0;
+    // incoming row offsets: lane r of warp 0 carries row (chunk start + r), fetched one chunk ahead
+    uint2 roff = make_uint2(0u, 0u);
+    if (has_in && wid == 0 && lane < R && y0 + lane < y1) roff = rowoff[(size_t)page * rows + y0 + lane];
     for (int c = 0; c < n_chunks; ++c, buf_sel ^= 1) {
         __syncwarp();                                         // every lane is done with slot (c-1) % NS
         if (lane == 0 && c + NS - 1 < n_chunks) PRL_ISSUE_TMA(c + NS - 1);
+        const int yc = y0 + c * R;
+        if (wid == 0 && lane < R) {
+            tot[buf_sel][lane][0] = roff;
+            roff = make_uint2(0u, 0u);
+            if (has_in && yc + R + lane < y1) roff = rowoff[(size_t)page * rows + yc + R + lane];
+        }
         mbar_wait(&bars[wid][c % NS], (uint32_t)((c / NS) & 1));
         const uint8_t* buf = slot + (size_t)(c % NS) * STAGE;
-        const int yc = y0 + c * R;
 
         // sweep 1: this warp's row totals
 #pragma unroll 2
@@ -207,7 +220,7 @@ integral_tma_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int cols
             }
             s = __reduce_add_sync(0xffffffffu, s);
             q = __reduce_add_sync(0xffffffffu, q);
-            if (lane == 0) tot[buf_sel][r][wid] = make_uint2(s, q);
+            if (lane == 0) tot[buf_sel][r][wid + 1] = make_uint2(s, q);
         }
         __syncthreads();
 
@@ -216,9 +229,13 @@ integral_tma_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int cols
         for (int r = 0; r < R; ++r) {
             const int y = yc + r;
             if (y < y1) {
-                const uint2 t = (lane < wid) ? tot[buf_sel][r][lane] : make_uint2(0u, 0u);
+                const uint2 t = (lane <= wid) ? tot[buf_sel][r][lane] : make_uint2(0u, 0u);
                 uint32_t off_s = __reduce_add_sync(0xffffffffu, t.x);
                 uint32_t off_q = __reduce_add_sync(0xffffffffu, t.y);
+                if (has_out && wid == nwarps - 1 && lane == 0) {       // running row total for the next column pass
+                    const uint2 own = tot[buf_sel][r][wid + 1];
+                    rowoff[(size_t)page * rows + y] = make_uint2(off_s + own.x, off_q + own.y);
+                }
                 uint32_t rs[J][4], rq[J][4];
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
@@ -510,7 +527,7 @@ int choose_bands(const prl_cuda_ctx* ctx, int n_pages, int rows, int ctas_per_sm
 {
     const int want = ctas_per_sm * ctx->num_sms;
     if (n_pages >= want - want / 4) return 1;   // >= 1.5 pages per SM: the batch alone fills the machine
-    int bands = (want + n_pages - 1) / n_pages;
+    int bands = want / n_pages;                 // floor: one full wave of CTAs, never a small second wave
     int max_bands = rows / 32; if (max_bands < 1) max_bands = 1;
     if (bands > max_bands) bands = max_bands;
     if (bands > 64) bands = 64;
@@ -520,7 +537,8 @@ int choose_bands(const prl_cuda_ctx* ctx, int n_pages, int rows, int ctas_per_sm
 template <int MAXW, int MINB, int J, int R, int NS>
 int launch_tma(prl_cuda_ctx* ctx, encode_tiled_fn enc, dim3 grid, int nwarps, const uint8_t* d_src, int n_pages,
                size_t src_step, size_t src_page_stride, int rows, int cols, int pad, int64_t* d_S, int64_t* d_Q,
-               size_t pitch, size_t plane_page_stride, int rpb, const int64_t* d_carry, uint32_t* d_imin, bool* launched)
+               size_t pitch, size_t plane_page_stride, int rpb, const int64_t* d_carry, uint32_t* d_imin, bool* launched,
+               int col0 = 0, uint2* rowoff = nullptr, int has_in = 0, int has_out = 0)
 {
     *launched = false;
     CUtensorMap tmap;
@@ -540,7 +558,8 @@ int launch_tma(prl_cuda_ctx* ctx, encode_tiled_fn enc, dim3 grid, int nwarps, co
         PRL_CUDA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    kfn<<<grid, nwarps * 32, smem, ctx->stream>>>(tmap, rows, cols, pad, d_S, d_Q, pitch, plane_page_stride, rpb, d_carry, d_imin);
+    kfn<<<grid, nwarps * 32, smem, ctx->stream>>>(tmap, rows, cols, pad, d_S, d_Q, pitch, plane_page_stride, rpb, d_carry, d_imin,
+                                                  col0, rowoff, has_in, has_out);
     *launched = true;
     return PRL_OK;
 }
@@ -597,14 +616,18 @@ int prl_k_integral(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int row
             const int nw = (Wp + 127) / 128;          // A4-class widths: 51 registers available at 2 CTAs/SM
             rc = launch_tma<20, 2, 1, R, 3>(ctx, enc, grid, nw, d_src, n_pages, src_step, src_page_stride, rows, cols, pad, d_S, d_Q,
                                             pitch, plane_page_stride, rpb, d_carry, d_imin, &launched);
-        } else if (narrow) {
-            const int nw = (Wp + 127) / 128;
-            rc = launch_tma<24, 2, 1, R, 3>(ctx, enc, grid, nw, d_src, n_pages, src_step, src_page_stride, rows, cols, pad, d_S, d_Q,
-                                            pitch, plane_page_stride, rpb, d_carry, d_imin, &launched);
         } else {
-            const int nw = (Wp + 255) / 256;
-            rc = launch_tma<32, 1, 2, R, 3>(ctx, enc, grid, nw, d_src, n_pages, src_step, src_page_stride, rows, cols, pad, d_S, d_Q,
-                                            pitch, plane_page_stride, rpb, d_carry, d_imin, &launched);
+            // wide page: column passes of <= 20 strips of 128 columns each, chained through rowoff
+            const int nw_total = (Wp + 127) / 128;
+            const int npass = (nw_total + 19) / 20, wp = (nw_total + npass - 1) / npass;
+            rc = prl_ensure(ctx, &ctx->d_misc, &ctx->d_misc_bytes, (size_t)n_pages * rows * sizeof(uint2)); if (rc) return rc;
+            for (int p = 0; p < npass; ++p) {
+                const int nw = std::min(wp, nw_total - p * wp);
+                rc = launch_tma<20, 2, 1, R, 3>(ctx, enc, grid, nw, d_src, n_pages, src_step, src_page_stride, rows, cols, pad, d_S, d_Q,
+                                                pitch, plane_page_stride, rpb, d_carry, d_imin, &launched, p * wp * 128,
+                                                (uint2*)ctx->d_misc, p > 0, p + 1 < npass);
+                if (rc || !launched) break;
+            }
         }
         if (rc) return rc;
         if (launched) {

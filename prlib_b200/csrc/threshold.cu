@@ -163,14 +163,17 @@ __device__ __forceinline__ void ldg256(const int64_t* p, long long& a, long long
     asm volatile("ld.global.nc.v4.s64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
 }
 
-template <int METHOD>
-__global__ void __launch_bounds__(kFT)
+// NT threads per CTA: 128 (512 columns loaded per row) for small windows, 256 (1024 columns) when the tap
+// distance d would otherwise waste a large share of each CTA's loads on the column halo
+template <int METHOD, int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT)     // <= 64 registers: 32 resident warps per SM
 threshold_fast_kernel(const ThrArgs A, const FastArgs F)
 {
-    __shared__ __align__(16) unsigned int sD[2][kFR][2][kFC];   // [buffer][row][plane S/Q][column]
+    constexpr int FC = NT * 4;                        // columns loaded per CTA row
+    __shared__ __align__(16) unsigned int sD[2][kFR][2][FC];   // [buffer][row][plane S/Q][column]
 
     const int page = blockIdx.z;
-    const int oc = (kFC - A.d) & ~3;                 // output columns per CTA
+    const int oc = (FC - A.d) & ~3;                  // output columns per CTA
     const int X0 = blockIdx.x * oc;
     const int x = X0 + 4 * threadIdx.x;              // this thread's first column (32-byte aligned in the planes)
     const int y_begin = blockIdx.y * F.rows_per_cta;
@@ -191,7 +194,7 @@ threshold_fast_kernel(const ThrArgs A, const FastArgs F)
     }
 
     const bool in_plane = x < (int)A.pitch;          // pitch is a multiple of 16 columns
-    const bool has_out = (4 * threadIdx.x + 3 + A.d < kFC) && (4 * (int)threadIdx.x < oc) && x < A.out_cols;
+    const bool has_out = (4 * threadIdx.x + 3 + A.d < FC) && (4 * (int)threadIdx.x < oc) && x < A.out_cols;
     const bool full4 = x + 3 < A.out_cols;
 
     int buf = 0;
@@ -497,19 +500,25 @@ int prl_k_threshold(prl_cuda_ctx* ctx, int method, int mode, const uint8_t* d_sr
     const bool fast = mode == 0 && fast_ok;
     prl_launch_scope ls(ctx, FAM_THRESHOLD);
     if (fast) {
-        const int oc = (kFC - g.d) & ~3;
-        // Rows per CTA.  Each S/Q row is fetched twice (as the bottom row of output row y-d, then as the
+        // Rows per CTA (rpc = 4).  Each S/Q row is fetched twice (as the bottom row of output row y-d, then as the
         // top row of y); the second fetch must hit L2, so the CTAs in flight have to cover a compact
         // set of rows: short tiles issued in raster order keep the live set at ~(in-flight rows + d)
         // rows of one or two pages (tens of MB), tall tiles thrash the 126 MB L2 (measured: 2x DRAM reads).
+        const bool wide = g.d > 64;
+        const int nt = wide ? 256 : 128;
+        const int oc = (nt * 4 - g.d) & ~3;
         dim3 fg((g.out_cols + oc - 1) / oc, (g.out_rows + rpc - 1) / rpc, n_pages);
+#define PRL_LAUNCH_FAST(M)                                                                            \
+        do { if (wide) threshold_fast_kernel<M, 256><<<fg, 256, 0, ctx->stream>>>(A, F);              \
+             else threshold_fast_kernel<M, 128><<<fg, 128, 0, ctx->stream>>>(A, F); } while (0)
         switch (method) {
-        case PRL_SAUVOLA:    threshold_fast_kernel<PRL_SAUVOLA><<<fg, kFT, 0, ctx->stream>>>(A, F); break;
-        case PRL_NIBLACK:    threshold_fast_kernel<PRL_NIBLACK><<<fg, kFT, 0, ctx->stream>>>(A, F); break;
-        case PRL_WOLFJOLION: threshold_fast_kernel<PRL_WOLFJOLION><<<fg, kFT, 0, ctx->stream>>>(A, F); break;
-        case PRL_NICK:       threshold_fast_kernel<PRL_NICK><<<fg, kFT, 0, ctx->stream>>>(A, F); break;
-        default:             threshold_fast_kernel<PRL_FENG><<<fg, kFT, 0, ctx->stream>>>(A, F); break;
+        case PRL_SAUVOLA:    PRL_LAUNCH_FAST(PRL_SAUVOLA); break;
+        case PRL_NIBLACK:    PRL_LAUNCH_FAST(PRL_NIBLACK); break;
+        case PRL_WOLFJOLION: PRL_LAUNCH_FAST(PRL_WOLFJOLION); break;
+        case PRL_NICK:       PRL_LAUNCH_FAST(PRL_NICK); break;
+        default:             PRL_LAUNCH_FAST(PRL_FENG); break;
         }
+#undef PRL_LAUNCH_FAST
     } else {
         switch (method) {
         case PRL_SAUVOLA:    launch_exact<PRL_SAUVOLA>(ctx, mode, A, grid); break;
