@@ -91,7 +91,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
 template <int J> __host__ __device__ constexpr int box_bytes() { return 128 * J + 16; }   // 16-byte aligned origin
 template <int J, int R> __host__ __device__ constexpr int stage_bytes() { return (R * box_bytes<J>() + 127) / 128 * 128; }
 
-template <int MAXW, int MINB, int J, int R, int NS>
+template <int MAXW, int MINB, int J, int R, int NS, bool MULTI>
 __global__ void __launch_bounds__(MAXW * 32, MINB)
 integral_tma_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int cols, int pad, int64_t* __restrict__ S,
                     int64_t* __restrict__ Q, size_t pitch, size_t page_stride, int rows_per_band,
@@ -117,7 +117,7 @@ integral_tma_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int cols
     Q += (size_t)page * page_stride;
 
     uint8_t* slot = smem_raw + (size_t)wid * (NS * STAGE);               // this warp's ring
-    const int X0 = col0 + wid * WC;
+    const int X0 = (MULTI ? col0 : 0) + wid * WC;
     const int Xl = X0 + 4 * lane;                                        // + 128 j
     // Box origin (source byte column, multiple of 16).  Normally the aligned byte below the strip's
     // first source column; a strip lying entirely in the right replicate border is moved left so
@@ -194,7 +194,7 @@ integral_tma_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int cols
     int buf_sel = 0;
     // incoming row offsets: lane r of warp 0 carries row (chunk start + r), fetched one chunk ahead
     uint2 roff = make_uint2(0u, 0u);
-    if (has_in && wid == 0 && lane < R && y0 + lane < y1) roff = rowoff[(size_t)page * rows + y0 + lane];
+    if (MULTI && has_in && wid == 0 && lane < R && y0 + lane < y1) roff = rowoff[(size_t)page * rows + y0 + lane];
     for (int c = 0; c < n_chunks; ++c, buf_sel ^= 1) {
         __syncwarp();                                         // every lane is done with slot (c-1) % NS
         if (lane == 0 && c + NS - 1 < n_chunks) PRL_ISSUE_TMA(c + NS - 1);
@@ -202,7 +202,7 @@ integral_tma_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int cols
         if (wid == 0 && lane < R) {
             tot[buf_sel][lane][0] = roff;
             roff = make_uint2(0u, 0u);
-            if (has_in && yc + R + lane < y1) roff = rowoff[(size_t)page * rows + yc + R + lane];
+            if (MULTI && has_in && yc + R + lane < y1) roff = rowoff[(size_t)page * rows + yc + R + lane];
         }
         mbar_wait(&bars[wid][c % NS], (uint32_t)((c / NS) & 1));
         const uint8_t* buf = slot + (size_t)(c % NS) * STAGE;
@@ -232,7 +232,7 @@ integral_tma_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int cols
                 const uint2 t = (lane <= wid) ? tot[buf_sel][r][lane] : make_uint2(0u, 0u);
                 uint32_t off_s = __reduce_add_sync(0xffffffffu, t.x);
                 uint32_t off_q = __reduce_add_sync(0xffffffffu, t.y);
-                if (has_out && wid == nwarps - 1 && lane == 0) {       // running row total for the next column pass
+                if (MULTI && has_out && wid == nwarps - 1 && lane == 0) {       // running row total for the next column pass
                     const uint2 own = tot[buf_sel][r][wid + 1];
                     rowoff[(size_t)page * rows + y] = make_uint2(off_s + own.x, off_q + own.y);
                 }
@@ -534,7 +534,7 @@ int choose_bands(const prl_cuda_ctx* ctx, int n_pages, int rows, int ctas_per_sm
     return bands < 1 ? 1 : bands;
 }
 
-template <int MAXW, int MINB, int J, int R, int NS>
+template <int MAXW, int MINB, int J, int R, int NS, bool MULTI>
 int launch_tma(prl_cuda_ctx* ctx, encode_tiled_fn enc, dim3 grid, int nwarps, const uint8_t* d_src, int n_pages,
                size_t src_step, size_t src_page_stride, int rows, int cols, int pad, int64_t* d_S, int64_t* d_Q,
                size_t pitch, size_t plane_page_stride, int rpb, const int64_t* d_carry, uint32_t* d_imin, bool* launched,
@@ -552,7 +552,7 @@ int launch_tma(prl_cuda_ctx* ctx, encode_tiled_fn enc, dim3 grid, int nwarps, co
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return PRL_OK;     // caller falls back to the generic kernel
     const size_t smem = (size_t)nwarps * NS * stage_bytes<J, R>();
-    auto kfn = integral_tma_kernel<MAXW, MINB, J, R, NS>;
+    auto kfn = integral_tma_kernel<MAXW, MINB, J, R, NS, MULTI>;
     static size_t configured = 0;
     if (smem > configured) {
         PRL_CUDA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -614,8 +614,12 @@ int prl_k_integral(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int row
         int rc;
         if (narrow && Wp <= 20 * 128) {
             const int nw = (Wp + 127) / 128;          // A4-class widths: 51 registers available at 2 CTAs/SM
-            rc = launch_tma<20, 2, 1, R, 3>(ctx, enc, grid, nw, d_src, n_pages, src_step, src_page_stride, rows, cols, pad, d_S, d_Q,
-                                            pitch, plane_page_stride, rpb, d_carry, d_imin, &launched);
+            rc = launch_tma<20, 2, 1, R, 3, false>(ctx, enc, grid, nw, d_src, n_pages, src_step, src_page_stride, rows, cols, pad, d_S, d_Q,
+                                                   pitch, plane_page_stride, rpb, d_carry, d_imin, &launched);
+        } else if (narrow) {
+            const int nw = (Wp + 127) / 128;          // up to 3072 columns: still one pass (42 registers, small spills)
+            rc = launch_tma<24, 2, 1, R, 3, false>(ctx, enc, grid, nw, d_src, n_pages, src_step, src_page_stride, rows, cols, pad, d_S, d_Q,
+                                                   pitch, plane_page_stride, rpb, d_carry, d_imin, &launched);
         } else {
             // wide page: column passes of <= 20 strips of 128 columns each, chained through rowoff
             const int nw_total = (Wp + 127) / 128;
@@ -623,7 +627,7 @@ int prl_k_integral(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int row
             rc = prl_ensure(ctx, &ctx->d_misc, &ctx->d_misc_bytes, (size_t)n_pages * rows * sizeof(uint2)); if (rc) return rc;
             for (int p = 0; p < npass; ++p) {
                 const int nw = std::min(wp, nw_total - p * wp);
-                rc = launch_tma<20, 2, 1, R, 3>(ctx, enc, grid, nw, d_src, n_pages, src_step, src_page_stride, rows, cols, pad, d_S, d_Q,
+                rc = launch_tma<20, 2, 1, R, 3, true>(ctx, enc, grid, nw, d_src, n_pages, src_step, src_page_stride, rows, cols, pad, d_S, d_Q,
                                                 pitch, plane_page_stride, rpb, d_carry, d_imin, &launched, p * wp * 128,
                                                 (uint2*)ctx->d_misc, p > 0, p + 1 < npass);
                 if (rc || !launched) break;
