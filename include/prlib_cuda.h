@@ -89,6 +89,15 @@ int prl_cuda_binarize_local(prl_cuda_ctx* ctx, int method, const uint8_t* src, i
                             size_t step, int window, const double* params, int morph_iters,
                             uint8_t* dst, size_t dst_step, int* out_rows, int* out_cols);
 
+/* Same, for the image exactly as the reference receives it (binarizeSauvola.cpp:49-52): channels = 1, 3 (BGR) or
+ * 4 (BGRA).  Multi-channel input is converted on the device (cv::cvtColor BGR2GRAY), so it crosses PCIe once.
+ * gray_out (may be NULL) receives the rows x cols gray image -- what the shim needs to reproduce the reference's
+ * side effect of leaving the padded gray image in imageInput. */
+int prl_cuda_binarize_local_image(prl_cuda_ctx* ctx, int method, const uint8_t* src, int rows, int cols,
+                                  size_t step, int channels, int window, const double* params, int morph_iters,
+                                  uint8_t* dst, size_t dst_step, int* out_rows, int* out_cols,
+                                  uint8_t* gray_out, size_t gray_step);
+
 /* Parity hook: the u8 threshold surface T8 = saturate_cast<uchar>(cvRound(T))
  * (thresholdsValues.convertTo(CV_8UC1), binarizeSauvola.cpp:119).  aux (may be NULL) receives
  * {I_min, s_max} as used by Wolf-Jolion / Feng (binarizeWolfJolion.cpp:115-119). */

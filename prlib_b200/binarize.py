@@ -43,7 +43,7 @@ def _local(image, method, window, params, morph, device):
         raise ValueError("Input image for binarization is empty")
     _check_window(window)                      # argument errors come first, as in the reference
     ctx = default_context(device)
-    return ctx.binarize_local(_gray(im, ctx), method, window, params, morph)
+    return ctx.binarize_image(im, method, window, params, morph)     # cvtColor (if needed) happens on the device
 
 
 def binarizeSauvola(imageInput, windowSize: int = 101, thresholdCoefficient: float = 0.01,

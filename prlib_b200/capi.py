@@ -30,6 +30,8 @@ SIGNATURES = {
     "prl_cuda_integral_u8": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),
     "prl_cuda_binarize_local": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, _f64p, C.c_int,
                                           C.c_void_p, C.c_size_t, _intp, _intp]),
+    "prl_cuda_binarize_local_image": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, _f64p, C.c_int,
+                                                C.c_void_p, C.c_size_t, _intp, _intp, C.c_void_p, C.c_size_t]),
     "prl_cuda_threshold_map": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, _f64p,
                                          C.c_void_p, C.c_size_t, _intp, _intp, _f64p]),
     "prl_cuda_bgr2gray": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]),

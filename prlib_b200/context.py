@@ -131,6 +131,26 @@ class Context:
                                                     max(ocol, 1), C.byref(a), C.byref(b)))
         return out
 
+    def binarize_image(self, image, method: int, window: int, params, morph_iters: int = 0, want_gray: bool = False):
+        """1-, 3- (BGR) or 4-channel (BGRA) image in, mask out; the cvtColor front step runs on the device."""
+        im = np.asarray(image)
+        if im.dtype != np.uint8:
+            raise TypeError("image must be uint8")
+        if im.ndim == 2:
+            im = im[:, :, None]
+        if im.ndim != 3 or im.shape[2] not in (1, 3, 4):
+            raise ValueError("expected an HxW, HxWx1, HxWx3 or HxWx4 uint8 image")
+        im = np.ascontiguousarray(im)
+        r, c, ch = im.shape
+        rc, orow, ocol = self.output_shape(method, r, c, window)
+        out = np.empty((max(orow, 0), max(ocol, 0)), np.uint8)
+        gray = np.empty((r, c), np.uint8) if want_gray else None
+        a, b = C.c_int(), C.c_int()
+        self._check(self._L.prl_cuda_binarize_local_image(self._h, method, im.ctypes.data, r, c, im.strides[0], ch, int(window),
+                                                          _params4(params), int(morph_iters), out.ctypes.data, max(ocol, 1),
+                                                          C.byref(a), C.byref(b), gray.ctypes.data if want_gray else None, c))
+        return (out, gray) if want_gray else out
+
     def threshold_map(self, gray, method: int, window: int, params):
         g = _as_u8_2d(gray)
         r, c = g.shape

@@ -166,7 +166,7 @@ extern "C" void prl_cuda_destroy(prl_cuda_ctx* c)
     for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto& ev : c->event_pool) cudaEventDestroy(ev);
     cudaFree(c->planes); cudaFree(c->carry); cudaFree(c->colsum); cudaFree(c->scalars);
-    cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_tmp); cudaFree(c->d_misc);
+    cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_tmp); cudaFree(c->d_misc); cudaFree(c->d_bgr);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -401,7 +401,8 @@ static int stage_in(prl_cuda_ctx* c, const uint8_t* src, int rows, size_t width_
 
 static int local_host(prl_cuda_ctx* c, int method, int mode, const uint8_t* src, int rows, int cols, size_t step,
                       int window, const double* params, int morph_iters, uint8_t* dst, size_t dst_step,
-                      int* out_rows, int* out_cols, double* aux)
+                      int* out_rows, int* out_cols, double* aux, int channels = 1, uint8_t* gray_out = nullptr,
+                      size_t gray_step = 0)
 {
     if (!c) return PRL_E_INVALID;
     if (!src || !dst || !params) return prl_set_err(c, PRL_E_INVALID, "null pointer");
@@ -410,9 +411,24 @@ static int local_host(prl_cuda_ctx* c, int method, int mode, const uint8_t* src,
     int rc = prl_make_geom(method, rows, cols, window, &g);
     if (rc) return prl_set_err(c, rc, rc == PRL_E_EMPTY_ROI ? "empty processingRect: min(rows, cols) <= windowSize"
                                                              : "empty image or window not (>1 and odd)");
-    if (step < (size_t)cols || dst_step < (size_t)g.out_cols) return prl_set_err(c, PRL_E_INVALID, "step smaller than row width");
+    if (channels != 1 && channels != 3 && channels != 4) return prl_set_err(c, PRL_E_INVALID, "channels must be 1, 3 or 4");
+    if (step < (size_t)cols * channels || dst_step < (size_t)g.out_cols || (gray_out && gray_step < (size_t)cols))
+        return prl_set_err(c, PRL_E_INVALID, "step smaller than row width");
     size_t in_step;
-    rc = stage_in(c, src, rows, cols, step, &in_step); if (rc) return rc;
+    if (channels == 1) {
+        rc = stage_in(c, src, rows, cols, step, &in_step); if (rc) return rc;
+    } else {
+        // cvtColor(BGR2GRAY) on the device: the 3/4-channel image crosses PCIe once, the gray one never goes back
+        // unless the caller asks for it (binarizeSauvola.cpp:49-52)
+        const size_t bstep = round16((size_t)cols * channels);
+        in_step = round16(cols);
+        rc = prl_ensure(c, (void**)&c->d_bgr, &c->d_bgr_bytes, bstep * rows); if (rc) return rc;
+        rc = prl_ensure(c, (void**)&c->d_in, &c->d_in_bytes, in_step * rows); if (rc) return rc;
+        PRL_CUDA_TRY(c, copy2d(c->d_bgr, bstep, src, step, (size_t)cols * channels, rows, cudaMemcpyHostToDevice, c->stream));
+        rc = prl_k_bgr2gray(c, c->d_bgr, rows, cols, bstep, channels, c->d_in, in_step); if (rc) return rc;
+    }
+    if (gray_out)
+        PRL_CUDA_TRY(c, copy2d(gray_out, gray_step, c->d_in, in_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
     // dense device mask when the caller's rows are dense too (a continuous cv::Mat): one linear D2H
     const size_t o_step = (dst_step == (size_t)g.out_cols) ? (size_t)g.out_cols : round16(g.out_cols);
     rc = prl_ensure(c, (void**)&c->d_out, &c->d_out_bytes, o_step * g.out_rows + 16); if (rc) return rc;
@@ -439,6 +455,15 @@ extern "C" int prl_cuda_binarize_local(prl_cuda_ctx* c, int method, const uint8_
                                        uint8_t* dst, size_t dst_step, int* out_rows, int* out_cols)
 {
     return local_host(c, method, 0, src, rows, cols, step, window, params, morph_iters, dst, dst_step, out_rows, out_cols, nullptr);
+}
+
+extern "C" int prl_cuda_binarize_local_image(prl_cuda_ctx* c, int method, const uint8_t* src, int rows, int cols,
+                                             size_t step, int channels, int window, const double* params,
+                                             int morph_iters, uint8_t* dst, size_t dst_step, int* out_rows,
+                                             int* out_cols, uint8_t* gray_out, size_t gray_step)
+{
+    return local_host(c, method, 0, src, rows, cols, step, window, params, morph_iters, dst, dst_step, out_rows, out_cols,
+                      nullptr, channels, gray_out, gray_step);
 }
 
 extern "C" int prl_cuda_threshold_map(prl_cuda_ctx* c, int method, const uint8_t* src, int rows, int cols,

@@ -35,6 +35,7 @@ struct prl_cuda_ctx {
     uint8_t* d_in = nullptr;    size_t d_in_bytes = 0;
     uint8_t* d_out = nullptr;   size_t d_out_bytes = 0;
     uint8_t* d_tmp = nullptr;   size_t d_tmp_bytes = 0;
+    uint8_t* d_bgr = nullptr;   size_t d_bgr_bytes = 0;    // 3/4-channel staging of the cvtColor front step
     void* d_misc = nullptr;     size_t d_misc_bytes = 0;   // histograms, thresholds, rect lists
     // pinned host staging
     uint8_t* h_pin = nullptr;   size_t h_pin_bytes = 0;

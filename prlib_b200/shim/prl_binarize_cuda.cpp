@@ -37,15 +37,6 @@ void check(prl_cuda_ctx* c, int rc)
     throw std::runtime_error("libprlib_cuda: " + msg);
 }
 
-// gray, continuous copy of the input (GPU cvtColor for 3/4-channel images)
-cv::Mat toGray(prl_cuda_ctx* c, const cv::Mat& in)
-{
-    if (in.channels() == 1) return in;
-    cv::Mat gray(in.rows, in.cols, CV_8UC1);
-    check(c, prl_cuda_bgr2gray(c, in.data, in.rows, in.cols, in.step, in.channels(), gray.data, gray.step));
-    return gray;
-}
-
 // what the reference leaves in `imageInput`: copyMakeBorder(gray, h, h, h, h, BORDER_REPLICATE)
 cv::Mat padReplicate(const cv::Mat& g, int h)
 {
@@ -69,12 +60,22 @@ void runLocal(int method, cv::Mat& imageInput, cv::Mat& outputImage, int windowS
         throw std::invalid_argument("Window size must satisfy the following condition: "
                                     "( (windowSize > 1) && ((windowSize % 2) == 1) ) ");
     prl_cuda_ctx* c = context();
-    cv::Mat gray = toGray(c, imageInput);
+    const int ch = imageInput.channels();
+    if (ch != 1 && ch != 3 && ch != 4) throw cv::Exception("cvtColor: unsupported number of channels");
     int orows = 0, ocols = 0;
-    check(c, prl_cuda_output_shape(method, gray.rows, gray.cols, windowSize, &orows, &ocols));
+    check(c, prl_cuda_output_shape(method, imageInput.rows, imageInput.cols, windowSize, &orows, &ocols));
     cv::Mat out(orows, ocols, CV_8UC1);
-    check(c, prl_cuda_binarize_local(c, method, gray.data, gray.rows, gray.cols, gray.step, windowSize, params, morph,
-                                     out.data, out.step, &orows, &ocols));
+    cv::Mat gray = imageInput;                       // 1 channel: the input itself
+#ifndef PRL_CUDA_NO_INPUT_SIDE_EFFECT
+    if (ch != 1) gray = cv::Mat(imageInput.rows, imageInput.cols, CV_8UC1);
+    uint8_t* gray_out = ch != 1 ? gray.data : nullptr;
+#else
+    uint8_t* gray_out = nullptr;
+#endif
+    // one call: the (possibly 3/4-channel) image goes up once, cvtColor + both kernels run on the device
+    check(c, prl_cuda_binarize_local_image(c, method, imageInput.data, imageInput.rows, imageInput.cols, imageInput.step, ch,
+                                           windowSize, params, morph, out.data, out.step, &orows, &ocols, gray_out,
+                                           gray_out ? gray.step : 0));
 #ifndef PRL_CUDA_NO_INPUT_SIDE_EFFECT
     const int w = windowSize < gray.rows ? (windowSize < gray.cols ? windowSize : gray.cols)
                                          : (gray.rows < gray.cols ? gray.rows : gray.cols);

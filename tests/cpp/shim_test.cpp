@@ -54,6 +54,23 @@ int main()
         EXPECT(in.ptr(0)[0] == page.ptr(0)[0] && in.ptr(h)[h] == page.ptr(0)[0] &&
                in.ptr(in.rows - 1)[in.cols - 1] == page.ptr(rows - 1)[cols - 1], "replicate border");
     }
+    {   // 3-channel input (what cv::imread hands to the samples): cvtColor on the device, same masks as the gray path
+        cv::Mat bgr(rows, cols, CV_8UC3), gray(rows, cols, CV_8UC1);
+        for (int y = 0; y < rows; ++y)
+            for (int x = 0; x < cols; ++x) {
+                const unsigned char b = page.ptr(y)[x], g = (unsigned char)(b ^ 0x5a), r = (unsigned char)(255 - b);
+                unsigned char* p = bgr.ptr(y) + 3 * x;
+                p[0] = b; p[1] = g; p[2] = r;
+                gray.ptr(y)[x] = (unsigned char)((b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15);
+            }
+        cv::Mat in3 = bgr.clone(), in1 = gray.clone(), out3, out1;
+        prl::binarizeSauvola(in3, out3, 15, 0.2, 0);
+        prl::binarizeSauvola(in1, out1, 15, 0.2, 0);
+        bool same_mask = out3.rows == out1.rows && out3.cols == out1.cols;
+        for (int y = 0; same_mask && y < out1.rows; ++y) same_mask = std::memcmp(out3.ptr(y), out1.ptr(y), (size_t)out1.cols) == 0;
+        EXPECT(same_mask, "BGR input gives the mask of its gray conversion");
+        EXPECT(in3.channels() == 1 && in3.rows == rows + 14 && in3.ptr(7)[7] == gray.ptr(0)[0], "BGR input replaced by the padded GRAY image");
+    }
     {   // header defaults
         cv::Mat in = page.clone(), out;
         prl::binarizeNICK(in, out);
