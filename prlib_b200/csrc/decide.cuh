@@ -13,6 +13,8 @@ struct FastArgs {
     float mu0, mu1;              // decision margin: mu = mu0 + mu1*|coeff|  (mu1 only for Wolf-Jolion)
     float n_floor;               // fast path only when N >= n_floor  (s* >= s_floor)
     float q_floor;               // q_win >= q_floor implies N >= n_floor (used by the variance-free pre-test)
+    // second tier (fused kernel): FP64 estimate from the exact integers, margin mu2 = t2_a + t2_b / s, valid for v >= t2_vmin
+    double t2_a, t2_b, t2_vmin, kw_d, c0_d, c1_d, c2_d;
     unsigned int w2;             // w*w
     int rows_per_cta;
 };
@@ -129,6 +131,30 @@ __device__ __forceinline__ bool fast_decide(unsigned int sw, unsigned int qw, un
     return false;                                       // near the rounding boundary, ill-conditioned, or NaN
 }
 
+// Second tier: FP64 estimate of T from the exact window sums.  Decides the pixel unless it lies within
+// mu2 = t2_a + t2_b / s of the rounding boundary (mu2 bounds the reference's own FP64 rounding, which depends
+// on the absolute integral values this caller does not have) or the window is too dark for the bound to hold.
+template <int METHOD>
+__device__ __noinline__ bool tier2_decide(unsigned int sw, unsigned int qw, unsigned int p, double kw, double c0, double c1,
+                                          double c2, double t2_a, double t2_b, double t2_vmin, unsigned int w2,
+                                          double imin, int& out)
+{
+    const unsigned long long N = (unsigned long long)w2 * qw - (unsigned long long)sw * sw;
+    const double v = (double)N * kw * kw;
+    if (!(v >= t2_vmin)) return false;
+    const double m = (double)sw * kw, s = sqrt(v);
+    double T;
+    if (METHOD == PRL_SAUVOLA) T = m * (s * c1 + c2);
+    else if (METHOD == PRL_NIBLACK) T = m + c0 * s;
+    else if (METHOD == PRL_NICK) T = m + c0 * sqrt(m * m + s * s);
+    else T = c1 * m + (c2 * imin - imin);
+    const double g = ((double)p - 0.5) - fmax(T, 0.0);
+    const double mu2 = t2_a + t2_b / s;
+    if (g > mu2) { out = 255; return true; }
+    if (g < -mu2) { out = 0; return true; }
+    return false;
+}
+
 // Host-side error analysis for the fast path: returns false when the margin is too large to be useful.
 //   reference FP64 error (vs exact real arithmetic), u = 2^-53:
 //     dm_ref <= 16 u kw Smax,  dq_ref <= 16 u kw Qmax,  dv_ref <= dq_ref + 2*255*dm_ref + u*2*255^2
@@ -148,20 +174,20 @@ inline bool fast_margins(int method, const double* params, const prl_geom& g, Fa
     if (!(dv_ref < 0.25 * s_floor * s_floor)) return false;
     const double ds_ref = dv_ref / s_floor + u * 128;
     const double dm = dm_ref + 3 * e * 255, ds = ds_ref + 8 * e * 128;   // ds: int->float, rsqrt (2 ulp), two products
-    double Acoef, Bcoef, Tmax, mu1 = 0.0;
+    double Acoef, Bcoef, Tmax, mu1 = 0.0, cd0 = 0.0, cd1 = 0.0, cd2 = 0.0;
     const double k = params[0];
     switch (method) {
     case PRL_SAUVOLA: {
         const double c1 = k * (1.0 / 128.0), c2 = 1.0 - k;
         Acoef = fabs(c2) + 128 * fabs(c1); Bcoef = 255 * fabs(c1); Tmax = 255 * Acoef;
-        F->c0 = (float)k; F->c1 = (float)c1; F->c2 = (float)c2; break;
+        F->c0 = (float)k; F->c1 = (float)c1; F->c2 = (float)c2; cd0 = k; cd1 = c1; cd2 = c2; break;
     }
     case PRL_NIBLACK:
         Acoef = 1; Bcoef = fabs(k); Tmax = 255 + 128 * fabs(k);
-        F->c0 = (float)k; F->c1 = F->c2 = 0; break;
+        F->c0 = (float)k; F->c1 = F->c2 = 0; cd0 = k; break;
     case PRL_NICK:
         Acoef = 1 + fabs(k); Bcoef = fabs(k); Tmax = 255 + fabs(k) * 286;
-        F->c0 = (float)k; F->c1 = F->c2 = 0; break;
+        F->c0 = (float)k; F->c1 = F->c2 = 0; cd0 = k; break;
     case PRL_WOLFJOLION:
         // T = m + (s*coeff - k)(m - imin), |coeff| = |k|/smax known only on the device:
         // dT/dm = 1 + s*coeff - k -> |.| <= 1 + |k| + 128|coeff|;  dT/ds = coeff (m - imin) -> <= 255 |coeff|
@@ -172,7 +198,7 @@ inline bool fast_margins(int method, const double* params, const prl_geom& g, Fa
     default: {   // Feng: T = p1*m + (k2*imin - imin)
         const double p1 = 1.0 + (1.0 - params[0]), k2 = params[2];
         Acoef = fabs(p1); Bcoef = 0; Tmax = 255 * fabs(p1) + 255 * (fabs(k2) + 1);
-        F->c0 = 0; F->c1 = (float)p1; F->c2 = (float)k2; break;
+        F->c0 = 0; F->c1 = (float)p1; F->c2 = (float)k2; cd1 = p1; cd2 = k2; break;
     }
     }
     if (!(Tmax < 1e6)) return false;
@@ -185,6 +211,11 @@ inline bool fast_margins(int method, const double* params, const prl_geom& g, Fa
     const double nf = s_floor * w2;
     F->n_floor = (float)(nf * nf * 1.0001);
     F->q_floor = (float)(nf * nf * 1.001 / (2.0 * g.w - 1.0));
+    // tier 2: |T_fp64 - T_ref| <= A dm_ref + B dv_ref / s + FP64 rounding of the estimate (<= 64 u Tmax), times 4
+    F->t2_a = 4 * (Acoef * dm_ref + Bcoef * u * 128 + 64 * u * (Tmax + 512));
+    F->t2_b = 4 * Bcoef * dv_ref;
+    F->t2_vmin = 16 * dv_ref;
+    F->kw_d = kw; F->c0_d = cd0; F->c1_d = cd1; F->c2_d = cd2;
     return true;
 }
 
