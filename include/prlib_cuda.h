@@ -63,7 +63,12 @@ int         prl_cuda_set_workspace_limit(prl_cuda_ctx* ctx, size_t bytes);
  *                            of only for the pixels its exact-integer/FP32 decision cannot settle;
  *   "disable_tma"     != 0 : kernel 1 uses its generic byte-load kernel instead of the TMA-staged one;
  *   "enable_fused"    != 0 : windows <= 31 (Sauvola/Niblack/NICK/Feng) run the fused strip kernel that never
- *                            materialises the int64 integral planes in HBM (experimental: correct, not yet faster). */
+ *                            materialises the int64 integral planes in HBM.  The batch call then returns only after
+ *                            the fused kernels finished (it reads a per-page counter back);
+ *   "fused_page_cap"  = n  : undecided pixels per page (0..128, default 128) the fused path finishes itself by
+ *                            brute force; a page with more is redone by kernel 1 + kernel 2 (test hook: 0);
+ *   "fused_no_tier2"  != 0 : the fused path skips its FP64 estimate, so every pixel its FP32 estimate cannot settle
+ *                            goes to the brute-force list (test hook for the list and the hand-back). */
 int         prl_cuda_set_option(prl_cuda_ctx* ctx, const char* name, long long value);
 
 /* Geometry of the reference's processingRect (binarizeSauvola.cpp:57,66; binarizeWolfJolion.cpp:58,69):
@@ -165,12 +170,14 @@ int prl_cuda_binarize_batch(const int* devices, int n_dev, int method, const uin
 /* ---- instrumentation ---------------------------------------------------------------------
  * With timing enabled every kernel launch is bracketed by CUDA events on the launching stream.
  * prl_cuda_timing_get sums them per kernel family ("integral", "threshold", "smax", "morph",
- * "otsu_hist", "otsu_search", "otsu_apply", "otsu_tiles", "synth", "bgr2gray", "band_carry", "fused", "fused_pre");
+ * "otsu_hist", "otsu_search", "otsu_apply", "otsu_tiles", "synth", "bgr2gray", "band_carry", "fused", "fused_pre", "fused_fix");
  * it synchronizes the stream. */
 int  prl_cuda_timing_enable(prl_cuda_ctx* ctx, int on);
 int  prl_cuda_timing_reset(prl_cuda_ctx* ctx);
 int  prl_cuda_timing_get(prl_cuda_ctx* ctx, const char* family, double* total_ms, long long* launches);
 long long prl_cuda_launch_count(const prl_cuda_ctx* ctx);   /* kernels launched since create/reset */
+/* pages the fused small-window path ("enable_fused") handed back to the two-kernel path since create */
+long long prl_cuda_fused_redo_count(const prl_cuda_ctx* ctx);
 
 #ifdef __cplusplus
 }

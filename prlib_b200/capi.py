@@ -57,6 +57,7 @@ SIGNATURES = {
     "prl_cuda_timing_reset": (C.c_int, [_ctx]),
     "prl_cuda_timing_get": (C.c_int, [_ctx, C.c_char_p, _f64p, C.POINTER(C.c_longlong)]),
     "prl_cuda_launch_count": (C.c_longlong, [_ctx]),
+    "prl_cuda_fused_redo_count": (C.c_longlong, [_ctx]),
 }
 
 _lib = None

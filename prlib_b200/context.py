@@ -10,7 +10,7 @@ from . import capi
 from .capi import PrlCudaError
 
 _FAMILIES = ("integral", "threshold", "smax", "morph", "otsu_hist", "otsu_search", "otsu_apply", "otsu_tiles",
-             "synth", "bgr2gray", "band_carry", "fused", "fused_pre")
+             "synth", "bgr2gray", "band_carry", "fused", "fused_pre", "fused_fix")
 
 
 def _params4(params) -> "C.Array":
@@ -104,6 +104,10 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self._L.prl_cuda_launch_count(self._h))
+
+    def fused_redo_count(self) -> int:
+        """Pages the fused small-window path handed back to the two-kernel path."""
+        return int(self._L.prl_cuda_fused_redo_count(self._h))
 
     # -- host-pointer entry points -------------------------------------------------------------
     def integral(self, gray, pad: int):

@@ -85,7 +85,7 @@ static void timing_collect(prl_cuda_ctx* ctx)
 }
 
 static const char* kFamilyNames[FAM_COUNT] = {"integral", "threshold", "smax", "morph", "otsu_hist", "otsu_search",
-                                              "otsu_apply", "otsu_tiles", "synth", "bgr2gray", "band_carry", "fused", "fused_pre"};
+                                              "otsu_apply", "otsu_tiles", "synth", "bgr2gray", "band_carry", "fused", "fused_pre", "fused_fix"};
 
 int prl_make_geom(int method, int rows, int cols, int window, prl_geom* g)
 {
@@ -165,7 +165,8 @@ extern "C" void prl_cuda_destroy(prl_cuda_ctx* c)
     cudaStreamSynchronize(c->stream);
     for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto& ev : c->event_pool) cudaEventDestroy(ev);
-    cudaFree(c->planes); cudaFree(c->carry); cudaFree(c->colsum); cudaFree(c->scalars);
+    cudaFree(c->planes); cudaFree(c->carry); cudaFree(c->colsum); cudaFree(c->scalars); cudaFree(c->fused_ws);
+    if (c->h_cnt) cudaFreeHost(c->h_cnt);
     cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_tmp); cudaFree(c->d_misc); cudaFree(c->d_bgr);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -204,6 +205,8 @@ extern "C" int prl_cuda_set_option(prl_cuda_ctx* c, const char* name, long long 
     if (strcmp(name, "exact_threshold") == 0) c->force_exact = value != 0;
     else if (strcmp(name, "disable_tma") == 0) c->no_tma = value != 0;
     else if (strcmp(name, "enable_fused") == 0) c->use_fused = value != 0;
+    else if (strcmp(name, "fused_no_tier2") == 0) c->fused_no_tier2 = value != 0;
+    else if (strcmp(name, "fused_page_cap") == 0) c->fused_page_cap = (int)std::min<long long>(std::max<long long>(value, 0), 128);
     else return prl_set_err(c, PRL_E_INVALID, "unknown option");
     return PRL_OK;
 }
@@ -240,6 +243,7 @@ extern "C" int prl_cuda_timing_get(prl_cuda_ctx* c, const char* family, double* 
     return prl_set_err(c, PRL_E_INVALID, "unknown kernel family");
 }
 extern "C" long long prl_cuda_launch_count(const prl_cuda_ctx* c) { return c ? c->launches : 0; }
+extern "C" long long prl_cuda_fused_redo_count(const prl_cuda_ctx* c) { return c ? c->fused_redo_pages : 0; }
 
 // ------------------------------------------------------------------------------------------------
 // device-resident batch entry points
@@ -258,43 +262,17 @@ static size_t planes_budget(prl_cuda_ctx* c, size_t want)
     return std::max(lim, c->planes_bytes);
 }
 
-// mode 0: masks (+morph), mode 1: T8 maps
-static int local_batch_dev(prl_cuda_ctx* c, int method, int mode, const uint8_t* d_src, int n_pages, int rows, int cols,
-                           size_t src_step, size_t src_page_stride, int window, const double* params, int morph_iters,
-                           uint8_t* d_dst, size_t dst_step, size_t dst_page_stride)
+// The two-kernel path over a batch: kernel 1 (integral planes) -> kernel 2 (threshold) [-> morphology], in chunks of
+// as many pages as the planes scratch holds.  mode 0: masks (+morph), mode 1: T8 maps
+static int planes_pages(prl_cuda_ctx* c, int method, int mode, const uint8_t* d_src, int n_pages, const prl_geom& g,
+                        size_t src_step, size_t src_page_stride, const double* params, int morph_iters,
+                        uint8_t* d_dst, size_t dst_step, size_t dst_page_stride)
 {
-    if (!c || !d_src || !d_dst || !params || n_pages <= 0) return prl_set_err(c, PRL_E_INVALID, "null pointer or empty batch");
-    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
-    prl_geom g;
-    int rc = prl_make_geom(method, rows, cols, window, &g);
-    if (rc) return prl_set_err(c, rc, rc == PRL_E_EMPTY_ROI ? "empty processingRect: min(rows, cols) <= windowSize"
-                                                             : "empty image or window not (>1 and odd)");
-    if ((size_t)g.out_cols > dst_step) return prl_set_err(c, PRL_E_INVALID, "dst_step smaller than out_cols");
-
-    rc = prl_ensure(c, &c->scalars, &c->scalars_bytes, (size_t)n_pages * 16);
-    if (rc) return rc;
-    // small windows, big batches: the fused path (planes never reach HBM)
-    if (mode == 0 && prl_fused_eligible(c, method, n_pages, g, params)) {
-        uint32_t* imin = (uint32_t*)c->scalars;
-        const bool with_morph = morph_iters != 0;
-        size_t t_step = round16((size_t)g.out_cols);
-        if (with_morph) {
-            rc = prl_ensure(c, (void**)&c->d_tmp, &c->d_tmp_bytes, (size_t)n_pages * g.out_rows * t_step);
-            if (rc) return rc;
-        }
-        rc = prl_k_fused(c, method, d_src, n_pages, g, src_step, src_page_stride, params, imin, with_morph ? c->d_tmp : d_dst,
-                         with_morph ? t_step : dst_step, with_morph ? (size_t)g.out_rows * t_step : dst_page_stride);
-        if (rc) return rc;
-        if (with_morph)
-            rc = prl_k_morph(c, c->d_tmp, d_dst, n_pages, g.out_rows, g.out_cols, t_step, (size_t)g.out_rows * t_step, dst_step,
-                             dst_page_stride, morph_iters);
-        return rc;
-    }
-
     const size_t plane_elems = (size_t)g.Hp * g.pitch;          // one plane of one page
     const size_t per_page = 2 * plane_elems * sizeof(int64_t);
     const size_t budget = std::min(planes_budget(c, (size_t)n_pages * per_page), c->workspace_limit);
     int chunk = (int)std::min<size_t>((size_t)n_pages, std::max<size_t>(1, budget / per_page));
+    int rc;
     if ((size_t)chunk * per_page > c->planes_bytes || !c->planes) {
         rc = prl_ensure(c, (void**)&c->planes, &c->planes_bytes, (size_t)chunk * per_page);
         if (rc) return rc;
@@ -316,7 +294,7 @@ static int local_batch_dev(prl_cuda_ctx* c, int method, int mode, const uint8_t*
         const int np = std::min(chunk, n_pages - p0);
         const uint8_t* src = d_src + (size_t)p0 * src_page_stride;
         uint8_t* dst = d_dst + (size_t)p0 * dst_page_stride;
-        rc = prl_k_integral(c, src, np, rows, cols, src_step, src_page_stride, g.h, S, Q, g.pitch, plane_elems, d_imin + p0);
+        rc = prl_k_integral(c, src, np, g.rows, g.cols, src_step, src_page_stride, g.h, S, Q, g.pitch, plane_elems, d_imin + p0);
         if (rc) return rc;
         const bool with_morph = morph_iters != 0 && mode == 0;
         // with a morphology tail kernel 2 writes the raw mask into the scratch and the tail writes the final one
@@ -331,6 +309,54 @@ static int local_batch_dev(prl_cuda_ctx* c, int method, int mode, const uint8_t*
         }
     }
     return PRL_OK;
+}
+
+static int local_batch_dev(prl_cuda_ctx* c, int method, int mode, const uint8_t* d_src, int n_pages, int rows, int cols,
+                           size_t src_step, size_t src_page_stride, int window, const double* params, int morph_iters,
+                           uint8_t* d_dst, size_t dst_step, size_t dst_page_stride)
+{
+    if (!c || !d_src || !d_dst || !params || n_pages <= 0) return prl_set_err(c, PRL_E_INVALID, "null pointer or empty batch");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    prl_geom g;
+    int rc = prl_make_geom(method, rows, cols, window, &g);
+    if (rc) return prl_set_err(c, rc, rc == PRL_E_EMPTY_ROI ? "empty processingRect: min(rows, cols) <= windowSize"
+                                                             : "empty image or window not (>1 and odd)");
+    if ((size_t)g.out_cols > dst_step) return prl_set_err(c, PRL_E_INVALID, "dst_step smaller than out_cols");
+
+    // small windows: the fused path (planes never reach HBM).  It is optimistic: pages on which too many pixels need
+    // the reference's exact FP64 arithmetic (large exactly-flat areas under Niblack / Feng) are reported back and redone
+    // by the two-kernel path below.
+    if (mode == 0 && prl_fused_eligible(c, method, n_pages, g, params)) {
+        rc = prl_ensure(c, &c->scalars, &c->scalars_bytes, (size_t)n_pages * 16);
+        if (rc) return rc;
+        uint32_t* imin = (uint32_t*)c->scalars;
+        const bool with_morph = morph_iters != 0;
+        const size_t t_step = round16((size_t)g.out_cols), t_page = (size_t)g.out_rows * t_step;
+        if (with_morph) {
+            rc = prl_ensure(c, (void**)&c->d_tmp, &c->d_tmp_bytes, (size_t)n_pages * t_page);
+            if (rc) return rc;
+        }
+        uint8_t* raw = with_morph ? c->d_tmp : d_dst;
+        const size_t raw_step = with_morph ? t_step : dst_step, raw_page = with_morph ? t_page : dst_page_stride;
+        std::vector<int> redo;
+        rc = prl_k_fused(c, method, d_src, n_pages, g, src_step, src_page_stride, params, imin, raw, raw_step, raw_page, &redo);
+        if (rc) return rc;
+        for (size_t i = 0; i < redo.size();) {                    // runs of consecutive pages
+            size_t j = i + 1;
+            while (j < redo.size() && redo[j] == redo[j - 1] + 1) ++j;
+            const int p0 = redo[i], np = (int)(j - i);
+            rc = planes_pages(c, method, 0, d_src + (size_t)p0 * src_page_stride, np, g, src_step, src_page_stride, params, 0,
+                              raw + (size_t)p0 * raw_page, raw_step, raw_page);
+            if (rc) return rc;
+            i = j;
+        }
+        if (with_morph)
+            rc = prl_k_morph(c, c->d_tmp, d_dst, n_pages, g.out_rows, g.out_cols, t_step, t_page, dst_step, dst_page_stride,
+                             morph_iters);
+        return rc;
+    }
+    return planes_pages(c, method, mode, d_src, n_pages, g, src_step, src_page_stride, params, morph_iters, d_dst, dst_step,
+                        dst_page_stride);
 }
 
 extern "C" int prl_cuda_binarize_local_batch_dev(prl_cuda_ctx* c, int method, const uint8_t* d_src, int n_pages,

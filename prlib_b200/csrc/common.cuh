@@ -31,6 +31,11 @@ struct prl_cuda_ctx {
     void* carry = nullptr;      size_t carry_bytes = 0;
     void* colsum = nullptr;     size_t colsum_bytes = 0;
     void* scalars = nullptr;    size_t scalars_bytes = 0;
+    void* fused_ws = nullptr;   size_t fused_ws_bytes = 0; // fused path: row sums per strip, fixup counters and lists
+    uint32_t* h_cnt = nullptr;  size_t h_cnt_bytes = 0;    // pinned read-back of the fused path's per-page counters
+    int fused_page_cap = 128;                              // undecided pixels per page the fused path finishes itself
+    bool fused_no_tier2 = false;                           // validation: fused path without its FP64 estimate tier
+    long long fused_redo_pages = 0;                        // pages the fused path handed back to the two-kernel path
     // device staging for host-pointer entry points
     uint8_t* d_in = nullptr;    size_t d_in_bytes = 0;
     uint8_t* d_out = nullptr;   size_t d_out_bytes = 0;
@@ -54,7 +59,7 @@ struct prl_cuda_ctx {
 
 enum prl_family {
     FAM_INTEGRAL = 0, FAM_THRESHOLD, FAM_SMAX, FAM_MORPH, FAM_OTSU_HIST, FAM_OTSU_SEARCH,
-    FAM_OTSU_APPLY, FAM_OTSU_TILES, FAM_SYNTH, FAM_BGR2GRAY, FAM_BAND_CARRY, FAM_FUSED, FAM_FUSED_PRE, FAM_COUNT
+    FAM_OTSU_APPLY, FAM_OTSU_TILES, FAM_SYNTH, FAM_BGR2GRAY, FAM_BAND_CARRY, FAM_FUSED, FAM_FUSED_PRE, FAM_FUSED_FIX, FAM_COUNT
 };
 
 int  prl_set_err(prl_cuda_ctx* ctx, int code, const char* what, cudaError_t ce = cudaSuccess);
@@ -96,7 +101,7 @@ int prl_k_threshold(prl_cuda_ctx* ctx, int method, int mode /*0 mask, 1 T8*/, co
 bool prl_fused_eligible(const prl_cuda_ctx* ctx, int method, int n_pages, const prl_geom& g, const double* params);
 int prl_k_fused(prl_cuda_ctx* ctx, int method, const uint8_t* d_src, int n_pages, const prl_geom& g, size_t src_step,
                 size_t src_page_stride, const double* params, uint32_t* d_imin, uint8_t* d_dst, size_t dst_step,
-                size_t dst_page_stride);
+                size_t dst_page_stride, std::vector<int>* redo_pages);
 int prl_k_morph(prl_cuda_ctx* ctx, uint8_t* d_in, uint8_t* d_out, int n_pages, int rows, int cols, size_t in_step,
                 size_t in_page_stride, size_t out_step, size_t out_page_stride, int iters);
 int prl_k_bgr2gray(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, int channels,

@@ -17,6 +17,11 @@ struct FastArgs {
     double t2_a, t2_b, t2_vmin, kw_d, c0_d, c1_d, c2_d;
     unsigned int w2;             // w*w
     int rows_per_cta;
+    // fused kernel: variance-free pre-test with bounds linear in m:  T in [pa_lo*m + pb_lo, pa_hi*m + pb_hi] for s in [0,128]
+    float pa_hi, pa_lo, pb_hi, pb_lo;
+    unsigned int qfloor_u;       // integer form of q_floor
+    double dv_ref;               // bound on |v_ref - v| of the reference's FP64 variance
+    int n32;                     // w^2 * (w-1)^2 * 255^2 < 2^32: N fits 32 bits
 };
 
 __device__ __forceinline__ int to_u8(double T)
@@ -134,14 +139,14 @@ __device__ __forceinline__ bool fast_decide(unsigned int sw, unsigned int qw, un
 // Second tier: FP64 estimate of T from the exact window sums.  Decides the pixel unless it lies within
 // mu2 = t2_a + t2_b / s of the rounding boundary (mu2 bounds the reference's own FP64 rounding, which depends
 // on the absolute integral values this caller does not have) or the window is too dark for the bound to hold.
+// Returns 0 / 255, or -1 when the pixel stays undecided.
 template <int METHOD>
-__device__ __noinline__ bool tier2_decide(unsigned int sw, unsigned int qw, unsigned int p, double kw, double c0, double c1,
-                                          double c2, double t2_a, double t2_b, double t2_vmin, unsigned int w2,
-                                          double imin, int& out)
+__device__ __noinline__ int tier2_decide(unsigned int sw, unsigned int qw, unsigned int p, double kw, double c0, double c1,
+                                         double c2, double t2_a, double t2_b, double t2_vmin, unsigned int w2, double imin)
 {
     const unsigned long long N = (unsigned long long)w2 * qw - (unsigned long long)sw * sw;
     const double v = (double)N * kw * kw;
-    if (!(v >= t2_vmin)) return false;
+    if (!(v >= t2_vmin)) return -1;
     const double m = (double)sw * kw, s = sqrt(v);
     double T;
     if (METHOD == PRL_SAUVOLA) T = m * (s * c1 + c2);
@@ -150,9 +155,9 @@ __device__ __noinline__ bool tier2_decide(unsigned int sw, unsigned int qw, unsi
     else T = c1 * m + (c2 * imin - imin);
     const double g = ((double)p - 0.5) - fmax(T, 0.0);
     const double mu2 = t2_a + t2_b / s;
-    if (g > mu2) { out = 255; return true; }
-    if (g < -mu2) { out = 0; return true; }
-    return false;
+    if (g > mu2) return 255;
+    if (g < -mu2) return 0;
+    return -1;
 }
 
 // Host-side error analysis for the fast path: returns false when the margin is too large to be useful.
@@ -216,6 +221,20 @@ inline bool fast_margins(int method, const double* params, const prl_geom& g, Fa
     F->t2_b = 4 * Bcoef * dv_ref;
     F->t2_vmin = 16 * dv_ref;
     F->kw_d = kw; F->c0_d = cd0; F->c1_d = cd1; F->c2_d = cd2;
+    F->dv_ref = dv_ref;
+    // linear bounds of T over s in [0,128] (m >= 0); sqrt(m^2+s^2) in [m, m+128] for NICK
+    double a0 = 1, a1 = 1, b0 = 0, b1 = 0;          // T(s=0) = a0*m + b0,  T(s=128) (or its bound) = a1*m + b1
+    switch (method) {
+    case PRL_SAUVOLA: a0 = cd2; a1 = cd2 + 128.0 * cd1; break;
+    case PRL_NIBLACK: b1 = 128.0 * k; break;
+    case PRL_NICK:    a0 = a1 = 1.0 + k; b1 = 128.0 * k; break;
+    case PRL_FENG:    a0 = a1 = cd1; break;         // + (k2*imin - imin), added per page on the device
+    default: break;
+    }
+    F->pa_hi = (float)(a0 > a1 ? a0 : a1); F->pa_lo = (float)(a0 > a1 ? a1 : a0);
+    F->pb_hi = (float)(b0 > b1 ? b0 : b1); F->pb_lo = (float)(b0 > b1 ? b1 : b0);
+    F->qfloor_u = (unsigned int)(nf * nf * 1.001 / (2.0 * g.w - 1.0)) + 2u;
+    F->n32 = ((double)g.w * g.w * (double)g.d * g.d * 65025.0 < 4294967296.0) ? 1 : 0;
     return true;
 }
 

@@ -1,44 +1,47 @@
 // fused.cu -- small-window path: the integral planes never reach HBM.
 //
-// Same results as kernel 1 + kernel 2 (integral.cu, threshold.cu) for Sauvola / Niblack / NICK / Feng with
-// windows up to 31, at 1 byte read + 1 byte written per pixel instead of ~35:
-//   * a page is cut into strips of 128 padded columns; ONE WARP owns a strip and walks down all rows, so
-//     there is no block barrier and no cross-warp row offset.  Window sums are differences of four integral
-//     taps, and differences do not care where the integral's origin is: the warp keeps a STRIP-LOCAL integral
-//     (row prefix starting at the strip's first column), running column sums in registers, the last d+1 rows
-//     of their low 32 bits in a shared-memory ring (S_win, Q_win < 2^32);
-//   * per row: dp4a lane prefixes + two 5-step shuffle scans (as kernel 1), ring write, then the output row
-//     d rows up: taps from the ring, exact integer window sums, FP32 decision (decide.cuh);
-//   * the rare pixel the FP32 estimate cannot settle needs the reference's FP64 arithmetic on the TRUE int64
-//     integral taps.  true = local + L, where L[Y] = S[Y][strip_start - 1] comes from a cheap pre-pass over
-//     the u8 page (strip_rowsum_kernel + strip_colscan_kernel, which also yields the page minimum), and the
-//     64-bit local Q is rebuilt from the lane's own 64-bit column sum plus low-word differences (each < 2^32).
-// Strips overlap by d columns (a strip emits 128 - d outputs), i.e. ~12 % redundant scan work at w = 15.
+// Same masks as kernel 1 + kernel 2 (integral.cu, threshold.cu) for Sauvola / Niblack / NICK / Feng with
+// windows up to 31, at ~1 byte read + 1 byte written per pixel instead of ~35.
+//
+// Window sums do not need an integral image at all: per column keep the running sum V over the last d rows
+// (add the entering row, subtract the leaving one), and take the horizontal window as a difference of the row
+// prefix of V.  So:
+//   * a page is cut into strips of 128 padded columns; ONE WARP owns a strip and walks down all rows (no block
+//     barrier, no cross-warp traffic).  Lane l owns 4 adjacent columns: V_S, V_Q in registers, the last d+1 rows
+//     of raw pixels in a 2 KB shared-memory ring (to subtract the leaving row and to fetch the centre pixel);
+//   * per row: update V, lane prefix + two 5-step shuffle scans of V, exchange of the prefix through a
+//     double-buffered shared row, window sums S_win / Q_win = prefix[x+d] - prefix[x]  (exact integers);
+//   * decision in three tiers, each sound on its own (decide.cuh):
+//       1. FP32 estimate (+ variance-free bounds), margin mu ~ 2e-3            -> settles ~99.9 % of the pixels
+//       2. FP64 estimate from the same exact integers, margin mu2 ~ 1e-5 that bounds the REFERENCE's own FP64
+//          rounding (which depends on the absolute int64 integral values, unknown here)
+//       3. the few pixels per page that are still undecided are written as the sentinel 128 and finished by
+//          fixup_kernel, which rebuilds the four true int64 taps by brute force (row prefixes at the strip start
+//          come from the pre-pass strip_rowsum_kernel) and evaluates the reference's FP64 formula literally.
+//   Strips overlap by d columns (a strip emits 128 - d outputs): ~12 % redundant work at w = 15.
 #include "common.cuh"
 #include "decide.cuh"
+#include <algorithm>
 
 namespace {
 
 constexpr int kFW = 128;          // scanned padded columns per warp strip
+constexpr int kSentinel = 128;    // mask value of a pixel left to fixup_kernel
+constexpr int kPageCap = 128;     // listed pixels per page; a page with more goes to the planes path
 
 struct FusedArgs {
     const uint8_t* src; size_t src_step, src_page_stride;
     uint8_t* dst; size_t dst_step, dst_page_stride;
-    const uint32_t* imin;            // per page
-    const longlong2* L;              // [page][Hp][ns] true {S, Q} integral just left of each strip
+    const uint32_t* imin;            // per page (Feng)
+    uint32_t* blocksum;              // [page][nblk][ns][2] {sum, sqsum} over a block of 32 padded rows x the strip's own ow columns
+    uint32_t* scount;                // [page] pixels left to the fixup
+    uint32_t* slist;                 // [page][kPageCap] (y << 16) | x
     int rows, cols, pad, d, Hp, Wp, out_rows, out_cols, ow, ns, n_pages;
+    uint32_t cap;                    // listed pixels per page the fixup takes (<= kPageCap)
+    int nb, band_rows, nblk;         // row bands per page, output rows per band, 32-row blocks per page
+    int no_tier2;                    // validation: skip the FP64 estimate, every tier-1 leftover goes to the list
     double kw, p0, p1, p2;
 };
-
-// 4 bytes at `p` (any alignment)
-__device__ __forceinline__ uint32_t ldg_u32_unaligned(const uint8_t* p)
-{
-    const uint32_t sh = (uint32_t)(uintptr_t)p & 3u;
-    const uint32_t* a = reinterpret_cast<const uint32_t*>(p - sh);
-    uint32_t w = __ldg(a);
-    if (sh) w = __funnelshift_r(w, __ldg(a + 1), 8 * sh);
-    return w;
-}
 
 __device__ __forceinline__ uint32_t warp_scan_u32(uint32_t v, int lane)
 {
@@ -50,234 +53,344 @@ __device__ __forceinline__ uint32_t warp_scan_u32(uint32_t v, int lane)
     return v;
 }
 
-// ---- pre-pass 1: rowpre[page][y][b] = {sum, sum of squares} of the padded columns X < b*ow of source row y
+// ---- pre-pass (Feng only): per-page minimum
 __global__ void __launch_bounds__(256)
-strip_rowsum_kernel(const uint8_t* __restrict__ src, size_t step, size_t page_stride, int rows, int cols, int pad,
-                    int ow, int ns, uint2* __restrict__ rowpre, uint32_t* __restrict__ imin)
+page_min_kernel(const uint8_t* __restrict__ src, size_t step, size_t page_stride, int rows, int cols, uint32_t* __restrict__ imin)
 {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int page = blockIdx.y;
-    const int y = blockIdx.x * 8 + wid;
-    if (y >= rows) return;
-    const int Wp = cols + 2 * pad;
-    const uint8_t* row = src + (size_t)page * page_stride + (size_t)y * step;
-    uint2* out = rowpre + ((size_t)page * rows + y) * ns;
-    uint32_t run_s = 0, run_q = 0, mn = 255u;
-    for (int b = 0; b < ns; ++b) {
-        if (lane == 0) out[b] = make_uint2(run_s, run_q);
-        const int X1 = min((b + 1) * ow, Wp);
-        uint32_t s = 0, q = 0;
-        for (int X = b * ow + lane; X < X1; X += 32) {
-            const uint32_t p = __ldg(row + min(max(X - pad, 0), cols - 1));
-            s += p; q += p * p; mn = min(mn, p);
-        }
-        run_s += __reduce_add_sync(0xffffffffu, s);
-        run_q += __reduce_add_sync(0xffffffffu, q);
+    const uint8_t* img = src + (size_t)page * page_stride;
+    uint32_t mn = 255u;
+    for (int y = blockIdx.x; y < rows; y += gridDim.x) {
+        const uint8_t* row = img + (size_t)y * step;
+        for (int x = threadIdx.x; x < cols; x += 256) mn = min(mn, (uint32_t)__ldg(row + x));
     }
-    // columns beyond the last strip start never enter an L value, but they do enter the page minimum
-    for (int X = ns * ow + lane; X < Wp; X += 32) mn = min(mn, (uint32_t)__ldg(row + min(max(X - pad, 0), cols - 1)));
     mn = __reduce_min_sync(0xffffffffu, mn);
-    if (lane == 0 && imin) atomicMin(imin + page, mn);
+    if ((threadIdx.x & 31) == 0) atomicMin(imin + page, mn);
 }
 
-// ---- pre-pass 2: L[page][Y][b] = sum over padded rows Y' <= Y of rowpre[page][clamp(Y' - pad)][b]
-__global__ void __launch_bounds__(128)
-strip_colscan_kernel(const uint2* __restrict__ rowpre, longlong2* __restrict__ L, int rows, int pad, int Hp, int ns,
-                     int n_pages)
+// byte i of w as an integer (one PRMT)
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int i) { return __byte_perm(w, 0u, 0x4440u + (uint32_t)i); }
+
+// one step of an inclusive warp scan: SHFL with its in-range predicate + predicated add
+__device__ __forceinline__ uint32_t scan_step(uint32_t v, int delta)
 {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= ns * n_pages) return;
-    const int page = idx / ns, b = idx - page * ns;
-    long long as = 0, aq = 0;
-    for (int Y = 0; Y < Hp; ++Y) {
-        const int y = min(max(Y - pad, 0), rows - 1);
-        const uint2 v = __ldg(rowpre + ((size_t)page * rows + y) * ns + b);
-        as += v.x; aq += v.y;
-        L[((size_t)page * Hp + Y) * ns + b] = make_longlong2(as, aq);
-    }
+    uint32_t r;
+    asm("{\n\t.reg .u32 t;\n\t.reg .pred p;\n\tshfl.sync.up.b32 t|p, %1, %2, 0x0, 0xffffffff;\n\tmov.u32 %0, %1;\n\t@p add.u32 %0, %0, t;\n\t}"
+        : "=r"(r) : "r"(v), "r"(delta));
+    return r;
+}
+__device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v)
+{
+    v = scan_step(v, 1); v = scan_step(v, 2); v = scan_step(v, 4); v = scan_step(v, 8); v = scan_step(v, 16);
+    return v;
 }
 
-// ---- the fused kernel: one warp = one strip of one page
-template <int METHOD, int RR, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+// ---- the fused kernel: one warp = one strip of one band of one page
+template <int METHOD, int RR, bool N32>
+__global__ void __launch_bounds__(128, 5)
 local_fused_kernel(const FusedArgs A, const FastArgs F)
 {
-    extern __shared__ __align__(16) uint32_t fsm[];
-    constexpr int WARP_WORDS = RR * kFW * 2 + 2 * RR * (kFW / 4) + 16;   // S ring, Q ring, pixel ring, Q-high-byte ring (+ slack)
+    constexpr int WARPS = 4;
+    // per warp: pixel ring [RR][32 words], prefix exchange [2][2 planes][128 words] (+ slack for tap over-reads)
+    constexpr int WARP_WORDS = RR * 32 + 2 * 2 * kFW + 16;
+    __shared__ __align__(16) uint32_t fsm[WARPS * WARP_WORDS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int gw = blockIdx.x * WARPS + wid;
-    if (gw >= A.ns * A.n_pages) return;                 // warps are independent: no block-level barrier below
-    const int page = gw / A.ns, strip = gw - page * A.ns;
+    const int per_page = A.ns * A.nb;
+    if (gw >= per_page * A.n_pages) return;             // warps are independent: no block-level barrier below
+    const int page = gw / per_page, rem = gw - page * per_page;
+    const int band = rem / A.ns, strip = rem - band * A.ns;
     const int x0 = strip * A.ow;                        // first scanned padded column == first output column
-    uint32_t* ringS = fsm + wid * WARP_WORDS;
-    uint32_t* ringQ = ringS + RR * kFW;
-    uint32_t* pixr = ringQ + RR * kFW;
-    uint32_t* ringH = pixr + RR * (kFW / 4);           // bits 32..39 of the local Q sums, one byte per column
+    uint32_t* pixr = fsm + wid * WARP_WORDS;
+    uint32_t* xch = pixr + RR * 32;
     const uint8_t* src = A.src + (size_t)page * A.src_page_stride;
-    uint8_t* dst = A.dst + (size_t)page * A.dst_page_stride;
     const int pad = A.pad, d = A.d;
+    // output rows [yo0, yo1) need the padded rows yo0+1 .. yo1-1+d; the first d-1 of them only warm the column sums up
+    const int yo0 = band * A.band_rows, yo1 = min(yo0 + A.band_rows, A.out_rows);
+    const int Ybeg = band == 0 ? 0 : yo0 + 1, Yend = yo1 - 1 + d;
+    const int own0 = band == 0 ? 0 : yo0 + d;           // padded rows this band accounts for in the block sums
 
     double imin = 0.0;
-    float iminf = 0.f;
-    if (METHOD == PRL_FENG) { imin = (double)A.imin[page]; iminf = (float)imin; }
+    float pbh = F.pb_hi, pbl = F.pb_lo;
+    if (METHOD == PRL_FENG) {
+        imin = (double)A.imin[page];
+        const float iminf = (float)imin, c3 = fmaf(F.c2, iminf, -iminf);
+        pbh += c3; pbl += c3;
+    }
     const float mu = F.mu0;
+    const float Hc = pbh + 0.5f + mu, Lc = pbl + 0.5f - mu;
 
     // lane's padded columns X = x0 + 4*lane + i  <->  source columns xs0 + i
     const int xs0 = x0 + 4 * lane - pad;
     const bool interior = (x0 >= pad) && (x0 + kFW - pad + 8 < A.cols);
     // raw fetch of one source row: two aligned words (interior) or four clamped bytes packed (edge strips);
-    // the funnel shift is applied only when the row is consumed, PF rows later, so the loads stay in flight
-    auto fetch = [&](int y, uint32_t& lo, uint32_t& hi) {
-        const uint8_t* row = src + (size_t)y * A.src_step;
+    // the funnel shift is applied when the row is consumed, one row later, so the loads stay in flight
+    auto fetch = [&](int Y, uint32_t& lo, uint32_t& hi, uint32_t& sh) {
+        const int sy = min(max(Y - pad, 0), A.rows - 1);
+        const uint8_t* row = src + (size_t)sy * A.src_step;
         if (interior) {
             const uint8_t* p = row + xs0;
+            sh = 8u * ((uint32_t)(uintptr_t)p & 3u);
             const uint32_t* a = reinterpret_cast<const uint32_t*>(p - ((uintptr_t)p & 3u));
             lo = __ldg(a); hi = __ldg(a + 1);
         } else {
             uint32_t w = 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) w |= (uint32_t)__ldg(row + min(max(xs0 + i, 0), A.cols - 1)) << (8 * i);
-            lo = w; hi = 0;
+            lo = w; hi = 0; sh = 0;
         }
     };
-    auto combine = [&](int y, uint32_t lo, uint32_t hi) -> uint32_t {
-        if (!interior) return lo;
-        const uint32_t sh = (uint32_t)(uintptr_t)(src + (size_t)y * A.src_step + xs0) & 3u;
-        return sh ? __funnelshift_r(lo, hi, 8 * sh) : lo;
-    };
 
-    // which of this lane's 4 outputs exist
     const int xo = x0 + 4 * lane;                       // output column of byte 0
     const bool lane_out = (4 * lane < A.ow) && (4 * lane + 3 + d < kFW) && xo < A.out_cols;
     const bool full4 = xo + 3 < A.out_cols;
+    uint32_t vmask = 0;                                 // valid output pixels of this lane
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (lane_out && xo + i < A.out_cols) vmask |= 1u << i;
+    const uint32_t ownmask = (4 * lane < A.ow) ? 0xffffffffu : 0u;  // ow is a multiple of 4
+    uint8_t* op = A.dst + (size_t)page * A.dst_page_stride + (size_t)yo0 * A.dst_step + xo;   // running output pointer
+    const bool st32 = full4 && ((((uintptr_t)op) | A.dst_step) & 3u) == 0;
+    uint32_t* bsum = A.blocksum + (((size_t)page * A.nblk) * A.ns + strip) * 2;
 
-    uint32_t accS[4] = {0, 0, 0, 0}, accQ[4] = {0, 0, 0, 0};
-    uint32_t qhi = 0;                                   // 4 packed 8-bit carry counters: high words of the local Q sums
-    int Y = 0;                                          // next padded row to emit
-    constexpr int PF = 4;                               // rows of prefetch distance
-    uint32_t plo[PF], phi[PF];
+    // zero the ring: rows above the band contribute nothing to the running sums
+    for (int i = lane; i < RR * 32; i += 32) pixr[i] = 0;
+    __syncwarp();
+
+    uint32_t vS[4] = {0, 0, 0, 0}, vQ[4] = {0, 0, 0, 0};   // column sums over the last d rows
+    uint32_t accS = 0, accQ = 0;                        // this lane's share of the current 32-row block sum
+    bool over = false;                                  // this lane saw the page's fixup list overflow
+    uint32_t nlo, nhi, nsh;
+    fetch(Ybeg, nlo, nhi, nsh);
+    for (int Y = Ybeg; Y <= Yend; ++Y) {
+        const uint32_t w = nsh ? __funnelshift_r(nlo, nhi, nsh) : nlo;
+        if (Y < Yend) fetch(Y + 1, nlo, nhi, nsh);
+        // block sums of the strip's own columns (only the brute-force fixup reads them)
+        if (Y >= own0) {
+            const uint32_t wm = w & ownmask;
+            accS = __dp4a(wm, 0x01010101u, accS);
+            accQ = __dp4a(wm, wm, accQ);
+            if ((Y & 31) == 31 || Y == Yend) {
+                const uint32_t ts = __reduce_add_sync(0xffffffffu, accS), tq = __reduce_add_sync(0xffffffffu, accQ);
+                if (lane == 0) {
+                    uint32_t* b = bsum + (size_t)(Y >> 5) * A.ns * 2;
+                    atomicAdd(b, ts); atomicAdd(b + 1, tq);
+                }
+                accS = accQ = 0;
+            }
+        }
+        // running column sums: + entering row Y, - row Y-d (this lane's own ring words: no sync needed)
+        const uint32_t wold = pixr[((Y - d) & (RR - 1)) * 32 + lane];
+        pixr[(Y & (RR - 1)) * 32 + lane] = w;
 #pragma unroll
-    for (int k = 0; k < PF; ++k) { plo[k] = phi[k] = 0; if (k < A.rows) fetch(k, plo[k], phi[k]); }
-    for (int y = 0; y < A.rows; ++y) {
-        const uint32_t w = combine(y, plo[0], phi[0]);
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t pn = byte_of(w, i), po = byte_of(wold, i);
+            const uint32_t df = pn - po;
+            vS[i] += df;
+            vQ[i] += df * (pn + po);
+        }
+        const int yo = Y - d;                           // output row whose window ends with this row
+        if (yo < yo0) continue;                         // (uniform across the warp)
+        if ((Y & 31) == 0) {
+            // the page already has more undecided pixels than the fixup takes: it will be redone, stop working on it
+            const uint32_t c = *reinterpret_cast<volatile uint32_t*>(A.scount + page);
+            if (__shfl_sync(0xffffffffu, c, 0) > A.cap) return;
+        }
+        // row prefix of V over the strip
+        const uint32_t a1 = vS[0] + vS[1], a2 = a1 + vS[2], a3 = a2 + vS[3];
+        const uint32_t b1 = vQ[0] + vQ[1], b2 = b1 + vQ[2], b3 = b2 + vQ[3];
+        const uint32_t es = warp_scan_incl(a3) - a3, eq = warp_scan_incl(b3) - b3;
+        const uint32_t pS[4] = {es + vS[0], es + a1, es + a2, es + a3};
+        const uint32_t pQ[4] = {eq + vQ[0], eq + b1, eq + b2, eq + b3};
+        uint32_t* xs = xch + (Y & 1) * (2 * kFW);
+        *reinterpret_cast<uint4*>(xs + 4 * lane) = make_uint4(pS[0], pS[1], pS[2], pS[3]);
+        *reinterpret_cast<uint4*>(xs + kFW + 4 * lane) = make_uint4(pQ[0], pQ[1], pQ[2], pQ[3]);
+        __syncwarp();                                   // prefix row (and every ring row up to Y) visible to all lanes
+        uint8_t* orow = op;
+        op += A.dst_step;
+        if (!lane_out) continue;
+        const uint2 s0 = *reinterpret_cast<const uint2*>(xs + 4 * lane + d), s1 = *reinterpret_cast<const uint2*>(xs + 4 * lane + d + 2);
+        const uint2 q0 = *reinterpret_cast<const uint2*>(xs + kFW + 4 * lane + d), q1 = *reinterpret_cast<const uint2*>(xs + kFW + 4 * lane + d + 2);
+        // exact window sums: columns x+1 .. x+d of the last d rows
+        const uint32_t sw[4] = {s0.x - pS[0], s0.y - pS[1], s1.x - pS[2], s1.y - pS[3]};
+        const uint32_t qw[4] = {q0.x - pQ[0], q0.y - pQ[1], q1.x - pQ[2], q1.y - pQ[3]};
+        // pixels p(yo, xo..xo+3): padded row yo+pad, strip byte offset 4*lane + pad
+        uint32_t p4;
+        {
+            const uint32_t* pr = pixr + ((yo + pad) & (RR - 1)) * 32;
+            const int bo = 4 * lane + pad;
+            p4 = pr[bo >> 2];
+            if (bo & 3) p4 = __funnelshift_r(p4, pr[(bo >> 2) + 1], 8 * (bo & 3));
+        }
+        // tier 0: variance-free bounds; sign bits instead of predicates
+        uint32_t o4 = 0, und = 0;
+        float m[4], pf[4];
 #pragma unroll
-        for (int k = 0; k + 1 < PF; ++k) { plo[k] = plo[k + 1]; phi[k] = phi[k + 1]; }
-        if (y + PF < A.rows) fetch(y + PF, plo[PF - 1], phi[PF - 1]);
-        // strip-local row prefix of this source row (u32)
-        const uint32_t a0 = w & 0xffu, a1 = __dp4a(w, 0x00000101u, 0u), a2 = __dp4a(w, 0x00010101u, 0u), a3 = __dp4a(w, 0x01010101u, 0u);
-        const uint32_t b0 = a0 * a0, b1 = __dp4a(w, w & 0x0000ffffu, 0u), b2 = __dp4a(w, w & 0x00ffffffu, 0u), b3 = __dp4a(w, w, 0u);
-        const uint32_t es = warp_scan_u32(a3, lane) - a3, eq = warp_scan_u32(b3, lane) - b3;
-        const uint32_t rs[4] = {es + a0, es + a1, es + a2, es + a3};
-        const uint32_t rq[4] = {eq + b0, eq + b1, eq + b2, eq + b3};
-        int rep = 1;                                    // row 0 / row rows-1 also feed the replicated border rows
-        if (y == 0) rep += pad;
-        if (y == A.rows - 1) rep += pad;
-        for (int k = 0; k < rep; ++k, ++Y) {
+        for (int i = 0; i < 4; ++i) {
+            m[i] = (float)sw[i] * F.kwf;
+            pf[i] = (float)byte_of(p4, i);
+            const int a = __float_as_int(fmaf(m[i], F.pa_hi, Hc - pf[i]));      // < 0  <=>  p - a_hi m > Hc : above every T
+            const int b = __float_as_int(fmaf(m[i], -F.pa_lo, pf[i] - Lc));     // < 0  <=>  p - a_lo m < Lc : below every T
+            const int c = (int)(qw[i] - F.qfloor_u);                            // < 0  <=>  window too dark for the bounds
+            o4 |= (uint32_t)((a & ~c) >> 31) & (0xffu << (8 * i));
+            und |= ((uint32_t)~((a | b) & ~c) >> 31) << i;
+        }
+        if (und) {
+            // p == 0 is never above its threshold
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (pf[i] == 0.f) und &= ~(1u << i);
+        }
+        und &= vmask;
+        if (METHOD != PRL_FENG && und) {
+            // tier 1: FP32 estimate from the exact N = w^2 Q - S^2 (all four pixels, branch-free)
+            uint32_t low = 0;                           // pixels whose variance is below the conditioning floor
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                accS[i] += rs[i];
-                const uint32_t old = accQ[i];
-                accQ[i] += rq[i];
-                qhi += (accQ[i] < old ? 1u : 0u) << (8 * i);
+                float fn;
+                if (N32) fn = (float)(F.w2 * qw[i] - sw[i] * sw[i]);
+                else fn = (float)((unsigned long long)F.w2 * qw[i] - (unsigned long long)sw[i] * sw[i]);
+                const float s = (fn * rsqrtf(fn)) * F.inv_w2f;          // fn == 0 gives NaN -> stays undecided
+                float T;
+                if (METHOD == PRL_SAUVOLA) T = m[i] * fmaf(s, F.c1, F.c2);
+                else if (METHOD == PRL_NIBLACK) T = fmaf(F.c0, s, m[i]);
+                else { const float r2 = fmaf(m[i], m[i], s * s); T = fmaf(F.c0, r2 * rsqrtf(r2), m[i]); }
+                const float g = (pf[i] - 0.5f) - fmaxf(T, 0.0f);
+                const bool ok = fn >= F.n_floor;
+                const bool d255 = ok && g > mu, d0 = ok && g < -mu;
+                if ((und >> i) & 1u) {
+                    if (d255) o4 |= 0xffu << (8 * i);
+                    if (d255 || d0) und &= ~(1u << i);
+                    if (!ok) low |= 1u << i;
+                }
             }
-            const int slot = Y & (RR - 1);
-            __syncwarp();                               // every lane is done reading the slot this row overwrites
-            *reinterpret_cast<uint4*>(ringS + slot * kFW + 4 * lane) = make_uint4(accS[0], accS[1], accS[2], accS[3]);
-            *reinterpret_cast<uint4*>(ringQ + slot * kFW + 4 * lane) = make_uint4(accQ[0], accQ[1], accQ[2], accQ[3]);
-            pixr[slot * (kFW / 4) + lane] = w;
-            ringH[slot * (kFW / 4) + lane] = qhi;
-            __syncwarp();
-            const int yo = Y - d;                       // output row whose bottom taps are this row
-            if (yo < 0 || yo >= A.out_rows || !lane_out) continue;
-            const int top = yo & (RR - 1);
-            const uint32_t* tS = ringS + top * kFW + 4 * lane;
-            const uint32_t* tQ = ringQ + top * kFW + 4 * lane;
-            const uint32_t* bS = ringS + slot * kFW + 4 * lane;
-            const uint32_t* bQ = ringQ + slot * kFW + 4 * lane;
-            const uint4 sa = *reinterpret_cast<const uint4*>(tS), qa = *reinterpret_cast<const uint4*>(tQ);
-            const uint2 sb0 = *reinterpret_cast<const uint2*>(tS + d), sb1 = *reinterpret_cast<const uint2*>(tS + d + 2);
-            const uint2 qb0 = *reinterpret_cast<const uint2*>(tQ + d), qb1 = *reinterpret_cast<const uint2*>(tQ + d + 2);
-            const uint2 sd0 = *reinterpret_cast<const uint2*>(bS + d), sd1 = *reinterpret_cast<const uint2*>(bS + d + 2);
-            const uint2 qd0 = *reinterpret_cast<const uint2*>(bQ + d), qd1 = *reinterpret_cast<const uint2*>(bQ + d + 2);
-            const uint32_t sA[4] = {sa.x, sa.y, sa.z, sa.w}, qA[4] = {qa.x, qa.y, qa.z, qa.w};
-            const uint32_t sB[4] = {sb0.x, sb0.y, sb1.x, sb1.y}, qB[4] = {qb0.x, qb0.y, qb1.x, qb1.y};
-            const uint32_t sD[4] = {sd0.x, sd0.y, sd1.x, sd1.y}, qD[4] = {qd0.x, qd0.y, qd1.x, qd1.y};
-            // pixels p(yo, xo..xo+3): padded row yo+pad, strip byte offset 4*lane + pad
-            uint32_t p4;
-            {
-                const uint32_t* pr = pixr + ((yo + pad) & (RR - 1)) * (kFW / 4);
-                const int bo = 4 * lane + pad;
-                p4 = pr[bo >> 2];
-                if (bo & 3) p4 = __funnelshift_r(p4, pr[(bo >> 2) + 1], 8 * (bo & 3));
+            low &= und;
+            if (low) {
+                // flat windows (s* < s_floor): the reference's s is NaN (-> T8 = 0 -> p > 0) or anywhere in [0, 0.28];
+                // decided only if every one of those outcomes gives 255
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (!((low >> i) & 1u)) continue;
+                    float Ta, Tb;
+                    const float sb = 0.28f;
+                    if (METHOD == PRL_SAUVOLA) { Ta = m[i] * F.c2; Tb = m[i] * fmaf(sb, F.c1, F.c2); }
+                    else if (METHOD == PRL_NIBLACK) { Ta = m[i]; Tb = fmaf(F.c0, sb, m[i]); }
+                    else { Ta = fmaf(F.c0, m[i], m[i]); Tb = fmaf(F.c0, sqrtf(fmaf(m[i], m[i], sb * sb)), m[i]); }
+                    const float Tmax = fmaxf(fmaxf(Ta, Tb), 0.0f);
+                    if ((pf[i] - 0.5f) - Tmax > mu) { o4 |= 0xffu << (8 * i); und &= ~(1u << i); }
+                }
             }
-            uint32_t o4 = 0;
+        }
+        if (und) {
+            // tier 2 (FP64 estimate), then the fixup list
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const uint32_t sw = (sD[i] - accS[i]) - (sB[i] - sA[i]);
-                const uint32_t qw = (qD[i] - accQ[i]) - (qB[i] - qA[i]);
-                const uint32_t p = (p4 >> (8 * i)) & 0xffu;
-                int o;
-                if (!fast_decide<METHOD, true>(sw, qw, p, F, iminf, 0.f, mu, o)) {
-                    o = 0;
-                    if (xo + i < A.out_cols) {
-                        // true int64 taps = strip-local + L.  The local S fits 32 bits; the local Q is 40 bits: low
-                        // word from the Q ring, bits 32..39 from the high-byte ring.
-                        const longlong2 Lt = __ldg(A.L + ((size_t)page * A.Hp + yo) * A.ns + strip);
-                        const longlong2 Lb = __ldg(A.L + ((size_t)page * A.Hp + Y) * A.ns + strip);
-                        const uint8_t* hT = reinterpret_cast<const uint8_t*>(ringH + top * (kFW / 4));
-                        const uint8_t* hB = reinterpret_cast<const uint8_t*>(ringH + slot * (kFW / 4));
-                        const int cl = 4 * lane + i, cr = cl + d;
-                        const long long qaa = (long long)(((unsigned long long)hT[cl] << 32) | qA[i]);
-                        const long long qbb = (long long)(((unsigned long long)hT[cr] << 32) | qB[i]);
-                        const long long qc = (long long)(((unsigned long long)hB[cl] << 32) | accQ[i]);
-                        const long long qdd = (long long)(((unsigned long long)hB[cr] << 32) | qD[i]);
-                        const int t8 = exact_t8_from_taps<METHOD>((long long)sA[i] + Lt.x, (long long)sB[i] + Lt.x,
-                                                                  (long long)accS[i] + Lb.x, (long long)sD[i] + Lb.x,
-                                                                  qaa + Lt.y, qbb + Lt.y, qc + Lb.y, qdd + Lb.y,
-                                                                  A.kw, A.p0, A.p1, A.p2, imin, 0.0);
-                        o = (int)p > t8 ? 255 : 0;
+                if (!((und >> i) & 1u)) continue;
+                const int r = A.no_tier2 ? -1 : tier2_decide<METHOD>(sw[i], qw[i], byte_of(p4, i), F.kw_d, F.c0_d, F.c1_d, F.c2_d,
+                                                                       F.t2_a, F.t2_b, F.t2_vmin, F.w2, imin);
+                if (r == 255) o4 |= 0xffu << (8 * i);
+                else if (r < 0) {
+                    o4 = (o4 & ~(0xffu << (8 * i))) | ((uint32_t)kSentinel << (8 * i));
+                    if (!over) {
+                        const uint32_t slot = atomicAdd(A.scount + page, 1u);
+                        if (slot < A.cap)
+                            A.slist[(size_t)page * kPageCap + slot] = ((uint32_t)yo << 16) | (uint32_t)(xo + i);
+                        else over = true;
                     }
                 }
-                o4 |= (uint32_t)o << (8 * i);
             }
-            uint8_t* orow = dst + (size_t)yo * A.dst_step + xo;
-            const unsigned int al = (unsigned int)(uintptr_t)orow & 3u;
-            if (!full4) {
-                for (int i = 0; i < 4; ++i) if (xo + i < A.out_cols) orow[i] = (uint8_t)(o4 >> (8 * i));
-            } else if (al == 0) {
-                *reinterpret_cast<unsigned int*>(orow) = o4;
-            } else if (al == 2) {
-                *reinterpret_cast<unsigned short*>(orow) = (unsigned short)o4;
-                *reinterpret_cast<unsigned short*>(orow + 2) = (unsigned short)(o4 >> 16);
-            } else {
-                orow[0] = (uint8_t)o4;
-                *reinterpret_cast<unsigned short*>(orow + 1) = (unsigned short)(o4 >> 8);
-                orow[3] = (uint8_t)(o4 >> 24);
+        }
+        if (st32) {
+            *reinterpret_cast<uint32_t*>(orow) = o4;
+        } else {
+            for (int i = 0; i < 4; ++i) if ((vmask >> i) & 1u) orow[i] = (uint8_t)(o4 >> (8 * i));
+        }
+    }
+}
+
+// ---- tier 3: finish the listed pixels with the reference's FP64 arithmetic on the true int64 taps.
+// For every listed pixel a whole warp rebuilds the four taps  S[Yt][X] = sum_{Y' <= Yt, X' <= X} P[Y'][X']  from
+//   (1) the block sums of whole 32-row blocks x whole strips to the left/above  (written by the fused kernel),
+//   (2) the rows of the last, partial block, columns left of the strip           (brute force, lanes over columns),
+//   (3) every row up to Yt, columns from the strip start to X                    (brute force, lanes over rows),
+// and lane 0 evaluates exact_t8_from_taps.  Pages whose list overflowed are left to the planes path.
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(128)
+fixup_kernel(const FusedArgs A)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int page = 0; page < A.n_pages; ++page) {
+        const uint32_t cnt = A.scount[page];
+        if (cnt == 0 || cnt > A.cap) continue;
+        const uint8_t* img = A.src + (size_t)page * A.src_page_stride;
+        const uint32_t* bs = A.blocksum + (size_t)page * A.nblk * A.ns * 2;
+        const double imin = METHOD == PRL_FENG ? (double)A.imin[page] : 0.0;
+        for (uint32_t e = warp; e < cnt; e += nwarps) {
+            const uint32_t ent = A.slist[(size_t)page * kPageCap + e];
+            const int y = (int)(ent >> 16), x = (int)(ent & 0xffffu);
+            const int b = x / A.ow, xs = b * A.ow;                    // strip whose start is <= x
+            const int Yb = y + A.d;                                   // bottom tap row
+            const int blk_t = (y + 1) >> 5, blk_b = (Yb + 1) >> 5;    // whole blocks at or above the tap rows
+            // (1) + (2): everything left of the strip start
+            unsigned long long lts = 0, ltq = 0, lbs = 0, lbq = 0;
+            for (int i = lane; i < blk_b * b; i += 32) {
+                const int bk = i / b, bb = i - bk * b;
+                const uint32_t s = bs[((size_t)bk * A.ns + bb) * 2], q = bs[((size_t)bk * A.ns + bb) * 2 + 1];
+                lbs += s; lbq += q;
+                if (bk < blk_t) { lts += s; ltq += q; }
+            }
+            for (int Yp = 32 * blk_t; Yp <= Yb; ++Yp) {
+                if (Yp > y && Yp < 32 * blk_b) { Yp = 32 * blk_b - 1; continue; }      // rows already inside whole blocks of the bottom tap
+                const uint8_t* row = img + (size_t)min(max(Yp - A.pad, 0), A.rows - 1) * A.src_step;
+                unsigned long long s = 0, q = 0;
+                for (int X = lane; X < xs; X += 32) { const unsigned long long p = row[min(max(X - A.pad, 0), A.cols - 1)]; s += p; q += p * p; }
+                if (Yp <= y && Yp >= 32 * blk_t) { lts += s; ltq += q; }
+                if (Yp >= 32 * blk_b) { lbs += s; lbq += q; }
+            }
+            // (3): from the strip start to the tap columns, every row
+            unsigned long long ta = 0, tb = 0, tc = 0, td = 0, ua = 0, ub = 0, uc = 0, ud = 0;
+            for (int Yp = lane; Yp <= Yb; Yp += 32) {
+                const uint8_t* row = img + (size_t)min(max(Yp - A.pad, 0), A.rows - 1) * A.src_step;
+                unsigned long long r1s = 0, r1q = 0;
+                for (int X = xs; X <= x; ++X) { const unsigned long long p = row[min(max(X - A.pad, 0), A.cols - 1)]; r1s += p; r1q += p * p; }
+                unsigned long long r2s = r1s, r2q = r1q;
+                for (int X = x + 1; X <= x + A.d; ++X) { const unsigned long long p = row[min(max(X - A.pad, 0), A.cols - 1)]; r2s += p; r2q += p * p; }
+                if (Yp <= y) { ta += r1s; tb += r2s; ua += r1q; ub += r2q; }
+                tc += r1s; td += r2s; uc += r1q; ud += r2q;
+            }
+            lts = warp_sum_u64(lts); ltq = warp_sum_u64(ltq); lbs = warp_sum_u64(lbs); lbq = warp_sum_u64(lbq);
+            ta = warp_sum_u64(ta) + lts; tb = warp_sum_u64(tb) + lts; tc = warp_sum_u64(tc) + lbs; td = warp_sum_u64(td) + lbs;
+            ua = warp_sum_u64(ua) + ltq; ub = warp_sum_u64(ub) + ltq; uc = warp_sum_u64(uc) + lbq; ud = warp_sum_u64(ud) + lbq;
+            if (lane == 0) {
+                const int t8 = exact_t8_from_taps<METHOD>((long long)ta, (long long)tb, (long long)tc, (long long)td,
+                                                          (long long)ua, (long long)ub, (long long)uc, (long long)ud,
+                                                          A.kw, A.p0, A.p1, A.p2, imin, 0.0);
+                const int p = img[(size_t)y * A.src_step + x];
+                A.dst[(size_t)page * A.dst_page_stride + (size_t)y * A.dst_step + x] = p > t8 ? 255 : 0;
             }
         }
     }
 }
 
-template <int METHOD, int RR, int WARPS>
-int launch_fused_t(prl_cuda_ctx* ctx, const FusedArgs& A, const FastArgs& F)
+template <int METHOD, int RR>
+void launch_fused_t(prl_cuda_ctx* ctx, const FusedArgs& A, const FastArgs& F)
 {
-    const size_t smem = (size_t)WARPS * (RR * kFW * 2 + 2 * RR * (kFW / 4) + 16) * sizeof(uint32_t);
-    auto kfn = local_fused_kernel<METHOD, RR, WARPS>;
-    static bool configured = false;
-    if (!configured) {
-        PRL_CUDA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    const int warps = A.ns * A.n_pages;
-    kfn<<<(warps + WARPS - 1) / WARPS, WARPS * 32, smem, ctx->stream>>>(A, F);
-    return PRL_OK;
+    const int warps = A.ns * A.nb * A.n_pages;
+    if (F.n32) local_fused_kernel<METHOD, RR, true><<<(warps + 3) / 4, 128, 0, ctx->stream>>>(A, F);
+    else local_fused_kernel<METHOD, RR, false><<<(warps + 3) / 4, 128, 0, ctx->stream>>>(A, F);
 }
 
 template <int METHOD>
-int launch_fused_m(prl_cuda_ctx* ctx, const FusedArgs& A, const FastArgs& F)
+void launch_fused_m(prl_cuda_ctx* ctx, const FusedArgs& A, const FastArgs& F)
 {
-    if (A.d + 1 <= 16) return launch_fused_t<METHOD, 16, 2>(ctx, A, F);
-    return launch_fused_t<METHOD, 32, 2>(ctx, A, F);
+    if (A.d + 1 <= 16) launch_fused_t<METHOD, 16>(ctx, A, F);
+    else launch_fused_t<METHOD, 32>(ctx, A, F);
 }
 
 }  // namespace
@@ -288,9 +401,7 @@ bool prl_fused_eligible(const prl_cuda_ctx* ctx, int method, int n_pages, const 
     if (!ctx->use_fused || ctx->force_exact) return false;   // opt-in: see DESIGN.md section 4 (F2)
     if (method == PRL_WOLFJOLION) return false;
     if ((g.d & 1) || g.d + 1 > 32 || g.d < 2) return false;
-    if (g.Hp > 100000) return false;                       // 8-bit carry counters of the local Q high words
-    const int ow = (kFW - g.d) & ~3;
-    const int ns = (g.out_cols + ow - 1) / ow;
+    if (g.rows > 65535 || g.cols > 65535) return false;   // fixup list packs (y, x) into 32 bits
     (void)n_pages;
     FastArgs F;
     return fast_margins(method, params, g, &F);
@@ -298,7 +409,7 @@ bool prl_fused_eligible(const prl_cuda_ctx* ctx, int method, int n_pages, const 
 
 int prl_k_fused(prl_cuda_ctx* ctx, int method, const uint8_t* d_src, int n_pages, const prl_geom& g, size_t src_step,
                 size_t src_page_stride, const double* params, uint32_t* d_imin, uint8_t* d_dst, size_t dst_step,
-                size_t dst_page_stride)
+                size_t dst_page_stride, std::vector<int>* redo_pages)
 {
     FastArgs F;
     if (!fast_margins(method, params, g, &F)) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "fused path not eligible");
@@ -315,37 +426,64 @@ int prl_k_fused(prl_cuda_ctx* ctx, int method, const uint8_t* d_src, int n_pages
     if (method == PRL_SAUVOLA) { A.p1 = params[0] * (1.0 / 128.0); A.p2 = 1.0 - params[0]; }
     if (method == PRL_FENG) { A.p1 = 1.0 + (1.0 - params[0]); A.p2 = params[2]; }
     A.imin = d_imin;
+    A.cap = (uint32_t)std::min(std::max(ctx->fused_page_cap, 0), kPageCap);
 
-    // scratch: rowpre (u32 pairs) in ctx->colsum, L (int64 pairs) in ctx->carry
-    const size_t rowpre_bytes = (size_t)n_pages * g.rows * A.ns * sizeof(uint2);
-    const size_t L_bytes = (size_t)n_pages * g.Hp * A.ns * sizeof(longlong2);
-    int rc = prl_ensure(ctx, &ctx->colsum, &ctx->colsum_bytes, rowpre_bytes); if (rc) return rc;
-    rc = prl_ensure(ctx, &ctx->carry, &ctx->carry_bytes, L_bytes); if (rc) return rc;
-    A.L = (const longlong2*)ctx->carry;
-    if (n_pages > 65535) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "more than 65535 pages per launch");
-    PRL_CUDA_TRY(ctx, cudaMemsetAsync(d_imin, 0xff, sizeof(uint32_t) * n_pages, ctx->stream));
+    // row bands: enough warps for ~8 waves of 20 warps per SM, bands a multiple of 32 rows and at least 256
     {
-        prl_launch_scope ls(ctx, FAM_FUSED_PRE);
-        strip_rowsum_kernel<<<dim3((g.rows + 7) / 8, n_pages), 256, 0, ctx->stream>>>(
-            d_src, src_step, src_page_stride, g.rows, g.cols, g.h, A.ow, A.ns, (uint2*)ctx->colsum, d_imin);
+        const long long want = 8LL * ctx->num_sms * 20;
+        int nb = (int)std::min<long long>((want + (long long)A.ns * n_pages - 1) / ((long long)A.ns * n_pages), (g.out_rows + 255) / 256);
+        nb = std::max(nb, 1);
+        A.band_rows = (((g.out_rows + nb - 1) / nb) + 31) & ~31;
+        A.nb = (g.out_rows + A.band_rows - 1) / A.band_rows;
     }
-    {
+    A.nblk = (g.Hp + 31) / 32;
+    A.no_tier2 = ctx->fused_no_tier2 ? 1 : 0;
+    // workspace: [scount: n_pages u32][slist: n_pages * kPageCap u32][blocksum]  (counters and block sums start at zero)
+    const size_t cnt_bytes = ((size_t)n_pages * 4 + 255) & ~(size_t)255;
+    const size_t list_bytes = (size_t)n_pages * kPageCap * 4;
+    const size_t bsum_bytes = (size_t)n_pages * A.nblk * A.ns * 2 * sizeof(uint32_t);
+    int rc = prl_ensure(ctx, &ctx->fused_ws, &ctx->fused_ws_bytes, cnt_bytes + list_bytes + bsum_bytes); if (rc) return rc;
+    A.scount = (uint32_t*)ctx->fused_ws;
+    A.slist = (uint32_t*)((uint8_t*)ctx->fused_ws + cnt_bytes);
+    A.blocksum = (uint32_t*)((uint8_t*)ctx->fused_ws + cnt_bytes + list_bytes);
+    PRL_CUDA_TRY(ctx, cudaMemsetAsync(A.scount, 0, cnt_bytes, ctx->stream));
+    PRL_CUDA_TRY(ctx, cudaMemsetAsync(A.blocksum, 0, bsum_bytes, ctx->stream));
+    if (method == PRL_FENG) {
+        PRL_CUDA_TRY(ctx, cudaMemsetAsync(d_imin, 0xff, sizeof(uint32_t) * n_pages, ctx->stream));
         prl_launch_scope ls(ctx, FAM_FUSED_PRE);
-        const int total = A.ns * n_pages;
-        strip_colscan_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>((const uint2*)ctx->colsum, (longlong2*)ctx->carry,
-                                                                         g.rows, g.h, g.Hp, A.ns, n_pages);
+        page_min_kernel<<<dim3(64, n_pages), 256, 0, ctx->stream>>>(d_src, src_step, src_page_stride, g.rows, g.cols, d_imin);
     }
     {
         prl_launch_scope ls(ctx, FAM_FUSED);
         switch (method) {
-        case PRL_SAUVOLA: rc = launch_fused_m<PRL_SAUVOLA>(ctx, A, F); break;
-        case PRL_NIBLACK: rc = launch_fused_m<PRL_NIBLACK>(ctx, A, F); break;
-        case PRL_NICK:    rc = launch_fused_m<PRL_NICK>(ctx, A, F); break;
-        case PRL_FENG:    rc = launch_fused_m<PRL_FENG>(ctx, A, F); break;
+        case PRL_SAUVOLA: launch_fused_m<PRL_SAUVOLA>(ctx, A, F); break;
+        case PRL_NIBLACK: launch_fused_m<PRL_NIBLACK>(ctx, A, F); break;
+        case PRL_NICK:    launch_fused_m<PRL_NICK>(ctx, A, F); break;
+        case PRL_FENG:    launch_fused_m<PRL_FENG>(ctx, A, F); break;
         default: return prl_set_err(ctx, PRL_E_INVALID, "method not served by the fused path");
         }
-        if (rc) return rc;
+    }
+    {
+        prl_launch_scope ls(ctx, FAM_FUSED_FIX);
+        const int grid = ctx->num_sms * 4;
+        switch (method) {
+        case PRL_SAUVOLA: fixup_kernel<PRL_SAUVOLA><<<grid, 128, 0, ctx->stream>>>(A); break;
+        case PRL_NIBLACK: fixup_kernel<PRL_NIBLACK><<<grid, 128, 0, ctx->stream>>>(A); break;
+        case PRL_NICK:    fixup_kernel<PRL_NICK><<<grid, 128, 0, ctx->stream>>>(A); break;
+        default:          fixup_kernel<PRL_FENG><<<grid, 128, 0, ctx->stream>>>(A); break;
+        }
     }
     PRL_CUDA_TRY(ctx, cudaGetLastError());
+    // read the per-page counters back: a page whose list overflowed is redone by the caller (two-kernel path)
+    if (ctx->h_cnt_bytes < (size_t)n_pages * 4) {
+        if (ctx->h_cnt) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->h_cnt); ctx->h_cnt = nullptr; ctx->h_cnt_bytes = 0; }
+        const size_t need = std::max<size_t>((size_t)n_pages * 4, 4096);
+        PRL_CUDA_TRY(ctx, cudaMallocHost((void**)&ctx->h_cnt, need));
+        ctx->h_cnt_bytes = need;
+    }
+    PRL_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_cnt, A.scount, (size_t)n_pages * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PRL_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int p = 0; p < n_pages; ++p)
+        if (ctx->h_cnt[p] > A.cap) { redo_pages->push_back(p); ++ctx->fused_redo_pages; }
     return PRL_OK;
 }

@@ -12,6 +12,8 @@ cols = int(sys.argv[6]) if len(sys.argv) > 6 else 2480
 params = {0: (0.2,), 1: (-0.2,), 2: (0.5,), 3: (-0.1,), 4: (0.75, 0.2, 0.03, 2.0)}[method]
 ctx = prlib_b200.Context(0)
 ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+if os.environ.get("PRL_FUSED"):
+    ctx.set_option("enable_fused", 1)
 rc, orow, ocol = ctx.output_shape(method, rows, cols, window)
 si = (cols + 15) // 16 * 16; so = (ocol + 15) // 16 * 16
 pages = torch.empty((pages_n, rows, si), dtype=torch.uint8, device="cuda")

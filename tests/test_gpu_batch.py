@@ -106,6 +106,34 @@ def test_fused_small_window_path_equals_planes_path_and_oracle(ctx, method, wind
     ctx.set_stream(None)
 
 
+def test_fused_path_hands_pages_back_when_its_fixup_list_overflows(ctx):
+    """Without its FP64 estimate tier the fused path lists every pixel its FP32 estimate cannot settle: with
+    fused_page_cap = 0 each such page is redone by kernel 1 + kernel 2, with 128 the brute-force fixup finishes the
+    pages that have few of them; the masks stay those of the oracle either way."""
+    n, rows, cols = 140, 300, 1000
+    rng = np.random.default_rng(5)
+    host = rng.integers(0, 256, (n, rows, cols), dtype=np.uint8)
+    host[::2] //= 16                                    # dark pages: many thresholds next to a rounding boundary
+    buf = torch.from_numpy(host).to("cuda:0")
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    rc, orow, ocol = ctx.output_shape(1, rows, cols, 15)
+    outs = []
+    for cap in (0, 128):
+        out = torch.zeros((n, orow, ocol), dtype=torch.uint8, device="cuda:0")
+        ctx.set_option("enable_fused", 1); ctx.set_option("fused_page_cap", cap); ctx.set_option("fused_no_tier2", 1)
+        before = ctx.fused_redo_count()
+        ctx.binarize_local_batch_dev(1, buf.data_ptr(), n, rows, cols, cols, rows * cols, 15, (-0.2,), 0, out.data_ptr(), ocol, orow * ocol)
+        torch.cuda.synchronize()
+        redone = ctx.fused_redo_count() - before
+        assert redone > 0 if cap == 0 else redone < n       # cap 128: some pages are finished by the fixup kernel
+        outs.append(out.cpu().numpy())
+    ctx.set_option("enable_fused", 0); ctx.set_option("fused_page_cap", 128); ctx.set_option("fused_no_tier2", 0)
+    assert np.array_equal(outs[0], outs[1])
+    for p in (0, 1, 2, 3, 138, 139):
+        assert np.array_equal(outs[0][p], CO.binarize_local(host[p], 1, 15, (-0.2,), 0)), p
+    ctx.set_stream(None)
+
+
 def test_fused_path_with_morphology_tail(ctx):
     n, rows, cols = 140, 300, 1000
     buf, step = _dev_pages(ctx, n, rows, cols, first=20)
