@@ -205,6 +205,7 @@ extern "C" int prl_cuda_set_option(prl_cuda_ctx* c, const char* name, long long 
     if (strcmp(name, "exact_threshold") == 0) c->force_exact = value != 0;
     else if (strcmp(name, "disable_tma") == 0) c->no_tma = value != 0;
     else if (strcmp(name, "enable_fused") == 0) c->use_fused = value != 0;
+    else if (strcmp(name, "morph_bytes") == 0) c->morph_bytes = value != 0;
     else if (strcmp(name, "fused_no_tier2") == 0) c->fused_no_tier2 = value != 0;
     else if (strcmp(name, "fused_page_cap") == 0) c->fused_page_cap = (int)std::min<long long>(std::max<long long>(value, 0), 128);
     else return prl_set_err(c, PRL_E_INVALID, "unknown option");
@@ -304,7 +305,7 @@ static int planes_pages(prl_cuda_ctx* c, int method, int mode, const uint8_t* d_
         if (rc) return rc;
         if (with_morph) {
             rc = prl_k_morph(c, c->d_tmp, dst, np, g.out_rows, g.out_cols, tmp_step, (size_t)g.out_rows * tmp_step,
-                             dst_step, dst_page_stride, morph_iters);
+                             dst_step, dst_page_stride, morph_iters, true);
             if (rc) return rc;
         }
     }
@@ -352,7 +353,7 @@ static int local_batch_dev(prl_cuda_ctx* c, int method, int mode, const uint8_t*
         }
         if (with_morph)
             rc = prl_k_morph(c, c->d_tmp, d_dst, n_pages, g.out_rows, g.out_cols, t_step, t_page, dst_step, dst_page_stride,
-                             morph_iters);
+                             morph_iters, true);
         return rc;
     }
     return planes_pages(c, method, mode, d_src, n_pages, g, src_step, src_page_stride, params, morph_iters, d_dst, dst_step,
@@ -547,7 +548,13 @@ extern "C" int prl_cuda_morph(prl_cuda_ctx* c, const uint8_t* src, int rows, int
     size_t in_step;
     int rc = stage_in(c, src, rows, cols, step, &in_step); if (rc) return rc;
     rc = prl_ensure(c, (void**)&c->d_tmp, &c->d_tmp_bytes, in_step * rows); if (rc) return rc;
-    rc = prl_k_morph(c, c->d_in, c->d_tmp, 1, rows, cols, in_step, in_step * rows, in_step, in_step * rows, morph_iters);
+    // a mask (only 0 and 255, what the reference's tail runs on) takes the bit-packed kernels; anything else the byte kernels
+    rc = prl_ensure(c, &c->d_misc, &c->d_misc_bytes, 256); if (rc) return rc;
+    rc = prl_k_not_binary(c, c->d_in, rows, cols, in_step, (int*)c->d_misc); if (rc) return rc;
+    int not_binary = 1;
+    PRL_CUDA_TRY(c, cudaMemcpyAsync(&not_binary, c->d_misc, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    rc = prl_k_morph(c, c->d_in, c->d_tmp, 1, rows, cols, in_step, in_step * rows, in_step, in_step * rows, morph_iters, !not_binary);
     if (rc) return rc;
     PRL_CUDA_TRY(c, cudaMemcpy2DAsync(dst, dst_step, c->d_tmp, in_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
     PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));

@@ -47,6 +47,7 @@ struct prl_cuda_ctx {
 
     bool force_exact = false;   // validation: kernel 2 runs the literal FP64 path for every pixel
     bool no_tma = false;        // validation: kernel 1 uses the generic (non-TMA) kernel
+    bool morph_bytes = false;   // validation: the morphology tail runs the byte kernels even on binary masks
     bool use_fused = false;     // opt-in: fused small-window strip kernel (integral planes never reach HBM)
 
     // instrumentation
@@ -103,7 +104,8 @@ int prl_k_fused(prl_cuda_ctx* ctx, int method, const uint8_t* d_src, int n_pages
                 size_t src_page_stride, const double* params, uint32_t* d_imin, uint8_t* d_dst, size_t dst_step,
                 size_t dst_page_stride, std::vector<int>* redo_pages);
 int prl_k_morph(prl_cuda_ctx* ctx, uint8_t* d_in, uint8_t* d_out, int n_pages, int rows, int cols, size_t in_step,
-                size_t in_page_stride, size_t out_step, size_t out_page_stride, int iters);
+                size_t in_page_stride, size_t out_step, size_t out_page_stride, int iters, bool binary);
+int prl_k_not_binary(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, int* d_flag);
 int prl_k_bgr2gray(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, int channels,
                    uint8_t* d_dst, size_t dst_step);
 int prl_k_synth(prl_cuda_ctx* ctx, uint8_t* d_dst, int n_pages, int rows, int cols, size_t step,

@@ -156,6 +156,25 @@ def test_morph_tail(ctx, noise_page, iters):
     assert np.array_equal(ctx.morph(raw, iters), O.morph(raw, iters))
 
 
+@pytest.mark.parametrize("shape", [(497, 625), (70, 2000), (300, 961), (33, 31), (5, 1000)])
+def test_morph_bit_kernels_equal_byte_kernels_and_oracle(ctx, shape):
+    """Bit-packed closing/opening (binary masks) vs the byte kernels vs cv2 dilate/erode, strip edges and n up to 15."""
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    mask = np.where(rng.random(shape) < 0.35, 0, 255).astype(np.uint8)
+    mask[:, : shape[1] // 3][rng.random((shape[0], shape[1] // 3)) < 0.5] = 255
+    for iters in (1, 2, 3, 4, 8, 15, -1, -2, -5, -15):
+        want = O.morph(mask, iters)
+        got = ctx.morph(mask, iters)
+        assert np.array_equal(got, want), iters
+        ctx.set_option("morph_bytes", 1)
+        try:
+            assert np.array_equal(ctx.morph(mask, iters), want), iters
+        finally:
+            ctx.set_option("morph_bytes", 0)
+    gray = rng.integers(0, 256, shape, dtype=np.uint8)              # not a mask: byte kernels, still cv2's result
+    assert np.array_equal(ctx.morph(gray, 2), O.morph(gray, 2))
+
+
 def test_header_defaults_end_to_end(ctx, golden):
     a4 = CO.synth_page(0)
     got = prlib_b200.binarizeSauvola(a4)            # w=101, k=0.01, morph=2 (binarizeSauvola.h:45-47)
