@@ -167,6 +167,18 @@ int prl_cuda_binarize_batch(const int* devices, int n_dev, int method, const uin
                             int rows, int cols, int window, const double* params, int morph_iters,
                             uint8_t* masks);
 
+/* ---- 1 bit per pixel ---------------------------------------------
+ * The masks in Leptonica's PIX layout, the reference's second image container (src/formatConvert.cpp:39-69
+ * writes PIX words with SET_DATA_BIT): rows of wpl = (cols + 31) / 32 32-bit words, pixel x of a row in word
+ * x >> 5 at bit 31 - (x & 31), 1 = black (mask byte 0), padding bits 0.  An eighth of the bytes over PCIe.
+ * prl_cuda_pack_mask_dev packs masks resident in HBM (d_bits: n_pages * rows * wpl words, dense);
+ * prl_cuda_binarize_batch_packed is prl_cuda_binarize_batch with `bits` receiving n_pages * out_rows * wpl words. */
+int prl_cuda_pack_mask_dev(prl_cuda_ctx* ctx, const uint8_t* d_mask, int n_pages, int rows, int cols, size_t step,
+                           size_t page_stride, uint32_t* d_bits);
+int prl_cuda_binarize_batch_packed(const int* devices, int n_dev, int method, const uint8_t* pages, int n_pages,
+                                   int rows, int cols, int window, const double* params, int morph_iters,
+                                   uint32_t* bits);
+
 /* ---- instrumentation ---------------------------------------------------------------------
  * With timing enabled every kernel launch is bracketed by CUDA events on the launching stream.
  * prl_cuda_timing_get sums them per kernel family ("integral", "threshold", "smax", "morph",

@@ -53,6 +53,9 @@ SIGNATURES = {
     "prl_cuda_synth_pages_dev": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_uint32, C.c_uint32]),
     "prl_cuda_binarize_batch": (C.c_int, [_intp, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, C.c_int,
                                           C.c_void_p]),
+    "prl_cuda_binarize_batch_packed": (C.c_int, [_intp, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, C.c_int,
+                                                 C.c_void_p]),
+    "prl_cuda_pack_mask_dev": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p]),
     "prl_cuda_timing_enable": (C.c_int, [_ctx, C.c_int]),
     "prl_cuda_timing_reset": (C.c_int, [_ctx]),
     "prl_cuda_timing_get": (C.c_int, [_ctx, C.c_char_p, _f64p, C.POINTER(C.c_longlong)]),

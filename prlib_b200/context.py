@@ -10,7 +10,7 @@ from . import capi
 from .capi import PrlCudaError
 
 _FAMILIES = ("integral", "threshold", "smax", "morph", "otsu_hist", "otsu_search", "otsu_apply", "otsu_tiles",
-             "synth", "bgr2gray", "band_carry", "fused", "fused_pre", "fused_fix")
+             "synth", "bgr2gray", "band_carry", "fused", "fused_pre", "fused_fix", "pack")
 
 
 def _params4(params) -> "C.Array":
@@ -222,6 +222,10 @@ class Context:
                                                               src_page_stride, window, _params4(params), morph_iters,
                                                               d_dst, dst_step, dst_page_stride))
 
+    def pack_mask_dev(self, d_mask, n_pages, rows, cols, step, page_stride, d_bits):
+        """u8 masks in HBM -> 1 bit per pixel, Leptonica PIX layout (prl_cuda_pack_mask_dev)."""
+        self._check(self._L.prl_cuda_pack_mask_dev(self._h, d_mask, n_pages, rows, cols, step, page_stride, d_bits))
+
     def integral_batch_dev(self, d_src, n_pages, rows, cols, src_step, src_page_stride, pad, d_sum, d_sqsum,
                            plane_pitch, plane_page_stride):
         self._check(self._L.prl_cuda_integral_u8_batch_dev(self._h, d_src, n_pages, rows, cols, src_step, src_page_stride,
@@ -254,9 +258,16 @@ def default_context(device: int = 0) -> Context:
     return d[device]
 
 
+def unpack_lept1(bits: np.ndarray, cols: int) -> np.ndarray:
+    """(..., rows, wpl) uint32 PIX words (pixel x at bit 31 - (x & 31) of word x >> 5, 1 = black) -> 0/255 u8 masks."""
+    b = np.unpackbits(np.ascontiguousarray(bits).astype(">u4").view(np.uint8), axis=-1)[..., :cols]
+    return ((1 - b) * 255).astype(np.uint8)
+
+
 def binarize_batch(pages: np.ndarray, method: int, window: int, params, morph_iters: int = 0, devices=None,
-                   out: np.ndarray | None = None) -> np.ndarray:
-    """Host batch + page dispatcher (prl_cuda_binarize_batch): (N, rows, cols) u8 -> (N, out_rows, out_cols)."""
+                   out: np.ndarray | None = None, packed: bool = False) -> np.ndarray:
+    """Host batch + page dispatcher (prl_cuda_binarize_batch): (N, rows, cols) u8 -> (N, out_rows, out_cols).
+    packed=True (prl_cuda_binarize_batch_packed): (N, out_rows, wpl) uint32 words, 1 bit per pixel, PIX layout."""
     L = capi.load()
     pages = np.asarray(pages)
     if pages.dtype != np.uint8 or pages.ndim != 3 or not pages.flags.c_contiguous:
@@ -268,17 +279,18 @@ def binarize_batch(pages: np.ndarray, method: int, window: int, params, morph_it
         raise ValueError("empty image or window not (>1 and odd)")
     if rc != capi.PRL_OK:
         raise PrlCudaError(rc, "empty processingRect: min(rows, cols) <= windowSize")
+    shape, dt = ((n, orow.value, (ocol.value + 31) // 32), np.uint32) if packed else ((n, orow.value, ocol.value), np.uint8)
     if out is None:
-        out = np.empty((n, orow.value, ocol.value), np.uint8)
-    elif out.shape != (n, orow.value, ocol.value) or out.dtype != np.uint8 or not out.flags.c_contiguous:
+        out = np.empty(shape, dt)
+    elif out.shape != shape or out.dtype != dt or not out.flags.c_contiguous:
         raise ValueError("out has the wrong shape/dtype")
     devs = None
     nd = 0
     if devices is not None:
         nd = len(devices)
         devs = (C.c_int * nd)(*devices)
-    rc = L.prl_cuda_binarize_batch(devs, nd, method, pages.ctypes.data, n, r, c, int(window), _params4(params),
-                                   int(morph_iters), out.ctypes.data)
+    fn = L.prl_cuda_binarize_batch_packed if packed else L.prl_cuda_binarize_batch
+    rc = fn(devs, nd, method, pages.ctypes.data, n, r, c, int(window), _params4(params), int(morph_iters), out.ctypes.data)
     if rc != capi.PRL_OK:
         msg = (L.prl_cuda_last_error(None) or b"").decode()
         if rc == capi.PRL_E_INVALID:

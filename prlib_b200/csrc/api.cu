@@ -85,7 +85,7 @@ static void timing_collect(prl_cuda_ctx* ctx)
 }
 
 static const char* kFamilyNames[FAM_COUNT] = {"integral", "threshold", "smax", "morph", "otsu_hist", "otsu_search",
-                                              "otsu_apply", "otsu_tiles", "synth", "bgr2gray", "band_carry", "fused", "fused_pre", "fused_fix"};
+                                              "otsu_apply", "otsu_tiles", "synth", "bgr2gray", "band_carry", "fused", "fused_pre", "fused_fix", "pack"};
 
 int prl_make_geom(int method, int rows, int cols, int window, prl_geom* g)
 {
@@ -539,6 +539,16 @@ extern "C" int prl_cuda_bgr2gray(prl_cuda_ctx* c, const uint8_t* src, int rows, 
     return PRL_OK;
 }
 
+extern "C" int prl_cuda_pack_mask_dev(prl_cuda_ctx* c, const uint8_t* d_mask, int n_pages, int rows, int cols, size_t step,
+                                      size_t page_stride, uint32_t* d_bits)
+{
+    if (!c) return PRL_E_INVALID;
+    if (!d_mask || !d_bits || n_pages <= 0 || rows <= 0 || cols <= 0 || step < (size_t)cols)
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    return prl_k_pack_mask(c, d_mask, n_pages, rows, cols, step, page_stride, d_bits);
+}
+
 extern "C" int prl_cuda_morph(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step,
                               int morph_iters, uint8_t* dst, size_t dst_step)
 {
@@ -659,14 +669,15 @@ struct DeviceWorker {
     static constexpr int NBUF = 3;
     uint8_t* d_in[NBUF] = {nullptr, nullptr, nullptr};
     uint8_t* d_out[NBUF] = {nullptr, nullptr, nullptr};
-    size_t in_bytes = 0, out_bytes = 0;
+    uint32_t* d_bits[NBUF] = {nullptr, nullptr, nullptr};     // packed variant: 1 bit per pixel leaves the device
+    size_t in_bytes = 0, out_bytes = 0, bits_bytes = 0;
     cudaEvent_t ev_in[NBUF], ev_comp[NBUF], ev_out[NBUF];
     bool events = false;
     ~DeviceWorker()
     {
         if (!ctx) return;
         cudaSetDevice(ctx->device);
-        for (int i = 0; i < NBUF; ++i) { cudaFree(d_in[i]); cudaFree(d_out[i]); }
+        for (int i = 0; i < NBUF; ++i) { cudaFree(d_in[i]); cudaFree(d_out[i]); cudaFree(d_bits[i]); }
         if (events) for (int i = 0; i < NBUF; ++i) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_comp[i]); cudaEventDestroy(ev_out[i]); }
         if (s_in) cudaStreamDestroy(s_in);
         if (s_out) cudaStreamDestroy(s_out);
@@ -701,13 +712,16 @@ DeviceWorker* get_worker(int device, std::string* err)
 
 // pages [p0, p1) of the batch on one device: 3-slot ring, H2D / kernels / D2H on three streams
 int run_shard(DeviceWorker* w, int method, const uint8_t* pages, int p0, int p1, int rows, int cols, int window,
-              const double* params, int morph_iters, uint8_t* masks, const prl_geom& g, std::string* err)
+              const double* params, int morph_iters, uint8_t* masks, const prl_geom& g, std::string* err,
+              uint32_t* packed = nullptr)
 {
     prl_cuda_ctx* c = w->ctx;
 #define SHARD_TRY(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { *err = std::string(#call) + ": " + cudaGetErrorString(_e); return PRL_E_CUDA; } } while (0)
     SHARD_TRY(cudaSetDevice(c->device));
-    const size_t in_step = round16(cols), o_step = (size_t)g.out_cols;    // masks dense on the device: linear D2H
+    // masks dense on the device: linear D2H.  Packed variant: aligned mask rows feed the pack kernel, the bits are dense.
+    const size_t in_step = round16(cols), o_step = packed ? round16((size_t)g.out_cols) : (size_t)g.out_cols;
     const size_t in_page = in_step * rows, out_page = o_step * g.out_rows;
+    const size_t wpl = ((size_t)g.out_cols + 31) / 32, bits_page = wpl * g.out_rows * sizeof(uint32_t);
     const size_t host_in_page = (size_t)rows * cols, host_out_page = (size_t)g.out_rows * g.out_cols;
     // chunk: about 64 MiB of input per slot (8 A4 pages; measured best of 4..64), at least 1 page
     int chunk = (int)std::max<size_t>(1, ((size_t)72 << 20) / in_page);
@@ -722,6 +736,14 @@ int run_shard(DeviceWorker* w, int method, const uint8_t* pages, int p0, int p1,
         for (int i = 0; i < DeviceWorker::NBUF; ++i) {
             SHARD_TRY(cudaMalloc((void**)&w->d_in[i], w->in_bytes));
             SHARD_TRY(cudaMalloc((void**)&w->d_out[i], w->out_bytes + 16));
+        }
+    }
+    if (packed && bits_page * chunk > w->bits_bytes) {
+        SHARD_TRY(cudaDeviceSynchronize());
+        w->bits_bytes = bits_page * chunk;
+        for (int i = 0; i < DeviceWorker::NBUF; ++i) {
+            cudaFree(w->d_bits[i]); w->d_bits[i] = nullptr;
+            SHARD_TRY(cudaMalloc((void**)&w->d_bits[i], w->bits_bytes));
         }
     }
     int it = 0;
@@ -739,10 +761,18 @@ int run_shard(DeviceWorker* w, int method, const uint8_t* pages, int p0, int p1,
         int rc = prl_cuda_binarize_local_batch_dev(c, method, w->d_in[slot], np, rows, cols, in_step, in_page, window,
                                                    params, morph_iters, w->d_out[slot], o_step, out_page);
         if (rc) { *err = c->err; return rc; }
+        if (packed) {
+            rc = prl_k_pack_mask(c, w->d_out[slot], np, g.out_rows, g.out_cols, o_step, out_page, w->d_bits[slot]);
+            if (rc) { *err = c->err; return rc; }
+        }
         SHARD_TRY(cudaEventRecord(w->ev_comp[slot], c->stream));
         SHARD_TRY(cudaStreamWaitEvent(w->s_out, w->ev_comp[slot], 0));
-        SHARD_TRY(copy2d(masks + (size_t)p * host_out_page, g.out_cols, w->d_out[slot], o_step, g.out_cols,
-                         (size_t)g.out_rows * np, cudaMemcpyDeviceToHost, w->s_out));
+        if (packed)
+            SHARD_TRY(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(packed) + (size_t)p * bits_page, w->d_bits[slot], bits_page * np,
+                                      cudaMemcpyDeviceToHost, w->s_out));
+        else
+            SHARD_TRY(copy2d(masks + (size_t)p * host_out_page, g.out_cols, w->d_out[slot], o_step, g.out_cols,
+                             (size_t)g.out_rows * np, cudaMemcpyDeviceToHost, w->s_out));
         SHARD_TRY(cudaEventRecord(w->ev_out[slot], w->s_out));
     }
     SHARD_TRY(cudaStreamSynchronize(w->s_out));
@@ -754,11 +784,11 @@ int run_shard(DeviceWorker* w, int method, const uint8_t* pages, int p0, int p1,
 
 }  // namespace
 
-extern "C" int prl_cuda_binarize_batch(const int* devices, int n_dev, int method, const uint8_t* pages, int n_pages,
-                                       int rows, int cols, int window, const double* params, int morph_iters,
-                                       uint8_t* masks)
+static int binarize_batch_impl(const int* devices, int n_dev, int method, const uint8_t* pages, int n_pages,
+                               int rows, int cols, int window, const double* params, int morph_iters,
+                               uint8_t* masks, uint32_t* packed)
 {
-    if (!pages || !masks || !params || n_pages <= 0) return prl_set_err(nullptr, PRL_E_INVALID, "null pointer or empty batch");
+    if (!pages || (!masks && !packed) || !params || n_pages <= 0) return prl_set_err(nullptr, PRL_E_INVALID, "null pointer or empty batch");
     prl_geom g;
     int rc = prl_make_geom(method, rows, cols, window, &g);
     if (rc) return prl_set_err(nullptr, rc, "bad geometry / window");
@@ -777,7 +807,7 @@ extern "C" int prl_cuda_binarize_batch(const int* devices, int n_dev, int method
         auto job = [&, gi, p0, p1]() {
             DeviceWorker* w = get_worker(devs[gi], &errs[gi]);
             if (!w) { rcs[gi] = PRL_E_CUDA; return; }
-            rcs[gi] = run_shard(w, method, pages, p0, p1, rows, cols, window, params, morph_iters, masks, g, &errs[gi]);
+            rcs[gi] = run_shard(w, method, pages, p0, p1, rows, cols, window, params, morph_iters, masks, g, &errs[gi], packed);
         };
         if (G == 1) job(); else threads.emplace_back(job);
     }
@@ -788,4 +818,18 @@ extern "C" int prl_cuda_binarize_batch(const int* devices, int n_dev, int method
             return prl_set_err(nullptr, rcs[gi], (std::string(buf) + errs[gi]).c_str());
         }
     return PRL_OK;
+}
+
+extern "C" int prl_cuda_binarize_batch(const int* devices, int n_dev, int method, const uint8_t* pages, int n_pages,
+                                       int rows, int cols, int window, const double* params, int morph_iters,
+                                       uint8_t* masks)
+{
+    return binarize_batch_impl(devices, n_dev, method, pages, n_pages, rows, cols, window, params, morph_iters, masks, nullptr);
+}
+
+extern "C" int prl_cuda_binarize_batch_packed(const int* devices, int n_dev, int method, const uint8_t* pages, int n_pages,
+                                              int rows, int cols, int window, const double* params, int morph_iters,
+                                              uint32_t* bits)
+{
+    return binarize_batch_impl(devices, n_dev, method, pages, n_pages, rows, cols, window, params, morph_iters, nullptr, bits);
 }

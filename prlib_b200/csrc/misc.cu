@@ -48,7 +48,55 @@ bgr2gray_kernel(const uint8_t* __restrict__ src, int rows, int cols, size_t step
     dst[(size_t)y * dst_step + x] = (uint8_t)(v >> 15);
 }
 
+// mask (0 / 255 bytes) -> 1 bit per pixel in Leptonica's PIX layout (the reference's other image container,
+// src/formatConvert.cpp:57-69): rows of wpl 32-bit words, pixel x in word x >> 5 at bit 31 - (x & 31), 1 = black.
+// One thread per output word: 32 mask bytes (two 16-byte loads when the row is aligned), gathered by dp4a.
+__device__ __forceinline__ int dp4a_su_m(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+__global__ void __launch_bounds__(256)
+pack_mask_kernel(const uint8_t* __restrict__ mask, int rows, int cols, size_t step, size_t page_stride, int wpl,
+                 uint32_t* __restrict__ bits, int aligned)
+{
+    const int wx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (wx >= wpl) return;
+    const uint8_t* p = mask + (size_t)blockIdx.z * page_stride + (size_t)y * step + 32 * wx;
+    const int nvalid = min(32, cols - 32 * wx);
+    uint32_t white = 0;                                   // bit i = pixel 32 wx + i is white (255)
+    if (aligned && nvalid > 16) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(p)), b = __ldg(reinterpret_cast<const uint4*>(p + 16));
+        const int v0 = dp4a_su_m(a.y, 0x80402010u, dp4a_su_m(a.x, 0x08040201u, 0));      // bytes are 0 / -1: v = -(8 bits)
+        const int v1 = dp4a_su_m(a.w, 0x80402010u, dp4a_su_m(a.z, 0x08040201u, 0));
+        const int v2 = dp4a_su_m(b.y, 0x80402010u, dp4a_su_m(b.x, 0x08040201u, 0));
+        const int v3 = dp4a_su_m(b.w, 0x80402010u, dp4a_su_m(b.z, 0x08040201u, 0));
+        white = 0u - ((uint32_t)v0 + ((uint32_t)v1 << 8) + ((uint32_t)v2 << 16) + ((uint32_t)v3 << 24));
+    } else {
+        for (int i = 0; i < nvalid; ++i) white |= (uint32_t)(p[i] != 0) << i;
+    }
+    const uint32_t valid = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+    bits[((size_t)blockIdx.z * rows + y) * wpl + wx] = __brev(~white & valid);
+}
+
 }  // namespace
+
+int prl_k_pack_mask(prl_cuda_ctx* ctx, const uint8_t* d_mask, int n_pages, int rows, int cols, size_t step,
+                    size_t page_stride, uint32_t* d_bits)
+{
+    if (rows > 65535 || n_pages > 65535) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "grid too large");
+    const int wpl = (cols + 31) / 32;
+    // 16-byte loads need aligned rows and a row pitch that covers the last, partly valid 32-byte group
+    const int aligned = ((((uintptr_t)d_mask) | step | page_stride) & 15) == 0 && step >= (size_t)(((cols + 15) / 16) * 16);
+    prl_launch_scope ls(ctx, FAM_PACK);
+    pack_mask_kernel<<<dim3((wpl + 255) / 256, rows, n_pages), 256, 0, ctx->stream>>>(d_mask, rows, cols, step, page_stride,
+                                                                                    wpl, d_bits, aligned);
+    PRL_CUDA_TRY(ctx, cudaGetLastError());
+    return PRL_OK;
+}
 
 int prl_k_synth(prl_cuda_ctx* ctx, uint8_t* d_dst, int n_pages, int rows, int cols, size_t step,
                 size_t page_stride, uint32_t seed, uint32_t first_page)

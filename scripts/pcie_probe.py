@@ -1,17 +1,19 @@
+"""PCIe ceiling for the e2e path: pinned H2D, D2H, and both at once (two streams), 8.7 MB pages."""
 import torch, time
-def bw(fn, nbytes, n=5):
-    fn(); torch.cuda.synchronize(); t=time.perf_counter()
-    for _ in range(n): fn()
-    torch.cuda.synchronize(); return nbytes*n/(time.perf_counter()-t)/1e9
-N=128; R,C=3508,2480
-h=torch.empty((N,R,C),dtype=torch.uint8).pin_memory(); d=torch.empty((N,R,C),dtype=torch.uint8,device='cuda')
-print('H2D contiguous GB/s', bw(lambda: d.copy_(h,non_blocking=True), h.numel()))
-print('D2H contiguous GB/s', bw(lambda: h.copy_(d,non_blocking=True), h.numel()))
-ho=torch.empty((N,R-1,C-1),dtype=torch.uint8).pin_memory(); do=torch.empty((N,R-1,C),dtype=torch.uint8,device='cuda')
-print('D2H 2D (odd width) GB/s', bw(lambda: ho.copy_(do[:,:,:C-1],non_blocking=True), ho.numel()))
-s1=torch.cuda.Stream(); s2=torch.cuda.Stream()
-def both():
-    with torch.cuda.stream(s1): d.copy_(h,non_blocking=True)
-    with torch.cuda.stream(s2): h2.copy_(d2,non_blocking=True)
-h2=torch.empty((N,R,C),dtype=torch.uint8).pin_memory(); d2=torch.empty((N,R,C),dtype=torch.uint8,device='cuda')
-print('bidirectional total GB/s', bw(both, 2*h.numel()))
+n = 128; B = 3508 * 2480
+h_in = torch.empty((n, B), dtype=torch.uint8).pin_memory(); h_out = torch.empty((n, B), dtype=torch.uint8).pin_memory()
+d_in = torch.empty((n, B), dtype=torch.uint8, device="cuda"); d_out = torch.empty((n, B), dtype=torch.uint8, device="cuda")
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+def run(h2d, d2h, chunk):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for rep in range(3):
+        for i in range(0, n, chunk):
+            if h2d:
+                with torch.cuda.stream(s1): d_in[i:i + chunk].copy_(h_in[i:i + chunk], non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2): h_out[i:i + chunk].copy_(d_out[i:i + chunk], non_blocking=True)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    return 3 * n * B / dt / 1e9
+for chunk in (1, 8, 32):
+    print(f"chunk {chunk:3d} pages: H2D {run(1, 0, chunk):6.1f} GB/s   D2H {run(0, 1, chunk):6.1f} GB/s   both {run(1, 1, chunk):6.1f} GB/s each way "
+          f"= {run(1, 1, chunk) * 1e9 / B:7.0f} pages/s ceiling", flush=True)

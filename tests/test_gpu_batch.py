@@ -247,3 +247,44 @@ def test_timing_hooks_count_launches(ctx):
     ctx.timing_enable(False)
     assert t["integral"]["launches"] == 1 and t["threshold"]["launches"] == 1
     assert t["integral"]["ms"] > 0 and ctx.launch_count() >= 2
+
+
+def lept1_words(mask):
+    """Leptonica 1 bpp words of a 0/255 mask, written the way src/formatConvert.cpp:57-69 fills a PIX:
+    SET_DATA_BIT(line, x) sets bit 31 - (x & 31) of word x >> 5 for a dark pixel."""
+    r, c = mask.shape
+    wpl = (c + 31) // 32
+    out = np.zeros((r, wpl), np.uint32)
+    ys, xs = np.nonzero(mask == 0)
+    np.bitwise_or.at(out, (ys, xs >> 5), (np.uint32(1) << (31 - (xs & 31)).astype(np.uint32)))
+    return out
+
+
+@pytest.mark.gpu
+def test_packed_batch_and_device_pack(ctx):
+    import torch
+    rng = np.random.default_rng(11)
+    pages = np.stack([CO.synth_page(p, 300, 421) for p in range(5)])
+    pages[4] = rng.integers(0, 256, pages[4].shape, dtype=np.uint8)
+    for method, window, params, morph in ((0, 15, (0.2,), 0), (3, 21, (-0.1,), 2)):
+        bits = prlib_b200.binarize_batch(pages, method, window, params, morph, devices=[0], packed=True)
+        masks = prlib_b200.binarize_batch(pages, method, window, params, morph, devices=[0])
+        assert bits.dtype == np.uint32 and bits.shape == (5, masks.shape[1], (masks.shape[2] + 31) // 32)
+        for p in range(5):
+            assert np.array_equal(masks[p], CO.binarize_local(pages[p], method, window, params, morph))
+            assert np.array_equal(bits[p], lept1_words(masks[p])), (method, p)
+        assert np.array_equal(prlib_b200.unpack_lept1(bits, masks.shape[2]), masks)
+    # device entry point, aligned and odd pitches, widths around the 16/32-byte group boundaries
+    for cols in (33, 64, 100, 417, 421):
+        m = np.where(rng.random((37, cols)) < 0.4, 0, 255).astype(np.uint8)
+        for step in (cols, (cols + 15) // 16 * 16):
+            buf = torch.zeros((2, 37, step), dtype=torch.uint8, device="cuda")
+            buf[:, :, :cols] = torch.from_numpy(np.stack([m, 255 - m])).cuda()
+            wpl = (cols + 31) // 32
+            out = torch.full((2, 37, wpl), -1, dtype=torch.int32, device="cuda")
+            ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+            ctx.pack_mask_dev(buf.data_ptr(), 2, 37, cols, step, 37 * step, out.data_ptr())
+            torch.cuda.synchronize()
+            got = out.cpu().numpy().view(np.uint32)
+            assert np.array_equal(got[0], lept1_words(m)) and np.array_equal(got[1], lept1_words(255 - m)), (cols, step)
+    ctx.set_stream(None)
