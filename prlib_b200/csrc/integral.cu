@@ -571,7 +571,6 @@ int prl_k_integral(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int row
                    size_t plane_page_stride, uint32_t* d_imin)
 {
     const int Wp = cols + 2 * pad;
-    if (Wp > 8192) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "padded width > 8192 columns is not supported yet");
     if (n_pages > 65535) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "more than 65535 pages per launch");
 
     // TMA path: 16-byte aligned source rows, 32-byte aligned planes, pitch % 4 == 0
@@ -580,6 +579,9 @@ int prl_k_integral(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int row
                         ((((uintptr_t)d_S) | ((uintptr_t)d_Q)) & 31) == 0 && (pitch & 3) == 0 && (plane_page_stride & 3) == 0;
     const bool vec_ok = ((((uintptr_t)d_S) | ((uintptr_t)d_Q)) & 15) == 0 && (pitch & 1) == 0 && (plane_page_stride & 1) == 0;
     const bool narrow = tma_ok && Wp <= 24 * 128;        // 128 columns per warp, up to 24 warps, 2 CTAs per SM
+    // wider pages run as chained column passes on the TMA path (any width); the generic kernel covers one pass only
+    if (Wp > 8192 && !tma_ok)
+        return prl_set_err(ctx, PRL_E_UNSUPPORTED, "padded width > 8192 columns needs 16-byte aligned pages and 32-byte aligned planes");
 
     constexpr int R = 8;
     int bands = choose_bands(ctx, n_pages, rows, 2);
@@ -641,6 +643,7 @@ int prl_k_integral(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int row
         // the driver rejected the tensor map (e.g. stride limits): fall through to the generic kernel
     }
     const int nwarps = (Wp + kWarpCols - 1) / kWarpCols;
+    if (nwarps > 32) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "padded width > 8192 columns: tensor map rejected, no generic path");
     if (nwarps <= 16)
         integral_generic_kernel<16, 4><<<grid, nwarps * 32, 0, ctx->stream>>>(
             d_src, src_step, src_page_stride, rows, cols, pad, d_S, d_Q, pitch, plane_page_stride, rpb, d_carry, d_imin, vec_ok);

@@ -175,6 +175,18 @@ def test_morph_bit_kernels_equal_byte_kernels_and_oracle(ctx, shape):
     assert np.array_equal(ctx.morph(gray, 2), O.morph(gray, 2))
 
 
+def test_pages_wider_than_8192_columns(ctx):
+    """Kernel 1 chains column passes of 2560 columns: integrals bit-exact and masks identical on a 9000-column strip."""
+    rng = np.random.default_rng(3)
+    page = rng.integers(0, 256, (120, 9000), dtype=np.uint8)
+    page[:, 4000:4700] = 255
+    S, Q = ctx.integral(page, 10)
+    Sw, Qw = CO.integrals_int64(page, 10)
+    assert np.array_equal(S, Sw) and np.array_equal(Q, Qw)
+    for m, w, p in ((0, 21, (0.2,)), (2, 21, (0.5,)), (3, 51, (-0.1,))):
+        assert np.array_equal(ctx.binarize_local(page, m, w, p, 0), CO.binarize_local(page, m, w, p, 0)), m
+
+
 def test_header_defaults_end_to_end(ctx, golden):
     a4 = CO.synth_page(0)
     got = prlib_b200.binarizeSauvola(a4)            # w=101, k=0.01, morph=2 (binarizeSauvola.h:45-47)
