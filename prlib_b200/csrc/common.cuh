@@ -47,7 +47,7 @@ struct prl_cuda_ctx {
 
     bool force_exact = false;   // validation: kernel 2 runs the literal FP64 path for every pixel
     bool no_tma = false;        // validation: kernel 1 uses the generic (non-TMA) kernel
-    int tile_prefetch = 4;      // tile Otsu: how many tiles ahead a warp pulls into L2 (0 = off)
+    int tile_prefetch = 0;      // tile Otsu: how many tiles ahead a warp pulls into L2 (0 = off)
     bool morph_bytes = false;   // validation: the morphology tail runs the byte kernels even on binary masks
     bool use_fused = false;     // opt-in: fused small-window strip kernel (integral planes never reach HBM)
 

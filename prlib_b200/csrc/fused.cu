@@ -43,16 +43,6 @@ struct FusedArgs {
     double kw, p0, p1, p2;
 };
 
-__device__ __forceinline__ uint32_t warp_scan_u32(uint32_t v, int lane)
-{
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= d) v += t;
-    }
-    return v;
-}
-
 // ---- pre-pass (Feng only): per-page minimum
 __global__ void __launch_bounds__(256)
 page_min_kernel(const uint8_t* __restrict__ src, size_t step, size_t page_stride, int rows, int cols, uint32_t* __restrict__ imin)
