@@ -95,6 +95,16 @@ __device__ __forceinline__ int exact_t8_from_taps(long long sa, long long sb, lo
     return to_u8(thr_value_p<METHOD>(m, s, p0, p1, p2, imin, coeff));
 }
 
+// (float)N for the exact variance numerator N = w^2 Q - S^2 without the slow 64-bit I2F (XU pipe, ~20 % of kernel 2's
+// stall samples when it was used): 32-bit arithmetic when N provably fits (w <= 15), else high and low words converted
+// separately (I2FP) and joined by one FMA -- one more rounding than a direct conversion, which the margin accounts for.
+__device__ __forceinline__ float n_to_float(const FastArgs& F, unsigned int sw, unsigned int qw)
+{
+    if (F.n32) return (float)(F.w2 * qw - sw * sw);
+    const unsigned long long N = (unsigned long long)F.w2 * qw - (unsigned long long)sw * sw;
+    return fmaf((float)(unsigned int)(N >> 32), 4294967296.0f, (float)(unsigned int)N);
+}
+
 // FP32 estimate of T from the exact window sums; returns false when the pixel must take the exact path
 // PRE: also try the variance-free bounds first (pays off where the decision arithmetic dominates: the fused
 // kernel and Sauvola in kernel 2; measured slower for Niblack / NICK in kernel 2)
@@ -120,8 +130,7 @@ __device__ __forceinline__ bool fast_decide(unsigned int sw, unsigned int qw, un
             if (pm - tlo < -mu) { out = 0; return true; }
         }
     }
-    const unsigned long long N = (unsigned long long)F.w2 * qw - (unsigned long long)sw * sw;   // exact, >= 0
-    const float fn = (float)N;
+    const float fn = n_to_float(F, sw, qw);            // N = w^2 Q - S^2, exact and >= 0 before the conversion
     const float s = (fn * rsqrtf(fn)) * F.inv_w2f;     // sqrt via MUFU.RSQ (2 ulp, covered by the margin); fn == 0 gives NaN -> exact path
     float T;
     if (METHOD == PRL_SAUVOLA) T = m * fmaf(s, F.c1, F.c2);
@@ -165,7 +174,7 @@ __device__ __noinline__ int tier2_decide(unsigned int sw, unsigned int qw, unsig
 //     dm_ref <= 16 u kw Smax,  dq_ref <= 16 u kw Qmax,  dv_ref <= dq_ref + 2*255*dm_ref + u*2*255^2
 //     ds_ref <= dv_ref / s_floor + u*128          (fast path requires s* >= s_floor)
 //   FP32 estimate error (exact integer inputs), e = 2^-24:
-//     dm_est <= 3 e 255,  ds_est <= 8 e 128   (N -> float, MUFU.RSQ at 2 ulp, two products)
+//     dm_est <= 3 e 255,  ds_est <= 10 e 128  (N -> float in up to two roundings, MUFU.RSQ at 2 ulp, two products)
 //   |dT| <= A dm + B ds + 8 e (Tmax + 512), A/B = sup |dT/dm|, |dT/ds| over m in [0,255], s in [0,128]
 inline bool fast_margins(int method, const double* params, const prl_geom& g, FastArgs* F)
 {
@@ -178,7 +187,7 @@ inline bool fast_margins(int method, const double* params, const prl_geom& g, Fa
     const double dv_ref = dq_ref + 510.0 * dm_ref + u * 2 * 65025.0;
     if (!(dv_ref < 0.25 * s_floor * s_floor)) return false;
     const double ds_ref = dv_ref / s_floor + u * 128;
-    const double dm = dm_ref + 3 * e * 255, ds = ds_ref + 8 * e * 128;   // ds: int->float, rsqrt (2 ulp), two products
+    const double dm = dm_ref + 3 * e * 255, ds = ds_ref + 10 * e * 128;  // ds: int->float (two-word: 2 roundings), rsqrt (2 ulp), two products
     double Acoef, Bcoef, Tmax, mu1 = 0.0, cd0 = 0.0, cd1 = 0.0, cd2 = 0.0;
     const double k = params[0];
     switch (method) {

@@ -237,7 +237,10 @@ local_fused_kernel(const FusedArgs A, const FastArgs F)
             for (int i = 0; i < 4; ++i) {
                 float fn;
                 if (N32) fn = (float)(F.w2 * qw[i] - sw[i] * sw[i]);
-                else fn = (float)((unsigned long long)F.w2 * qw[i] - (unsigned long long)sw[i] * sw[i]);
+                else {
+                    const unsigned long long N = (unsigned long long)F.w2 * qw[i] - (unsigned long long)sw[i] * sw[i];
+                    fn = fmaf((float)(unsigned int)(N >> 32), 4294967296.0f, (float)(unsigned int)N);
+                }
                 const float s = (fn * rsqrtf(fn)) * F.inv_w2f;          // fn == 0 gives NaN -> stays undecided
                 float T;
                 if (METHOD == PRL_SAUVOLA) T = m[i] * fmaf(s, F.c1, F.c2);
