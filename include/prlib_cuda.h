@@ -167,6 +167,27 @@ int prl_cuda_binarize_batch(const int* devices, int n_dev, int method, const uin
                             int rows, int cols, int window, const double* params, int morph_iters,
                             uint8_t* masks);
 
+/* ---- edge front-end of prl::binarizeLocalOtsu -----------------------
+ * prl_cuda_canny_edge_detection = CannyEdgeDetection (src/imageLibCommon.cpp:244-324: GaussianBlur k x k sigma 0,
+ * Otsu value of the blurred image, cv::Canny(lowerCoeff * upper, upper = upperCoeff * otsu), closing (morph_iters > 0)
+ * or opening (< 0)) followed by `post_dilate` dilations (binarizeLocalOtsu.cpp:92 uses 3); single-channel u8 in,
+ * 0/255 edge map out, bit-identical to OpenCV 4.x.  PRL_E_INVALID mirrors the reference's std::invalid_argument
+ * checks (:248-272) and OpenCV's odd-kernel assertion.  The contour step (cv::findContours, :104-110) stays with the
+ * caller; its rectangles go to prl_cuda_otsu_rects.  prl_cuda_gaussian_blur / prl_cuda_canny are the two building
+ * blocks alone (cv::GaussianBlur on CV_8U with BORDER_DEFAULT; cv::Canny with aperture 3, L1 gradient). */
+/* the 8.8 fixed-point Gaussian coefficients cv::GaussianBlur uses on CV_8U (host-only helper; n odd, <= 63; k[n]) */
+int prl_cuda_gauss_kernel_fixed(int n, double sigma, int* k);
+int prl_cuda_gaussian_blur(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step, int ksize,
+                           double sigma, uint8_t* dst, size_t dst_step);
+int prl_cuda_canny(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step, double low, double high,
+                   uint8_t* dst, size_t dst_step);
+int prl_cuda_canny_edge_detection(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step,
+                                  int gauss_ksize, double upper_coeff, double lower_coeff, int morph_iters,
+                                  int post_dilate, uint8_t* dst, size_t dst_step);
+int prl_cuda_canny_edge_detection_dev(prl_cuda_ctx* ctx, const uint8_t* d_gray, int rows, int cols, size_t step,
+                                      int gauss_ksize, double upper_coeff, double lower_coeff, int morph_iters,
+                                      int post_dilate, uint8_t* d_dst, size_t dst_step);
+
 /* ---- 1 bit per pixel ---------------------------------------------
  * The masks in Leptonica's PIX layout, the reference's second image container (src/formatConvert.cpp:39-69
  * writes PIX words with SET_DATA_BIT): rows of wpl = (cols + 31) / 32 32-bit words, pixel x of a row in word

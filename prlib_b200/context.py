@@ -10,7 +10,7 @@ from . import capi
 from .capi import PrlCudaError
 
 _FAMILIES = ("integral", "threshold", "smax", "morph", "otsu_hist", "otsu_search", "otsu_apply", "otsu_tiles",
-             "synth", "bgr2gray", "band_carry", "fused", "fused_pre", "fused_fix", "pack")
+             "synth", "bgr2gray", "band_carry", "fused", "fused_pre", "fused_fix", "pack", "edges")
 
 
 def _params4(params) -> "C.Array":
@@ -213,6 +213,33 @@ class Context:
         out = np.empty(g.shape, np.uint8)
         self._check(self._L.prl_cuda_otsu_tiles(self._h, g.ctypes.data, g.shape[0], g.shape[1], g.strides[0],
                                                 int(tile_w), int(tile_h), float(maxval), out.ctypes.data, g.shape[1]))
+        return out
+
+    # -- edge front-end of prl::binarizeLocalOtsu ---------------------------
+    def gaussian_blur(self, gray, ksize: int, sigma: float = 0.0):
+        """cv::GaussianBlur on CV_8U (fixed point, BORDER_REFLECT_101)."""
+        g = _as_u8_2d(gray)
+        out = np.empty(g.shape, np.uint8)
+        self._check(self._L.prl_cuda_gaussian_blur(self._h, g.ctypes.data, g.shape[0], g.shape[1], g.strides[0], int(ksize),
+                                                   float(sigma), out.ctypes.data, g.shape[1]))
+        return out
+
+    def canny(self, gray, low: float, high: float):
+        """cv::Canny, aperture 3, L1 gradient."""
+        g = _as_u8_2d(gray)
+        out = np.empty(g.shape, np.uint8)
+        self._check(self._L.prl_cuda_canny(self._h, g.ctypes.data, g.shape[0], g.shape[1], g.strides[0], float(low), float(high),
+                                           out.ctypes.data, g.shape[1]))
+        return out
+
+    def canny_edge_detection(self, gray, ksize: int = 19, upper_coeff: float = 0.15, lower_coeff: float = 0.01,
+                             morph_iters: int = 1, post_dilate: int = 0):
+        """CannyEdgeDetection (imageLibCommon.cpp:244-324) + `post_dilate` dilations (binarizeLocalOtsu.cpp:92)."""
+        g = _as_u8_2d(gray)
+        out = np.empty(g.shape, np.uint8)
+        self._check(self._L.prl_cuda_canny_edge_detection(self._h, g.ctypes.data, g.shape[0], g.shape[1], g.strides[0], int(ksize),
+                                                          float(upper_coeff), float(lower_coeff), int(morph_iters),
+                                                          int(post_dilate), out.ctypes.data, g.shape[1]))
         return out
 
     # -- device-pointer entry points (raw addresses: torch .data_ptr() or cudaMalloc) ----------

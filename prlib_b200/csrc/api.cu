@@ -85,7 +85,7 @@ static void timing_collect(prl_cuda_ctx* ctx)
 }
 
 static const char* kFamilyNames[FAM_COUNT] = {"integral", "threshold", "smax", "morph", "otsu_hist", "otsu_search",
-                                              "otsu_apply", "otsu_tiles", "synth", "bgr2gray", "band_carry", "fused", "fused_pre", "fused_fix", "pack"};
+                                              "otsu_apply", "otsu_tiles", "synth", "bgr2gray", "band_carry", "fused", "fused_pre", "fused_fix", "pack", "edges"};
 
 int prl_make_geom(int method, int rows, int cols, int window, prl_geom* g)
 {
@@ -167,7 +167,7 @@ extern "C" void prl_cuda_destroy(prl_cuda_ctx* c)
     for (auto& ev : c->event_pool) cudaEventDestroy(ev);
     cudaFree(c->planes); cudaFree(c->carry); cudaFree(c->colsum); cudaFree(c->scalars); cudaFree(c->fused_ws);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
-    cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_tmp); cudaFree(c->d_misc); cudaFree(c->d_bgr);
+    cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_tmp); cudaFree(c->d_misc); cudaFree(c->d_bgr); cudaFree(c->edges_ws);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -594,6 +594,108 @@ static int otsu_host(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, si
     PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (thr) *thr = t;
     return PRL_OK;
+}
+
+// ---- edge front-end of prl::binarizeLocalOtsu ---------------------------------
+// workspace: [blur u8][rows 8.8 u16][edge map A][edge map B][Otsu value][Canny scratch]
+struct EdgesWs { uint8_t* blur; uint16_t* tmp16; uint8_t* ea; uint8_t* eb; int32_t* thr; void* canny; size_t p16; };
+
+static int edges_ws(prl_cuda_ctx* c, int rows, int cols, EdgesWs* w)
+{
+    const size_t p16 = round16((size_t)cols), img = (p16 * rows + 255) & ~(size_t)255;
+    const size_t need = img * 5 + 256 + prl_canny_scratch_bytes(rows, cols);
+    int rc = prl_ensure(c, &c->edges_ws, &c->edges_ws_bytes, need); if (rc) return rc;
+    uint8_t* b = (uint8_t*)c->edges_ws;
+    w->p16 = p16; w->blur = b; w->tmp16 = (uint16_t*)(b + img); w->ea = b + 3 * img; w->eb = b + 4 * img;
+    w->thr = (int32_t*)(b + 5 * img); w->canny = b + 5 * img + 256;
+    return PRL_OK;
+}
+
+// CannyEdgeDetection (imageLibCommon.cpp:244-324) + the dilation of binarizeLocalOtsu.cpp:92, gray image in HBM
+extern "C" int prl_cuda_canny_edge_detection_dev(prl_cuda_ctx* c, const uint8_t* d_gray, int rows, int cols, size_t step,
+                                                 int gauss_ksize, double upper_coeff, double lower_coeff, int morph_iters,
+                                                 int post_dilate, uint8_t* d_dst, size_t dst_step)
+{
+    if (!c) return PRL_E_INVALID;
+    if (!d_gray || !d_dst || rows <= 0 || cols <= 0 || step < (size_t)cols || dst_step < (size_t)cols)
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    // the reference's own argument checks (imageLibCommon.cpp:248-272); cv::GaussianBlur needs an odd size
+    if (gauss_ksize < 3 || (gauss_ksize & 1) == 0 || gauss_ksize > 63)
+        return prl_set_err(c, PRL_E_INVALID, "Gaussian blur kernel size must be odd and in [3, 63]");
+    if (!(upper_coeff >= 0 && upper_coeff <= 1) || !(lower_coeff >= 0 && lower_coeff <= 1) || lower_coeff > upper_coeff)
+        return prl_set_err(c, PRL_E_INVALID, "Canny threshold coefficients must satisfy 0 <= lower <= upper <= 1");
+    if (post_dilate < 0 || post_dilate > 15 || morph_iters > 15 || morph_iters < -15)
+        return prl_set_err(c, PRL_E_INVALID, "morphology iteration counts must be within [-15, 15] / [0, 15]");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    EdgesWs w;
+    int rc = edges_ws(c, rows, cols, &w); if (rc) return rc;
+    const size_t page = w.p16 * rows;
+    rc = prl_k_gaussian_blur(c, d_gray, rows, cols, step, gauss_ksize, 0.0, w.blur, w.p16, w.tmp16); if (rc) return rc;
+    rc = prl_k_otsu_global(c, w.blur, 1, rows, cols, w.p16, page, 255.0, nullptr, 0, 0, w.thr, false); if (rc) return rc;
+    const bool last_is_canny = morph_iters == 0 && post_dilate == 0;
+    rc = prl_k_canny(c, w.blur, rows, cols, w.p16, w.thr, upper_coeff, lower_coeff, 0, 0, last_is_canny ? d_dst : w.ea,
+                     last_is_canny ? dst_step : w.p16, w.canny);
+    if (rc) return rc;
+    if (morph_iters != 0) {
+        const bool last = post_dilate == 0;
+        rc = prl_k_morph(c, w.ea, last ? d_dst : w.eb, 1, rows, cols, w.p16, page, last ? dst_step : w.p16, last ? dst_step * rows : page,
+                         morph_iters, true);
+        if (rc) return rc;
+    }
+    if (post_dilate > 0)
+        rc = prl_k_morph_single(c, morph_iters != 0 ? w.eb : w.ea, d_dst, 1, rows, cols, w.p16, page, dst_step, dst_step * rows, post_dilate, true);
+    return rc;
+}
+
+static int edges_host(prl_cuda_ctx* c, int what, const uint8_t* src, int rows, int cols, size_t step, int ksize, double a, double b,
+                      int morph_iters, int post_dilate, uint8_t* dst, size_t dst_step)
+{
+    if (!c) return PRL_E_INVALID;
+    if (!src || !dst || rows <= 0 || cols <= 0 || step < (size_t)cols || dst_step < (size_t)cols)
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    size_t in_step;
+    int rc = stage_in(c, src, rows, cols, step, &in_step); if (rc) return rc;
+    const size_t o_step = round16(cols);
+    rc = prl_ensure(c, (void**)&c->d_out, &c->d_out_bytes, o_step * rows); if (rc) return rc;
+    if (what == 0) {
+        EdgesWs w; rc = edges_ws(c, rows, cols, &w); if (rc) return rc;
+        rc = prl_k_gaussian_blur(c, c->d_in, rows, cols, in_step, ksize, a, c->d_out, o_step, w.tmp16);
+    } else if (what == 1) {
+        EdgesWs w; rc = edges_ws(c, rows, cols, &w); if (rc) return rc;
+        rc = prl_k_canny(c, c->d_in, rows, cols, in_step, nullptr, 0, 0, a, b, c->d_out, o_step, w.canny);
+    } else {
+        rc = prl_cuda_canny_edge_detection_dev(c, c->d_in, rows, cols, in_step, ksize, a, b, morph_iters, post_dilate, c->d_out, o_step);
+    }
+    if (rc) return rc;
+    PRL_CUDA_TRY(c, cudaMemcpy2DAsync(dst, dst_step, c->d_out, o_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
+    PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return PRL_OK;
+}
+
+extern "C" int prl_cuda_gauss_kernel_fixed(int n, double sigma, int* k)
+{
+    if (!k) return PRL_E_INVALID;
+    return prl_gauss_kernel_fixed(n, sigma, k);
+}
+
+extern "C" int prl_cuda_gaussian_blur(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step, int ksize,
+                                      double sigma, uint8_t* dst, size_t dst_step)
+{
+    return edges_host(c, 0, src, rows, cols, step, ksize, sigma, 0, 0, 0, dst, dst_step);
+}
+
+extern "C" int prl_cuda_canny(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step, double low, double high,
+                              uint8_t* dst, size_t dst_step)
+{
+    return edges_host(c, 1, src, rows, cols, step, 0, low, high, 0, 0, dst, dst_step);
+}
+
+extern "C" int prl_cuda_canny_edge_detection(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step,
+                                             int gauss_ksize, double upper_coeff, double lower_coeff, int morph_iters,
+                                             int post_dilate, uint8_t* dst, size_t dst_step)
+{
+    return edges_host(c, 2, src, rows, cols, step, gauss_ksize, upper_coeff, lower_coeff, morph_iters, post_dilate, dst, dst_step);
 }
 
 extern "C" int prl_cuda_otsu_threshold(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step, int* thr)

@@ -42,6 +42,7 @@ struct prl_cuda_ctx {
     uint8_t* d_tmp = nullptr;   size_t d_tmp_bytes = 0;
     uint8_t* d_bgr = nullptr;   size_t d_bgr_bytes = 0;    // 3/4-channel staging of the cvtColor front step
     void* d_misc = nullptr;     size_t d_misc_bytes = 0;   // histograms, thresholds, rect lists
+    void* edges_ws = nullptr;   size_t edges_ws_bytes = 0; // edge front-end: blurred image, 8.8 rows, class map, labels, flags
     // pinned host staging
     uint8_t* h_pin = nullptr;   size_t h_pin_bytes = 0;
 
@@ -61,7 +62,7 @@ struct prl_cuda_ctx {
 
 enum prl_family {
     FAM_INTEGRAL = 0, FAM_THRESHOLD, FAM_SMAX, FAM_MORPH, FAM_OTSU_HIST, FAM_OTSU_SEARCH,
-    FAM_OTSU_APPLY, FAM_OTSU_TILES, FAM_SYNTH, FAM_BGR2GRAY, FAM_BAND_CARRY, FAM_FUSED, FAM_FUSED_PRE, FAM_FUSED_FIX, FAM_PACK, FAM_COUNT
+    FAM_OTSU_APPLY, FAM_OTSU_TILES, FAM_SYNTH, FAM_BGR2GRAY, FAM_BAND_CARRY, FAM_FUSED, FAM_FUSED_PRE, FAM_FUSED_FIX, FAM_PACK, FAM_EDGES, FAM_COUNT
 };
 
 int  prl_set_err(prl_cuda_ctx* ctx, int code, const char* what, cudaError_t ce = cudaSuccess);
@@ -106,6 +107,14 @@ int prl_k_fused(prl_cuda_ctx* ctx, int method, const uint8_t* d_src, int n_pages
                 size_t dst_page_stride, std::vector<int>* redo_pages);
 int prl_k_morph(prl_cuda_ctx* ctx, uint8_t* d_in, uint8_t* d_out, int n_pages, int rows, int cols, size_t in_step,
                 size_t in_page_stride, size_t out_step, size_t out_page_stride, int iters, bool binary);
+int prl_k_morph_single(prl_cuda_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int n_pages, int rows, int cols, size_t in_step,
+                       size_t in_page_stride, size_t out_step, size_t out_page_stride, int n, bool dilate);
+int prl_gauss_kernel_fixed(int n, double sigma, int* k);
+int prl_k_gaussian_blur(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, int ksize, double sigma,
+                        uint8_t* d_dst, size_t dst_step, uint16_t* d_tmp);
+int prl_k_canny(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, const int32_t* d_otsu,
+                double upper_coeff, double lower_coeff, double low, double high, uint8_t* d_dst, size_t dst_step, void* scratch);
+size_t prl_canny_scratch_bytes(int rows, int cols);
 int prl_k_not_binary(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, int* d_flag);
 int prl_k_pack_mask(prl_cuda_ctx* ctx, const uint8_t* d_mask, int n_pages, int rows, int cols, size_t step,
                     size_t page_stride, uint32_t* d_bits);

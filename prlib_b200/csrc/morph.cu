@@ -223,7 +223,7 @@ __device__ __forceinline__ uint32_t hbits(uint32_t b, int n, int lane)
 template <bool CLOSE, int RR>
 __global__ void __launch_bounds__(128)
 morph_bits_kernel(const uint8_t* __restrict__ src, size_t src_step, size_t src_page_stride, uint8_t* __restrict__ dst,
-                  size_t dst_step, size_t dst_page_stride, int rows, int cols, int n, int ns, int nb, int band_rows, int n_pages)
+                  size_t dst_step, size_t dst_page_stride, int rows, int cols, int n1, int n2, int ns, int nb, int band_rows, int n_pages)
 {
     __shared__ uint32_t ring[4][2][RR][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -256,27 +256,28 @@ morph_bits_kernel(const uint8_t* __restrict__ src, size_t src_step, size_t src_p
             if (ld1) b = __ldg(reinterpret_cast<const uint4*>(p + 16));
         }
     };
+    // first operator over (2 n1 + 1)^2, second over (2 n2 + 1)^2 (n2 = 0: the first operator alone)
     uint4 na, nbv;
-    fetch(y0 - 2 * n, na, nbv);
-    for (int Y = y0 - 2 * n; Y < y1 + 2 * n; ++Y) {
+    fetch(y0 - n1 - n2, na, nbv);
+    for (int Y = y0 - n1 - n2; Y < y1 + n1 + n2; ++Y) {
         uint32_t b = pack32(na, nbv);
         fetch(Y + 1, na, nbv);
         // first operator; what lies outside the image is ignored = its neutral value
         const bool in1 = Y >= 0 && Y < rows;
         b = CLOSE ? (in1 ? (b & colmask) : 0u) : (in1 ? (b | ~colmask) : ones);
-        ringA[Y & (RR - 1)][lane] = hbits<CLOSE>(b, n, lane);
-        if (Y < y0) continue;
-        const int yd = Y - n;                             // row whose first-operator window is complete
+        ringA[Y & (RR - 1)][lane] = hbits<CLOSE>(b, n1, lane);
+        if (Y < y0 + n1 - n2) continue;
+        const int yd = Y - n1;                            // row whose first-operator window is complete
         uint32_t D = ringA[Y & (RR - 1)][lane];
-        for (int j = 1; j <= 2 * n; ++j) { const uint32_t v = ringA[(Y - j) & (RR - 1)][lane]; D = CLOSE ? (D | v) : (D & v); }
+        for (int j = 1; j <= 2 * n1; ++j) { const uint32_t v = ringA[(Y - j) & (RR - 1)][lane]; D = CLOSE ? (D | v) : (D & v); }
         // second operator
         const bool in2 = yd >= 0 && yd < rows;
         D = CLOSE ? (in2 ? (D | ~colmask) : ones) : (in2 ? (D & colmask) : 0u);
-        ringB[yd & (RR - 1)][lane] = hbits<!CLOSE>(D, n, lane);
-        const int ye = yd - n;
+        ringB[yd & (RR - 1)][lane] = hbits<!CLOSE>(D, n2, lane);
+        const int ye = yd - n2;
         if (ye < y0 || ye >= y1) continue;
         uint32_t E = ringB[yd & (RR - 1)][lane];
-        for (int j = 1; j <= 2 * n; ++j) { const uint32_t v = ringB[(yd - j) & (RR - 1)][lane]; E = CLOSE ? (E & v) : (E | v); }
+        for (int j = 1; j <= 2 * n2; ++j) { const uint32_t v = ringB[(yd - j) & (RR - 1)][lane]; E = CLOSE ? (E & v) : (E | v); }
         // store row ye: shift the bit row so that this lane's 32 bytes start on a 16-byte boundary
         uint8_t* drow = dst + (size_t)ye * dst_step;
         const int m = (int)((uintptr_t)(drow + xs) & 15);
@@ -303,10 +304,11 @@ morph_bits_kernel(const uint8_t* __restrict__ src, size_t src_step, size_t src_p
 
 template <bool CLOSE>
 void launch_bits(prl_cuda_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int n_pages, int rows, int cols, size_t in_step,
-                 size_t in_page_stride, size_t out_step, size_t out_page_stride, int n)
+                 size_t in_page_stride, size_t out_step, size_t out_page_stride, int n1, int n2)
 {
+    const int n = std::max(n1, n2);
     const int ns = (cols + kBStrip - 1) / kBStrip;
-    // row bands: about one wave of 48 resident warps per SM; a band redoes 4n rows of its neighbours
+    // row bands: about one wave of 48 resident warps per SM; a band redoes 2 (n1 + n2) rows of its neighbours
     const long long want = (long long)ctx->num_sms * 48;
     int nb = (int)((want + (long long)ns * n_pages - 1) / ((long long)ns * n_pages));
     nb = std::max(1, std::min(nb, (rows + 63) / 64));
@@ -316,10 +318,10 @@ void launch_bits(prl_cuda_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int n_p
     const unsigned grid = (unsigned)((warps + 3) / 4);
     if (2 * n + 1 <= 8)
         morph_bits_kernel<CLOSE, 8><<<grid, 128, 0, ctx->stream>>>(d_in, in_step, in_page_stride, d_out, out_step, out_page_stride,
-                                                                   rows, cols, n, ns, nb, band_rows, n_pages);
+                                                                   rows, cols, n1, n2, ns, nb, band_rows, n_pages);
     else
         morph_bits_kernel<CLOSE, 32><<<grid, 128, 0, ctx->stream>>>(d_in, in_step, in_page_stride, d_out, out_step, out_page_stride,
-                                                                    rows, cols, n, ns, nb, band_rows, n_pages);
+                                                                    rows, cols, n1, n2, ns, nb, band_rows, n_pages);
 }
 
 // ---- generic fallback: one separable pass per launch -----------------------------------------
@@ -399,8 +401,8 @@ int prl_k_morph(prl_cuda_ctx* ctx, uint8_t* d_in, uint8_t* d_out, int n_pages, i
     const int n = iters > 0 ? iters : -iters;
     if (binary && !ctx->morph_bytes && n <= 15 && ((((uintptr_t)d_in) | in_step | in_page_stride) & 15) == 0) {
         prl_launch_scope ls(ctx, FAM_MORPH);
-        if (iters > 0) launch_bits<true>(ctx, d_in, d_out, n_pages, rows, cols, in_step, in_page_stride, out_step, out_page_stride, n);
-        else launch_bits<false>(ctx, d_in, d_out, n_pages, rows, cols, in_step, in_page_stride, out_step, out_page_stride, n);
+        if (iters > 0) launch_bits<true>(ctx, d_in, d_out, n_pages, rows, cols, in_step, in_page_stride, out_step, out_page_stride, n, n);
+        else launch_bits<false>(ctx, d_in, d_out, n_pages, rows, cols, in_step, in_page_stride, out_step, out_page_stride, n, n);
         PRL_CUDA_TRY(ctx, cudaGetLastError());
         return PRL_OK;
     }
@@ -428,5 +430,20 @@ int prl_k_morph(prl_cuda_ctx* ctx, uint8_t* d_in, uint8_t* d_out, int n_pages, i
     for (int p = 0; p < n_pages; ++p)
         PRL_CUDA_TRY(ctx, cudaMemcpy2DAsync(d_out + (size_t)p * out_page_stride, out_step, d_in + (size_t)p * in_page_stride, in_step,
                                             cols, rows, cudaMemcpyDeviceToDevice, ctx->stream));
+    return PRL_OK;
+}
+
+// One operator alone on binary masks: cv::dilate (dilate = true) or cv::erode with the 3x3 element, n iterations
+// (binarizeLocalOtsu.cpp:92).  d_in 16-byte aligned (library scratch), 1 <= n <= 15.
+int prl_k_morph_single(prl_cuda_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int n_pages, int rows, int cols, size_t in_step,
+                       size_t in_page_stride, size_t out_step, size_t out_page_stride, int n, bool dilate)
+{
+    if (n_pages > 65535 || rows > 65535) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "grid too large");
+    if (n < 1 || n > 15 || ((((uintptr_t)d_in) | in_step | in_page_stride) & 15) != 0)
+        return prl_set_err(ctx, PRL_E_UNSUPPORTED, "single binary operator: 1 <= n <= 15 and 16-byte aligned input");
+    prl_launch_scope ls(ctx, FAM_MORPH);
+    if (dilate) launch_bits<true>(ctx, d_in, d_out, n_pages, rows, cols, in_step, in_page_stride, out_step, out_page_stride, n, 0);
+    else launch_bits<false>(ctx, d_in, d_out, n_pages, rows, cols, in_step, in_page_stride, out_step, out_page_stride, n, 0);
+    PRL_CUDA_TRY(ctx, cudaGetLastError());
     return PRL_OK;
 }

@@ -1,0 +1,87 @@
+"""Edge front-end of prl::binarizeLocalOtsu: GaussianBlur, Canny, CannyEdgeDetection and the
+whole function against the real OpenCV calls in the reference's order (oracle/prl_oracle.py)."""
+import numpy as np
+import pytest
+
+import prlib_b200
+from oracle import c_oracle as CO
+from oracle import prl_oracle as O
+
+
+def test_gauss_fixed_point_coefficients_reproduce_cv2_blur():
+    """Host-side coefficient derivation (no GPU): a numpy 8.8 / 16.16 convolution with the library's coefficients equals
+    cv2.GaussianBlur bit for bit, for many kernel sizes and sigmas."""
+    import ctypes as C
+    import cv2
+    L = prlib_b200.capi.load()
+    fn = L.prl_cuda_gauss_kernel_fixed
+    fn.restype = C.c_int; fn.argtypes = [C.c_int, C.c_double, C.POINTER(C.c_int)]
+    rng = np.random.default_rng(0)
+    src = rng.integers(0, 256, (90, 130), dtype=np.uint8)
+    for k in (3, 5, 7, 9, 13, 19, 25, 31, 41, 63):
+        for sigma in (0.0, 0.8, 2.0, 3.2, 9.5):
+            buf = (C.c_int * 63)()
+            assert fn(k, sigma, buf) == 0
+            kk = np.array(buf[:k], np.int64)
+            assert kk.sum() == 256
+            r = k // 2
+            p = cv2.copyMakeBorder(src, r, r, r, r, cv2.BORDER_REFLECT_101).astype(np.int64)
+            h = sum(p[:, i:i + src.shape[1]] * kk[i] for i in range(k))
+            v = sum(h[j:j + src.shape[0], :] * kk[j] for j in range(k))
+            mine = np.clip((v + 32768) >> 16, 0, 255).astype(np.uint8)
+            assert np.array_equal(mine, O.gaussian_blur(src, k, sigma)), (k, sigma)
+    buf = (C.c_int * 63)()
+    assert fn(4, 0.0, buf) != 0 and fn(65, 0.0, buf) != 0
+
+
+@pytest.mark.gpu
+def test_gaussian_blur_bit_exact(ctx, noise_page):
+    page = CO.synth_page(2, 700, 900)
+    for img in (noise_page, page, noise_page[:7, :300], noise_page[:200, :5], noise_page[:1, :1]):
+        img = np.ascontiguousarray(img)
+        for k, sigma in ((3, 0), (5, 0), (7, 0), (19, 0), (31, 0), (9, 1.7), (63, 0)):
+            assert np.array_equal(ctx.gaussian_blur(img, k, sigma), O.gaussian_blur(img, k, sigma)), (img.shape, k, sigma)
+    with pytest.raises(ValueError):
+        ctx.gaussian_blur(noise_page, 4)
+
+
+@pytest.mark.gpu
+def test_canny_bit_exact(ctx, noise_page, real_crops):
+    blurred = O.gaussian_blur(noise_page, 9)
+    page = O.gaussian_blur(CO.synth_page(1, 900, 700), 19)
+    flat = np.full((50, 60), 77, np.uint8)
+    steps = np.zeros((64, 64), np.uint8); steps[:, 32:] = 200; steps[40:, :] = 90
+    imgs = [noise_page, blurred, page, flat, steps, np.ascontiguousarray(noise_page[:3, :40]), np.ascontiguousarray(noise_page[:40, :2])]
+    imgs += [np.ascontiguousarray(v) for k, v in real_crops.items() if getattr(v, "ndim", 0) == 2][:2]
+    for img in imgs:
+        for lo, hi in ((0.28, 28.05), (10.5, 40.2), (50, 150), (150, 50), (0, 0), (300, 900)):
+            assert np.array_equal(ctx.canny(img, lo, hi), O.canny(img, lo, hi)), (img.shape, lo, hi)
+
+
+@pytest.mark.gpu
+def test_canny_edge_detection_chain(ctx, noise_page):
+    page = CO.synth_page(0, 1100, 900)
+    for img in (page, noise_page):
+        for k, up, lo, it, post in ((19, 0.15, 0.01, 1, 3), (19, 0.15, 0.01, 1, 0), (5, 0.5, 0.2, 0, 0), (9, 0.3, 0.1, -1, 2),
+                                    (19, 1.0, 1.0, 2, 3)):
+            want = O.local_otsu_edges(img, k, up, lo, it, post)
+            assert np.array_equal(ctx.canny_edge_detection(img, k, up, lo, it, post), want), (img.shape, k, up, lo, it, post)
+    for bad in ((2, 0.15, 0.01), (4, 0.15, 0.01), (19, 1.5, 0.01), (19, 0.1, 0.2), (19, 0.15, -0.1)):
+        with pytest.raises(ValueError):
+            ctx.canny_edge_detection(page, *bad)
+
+
+@pytest.mark.gpu
+def test_binarize_local_otsu_end_to_end(ctx, real_crops):
+    """prl::binarizeLocalOtsu with its header defaults: device edge map + host findContours + device rect loop equals the
+    reference's OpenCV sequence."""
+    page = CO.synth_page(3, 1200, 1000)
+    assert np.array_equal(prlib_b200.binarizeLocalOtsu(page), O.binarizeLocalOtsu(page))
+    assert np.array_equal(prlib_b200.binarizeLocalOtsu(page, 255.0, 0.0, 9, 0.3, 0.1, 2), O.binarizeLocalOtsu(page, 255.0, 0.0, 9, 0.3, 0.1, 2))
+    assert np.array_equal(prlib_b200.binarizeLocalOtsu(page, 100.0), O.binarizeLocalOtsu(page, 100.0))
+    bgr = real_crops["bgr_0037"]
+    assert np.array_equal(prlib_b200.binarizeLocalOtsu(bgr), O.binarizeLocalOtsu(bgr))
+    with pytest.raises(ValueError):
+        prlib_b200.binarizeLocalOtsu(page, 300.0)
+    with pytest.raises(ValueError):
+        prlib_b200.binarizeLocalOtsu(np.full((80, 80), 200, np.uint8))      # no edges -> no contours -> invalid_argument
