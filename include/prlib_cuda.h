@@ -188,6 +188,16 @@ int prl_cuda_canny_edge_detection_dev(prl_cuda_ctx* ctx, const uint8_t* d_gray, 
                                       int gauss_ksize, double upper_coeff, double lower_coeff, int morph_iters,
                                       int post_dilate, uint8_t* d_dst, size_t dst_step);
 
+/* prl::binarizeLocalOtsu (binarizeLocalOtsu.h:50-57 with CLAHEClipLimit = 0) in one call: the edge map above with
+ * post_dilate = 3, the bounding rectangles of its top-level contours -- what cv::findContours(RETR_EXTERNAL) +
+ * cv::boundingRect return (binarizeLocalOtsu.cpp:104-105,150), found by a union-find labelling on the device -- and
+ * the per-rectangle Otsu loop (:138-162).  *n_rects receives the number of rectangles; rects_out (optional, rects_cap
+ * x,y,w,h quadruples) a copy of them in no particular order.  PRL_E_INVALID when there is no contour
+ * (RemoveChildrenContours throws std::invalid_argument, imageLibCommon.cpp:643-646). */
+int prl_cuda_binarize_local_otsu(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step, double maxval,
+                                 int gauss_ksize, double upper_coeff, double lower_coeff, int morph_iters,
+                                 uint8_t* dst, size_t dst_step, int* n_rects, int32_t* rects_out, int rects_cap);
+
 /* ---- 1 bit per pixel ---------------------------------------------
  * The masks in Leptonica's PIX layout, the reference's second image container (src/formatConvert.cpp:39-69
  * writes PIX words with SET_DATA_BIT): rows of wpl = (cols + 31) / 32 32-bit words, pixel x of a row in word

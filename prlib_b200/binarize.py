@@ -102,10 +102,9 @@ def binarizeLocalOtsuRects(image, rects, maxValue: float = 255.0, device: int = 
 def binarizeLocalOtsu(image, maxValue: float = 255.0, CLAHEClipLimit: float = 0.0, GaussianBlurKernelSize: int = 19,
                       CannyUpperThresholdCoeff: float = 0.15, CannyLowerThresholdCoeff: float = 0.01, CannyMorphIters: int = 1,
                       device: int = 0) -> np.ndarray:
-    """prl::binarizeLocalOtsu (binarizeLocalOtsu.h:50-57, same defaults).  On the device: blur, Otsu value, Canny,
-    closing, dilation (prl_cuda_canny_edge_detection) and the per-rectangle Otsu loop (prl_cuda_otsu_rects).  On the
-    host, as in INTEGRATION.md: cv::findContours(RETR_EXTERNAL) + boundingRect of the edge map (binarizeLocalOtsu.cpp:
-    104-110,150) -- OpenCV is the reference's own dependency and is imported here for that call only."""
+    """prl::binarizeLocalOtsu (binarizeLocalOtsu.h:50-57, same defaults), all on the device: blur, Otsu value, Canny,
+    closing, dilation, bounding rectangles of the top-level contours and the per-rectangle Otsu loop
+    (prl_cuda_binarize_local_otsu)."""
     image = np.asarray(image)
     if image.size == 0:
         raise ValueError("Input image for binarization is empty")                   # binarizeLocalOtsu.cpp:47-50
@@ -118,14 +117,8 @@ def binarizeLocalOtsu(image, maxValue: float = 255.0, CLAHEClipLimit: float = 0.
     ctx = default_context(device)
     # (the reference converts with COLOR_RGB2GRAY here, binarizeLocalOtsu.cpp:63: channel 0 is weighted as red)
     gray = ctx.bgr2gray(np.ascontiguousarray(image[:, :, 2::-1])) if image.ndim == 3 else _gray(image, ctx)
-    edges = ctx.canny_edge_detection(gray, GaussianBlurKernelSize, CannyUpperThresholdCoeff, CannyLowerThresholdCoeff,
-                                     CannyMorphIters, 3)
-    import cv2
-    contours, _ = cv2.findContours(edges, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
-    if len(contours) == 0:
-        raise ValueError("Contours array is empty")                                 # imageLibCommon.cpp:643-646
-    rects = [cv2.boundingRect(c) for c in contours if len(c) >= 3]                  # :717-737 with a flat hierarchy
-    return ctx.otsu_rects(gray, rects, maxValue)
+    return ctx.binarize_local_otsu(gray, maxValue, GaussianBlurKernelSize, CannyUpperThresholdCoeff, CannyLowerThresholdCoeff,
+                                   CannyMorphIters)
 
 
 def binarizeLocalOtsuTiles(image, tileWidth: int = 64, tileHeight: int = 64, maxValue: float = 255.0,

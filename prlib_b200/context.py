@@ -242,6 +242,19 @@ class Context:
                                                           int(post_dilate), out.ctypes.data, g.shape[1]))
         return out
 
+    def binarize_local_otsu(self, gray, maxval: float = 255.0, ksize: int = 19, upper_coeff: float = 0.15, lower_coeff: float = 0.01,
+                            morph_iters: int = 1, return_rects: bool = False):
+        """prl::binarizeLocalOtsu on a gray image, all on the device (prl_cuda_binarize_local_otsu)."""
+        g = _as_u8_2d(gray)
+        out = np.empty(g.shape, np.uint8)
+        n = C.c_int()
+        cap = 65535 if return_rects else 0
+        rects = np.zeros((max(cap, 1), 4), np.int32)
+        self._check(self._L.prl_cuda_binarize_local_otsu(self._h, g.ctypes.data, g.shape[0], g.shape[1], g.strides[0], float(maxval),
+                                                         int(ksize), float(upper_coeff), float(lower_coeff), int(morph_iters),
+                                                         out.ctypes.data, g.shape[1], C.byref(n), rects.ctypes.data if cap else None, cap))
+        return (out, rects[:n.value]) if return_rects else out
+
     # -- device-pointer entry points (raw addresses: torch .data_ptr() or cudaMalloc) ----------
     def binarize_local_batch_dev(self, method, d_src, n_pages, rows, cols, src_step, src_page_stride, window, params,
                                  morph_iters, d_dst, dst_step, dst_page_stride):

@@ -167,7 +167,7 @@ extern "C" void prl_cuda_destroy(prl_cuda_ctx* c)
     for (auto& ev : c->event_pool) cudaEventDestroy(ev);
     cudaFree(c->planes); cudaFree(c->carry); cudaFree(c->colsum); cudaFree(c->scalars); cudaFree(c->fused_ws);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
-    cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_tmp); cudaFree(c->d_misc); cudaFree(c->d_bgr); cudaFree(c->edges_ws);
+    cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_tmp); cudaFree(c->d_misc); cudaFree(c->d_bgr); cudaFree(c->edges_ws); cudaFree(c->rects_ws);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -668,6 +668,49 @@ static int edges_host(prl_cuda_ctx* c, int what, const uint8_t* src, int rows, i
         rc = prl_cuda_canny_edge_detection_dev(c, c->d_in, rows, cols, in_step, ksize, a, b, morph_iters, post_dilate, c->d_out, o_step);
     }
     if (rc) return rc;
+    PRL_CUDA_TRY(c, cudaMemcpy2DAsync(dst, dst_step, c->d_out, o_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
+    PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return PRL_OK;
+}
+
+// prl::binarizeLocalOtsu (binarizeLocalOtsu.cpp:38-163, CLAHE off) in one call: edge map, bounding rectangles of the
+// top-level contours and the per-rectangle Otsu loop all on the device; the image crosses PCIe once each way.
+extern "C" int prl_cuda_binarize_local_otsu(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step, double maxval,
+                                            int gauss_ksize, double upper_coeff, double lower_coeff, int morph_iters,
+                                            uint8_t* dst, size_t dst_step, int* n_rects, int32_t* rects_out, int rects_cap)
+{
+    if (!c) return PRL_E_INVALID;
+    if (!src || !dst || rows <= 0 || cols <= 0 || step < (size_t)cols || dst_step < (size_t)cols)
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    if (!(maxval >= 0 && maxval <= 255)) return prl_set_err(c, PRL_E_INVALID, "Max value must be in range [0; 255]");   // :52-55
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    size_t in_step;
+    int rc = stage_in(c, src, rows, cols, step, &in_step); if (rc) return rc;
+    const size_t o_step = round16(cols);
+    rc = prl_ensure(c, (void**)&c->d_out, &c->d_out_bytes, o_step * rows); if (rc) return rc;
+    rc = prl_ensure(c, (void**)&c->d_tmp, &c->d_tmp_bytes, o_step * rows); if (rc) return rc;
+    // edge map (binarizeLocalOtsu.cpp:85-92) -> d_tmp
+    rc = prl_cuda_canny_edge_detection_dev(c, c->d_in, rows, cols, in_step, gauss_ksize, upper_coeff, lower_coeff, morph_iters, 3,
+                                           c->d_tmp, o_step);
+    if (rc) return rc;
+    // rectangles (:104-110,150); the list never leaves the device on its way to the Otsu loop
+    constexpr int kCap = 65535;
+    const size_t list_bytes = (256 + (size_t)kCap * 16 + (size_t)kCap * 4 + 255) & ~(size_t)255;
+    rc = prl_ensure(c, &c->rects_ws, &c->rects_ws_bytes, list_bytes + prl_rects_scratch_bytes(rows, cols)); if (rc) return rc;
+    int* d_count = (int*)c->rects_ws;
+    int32_t* d_xywh = (int32_t*)((uint8_t*)c->rects_ws + 256);
+    int32_t* d_thr = d_xywh + (size_t)kCap * 4;
+    rc = prl_k_external_rects(c, c->d_tmp, rows, cols, o_step, d_count, d_xywh, kCap, (uint8_t*)c->rects_ws + list_bytes);
+    if (rc) return rc;
+    int count = 0;
+    PRL_CUDA_TRY(c, cudaMemcpyAsync(&count, d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (n_rects) *n_rects = count;
+    if (count == 0) return prl_set_err(c, PRL_E_INVALID, "Contours array is empty");                  // imageLibCommon.cpp:643-646
+    if (count > kCap) return prl_set_err(c, PRL_E_UNSUPPORTED, "more than 65535 contours");
+    if (rects_out && rects_cap > 0)
+        PRL_CUDA_TRY(c, cudaMemcpyAsync(rects_out, d_xywh, (size_t)std::min(count, rects_cap) * 16, cudaMemcpyDeviceToHost, c->stream));
+    rc = prl_k_otsu_rects(c, c->d_in, rows, cols, in_step, d_xywh, count, maxval, c->d_out, o_step, d_thr); if (rc) return rc;
     PRL_CUDA_TRY(c, cudaMemcpy2DAsync(dst, dst_step, c->d_out, o_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
     PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return PRL_OK;

@@ -190,6 +190,135 @@ ccl_emit_kernel(const uint8_t* __restrict__ cls, size_t cstep, int rows, int col
     dst[(size_t)y * dstep + x] = out;
 }
 
+// ---- contours -> rectangles: cv::findContours(RETR_EXTERNAL) + cv::boundingRect without the contours ------------
+// RETR_EXTERNAL keeps one outer border per 8-connected component of non-zero pixels that does not lie inside a hole
+// of another component; the rectangle loop only needs its bounding box.  Topologically (Suzuki-Abe, 8-connected
+// 1-pixels / 4-connected 0-pixels): a component is top-level iff one of its pixels has, in its 4-neighbourhood, a
+// 0-pixel of the background component that reaches the image frame (or the frame itself).  So: label 1-pixels with
+// 8-connectivity and 0-pixels with 4-connectivity in ONE union-find forest (plus a node for the frame), then every
+// border pixel of a component votes "top-level" and stretches its root's bounding box.
+// Rows are labelled by runs first (no atomics: every pixel points at the start of its horizontal run), so the
+// atomicMin unions only happen once per vertically overlapping pair of runs.
+__device__ __forceinline__ int uf_find_c(int* L, int x)
+{
+    for (;;) {
+        const int p = L[x];
+        if (p == x) return x;
+        const int gp = L[p];
+        if (gp != p) atomicMin(&L[x], gp);                   // path halving; labels only ever decrease
+        x = p;
+    }
+}
+__device__ __forceinline__ void uf_union_c(int* L, int a, int b)
+{
+    for (;;) {
+        a = uf_find_c(L, a); b = uf_find_c(L, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }
+        const int old = atomicMin(&L[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+// one CTA per row: L[y * cols + x] = y * cols + (start of the horizontal run of equal class that holds x)
+__global__ void __launch_bounds__(256)
+ccl_runs_kernel(const uint8_t* __restrict__ E, size_t estep, int rows, int cols, int* __restrict__ L)
+{
+    __shared__ int wmax[8];
+    const int y = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint8_t* row = E + (size_t)y * estep;
+    const int seg = (cols + 255) / 256, x0 = tid * seg, x1 = min(x0 + seg, cols);
+    int last = -1;                                            // last run start inside this thread's segment
+    for (int x = x0; x < x1; ++x)
+        if (x == 0 || (row[x] != 0) != (row[x - 1] != 0)) last = x;
+    // exclusive running maximum over the threads to the left
+    int v = last;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v = max(v, t); }
+    if (lane == 31) wmax[wid] = v;
+    __syncthreads();
+    int carry = -1;
+    for (int k = 0; k < wid; ++k) carry = max(carry, wmax[k]);
+    int prev = __shfl_up_sync(0xffffffffu, v, 1);
+    if (lane == 0) prev = -1;
+    int cur = max(carry, prev);
+    for (int x = x0; x < x1; ++x) {
+        if (x == 0 || (row[x] != 0) != (row[x - 1] != 0)) cur = x;
+        L[y * cols + x] = y * cols + cur;
+    }
+    if (y == 0 && tid == 0) L[rows * cols] = rows * cols;     // the frame node
+}
+
+__global__ void __launch_bounds__(256)
+ccl_vmerge_kernel(const uint8_t* __restrict__ E, size_t estep, int rows, int cols, int* __restrict__ L)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cols) return;
+    const uint8_t* row = E + (size_t)y * estep;
+    const bool c = row[x] != 0;
+    const bool cw = x > 0 ? row[x - 1] != 0 : !c;             // "different class" at the row start
+    const int p = y * cols + x;
+    if (y > 0) {
+        const uint8_t* up = row - estep;
+        const bool cn = up[x] != 0;
+        const bool cnw = x > 0 ? up[x - 1] != 0 : !cn;
+        if (cn == c) {
+            if (cw != c || cnw != cn) uf_union_c(L, p, p - cols);       // first column of this overlap of two runs
+        } else if (c) {
+            // 8-connectivity of the 1-pixels: diagonal neighbours that no 4-neighbour already bridges
+            if (x > 0 && cnw && !cw) uf_union_c(L, p, p - cols - 1);
+            if (x + 1 < cols && up[x + 1] != 0) uf_union_c(L, p, p - cols + 1);
+        }
+    }
+    if (!c) {
+        // 0-pixels on the image border belong to the outer background (findContours works on a zero-framed copy)
+        const bool run_start = cw != c;
+        if (((y == 0 || y == rows - 1) && run_start) || x == 0 || x == cols - 1) uf_union_c(L, p, rows * cols);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ccl_border_kernel(const uint8_t* __restrict__ E, size_t estep, int rows, int cols, int* __restrict__ L, uint8_t* __restrict__ top,
+                  int* __restrict__ bx0, int* __restrict__ by0, int* __restrict__ bx1, int* __restrict__ by1)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cols) return;
+    const uint8_t* row = E + (size_t)y * estep;
+    if (!row[x]) return;
+    // 4-neighbours: outside the image (= frame), 0-pixel, or 1-pixel
+    const bool oW = x == 0, oE = x == cols - 1, oN = y == 0, oS = y == rows - 1;
+    const uint8_t* up = row - estep;
+    const uint8_t* dn = row + estep;
+    const bool zW = !oW && !row[x - 1], zE = !oE && !row[x + 1], zN = !oN && !up[x], zS = !oS && !dn[x];
+    if (!(oW | oE | oN | oS | zW | zE | zN | zS)) return;     // interior pixel: neither a vote nor a bounding-box extreme
+    const int p = y * cols + x, root = uf_find_c(L, p);
+    bool outer = oW | oE | oN | oS;
+    if (!outer) {
+        const int fr = uf_find_c(L, rows * cols);
+        outer = (zW && uf_find_c(L, p - 1) == fr) || (zE && uf_find_c(L, p + 1) == fr) ||
+                (zN && uf_find_c(L, p - cols) == fr) || (zS && uf_find_c(L, p + cols) == fr);
+    }
+    if (outer) top[root] = 1;
+    atomicMin(&bx0[root], x); atomicMin(&by0[root], y); atomicMax(&bx1[root], x); atomicMax(&by1[root], y);
+}
+
+__global__ void __launch_bounds__(256)
+ccl_rects_kernel(const uint8_t* __restrict__ E, size_t estep, int rows, int cols, const int* __restrict__ L, const uint8_t* __restrict__ top,
+                 const int* __restrict__ bx0, const int* __restrict__ by0, const int* __restrict__ bx1, const int* __restrict__ by1,
+                 int* __restrict__ count, int32_t* __restrict__ xywh, int cap)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cols) return;
+    const int p = y * cols + x;
+    if (!E[(size_t)y * estep + x] || L[p] != p || !top[p]) return;
+    const int slot = atomicAdd(count, 1);
+    if (slot < cap) {
+        xywh[4 * slot] = bx0[p]; xywh[4 * slot + 1] = by0[p];
+        xywh[4 * slot + 2] = bx1[p] - bx0[p] + 1; xywh[4 * slot + 3] = by1[p] - by0[p] + 1;
+    }
+}
+
 inline size_t r16(size_t v) { return (v + 15) & ~(size_t)15; }
 inline size_t r256(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -279,4 +408,38 @@ int prl_k_canny(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, siz
 size_t prl_canny_scratch_bytes(int rows, int cols)
 {
     return r256(r16((size_t)cols) * rows) + r256((size_t)rows * cols * sizeof(int)) + r256((size_t)rows * cols);
+}
+
+// Bounding rectangles of the top-level components of a 0/255 map (what cv::findContours(RETR_EXTERNAL) +
+// cv::boundingRect give, binarizeLocalOtsu.cpp:104-105,150).  d_count: one int; d_xywh: cap x 4 ints.
+// scratch: labels (rows*cols + 1) int32 | top rows*cols bytes | 4 x rows*cols int32 boxes
+size_t prl_rects_scratch_bytes(int rows, int cols)
+{
+    const size_t n = (size_t)rows * cols;
+    return r256((n + 1) * sizeof(int)) + r256(n) + 4 * r256(n * sizeof(int));
+}
+
+int prl_k_external_rects(prl_cuda_ctx* ctx, const uint8_t* d_edges, int rows, int cols, size_t step, int* d_count,
+                         int32_t* d_xywh, int cap, void* scratch)
+{
+    if (rows > 65535 || (long long)rows * cols >= 0x7fffffffLL) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "image too large");
+    const size_t n = (size_t)rows * cols;
+    uint8_t* b = (uint8_t*)scratch;
+    int* L = (int*)b; b += r256((n + 1) * sizeof(int));
+    uint8_t* top = b; b += r256(n);
+    int* bx0 = (int*)b; b += r256(n * sizeof(int));
+    int* by0 = (int*)b; b += r256(n * sizeof(int));
+    int* bx1 = (int*)b; b += r256(n * sizeof(int));
+    int* by1 = (int*)b;
+    PRL_CUDA_TRY(ctx, cudaMemsetAsync(top, 0, n, ctx->stream));
+    PRL_CUDA_TRY(ctx, cudaMemsetAsync(bx0, 0x7f, 2 * r256(n * sizeof(int)), ctx->stream));      // x0, y0 = 0x7f7f7f7f
+    PRL_CUDA_TRY(ctx, cudaMemsetAsync(bx1, 0xff, 2 * r256(n * sizeof(int)), ctx->stream));      // x1, y1 = -1
+    PRL_CUDA_TRY(ctx, cudaMemsetAsync(d_count, 0, sizeof(int), ctx->stream));
+    dim3 grid((cols + 255) / 256, rows);
+    { prl_launch_scope ls(ctx, FAM_EDGES); ccl_runs_kernel<<<rows, 256, 0, ctx->stream>>>(d_edges, step, rows, cols, L); }
+    { prl_launch_scope ls(ctx, FAM_EDGES); ccl_vmerge_kernel<<<grid, 256, 0, ctx->stream>>>(d_edges, step, rows, cols, L); }
+    { prl_launch_scope ls(ctx, FAM_EDGES); ccl_border_kernel<<<grid, 256, 0, ctx->stream>>>(d_edges, step, rows, cols, L, top, bx0, by0, bx1, by1); }
+    { prl_launch_scope ls(ctx, FAM_EDGES); ccl_rects_kernel<<<grid, 256, 0, ctx->stream>>>(d_edges, step, rows, cols, L, top, bx0, by0, bx1, by1, d_count, d_xywh, cap); }
+    PRL_CUDA_TRY(ctx, cudaGetLastError());
+    return PRL_OK;
 }

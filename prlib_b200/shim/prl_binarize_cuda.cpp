@@ -144,3 +144,23 @@ double prl::thresholdOtsu(const cv::Mat& src, cv::Mat& dst, double maxValue)
     dst = out;
     return (double)thr;
 }
+
+void prl::localOtsuEdges(const cv::Mat& imageToProc, cv::Mat& resultCanny, int GaussianBlurKernelSize,
+                         double CannyUpperThresholdCoeff, double CannyLowerThresholdCoeff, int CannyMorphIters, int postDilate)
+{
+    if (imageToProc.empty()) throw std::invalid_argument("Image for histograms extraction is empty");          // :248-251
+    if (GaussianBlurKernelSize < 3) throw std::invalid_argument("Gaussian blur kernel size is lesser than 3");   // :253-256
+    if (CannyUpperThresholdCoeff < 0 || CannyUpperThresholdCoeff > 1)
+        throw std::invalid_argument("Canny upper threshold coefficient isn't in range [0;1]");                   // :258-261
+    if (CannyLowerThresholdCoeff < 0 || CannyLowerThresholdCoeff > 1)
+        throw std::invalid_argument("Canny lower threshold coefficient isn't in range [0;1]");                   // :263-266
+    if (CannyLowerThresholdCoeff > CannyUpperThresholdCoeff)
+        throw std::invalid_argument("Canny lower threshold coefficient is greater than Canny upper threshold coefficient");
+    if (imageToProc.channels() != 1) throw std::invalid_argument("expected a single-channel image");
+    prl_cuda_ctx* c = context();
+    cv::Mat out(imageToProc.rows, imageToProc.cols, CV_8UC1);
+    check(c, prl_cuda_canny_edge_detection(c, imageToProc.data, imageToProc.rows, imageToProc.cols, imageToProc.step,
+                                           GaussianBlurKernelSize, CannyUpperThresholdCoeff, CannyLowerThresholdCoeff,
+                                           CannyMorphIters, postDilate, out.data, out.step));
+    resultCanny = out;
+}

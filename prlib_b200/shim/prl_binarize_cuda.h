@@ -38,6 +38,12 @@ CV_EXPORTS void binarizeLocalOtsuRects(const cv::Mat& gray, const std::vector<in
 // cv::threshold(src, dst, 128, maxValue, THRESH_BINARY | THRESH_OTSU) (deskew.cpp:224, removeLines.cpp:45);
 // returns the threshold like cv::threshold does.
 CV_EXPORTS double thresholdOtsu(const cv::Mat& src, cv::Mat& dst, double maxValue = 255);
+// The edge map prl::binarizeLocalOtsu feeds to cv::findContours: CannyEdgeDetection(imageToProc, resultCanny, ...)
+// (imageLibCommon.cpp:244-324) followed by cv::dilate(resultCanny, ..., postDilate = 3) (binarizeLocalOtsu.cpp:88-92),
+// single-channel input, same std::invalid_argument checks as the reference.
+CV_EXPORTS void localOtsuEdges(const cv::Mat& imageToProc, cv::Mat& resultCanny, int GaussianBlurKernelSize = 19,
+                               double CannyUpperThresholdCoeff = 0.15, double CannyLowerThresholdCoeff = 0.01,
+                               int CannyMorphIters = 1, int postDilate = 3);
 }  // namespace prl
 
 #endif  // PRL_BINARIZE_CUDA_H

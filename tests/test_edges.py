@@ -72,6 +72,25 @@ def test_canny_edge_detection_chain(ctx, noise_page):
 
 
 @pytest.mark.gpu
+def test_contour_rectangles_equal_findcontours(ctx, noise_page, real_crops):
+    """Device rectangles == cv2.findContours(RETR_EXTERNAL) + boundingRect as a set, including pages where components
+    sit inside holes of other components (those must be left out)."""
+    import cv2
+    pages = [CO.synth_page(0, 1500, 1300), CO.synth_page(5, 700, 2000), noise_page] + \
+            [np.ascontiguousarray(v) for k, v in real_crops.items() if getattr(v, "ndim", 0) == 2]
+    nested_seen = False
+    for page in pages:
+        edges = O.local_otsu_edges(page)
+        want = sorted(O.contour_rects(edges))
+        n_cc, _ = cv2.connectedComponents((edges > 0).astype(np.uint8), connectivity=8)
+        nested_seen |= (n_cc - 1) > len(want)
+        mask, rects = ctx.binarize_local_otsu(page, return_rects=True)
+        assert sorted(map(tuple, rects.tolist())) == want, page.shape
+        assert np.array_equal(mask, O.binarizeLocalOtsu(page)), page.shape
+    assert nested_seen                                  # the enclosure rule was exercised
+
+
+@pytest.mark.gpu
 def test_binarize_local_otsu_end_to_end(ctx, real_crops):
     """prl::binarizeLocalOtsu with its header defaults: device edge map + host findContours + device rect loop equals the
     reference's OpenCV sequence."""
