@@ -193,9 +193,10 @@ int prl_cuda_canny_edge_detection_dev(prl_cuda_ctx* ctx, const uint8_t* d_gray, 
  * cv::boundingRect return (binarizeLocalOtsu.cpp:104-105,150), found by a union-find labelling on the device -- and
  * the per-rectangle Otsu loop (:138-162).  *n_rects receives the number of rectangles; rects_out (optional, rects_cap
  * x,y,w,h quadruples) a copy of them in no particular order.  PRL_E_INVALID when there is no contour
- * (RemoveChildrenContours throws std::invalid_argument, imageLibCommon.cpp:643-646). */
-int prl_cuda_binarize_local_otsu(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step, double maxval,
-                                 int gauss_ksize, double upper_coeff, double lower_coeff, int morph_iters,
+ * (RemoveChildrenContours throws std::invalid_argument, imageLibCommon.cpp:643-646).  channels 3 or 4: interleaved
+ * 8-bit, converted like cv::cvtColor(COLOR_RGB2GRAY) -- the code the reference uses here (binarizeLocalOtsu.cpp:63). */
+int prl_cuda_binarize_local_otsu(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step, int channels,
+                                 double maxval, int gauss_ksize, double upper_coeff, double lower_coeff, int morph_iters,
                                  uint8_t* dst, size_t dst_step, int* n_rects, int32_t* rects_out, int rects_cap);
 
 /* ---- 1 bit per pixel ---------------------------------------------

@@ -115,9 +115,8 @@ def binarizeLocalOtsu(image, maxValue: float = 255.0, CLAHEClipLimit: float = 0.
     if GaussianBlurKernelSize < 3:
         raise ValueError("Gaussian blur kernel size is lesser than 3")              # imageLibCommon.cpp:253-256
     ctx = default_context(device)
-    # (the reference converts with COLOR_RGB2GRAY here, binarizeLocalOtsu.cpp:63: channel 0 is weighted as red)
-    gray = ctx.bgr2gray(np.ascontiguousarray(image[:, :, 2::-1])) if image.ndim == 3 else _gray(image, ctx)
-    return ctx.binarize_local_otsu(gray, maxValue, GaussianBlurKernelSize, CannyUpperThresholdCoeff, CannyLowerThresholdCoeff,
+    # (3/4-channel input is converted with COLOR_RGB2GRAY on the device, as binarizeLocalOtsu.cpp:63 does)
+    return ctx.binarize_local_otsu(image, maxValue, GaussianBlurKernelSize, CannyUpperThresholdCoeff, CannyLowerThresholdCoeff,
                                    CannyMorphIters)
 
 

@@ -242,17 +242,21 @@ class Context:
                                                           int(post_dilate), out.ctypes.data, g.shape[1]))
         return out
 
-    def binarize_local_otsu(self, gray, maxval: float = 255.0, ksize: int = 19, upper_coeff: float = 0.15, lower_coeff: float = 0.01,
+    def binarize_local_otsu(self, image, maxval: float = 255.0, ksize: int = 19, upper_coeff: float = 0.15, lower_coeff: float = 0.01,
                             morph_iters: int = 1, return_rects: bool = False):
-        """prl::binarizeLocalOtsu on a gray image, all on the device (prl_cuda_binarize_local_otsu)."""
-        g = _as_u8_2d(gray)
-        out = np.empty(g.shape, np.uint8)
+        """prl::binarizeLocalOtsu, all on the device (prl_cuda_binarize_local_otsu).  image: (H, W) gray or (H, W, 3|4)."""
+        im = np.ascontiguousarray(image)
+        if im.dtype != np.uint8 or im.ndim not in (2, 3):
+            raise ValueError("image must be uint8, (H, W) or (H, W, C)")
+        ch = 1 if im.ndim == 2 else im.shape[2]
+        out = np.empty(im.shape[:2], np.uint8)
         n = C.c_int()
         cap = 65535 if return_rects else 0
         rects = np.zeros((max(cap, 1), 4), np.int32)
-        self._check(self._L.prl_cuda_binarize_local_otsu(self._h, g.ctypes.data, g.shape[0], g.shape[1], g.strides[0], float(maxval),
-                                                         int(ksize), float(upper_coeff), float(lower_coeff), int(morph_iters),
-                                                         out.ctypes.data, g.shape[1], C.byref(n), rects.ctypes.data if cap else None, cap))
+        self._check(self._L.prl_cuda_binarize_local_otsu(self._h, im.ctypes.data, im.shape[0], im.shape[1], im.strides[0], ch,
+                                                         float(maxval), int(ksize), float(upper_coeff), float(lower_coeff),
+                                                         int(morph_iters), out.ctypes.data, im.shape[1], C.byref(n),
+                                                         rects.ctypes.data if cap else None, cap))
         return (out, rects[:n.value]) if return_rects else out
 
     # -- device-pointer entry points (raw addresses: torch .data_ptr() or cudaMalloc) ----------

@@ -675,17 +675,29 @@ static int edges_host(prl_cuda_ctx* c, int what, const uint8_t* src, int rows, i
 
 // prl::binarizeLocalOtsu (binarizeLocalOtsu.cpp:38-163, CLAHE off) in one call: edge map, bounding rectangles of the
 // top-level contours and the per-rectangle Otsu loop all on the device; the image crosses PCIe once each way.
-extern "C" int prl_cuda_binarize_local_otsu(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step, double maxval,
-                                            int gauss_ksize, double upper_coeff, double lower_coeff, int morph_iters,
+extern "C" int prl_cuda_binarize_local_otsu(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step, int channels,
+                                            double maxval, int gauss_ksize, double upper_coeff, double lower_coeff, int morph_iters,
                                             uint8_t* dst, size_t dst_step, int* n_rects, int32_t* rects_out, int rects_cap)
 {
     if (!c) return PRL_E_INVALID;
-    if (!src || !dst || rows <= 0 || cols <= 0 || step < (size_t)cols || dst_step < (size_t)cols)
+    if (!src || !dst || rows <= 0 || cols <= 0 || (channels != 1 && channels != 3 && channels != 4) ||
+        step < (size_t)cols * channels || dst_step < (size_t)cols)
         return prl_set_err(c, PRL_E_INVALID, "bad argument");
     if (!(maxval >= 0 && maxval <= 255)) return prl_set_err(c, PRL_E_INVALID, "Max value must be in range [0; 255]");   // :52-55
     PRL_CUDA_TRY(c, cudaSetDevice(c->device));
     size_t in_step;
-    int rc = stage_in(c, src, rows, cols, step, &in_step); if (rc) return rc;
+    int rc;
+    if (channels == 1) {
+        rc = stage_in(c, src, rows, cols, step, &in_step); if (rc) return rc;
+    } else {
+        // cv::cvtColor(inputImage, ..., COLOR_RGB2GRAY) (binarizeLocalOtsu.cpp:63) on the device
+        const size_t bstep = round16((size_t)cols * channels);
+        in_step = round16(cols);
+        rc = prl_ensure(c, (void**)&c->d_bgr, &c->d_bgr_bytes, bstep * rows); if (rc) return rc;
+        rc = prl_ensure(c, (void**)&c->d_in, &c->d_in_bytes, in_step * rows); if (rc) return rc;
+        PRL_CUDA_TRY(c, copy2d(c->d_bgr, bstep, src, step, (size_t)cols * channels, rows, cudaMemcpyHostToDevice, c->stream));
+        rc = prl_k_bgr2gray(c, c->d_bgr, rows, cols, bstep, channels, c->d_in, in_step, true); if (rc) return rc;
+    }
     const size_t o_step = round16(cols);
     rc = prl_ensure(c, (void**)&c->d_out, &c->d_out_bytes, o_step * rows); if (rc) return rc;
     rc = prl_ensure(c, (void**)&c->d_tmp, &c->d_tmp_bytes, o_step * rows); if (rc) return rc;

@@ -123,7 +123,7 @@ int prl_k_not_binary(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols
 int prl_k_pack_mask(prl_cuda_ctx* ctx, const uint8_t* d_mask, int n_pages, int rows, int cols, size_t step,
                     size_t page_stride, uint32_t* d_bits);
 int prl_k_bgr2gray(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, int channels,
-                   uint8_t* d_dst, size_t dst_step);
+                   uint8_t* d_dst, size_t dst_step, bool rgb = false);
 int prl_k_synth(prl_cuda_ctx* ctx, uint8_t* d_dst, int n_pages, int rows, int cols, size_t step,
                 size_t page_stride, uint32_t seed, uint32_t first_page);
 int prl_k_otsu_global(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int rows, int cols, size_t src_step,

@@ -38,13 +38,14 @@ synth_kernel(uint8_t* __restrict__ dst, int rows, int cols, size_t step, size_t 
 // (binarizeSauvola.cpp:49-52).
 __global__ void __launch_bounds__(256)
 bgr2gray_kernel(const uint8_t* __restrict__ src, int rows, int cols, size_t step, int channels,
-                uint8_t* __restrict__ dst, size_t dst_step)
+                uint8_t* __restrict__ dst, size_t dst_step, int rgb)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     if (x >= cols) return;
     const uint8_t* p = src + (size_t)y * step + (size_t)x * channels;
-    const uint32_t v = (uint32_t)p[0] * 3735u + (uint32_t)p[1] * 19235u + (uint32_t)p[2] * 9798u + 16384u;
+    // rgb: COLOR_RGB2GRAY (channel 0 is red), as binarizeLocalOtsu.cpp:63 calls it
+    const uint32_t v = (uint32_t)p[rgb ? 2 : 0] * 3735u + (uint32_t)p[1] * 19235u + (uint32_t)p[rgb ? 0 : 2] * 9798u + 16384u;
     dst[(size_t)y * dst_step + x] = (uint8_t)(v >> 15);
 }
 
@@ -110,12 +111,12 @@ int prl_k_synth(prl_cuda_ctx* ctx, uint8_t* d_dst, int n_pages, int rows, int co
 }
 
 int prl_k_bgr2gray(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, int channels,
-                   uint8_t* d_dst, size_t dst_step)
+                   uint8_t* d_dst, size_t dst_step, bool rgb)
 {
     if (rows > 65535) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "grid too large");
     prl_launch_scope ls(ctx, FAM_BGR2GRAY);
     bgr2gray_kernel<<<dim3((cols + 255) / 256, rows), 256, 0, ctx->stream>>>(d_src, rows, cols, step, channels,
-                                                                           d_dst, dst_step);
+                                                                           d_dst, dst_step, rgb ? 1 : 0);
     PRL_CUDA_TRY(ctx, cudaGetLastError());
     return PRL_OK;
 }

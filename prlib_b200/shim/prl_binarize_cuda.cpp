@@ -164,3 +164,41 @@ void prl::localOtsuEdges(const cv::Mat& imageToProc, cv::Mat& resultCanny, int G
                                            CannyMorphIters, postDilate, out.data, out.step));
     resultCanny = out;
 }
+
+#ifdef PRL_CUDA_HAVE_CLAHE
+#include "imageLibCommon.h"
+#endif
+
+void prl::binarizeLocalOtsu(cv::Mat& inputImage, cv::Mat& outputImage, double maxValue, double CLAHEClipLimit,
+                            int GaussianBlurKernelSize, double CannyUpperThresholdCoeff, double CannyLowerThresholdCoeff,
+                            int CannyMorphIters)
+{
+    if (inputImage.empty()) throw std::invalid_argument("Input image for binarization is empty");                // :47-50
+    if (!(maxValue >= 0 && maxValue <= 255)) throw std::invalid_argument("Max value must be in range [0; 255]");  // :52-55
+    if (GaussianBlurKernelSize < 3) throw std::invalid_argument("Gaussian blur kernel size is lesser than 3");
+    if (CannyUpperThresholdCoeff < 0 || CannyUpperThresholdCoeff > 1 || CannyLowerThresholdCoeff < 0 ||
+        CannyLowerThresholdCoeff > 1 || CannyLowerThresholdCoeff > CannyUpperThresholdCoeff)
+        throw std::invalid_argument("Canny threshold coefficients must satisfy 0 <= lower <= upper <= 1");
+    prl_cuda_ctx* c = context();
+    cv::Mat out(inputImage.rows, inputImage.cols, CV_8UC1);
+    int n = 0;
+    if (CLAHEClipLimit > 0) {
+#ifdef PRL_CUDA_HAVE_CLAHE
+        // gray conversion on the host as the reference does, then its own CLAHE step, then the device path
+        cv::Mat gray;
+        if (inputImage.channels() != 1) cv::cvtColor(inputImage, gray, cv::COLOR_RGB2GRAY); else gray = inputImage.clone();
+        EnhanceLocalContrastByCLAHE(gray, gray, CLAHEClipLimit, true);
+        check(c, prl_cuda_binarize_local_otsu(c, gray.data, gray.rows, gray.cols, gray.step, 1, maxValue, GaussianBlurKernelSize,
+                                              CannyUpperThresholdCoeff, CannyLowerThresholdCoeff, CannyMorphIters, out.data,
+                                              out.step, &n, nullptr, 0));
+        outputImage = out;
+        return;
+#else
+        throw std::runtime_error("prl::binarizeLocalOtsu: CLAHEClipLimit > 0 needs PRL_CUDA_HAVE_CLAHE (EnhanceLocalContrastByCLAHE)");
+#endif
+    }
+    check(c, prl_cuda_binarize_local_otsu(c, inputImage.data, inputImage.rows, inputImage.cols, inputImage.step,
+                                          inputImage.channels(), maxValue, GaussianBlurKernelSize, CannyUpperThresholdCoeff,
+                                          CannyLowerThresholdCoeff, CannyMorphIters, out.data, out.step, &n, nullptr, 0));
+    outputImage = out;
+}

@@ -38,6 +38,14 @@ CV_EXPORTS void binarizeLocalOtsuRects(const cv::Mat& gray, const std::vector<in
 // cv::threshold(src, dst, 128, maxValue, THRESH_BINARY | THRESH_OTSU) (deskew.cpp:224, removeLines.cpp:45);
 // returns the threshold like cv::threshold does.
 CV_EXPORTS double thresholdOtsu(const cv::Mat& src, cv::Mat& dst, double maxValue = 255);
+// prl::binarizeLocalOtsu with the reference's signature and defaults (binarizeLocalOtsu.h:50-57); blur, Otsu value, Canny,
+// morphology, top-level contour rectangles and the rectangle loop all run on the device.  CLAHEClipLimit > 0 (off by
+// default) needs the reference's EnhanceLocalContrastByCLAHE: define PRL_CUDA_HAVE_CLAHE when building inside PRLib
+// (imageLibCommon.h is then included and called first, binarizeLocalOtsu.cpp:79-82); without it the call throws.
+CV_EXPORTS void binarizeLocalOtsu(cv::Mat& inputImage, cv::Mat& outputImage, double maxValue = 255.0,
+                                  double CLAHEClipLimit = 0.0, int GaussianBlurKernelSize = 19,
+                                  double CannyUpperThresholdCoeff = 0.15, double CannyLowerThresholdCoeff = 0.01,
+                                  int CannyMorphIters = 1);
 // The edge map prl::binarizeLocalOtsu feeds to cv::findContours: CannyEdgeDetection(imageToProc, resultCanny, ...)
 // (imageLibCommon.cpp:244-324) followed by cv::dilate(resultCanny, ..., postDilate = 3) (binarizeLocalOtsu.cpp:88-92),
 // single-channel input, same std::invalid_argument checks as the reference.

@@ -92,6 +92,25 @@ int main()
         double t = prl::thresholdOtsu(page, dst, 255);
         EXPECT((int)t == thr && same(dst, want, rows, cols), "global Otsu equals the oracle");
     }
+    {   // prl::binarizeLocalOtsu with the header defaults: every pixel is 0 or 255, black only inside the edge map's reach,
+        // flat image -> no contour -> std::invalid_argument like RemoveChildrenContours (imageLibCommon.cpp:643-646)
+        cv::Mat in = page.clone(), out, edges;
+        prl::binarizeLocalOtsu(in, out);
+        prl::localOtsuEdges(page, edges);
+        bool ok = out.rows == rows && out.cols == cols && edges.rows == rows && edges.cols == cols;
+        long black = 0;
+        for (int y = 0; ok && y < rows; ++y)
+            for (int x = 0; x < cols; ++x) {
+                const unsigned char v = out.ptr(y)[x];
+                ok = ok && (v == 0 || v == 255);
+                black += v == 0;
+            }
+        EXPECT(ok && black > 0, "binarizeLocalOtsu runs with the reference defaults");
+        cv::Mat flat(64, 64, CV_8UC1); std::memset(flat.data, 180, 64 * 64);
+        bool thrown = false;
+        try { prl::binarizeLocalOtsu(flat, out); } catch (const std::invalid_argument&) { thrown = true; }
+        EXPECT(thrown, "no contours -> invalid_argument");
+    }
     std::printf(fails ? "shim_test: %d failure(s)\n" : "shim_test: all ok\n", fails);
     return fails ? 1 : 0;
 }
