@@ -299,8 +299,12 @@ ccl_border_kernel(const uint8_t* __restrict__ E, size_t estep, int rows, int col
         outer = (zW && uf_find_c(L, p - 1) == fr) || (zE && uf_find_c(L, p + 1) == fr) ||
                 (zN && uf_find_c(L, p - cols) == fr) || (zS && uf_find_c(L, p + cols) == fr);
     }
-    if (outer) top[root] = 1;
-    atomicMin(&bx0[root], x); atomicMin(&by0[root], y); atomicMax(&bx1[root], x); atomicMax(&by1[root], y);
+    if (outer && !top[root]) top[root] = 1;
+    // look before the atomic: after the first few pixels of a component almost none still stretches its box
+    if (x < bx0[root]) atomicMin(&bx0[root], x);
+    if (y < by0[root]) atomicMin(&by0[root], y);
+    if (x > bx1[root]) atomicMax(&bx1[root], x);
+    if (y > by1[root]) atomicMax(&by1[root], y);
 }
 
 __global__ void __launch_bounds__(256)
