@@ -199,6 +199,13 @@ int prl_cuda_binarize_local_otsu(prl_cuda_ctx* ctx, const uint8_t* src, int rows
                                  double maxval, int gauss_ksize, double upper_coeff, double lower_coeff, int morph_iters,
                                  uint8_t* dst, size_t dst_step, int* n_rects, int32_t* rects_out, int rects_cap);
 
+/* ---- prl::removeLines (src/removeLines.cpp:30-77; a Global-Otsu caller) -------------
+ * bw = cv::threshold(~gray, OTSU); horizontal / vertical = opening of bw by a 1 x cols/50 / rows/50 x 1 element;
+ * out = ~(bw - horizontal - vertical).  channels 1, or 3 = BGR (cvtColor BGR2GRAY, :33-36).  Needs rows, cols >= 50
+ * (PRL_E_UNSUPPORTED below that, where the reference's empty structuring element means OpenCV's default 3x3). */
+int prl_cuda_remove_lines(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step, int channels,
+                          uint8_t* dst, size_t dst_step);
+
 /* ---- 1 bit per pixel ---------------------------------------------
  * The masks in Leptonica's PIX layout, the reference's second image container (src/formatConvert.cpp:39-69
  * writes PIX words with SET_DATA_BIT): rows of wpl = (cols + 31) / 32 32-bit words, pixel x of a row in word

@@ -8,9 +8,9 @@ from . import capi
 from .capi import PrlCudaError, SAUVOLA, NIBLACK, WOLFJOLION, NICK, FENG
 from .context import Context, default_context, binarize_batch, unpack_lept1
 from .binarize import (binarizeSauvola, binarizeNiblack, binarizeWolfJolion, binarizeNICK, binarizeFeng,
-                       padded_gray, otsuThreshold, binarizeLocalOtsuRects, binarizeLocalOtsuTiles, binarizeLocalOtsu)
+                       padded_gray, otsuThreshold, binarizeLocalOtsuRects, binarizeLocalOtsuTiles, binarizeLocalOtsu, removeLines)
 
 __all__ = ["capi", "PrlCudaError", "Context", "default_context", "binarize_batch", "unpack_lept1", "SAUVOLA", "NIBLACK",
            "WOLFJOLION", "NICK", "FENG", "binarizeSauvola", "binarizeNiblack", "binarizeWolfJolion",
            "binarizeNICK", "binarizeFeng", "padded_gray", "otsuThreshold", "binarizeLocalOtsuRects",
-           "binarizeLocalOtsuTiles", "binarizeLocalOtsu"]
+           "binarizeLocalOtsuTiles", "binarizeLocalOtsu", "removeLines"]

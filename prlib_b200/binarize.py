@@ -120,6 +120,11 @@ def binarizeLocalOtsu(image, maxValue: float = 255.0, CLAHEClipLimit: float = 0.
                                    CannyMorphIters)
 
 
+def removeLines(image, device: int = 0) -> np.ndarray:
+    """prl::removeLines (src/removeLines.h, removeLines.cpp:30-77)."""
+    return default_context(device).remove_lines(np.asarray(image))
+
+
 def binarizeLocalOtsuTiles(image, tileWidth: int = 64, tileHeight: int = 64, maxValue: float = 255.0,
                            device: int = 0) -> np.ndarray:
     """Same loop with rects := the regular tile grid (BASELINE.json config 4)."""

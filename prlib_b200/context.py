@@ -10,7 +10,7 @@ from . import capi
 from .capi import PrlCudaError
 
 _FAMILIES = ("integral", "threshold", "smax", "morph", "otsu_hist", "otsu_search", "otsu_apply", "otsu_tiles",
-             "synth", "bgr2gray", "band_carry", "fused", "fused_pre", "fused_fix", "pack", "edges")
+             "synth", "bgr2gray", "band_carry", "fused", "fused_pre", "fused_fix", "pack", "edges", "lines")
 
 
 def _params4(params) -> "C.Array":
@@ -258,6 +258,17 @@ class Context:
                                                          int(morph_iters), out.ctypes.data, im.shape[1], C.byref(n),
                                                          rects.ctypes.data if cap else None, cap))
         return (out, rects[:n.value]) if return_rects else out
+
+    def remove_lines(self, image):
+        """prl::removeLines (removeLines.cpp:30-77).  image: (H, W) gray or (H, W, 3) BGR."""
+        im = np.ascontiguousarray(image)
+        if im.dtype != np.uint8 or im.ndim not in (2, 3):
+            raise ValueError("image must be uint8, (H, W) or (H, W, 3)")
+        ch = 1 if im.ndim == 2 else im.shape[2]
+        out = np.empty(im.shape[:2], np.uint8)
+        self._check(self._L.prl_cuda_remove_lines(self._h, im.ctypes.data, im.shape[0], im.shape[1], im.strides[0], ch,
+                                                  out.ctypes.data, im.shape[1]))
+        return out
 
     # -- device-pointer entry points (raw addresses: torch .data_ptr() or cudaMalloc) ----------
     def binarize_local_batch_dev(self, method, d_src, n_pages, rows, cols, src_step, src_page_stride, window, params,

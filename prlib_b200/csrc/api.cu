@@ -85,7 +85,7 @@ static void timing_collect(prl_cuda_ctx* ctx)
 }
 
 static const char* kFamilyNames[FAM_COUNT] = {"integral", "threshold", "smax", "morph", "otsu_hist", "otsu_search",
-                                              "otsu_apply", "otsu_tiles", "synth", "bgr2gray", "band_carry", "fused", "fused_pre", "fused_fix", "pack", "edges"};
+                                              "otsu_apply", "otsu_tiles", "synth", "bgr2gray", "band_carry", "fused", "fused_pre", "fused_fix", "pack", "edges", "lines"};
 
 int prl_make_geom(int method, int rows, int cols, int window, prl_geom* g)
 {
@@ -723,6 +723,36 @@ extern "C" int prl_cuda_binarize_local_otsu(prl_cuda_ctx* c, const uint8_t* src,
     if (rects_out && rects_cap > 0)
         PRL_CUDA_TRY(c, cudaMemcpyAsync(rects_out, d_xywh, (size_t)std::min(count, rects_cap) * 16, cudaMemcpyDeviceToHost, c->stream));
     rc = prl_k_otsu_rects(c, c->d_in, rows, cols, in_step, d_xywh, count, maxval, c->d_out, o_step, d_thr); if (rc) return rc;
+    PRL_CUDA_TRY(c, cudaMemcpy2DAsync(dst, dst_step, c->d_out, o_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
+    PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return PRL_OK;
+}
+
+// prl::removeLines (src/removeLines.cpp:30-77): 1 or 3 (BGR) channels in, 0/255 image out
+extern "C" int prl_cuda_remove_lines(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step, int channels,
+                                     uint8_t* dst, size_t dst_step)
+{
+    if (!c) return PRL_E_INVALID;
+    if (!src || !dst || rows <= 0 || cols <= 0 || (channels != 1 && channels != 3) || step < (size_t)cols * channels ||
+        dst_step < (size_t)cols)
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    size_t in_step;
+    int rc;
+    if (channels == 1) {
+        rc = stage_in(c, src, rows, cols, step, &in_step); if (rc) return rc;
+    } else {
+        const size_t bstep = round16((size_t)cols * channels);
+        in_step = round16(cols);
+        rc = prl_ensure(c, (void**)&c->d_bgr, &c->d_bgr_bytes, bstep * rows); if (rc) return rc;
+        rc = prl_ensure(c, (void**)&c->d_in, &c->d_in_bytes, in_step * rows); if (rc) return rc;
+        PRL_CUDA_TRY(c, copy2d(c->d_bgr, bstep, src, step, (size_t)cols * channels, rows, cudaMemcpyHostToDevice, c->stream));
+        rc = prl_k_bgr2gray(c, c->d_bgr, rows, cols, bstep, channels, c->d_in, in_step, false); if (rc) return rc;   // COLOR_BGR2GRAY :35
+    }
+    const size_t o_step = round16(cols);
+    rc = prl_ensure(c, (void**)&c->d_out, &c->d_out_bytes, o_step * rows); if (rc) return rc;
+    rc = prl_ensure(c, &c->edges_ws, &c->edges_ws_bytes, prl_lines_scratch_bytes(rows, cols)); if (rc) return rc;
+    rc = prl_k_remove_lines(c, c->d_in, rows, cols, in_step, c->d_out, o_step, c->edges_ws); if (rc) return rc;
     PRL_CUDA_TRY(c, cudaMemcpy2DAsync(dst, dst_step, c->d_out, o_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
     PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return PRL_OK;

@@ -63,7 +63,7 @@ struct prl_cuda_ctx {
 
 enum prl_family {
     FAM_INTEGRAL = 0, FAM_THRESHOLD, FAM_SMAX, FAM_MORPH, FAM_OTSU_HIST, FAM_OTSU_SEARCH,
-    FAM_OTSU_APPLY, FAM_OTSU_TILES, FAM_SYNTH, FAM_BGR2GRAY, FAM_BAND_CARRY, FAM_FUSED, FAM_FUSED_PRE, FAM_FUSED_FIX, FAM_PACK, FAM_EDGES, FAM_COUNT
+    FAM_OTSU_APPLY, FAM_OTSU_TILES, FAM_SYNTH, FAM_BGR2GRAY, FAM_BAND_CARRY, FAM_FUSED, FAM_FUSED_PRE, FAM_FUSED_FIX, FAM_PACK, FAM_EDGES, FAM_LINES, FAM_COUNT
 };
 
 int  prl_set_err(prl_cuda_ctx* ctx, int code, const char* what, cudaError_t ce = cudaSuccess);
@@ -117,6 +117,9 @@ int prl_k_canny(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, siz
                 double upper_coeff, double lower_coeff, double low, double high, uint8_t* d_dst, size_t dst_step, void* scratch);
 size_t prl_canny_scratch_bytes(int rows, int cols);
 size_t prl_rects_scratch_bytes(int rows, int cols);
+size_t prl_lines_scratch_bytes(int rows, int cols);
+int prl_k_remove_lines(prl_cuda_ctx* ctx, const uint8_t* d_gray, int rows, int cols, size_t step, uint8_t* d_dst, size_t dst_step,
+                       void* scratch);
 int prl_k_external_rects(prl_cuda_ctx* ctx, const uint8_t* d_edges, int rows, int cols, size_t step, int* d_count,
                          int32_t* d_xywh, int cap, void* scratch);
 int prl_k_not_binary(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, int* d_flag);

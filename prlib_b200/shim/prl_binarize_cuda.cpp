@@ -28,12 +28,15 @@ prl_cuda_ctx* context()
     return t.ctx;
 }
 
+// cv::Exception as OpenCV itself would raise it (CV_Assert -> code -215)
+cv::Exception cvError(const std::string& msg) { return cv::Exception(-215, msg, "prl (libprlib_cuda)", __FILE__, __LINE__); }
+
 void check(prl_cuda_ctx* c, int rc)
 {
     if (rc == PRL_OK) return;
     const std::string msg = prl_cuda_last_error(c);
     if (rc == PRL_E_INVALID) throw std::invalid_argument(msg);
-    if (rc == PRL_E_EMPTY_ROI) throw cv::Exception(msg);      // cv::Mat::operator()(Rect) would assert
+    if (rc == PRL_E_EMPTY_ROI) throw cvError(msg);            // cv::Mat::operator()(Rect) would assert
     throw std::runtime_error("libprlib_cuda: " + msg);
 }
 
@@ -61,7 +64,7 @@ void runLocal(int method, cv::Mat& imageInput, cv::Mat& outputImage, int windowS
                                     "( (windowSize > 1) && ((windowSize % 2) == 1) ) ");
     prl_cuda_ctx* c = context();
     const int ch = imageInput.channels();
-    if (ch != 1 && ch != 3 && ch != 4) throw cv::Exception("cvtColor: unsupported number of channels");
+    if (ch != 1 && ch != 3 && ch != 4) throw cvError("cvtColor: unsupported number of channels");
     int orows = 0, ocols = 0;
     check(c, prl_cuda_output_shape(method, imageInput.rows, imageInput.cols, windowSize, &orows, &ocols));
     cv::Mat out(orows, ocols, CV_8UC1);
@@ -200,5 +203,15 @@ void prl::binarizeLocalOtsu(cv::Mat& inputImage, cv::Mat& outputImage, double ma
     check(c, prl_cuda_binarize_local_otsu(c, inputImage.data, inputImage.rows, inputImage.cols, inputImage.step,
                                           inputImage.channels(), maxValue, GaussianBlurKernelSize, CannyUpperThresholdCoeff,
                                           CannyLowerThresholdCoeff, CannyMorphIters, out.data, out.step, &n, nullptr, 0));
+    outputImage = out;
+}
+
+void prl::removeLines(const cv::Mat& inputImage, cv::Mat& outputImage)
+{
+    if (inputImage.empty()) throw cvError("removeLines: empty image");     // (the reference would fail inside cv::threshold)
+    prl_cuda_ctx* c = context();
+    cv::Mat out(inputImage.rows, inputImage.cols, CV_8UC1);
+    check(c, prl_cuda_remove_lines(c, inputImage.data, inputImage.rows, inputImage.cols, inputImage.step, inputImage.channels(),
+                                   out.data, out.step));
     outputImage = out;
 }

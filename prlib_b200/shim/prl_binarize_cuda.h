@@ -46,6 +46,8 @@ CV_EXPORTS void binarizeLocalOtsu(cv::Mat& inputImage, cv::Mat& outputImage, dou
                                   double CLAHEClipLimit = 0.0, int GaussianBlurKernelSize = 19,
                                   double CannyUpperThresholdCoeff = 0.15, double CannyLowerThresholdCoeff = 0.01,
                                   int CannyMorphIters = 1);
+// prl::removeLines (removeLines.h, removeLines.cpp:30-77), 1- or 3-channel (BGR) input.
+CV_EXPORTS void removeLines(const cv::Mat& inputImage, cv::Mat& outputImage);
 // The edge map prl::binarizeLocalOtsu feeds to cv::findContours: CannyEdgeDetection(imageToProc, resultCanny, ...)
 // (imageLibCommon.cpp:244-324) followed by cv::dilate(resultCanny, ..., postDilate = 3) (binarizeLocalOtsu.cpp:88-92),
 // single-channel input, same std::invalid_argument checks as the reference.

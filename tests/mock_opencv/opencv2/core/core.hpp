@@ -20,9 +20,12 @@
 
 namespace cv {
 
+// same constructor as the real cv::Exception (core.hpp): code, error text, function, file, line
 class Exception : public std::runtime_error {
 public:
-    explicit Exception(const std::string& m) : std::runtime_error(m) {}
+    Exception(int _code, const std::string& _err, const std::string& _func, const std::string& _file, int _line)
+        : std::runtime_error(_err), code(_code), err(_err), func(_func), file(_file), line(_line) {}
+    int code; std::string err, func, file; int line;
 };
 
 class Mat {

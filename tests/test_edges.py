@@ -104,3 +104,29 @@ def test_binarize_local_otsu_end_to_end(ctx, real_crops):
         prlib_b200.binarizeLocalOtsu(page, 300.0)
     with pytest.raises(ValueError):
         prlib_b200.binarizeLocalOtsu(np.full((80, 80), 200, np.uint8))      # no edges -> no contours -> invalid_argument
+
+
+def _page_with_rules(rows, cols, seed):
+    page = CO.synth_page(seed, rows, cols).copy()
+    rng = np.random.default_rng(seed)
+    for _ in range(6):
+        y = int(rng.integers(10, rows - 10)); x0 = int(rng.integers(0, cols // 2)); x1 = int(rng.integers(cols // 2, cols))
+        page[y:y + int(rng.integers(1, 4)), x0:x1] = rng.integers(0, 60)
+    for _ in range(5):
+        x = int(rng.integers(10, cols - 10)); y0 = int(rng.integers(0, rows // 2)); y1 = int(rng.integers(rows // 2, rows))
+        page[y0:y1, x:x + int(rng.integers(1, 4))] = rng.integers(0, 60)
+    return page
+
+
+@pytest.mark.gpu
+def test_remove_lines_equals_the_opencv_sequence(ctx, noise_page, real_crops):
+    """prl::removeLines (a Global-Otsu caller, SURVEY 8 F4): inverted Otsu threshold, long 1-D openings with even and odd
+    element lengths (asymmetric anchors), subtraction, inversion."""
+    imgs = [_page_with_rules(900, 1237, 1), _page_with_rules(1500, 1000, 2), _page_with_rules(700, 2000, 3),
+            _page_with_rules(411, 333, 4), noise_page, np.ascontiguousarray(noise_page[:50, :50]),
+            np.ascontiguousarray(noise_page[:99, :150]), real_crops["bgr_0037"]]
+    imgs += [np.ascontiguousarray(v) for k, v in real_crops.items() if getattr(v, "ndim", 0) == 2]
+    for img in imgs:
+        assert np.array_equal(prlib_b200.removeLines(img), O.removeLines(img)), img.shape
+    with pytest.raises(prlib_b200.PrlCudaError):
+        prlib_b200.removeLines(np.zeros((40, 200), np.uint8))
