@@ -199,6 +199,12 @@ int prl_cuda_binarize_local_otsu(prl_cuda_ctx* ctx, const uint8_t* src, int rows
                                  double maxval, int gauss_ksize, double upper_coeff, double lower_coeff, int morph_iters,
                                  uint8_t* dst, size_t dst_step, int* n_rects, int32_t* rects_out, int rects_cap);
 
+/* The contour step alone: bounding rectangles (x, y, w, h) of the top-level contours of a binary image (non-zero =
+ * foreground), the set cv::findContours(RETR_EXTERNAL, ...) + cv::boundingRect give (binarizeLocalOtsu.cpp:104-105,150),
+ * in no particular order.  *n_rects = how many exist (may exceed rects_cap; only rects_cap are written). */
+int prl_cuda_external_rects(prl_cuda_ctx* ctx, const uint8_t* mask, int rows, int cols, size_t step, int32_t* rects_out,
+                            int rects_cap, int* n_rects);
+
 /* ---- prl::removeLines (src/removeLines.cpp:30-77; a Global-Otsu caller) -------------
  * bw = cv::threshold(~gray, OTSU); horizontal / vertical = opening of bw by a 1 x cols/50 / rows/50 x 1 element;
  * out = ~(bw - horizontal - vertical).  channels 1, or 3 = BGR (cvtColor BGR2GRAY, :33-36).  Needs rows, cols >= 50

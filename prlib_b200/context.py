@@ -259,6 +259,15 @@ class Context:
                                                          rects.ctypes.data if cap else None, cap))
         return (out, rects[:n.value]) if return_rects else out
 
+    def external_rects(self, mask, cap: int = 65535):
+        """(x, y, w, h) of the top-level contours of a binary image: cv::findContours(RETR_EXTERNAL) + cv::boundingRect as a set."""
+        m = _as_u8_2d(mask, "mask")
+        rects = np.zeros((max(cap, 1), 4), np.int32)
+        n = C.c_int()
+        self._check(self._L.prl_cuda_external_rects(self._h, m.ctypes.data, m.shape[0], m.shape[1], m.strides[0], rects.ctypes.data,
+                                                    int(cap), C.byref(n)))
+        return rects[:min(n.value, cap)]
+
     def remove_lines(self, image):
         """prl::removeLines (removeLines.cpp:30-77).  image: (H, W) gray or (H, W, 3) BGR."""
         im = np.ascontiguousarray(image)

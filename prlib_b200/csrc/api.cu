@@ -728,6 +728,33 @@ extern "C" int prl_cuda_binarize_local_otsu(prl_cuda_ctx* c, const uint8_t* src,
     return PRL_OK;
 }
 
+// bounding rectangles of the top-level contours of a binary image (non-zero = foreground): the set
+// cv::findContours(RETR_EXTERNAL) + cv::boundingRect returns (binarizeLocalOtsu.cpp:104-105,150)
+extern "C" int prl_cuda_external_rects(prl_cuda_ctx* c, const uint8_t* mask, int rows, int cols, size_t step, int32_t* rects_out,
+                                       int rects_cap, int* n_rects)
+{
+    if (!c) return PRL_E_INVALID;
+    if (!mask || rows <= 0 || cols <= 0 || step < (size_t)cols || rects_cap < 0 || (rects_cap > 0 && !rects_out) || !n_rects)
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    size_t in_step;
+    int rc = stage_in(c, mask, rows, cols, step, &in_step); if (rc) return rc;
+    const int cap = std::max(rects_cap, 1);
+    const size_t list_bytes = (256 + (size_t)cap * 16 + 255) & ~(size_t)255;
+    rc = prl_ensure(c, &c->rects_ws, &c->rects_ws_bytes, list_bytes + prl_rects_scratch_bytes(rows, cols)); if (rc) return rc;
+    int* d_count = (int*)c->rects_ws;
+    int32_t* d_xywh = (int32_t*)((uint8_t*)c->rects_ws + 256);
+    rc = prl_k_external_rects(c, c->d_in, rows, cols, in_step, d_count, d_xywh, rects_cap, (uint8_t*)c->rects_ws + list_bytes);
+    if (rc) return rc;
+    int count = 0;
+    PRL_CUDA_TRY(c, cudaMemcpyAsync(&count, d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    *n_rects = count;
+    if (rects_cap > 0 && count > 0)
+        PRL_CUDA_TRY(c, cudaMemcpy(rects_out, d_xywh, (size_t)std::min(count, rects_cap) * 16, cudaMemcpyDeviceToHost));
+    return PRL_OK;
+}
+
 // prl::removeLines (src/removeLines.cpp:30-77): 1 or 3 (BGR) channels in, 0/255 image out
 extern "C" int prl_cuda_remove_lines(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step, int channels,
                                      uint8_t* dst, size_t dst_step)

@@ -130,3 +130,41 @@ def test_remove_lines_equals_the_opencv_sequence(ctx, noise_page, real_crops):
         assert np.array_equal(prlib_b200.removeLines(img), O.removeLines(img)), img.shape
     with pytest.raises(prlib_b200.PrlCudaError):
         prlib_b200.removeLines(np.zeros((40, 200), np.uint8))
+
+
+@pytest.mark.gpu
+def test_external_rects_on_adversarial_topologies(ctx):
+    """The union-find labelling against cv2.findContours(RETR_EXTERNAL): nested rings (components inside holes are
+    dropped, components inside components inside holes too), diagonal-only links (8-connected foreground), diagonal
+    gaps that do NOT open a ring (4-connected background), components touching every border, random masks."""
+    import cv2
+    def want(mask):
+        cs, _ = cv2.findContours(mask.copy(), cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+        return sorted(cv2.boundingRect(c) for c in cs)
+    masks = []
+    m = np.zeros((40, 50), np.uint8)
+    m[2:30, 3:40] = 255; m[5:27, 6:37] = 0; m[8:24, 9:34] = 255; m[11:21, 12:31] = 0; m[14:18, 15:28] = 255      # ring in ring in ring
+    m[33:38, 1:9] = 255; m[35, 4] = 0                                                                              # ring with a 1-pixel hole
+    masks.append(m)
+    m = np.zeros((30, 30), np.uint8)
+    for i in range(25): m[i, i] = 255                                                                              # a pure diagonal: one component
+    m[3, 20] = 255; m[4, 21] = 255; m[5, 20] = 255; m[4, 19] = 255                                                 # diamond: the centre hole is closed
+    m[4, 20] = 0
+    masks.append(m)
+    m = np.zeros((20, 20), np.uint8)
+    m[5:15, 5:15] = 255; m[7:13, 7:13] = 0; m[9:11, 9:11] = 255                                                    # square ring with an island ...
+    m[5, 5] = 0                                                                                                    # ... and a missing corner pixel: still closed for 4-connected background
+    masks.append(m)
+    m = np.full((16, 23), 255, np.uint8); m[3:13, 4:19] = 0; m[6:9, 8:12] = 255                                    # frame touching all borders, island inside
+    masks.append(m)
+    masks.append(np.zeros((9, 9), np.uint8))
+    masks.append(np.full((7, 5), 255, np.uint8))
+    rng = np.random.default_rng(7)
+    for shape, p in (((64, 64), 0.5), ((64, 64), 0.62), ((120, 333), 0.55), ((257, 300), 0.4), ((33, 1000), 0.6), ((1, 50), 0.5),
+                     ((50, 1), 0.5), ((200, 200), 0.7)):
+        masks.append(np.where(rng.random(shape) < p, 255, 0).astype(np.uint8))
+    coarse = np.kron(np.where(rng.random((40, 40)) < 0.55, 255, 0).astype(np.uint8), np.ones((5, 5), np.uint8))   # blobs with holes
+    masks.append(np.ascontiguousarray(coarse))
+    for i, m in enumerate(masks):
+        got = sorted(map(tuple, ctx.external_rects(m).tolist()))
+        assert got == want(m), (i, m.shape)
