@@ -553,11 +553,8 @@ int launch_tma(prl_cuda_ctx* ctx, encode_tiled_fn enc, dim3 grid, int nwarps, co
     if (cr != CUDA_SUCCESS) return PRL_OK;     // caller falls back to the generic kernel
     const size_t smem = (size_t)nwarps * NS * stage_bytes<J, R>();
     auto kfn = integral_tma_kernel<MAXW, MINB, J, R, NS, MULTI>;
-    static size_t configured = 0;
-    if (smem > configured) {
-        PRL_CUDA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    // (per device: the attribute lives in the current device's copy of the function, so no process-wide cache)
+    PRL_CUDA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kfn<<<grid, nwarps * 32, smem, ctx->stream>>>(tmap, rows, cols, pad, d_S, d_Q, pitch, plane_page_stride, rpb, d_carry, d_imin,
                                                   col0, rowoff, has_in, has_out);
     *launched = true;

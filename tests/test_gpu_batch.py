@@ -288,3 +288,23 @@ def test_packed_batch_and_device_pack(ctx):
             got = out.cpu().numpy().view(np.uint32)
             assert np.array_equal(got[0], lept1_words(m)) and np.array_equal(got[1], lept1_words(255 - m)), (cols, step)
     ctx.set_stream(None)
+
+
+@pytest.mark.gpu
+def test_every_device_of_the_box_and_the_page_dispatcher():
+    """Each visible device alone and all of them together give the masks of device 0 (found on a 2-GPU box: a
+    process-wide cache of cudaFuncSetAttribute left kernel 1 unconfigured on the second device)."""
+    n_dev = capi.load().prl_cuda_device_count()
+    pages = np.stack([CO.synth_page(p, 400, 700) for p in range(7)])
+    want = prlib_b200.binarize_batch(pages, 0, 15, (0.2,), 0, devices=[0])
+    for p in range(7):
+        assert np.array_equal(want[p], CO.binarize_local(pages[p], 0, 15, (0.2,), 0))
+    for d in range(1, n_dev):
+        assert np.array_equal(prlib_b200.binarize_batch(pages, 0, 15, (0.2,), 0, devices=[d]), want), d
+        c = prlib_b200.Context(d)
+        assert np.array_equal(c.binarize_local(pages[0], 3, 21, (-0.1,), 2), CO.binarize_local(pages[0], 3, 21, (-0.1,), 2))
+        assert np.array_equal(c.otsu_tiles(pages[1], 64, 64), O.otsu_tiles(pages[1], 64, 64))
+        c.close()
+    assert np.array_equal(prlib_b200.binarize_batch(pages, 0, 15, (0.2,), 0, devices=list(range(n_dev))), want)
+    assert np.array_equal(prlib_b200.binarize_batch(pages, 2, 15, (0.5,), 1, devices=None),
+                          prlib_b200.binarize_batch(pages, 2, 15, (0.5,), 1, devices=[0]))
