@@ -188,7 +188,13 @@ int prl_cuda_canny_edge_detection_dev(prl_cuda_ctx* ctx, const uint8_t* d_gray, 
                                       int gauss_ksize, double upper_coeff, double lower_coeff, int morph_iters,
                                       int post_dilate, uint8_t* d_dst, size_t dst_step);
 
-/* prl::binarizeLocalOtsu (binarizeLocalOtsu.h:50-57 with CLAHEClipLimit = 0) in one call: the edge map above with
+/* EnhanceLocalContrastByCLAHE for one channel (imageLibCommon.cpp:326-346): cv::createCLAHE() (8 x 8 tiles) with the given
+ * clip limit, then cv::equalizeHist when `equalize` is non-zero.  Bit-identical to OpenCV 4.x. */
+int prl_cuda_clahe(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step, double clip_limit, int equalize,
+                   uint8_t* dst, size_t dst_step);
+
+/* prl::binarizeLocalOtsu (binarizeLocalOtsu.h:50-57) in one call: clahe_clip_limit > 0 first enhances the gray image
+ * (CLAHE + equalizeHist, binarizeLocalOtsu.cpp:79-82); then the edge map above with
  * post_dilate = 3, the bounding rectangles of its top-level contours -- what cv::findContours(RETR_EXTERNAL) +
  * cv::boundingRect return (binarizeLocalOtsu.cpp:104-105,150), found by a union-find labelling on the device -- and
  * the per-rectangle Otsu loop (:138-162).  *n_rects receives the number of rectangles; rects_out (optional, rects_cap
@@ -196,7 +202,7 @@ int prl_cuda_canny_edge_detection_dev(prl_cuda_ctx* ctx, const uint8_t* d_gray, 
  * (RemoveChildrenContours throws std::invalid_argument, imageLibCommon.cpp:643-646).  channels 3 or 4: interleaved
  * 8-bit, converted like cv::cvtColor(COLOR_RGB2GRAY) -- the code the reference uses here (binarizeLocalOtsu.cpp:63). */
 int prl_cuda_binarize_local_otsu(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step, int channels,
-                                 double maxval, int gauss_ksize, double upper_coeff, double lower_coeff, int morph_iters,
+                                 double maxval, double clahe_clip_limit, int gauss_ksize, double upper_coeff, double lower_coeff, int morph_iters,
                                  uint8_t* dst, size_t dst_step, int* n_rects, int32_t* rects_out, int rects_cap);
 
 /* The contour step alone: bounding rectangles (x, y, w, h) of the top-level contours of a binary image (non-zero =

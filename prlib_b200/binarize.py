@@ -110,14 +110,12 @@ def binarizeLocalOtsu(image, maxValue: float = 255.0, CLAHEClipLimit: float = 0.
         raise ValueError("Input image for binarization is empty")                   # binarizeLocalOtsu.cpp:47-50
     if not (0 <= maxValue <= 255):
         raise ValueError("Max value must be in range [0; 255]")                     # :52-55
-    if CLAHEClipLimit > 0:
-        raise NotImplementedError("the CLAHE pre-step (EnhanceLocalContrastByCLAHE) is not part of libprlib_cuda")
     if GaussianBlurKernelSize < 3:
         raise ValueError("Gaussian blur kernel size is lesser than 3")              # imageLibCommon.cpp:253-256
     ctx = default_context(device)
     # (3/4-channel input is converted with COLOR_RGB2GRAY on the device, as binarizeLocalOtsu.cpp:63 does)
     return ctx.binarize_local_otsu(image, maxValue, GaussianBlurKernelSize, CannyUpperThresholdCoeff, CannyLowerThresholdCoeff,
-                                   CannyMorphIters)
+                                   CannyMorphIters, clahe_clip_limit=max(CLAHEClipLimit, 0.0))
 
 
 def removeLines(image, device: int = 0) -> np.ndarray:

@@ -56,7 +56,8 @@ SIGNATURES = {
     "prl_cuda_binarize_batch_packed": (C.c_int, [_intp, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, C.c_int,
                                                  C.c_void_p]),
     "prl_cuda_pack_mask_dev": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p]),
-    "prl_cuda_binarize_local_otsu": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double,
+    "prl_cuda_clahe": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_double, C.c_int, C.c_void_p, C.c_size_t]),
+    "prl_cuda_binarize_local_otsu": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
                                                C.c_int, C.c_void_p, C.c_size_t, _intp, C.c_void_p, C.c_int]),
     "prl_cuda_external_rects": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, _intp]),
     "prl_cuda_remove_lines": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]),

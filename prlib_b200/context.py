@@ -242,8 +242,16 @@ class Context:
                                                           int(post_dilate), out.ctypes.data, g.shape[1]))
         return out
 
+    def clahe(self, gray, clip_limit: float, equalize: bool = True):
+        """EnhanceLocalContrastByCLAHE for one channel: cv::createCLAHE()->apply (+ cv::equalizeHist)."""
+        g = _as_u8_2d(gray)
+        out = np.empty(g.shape, np.uint8)
+        self._check(self._L.prl_cuda_clahe(self._h, g.ctypes.data, g.shape[0], g.shape[1], g.strides[0], float(clip_limit), int(equalize),
+                                           out.ctypes.data, g.shape[1]))
+        return out
+
     def binarize_local_otsu(self, image, maxval: float = 255.0, ksize: int = 19, upper_coeff: float = 0.15, lower_coeff: float = 0.01,
-                            morph_iters: int = 1, return_rects: bool = False):
+                            morph_iters: int = 1, return_rects: bool = False, clahe_clip_limit: float = 0.0):
         """prl::binarizeLocalOtsu, all on the device (prl_cuda_binarize_local_otsu).  image: (H, W) gray or (H, W, 3|4)."""
         im = np.ascontiguousarray(image)
         if im.dtype != np.uint8 or im.ndim not in (2, 3):
@@ -254,7 +262,7 @@ class Context:
         cap = 65535 if return_rects else 0
         rects = np.zeros((max(cap, 1), 4), np.int32)
         self._check(self._L.prl_cuda_binarize_local_otsu(self._h, im.ctypes.data, im.shape[0], im.shape[1], im.strides[0], ch,
-                                                         float(maxval), int(ksize), float(upper_coeff), float(lower_coeff),
+                                                         float(maxval), float(clahe_clip_limit), int(ksize), float(upper_coeff), float(lower_coeff),
                                                          int(morph_iters), out.ctypes.data, im.shape[1], C.byref(n),
                                                          rects.ctypes.data if cap else None, cap))
         return (out, rects[:n.value]) if return_rects else out

@@ -167,7 +167,7 @@ extern "C" void prl_cuda_destroy(prl_cuda_ctx* c)
     for (auto& ev : c->event_pool) cudaEventDestroy(ev);
     cudaFree(c->planes); cudaFree(c->carry); cudaFree(c->colsum); cudaFree(c->scalars); cudaFree(c->fused_ws);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
-    cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_tmp); cudaFree(c->d_misc); cudaFree(c->d_bgr); cudaFree(c->edges_ws); cudaFree(c->rects_ws);
+    cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_tmp); cudaFree(c->d_misc); cudaFree(c->d_bgr); cudaFree(c->edges_ws); cudaFree(c->rects_ws); cudaFree(c->clahe_ws);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -675,8 +675,37 @@ static int edges_host(prl_cuda_ctx* c, int what, const uint8_t* src, int rows, i
 
 // prl::binarizeLocalOtsu (binarizeLocalOtsu.cpp:38-163, CLAHE off) in one call: edge map, bounding rectangles of the
 // top-level contours and the per-rectangle Otsu loop all on the device; the image crosses PCIe once each way.
+// EnhanceLocalContrastByCLAHE on d_gray (rows x cols, pitch step) -> returns the enhanced image inside c->clahe_ws (pitch round16(cols))
+static int clahe_dev(prl_cuda_ctx* c, const uint8_t* d_gray, int rows, int cols, size_t step, double clip_limit, bool equalize,
+                     uint8_t** d_enh)
+{
+    const size_t p16 = round16((size_t)cols), img = (p16 * rows + 255) & ~(size_t)255;
+    int rc = prl_ensure(c, &c->clahe_ws, &c->clahe_ws_bytes, 2 * img + 64 * 256 + 256 * 4 + 256 + 256); if (rc) return rc;
+    uint8_t* b = (uint8_t*)c->clahe_ws;
+    rc = prl_k_clahe(c, d_gray, rows, cols, step, clip_limit, equalize, b, p16, b + img, b + 2 * img); if (rc) return rc;
+    *d_enh = b;
+    return PRL_OK;
+}
+
+// EnhanceLocalContrastByCLAHE (imageLibCommon.cpp:326-346,378-396) for a single-channel image
+extern "C" int prl_cuda_clahe(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step, double clip_limit, int equalize,
+                              uint8_t* dst, size_t dst_step)
+{
+    if (!c) return PRL_E_INVALID;
+    if (!src || !dst || rows <= 0 || cols <= 0 || step < (size_t)cols || dst_step < (size_t)cols)
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    size_t in_step;
+    int rc = stage_in(c, src, rows, cols, step, &in_step); if (rc) return rc;
+    uint8_t* enh = nullptr;
+    rc = clahe_dev(c, c->d_in, rows, cols, in_step, clip_limit, equalize != 0, &enh); if (rc) return rc;
+    PRL_CUDA_TRY(c, cudaMemcpy2DAsync(dst, dst_step, enh, round16((size_t)cols), cols, rows, cudaMemcpyDeviceToHost, c->stream));
+    PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return PRL_OK;
+}
+
 extern "C" int prl_cuda_binarize_local_otsu(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step, int channels,
-                                            double maxval, int gauss_ksize, double upper_coeff, double lower_coeff, int morph_iters,
+                                            double maxval, double clahe_clip_limit, int gauss_ksize, double upper_coeff, double lower_coeff, int morph_iters,
                                             uint8_t* dst, size_t dst_step, int* n_rects, int32_t* rects_out, int rects_cap)
 {
     if (!c) return PRL_E_INVALID;
@@ -701,8 +730,15 @@ extern "C" int prl_cuda_binarize_local_otsu(prl_cuda_ctx* c, const uint8_t* src,
     const size_t o_step = round16(cols);
     rc = prl_ensure(c, (void**)&c->d_out, &c->d_out_bytes, o_step * rows); if (rc) return rc;
     rc = prl_ensure(c, (void**)&c->d_tmp, &c->d_tmp_bytes, o_step * rows); if (rc) return rc;
+    // imageToProc: the gray image, or its CLAHE + equalizeHist enhancement (binarizeLocalOtsu.cpp:79-82)
+    const uint8_t* d_proc = c->d_in;
+    if (clahe_clip_limit > 0) {
+        uint8_t* enh = nullptr;
+        rc = clahe_dev(c, c->d_in, rows, cols, in_step, clahe_clip_limit, true, &enh); if (rc) return rc;
+        d_proc = enh; in_step = round16((size_t)cols);
+    }
     // edge map (binarizeLocalOtsu.cpp:85-92) -> d_tmp
-    rc = prl_cuda_canny_edge_detection_dev(c, c->d_in, rows, cols, in_step, gauss_ksize, upper_coeff, lower_coeff, morph_iters, 3,
+    rc = prl_cuda_canny_edge_detection_dev(c, d_proc, rows, cols, in_step, gauss_ksize, upper_coeff, lower_coeff, morph_iters, 3,
                                            c->d_tmp, o_step);
     if (rc) return rc;
     // rectangles (:104-110,150); the list never leaves the device on its way to the Otsu loop
@@ -722,7 +758,7 @@ extern "C" int prl_cuda_binarize_local_otsu(prl_cuda_ctx* c, const uint8_t* src,
     if (count > kCap) return prl_set_err(c, PRL_E_UNSUPPORTED, "more than 65535 contours");
     if (rects_out && rects_cap > 0)
         PRL_CUDA_TRY(c, cudaMemcpyAsync(rects_out, d_xywh, (size_t)std::min(count, rects_cap) * 16, cudaMemcpyDeviceToHost, c->stream));
-    rc = prl_k_otsu_rects(c, c->d_in, rows, cols, in_step, d_xywh, count, maxval, c->d_out, o_step, d_thr); if (rc) return rc;
+    rc = prl_k_otsu_rects(c, d_proc, rows, cols, in_step, d_xywh, count, maxval, c->d_out, o_step, d_thr); if (rc) return rc;
     PRL_CUDA_TRY(c, cudaMemcpy2DAsync(dst, dst_step, c->d_out, o_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
     PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return PRL_OK;

@@ -42,6 +42,7 @@ struct prl_cuda_ctx {
     uint8_t* d_tmp = nullptr;   size_t d_tmp_bytes = 0;
     uint8_t* d_bgr = nullptr;   size_t d_bgr_bytes = 0;    // 3/4-channel staging of the cvtColor front step
     void* d_misc = nullptr;     size_t d_misc_bytes = 0;   // histograms, thresholds, rect lists
+    void* clahe_ws = nullptr;   size_t clahe_ws_bytes = 0; // CLAHE: enhanced image, intermediate, LUTs
     void* rects_ws = nullptr;   size_t rects_ws_bytes = 0; // contour rectangles: count, list, thresholds, labels, boxes
     void* edges_ws = nullptr;   size_t edges_ws_bytes = 0; // edge front-end: blurred image, 8.8 rows, class map, labels, flags
     // pinned host staging
@@ -115,6 +116,8 @@ int prl_k_gaussian_blur(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int c
                         uint8_t* d_dst, size_t dst_step, uint16_t* d_tmp);
 int prl_k_canny(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, const int32_t* d_otsu,
                 double upper_coeff, double lower_coeff, double low, double high, uint8_t* d_dst, size_t dst_step, void* scratch);
+int prl_k_clahe(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, double clip_limit, bool equalize,
+                uint8_t* d_dst, size_t dst_step, uint8_t* d_tmp, void* scratch);
 size_t prl_canny_scratch_bytes(int rows, int cols);
 size_t prl_rects_scratch_bytes(int rows, int cols);
 size_t prl_lines_scratch_bytes(int rows, int cols);

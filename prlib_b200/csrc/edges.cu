@@ -323,6 +323,123 @@ ccl_rects_kernel(const uint8_t* __restrict__ E, size_t estep, int rows, int cols
     }
 }
 
+// ---- CLAHE + equalizeHist: EnhanceLocalContrastByCLAHE (imageLibCommon.cpp:326-346), the optional first step of
+// prl::binarizeLocalOtsu (binarizeLocalOtsu.cpp:79-82).  cv::createCLAHE() defaults: 8 x 8 tiles; the image is extended
+// to a multiple of the tile grid with BORDER_REFLECT_101 on the bottom / right; per tile: histogram, clip at
+// max(int(clipLimit * area / 256), 1) with OpenCV's redistribution (equal share + one more in every (256 / residual)-th
+// bin), LUT = round(cumsum * (255.f / area)); per pixel: bilinear blend of the four neighbouring tiles' LUTs in FP32
+// with OpenCV's operation order (no FMA).  equalizeHist: LUT = round(cumsum over bins above the first non-empty one
+// * (255.f / (total - hist[first]))).
+constexpr int kClaheTiles = 8;
+
+__global__ void __launch_bounds__(256)
+clahe_lut_kernel(const uint8_t* __restrict__ src, size_t step, int rows, int cols, int tw, int th, int clip, float lut_scale,
+                 uint8_t* __restrict__ luts)
+{
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t part[8];
+    const int tx = blockIdx.x % kClaheTiles, ty = blockIdx.x / kClaheTiles, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < tw * th; i += 256) {
+        const int y = ty * th + i / tw, x = tx * tw + i % tw;
+        atomicAdd(&hist[src[(size_t)reflect101(y, rows) * step + reflect101(x, cols)]], 1u);
+    }
+    __syncthreads();
+    uint32_t h = hist[tid];
+    if (clip > 0) {
+        uint32_t ex = h > (uint32_t)clip ? h - clip : 0u;
+        h = min(h, (uint32_t)clip);
+        ex = __reduce_add_sync(0xffffffffu, ex);
+        if (lane == 0) part[wid] = ex;
+        __syncthreads();
+        uint32_t clipped = 0;
+        for (int k = 0; k < 8; ++k) clipped += part[k];
+        const uint32_t batch = clipped / 256u, residual = clipped - batch * 256u;
+        h += batch;
+        if (residual != 0) {
+            const uint32_t st = max(256u / residual, 1u);
+            if (tid % st == 0 && tid / st < residual) h += 1;
+        }
+        __syncthreads();
+    }
+    // inclusive prefix sum over the 256 bins
+    uint32_t v = h;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t; }
+    if (lane == 31) part[wid] = v;
+    __syncthreads();
+    for (int k = 0; k < wid; ++k) v += part[k];
+    const int r = __float2int_rn(__fmul_rn((float)v, lut_scale));
+    luts[(size_t)blockIdx.x * 256 + tid] = (uint8_t)min(max(r, 0), 255);
+}
+
+__global__ void __launch_bounds__(256)
+clahe_interp_kernel(const uint8_t* __restrict__ src, size_t step, int rows, int cols, float inv_tw, float inv_th,
+                    const uint8_t* __restrict__ luts, uint8_t* __restrict__ dst, size_t dstep)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cols) return;
+    const float txf = __fadd_rn(__fmul_rn((float)x, inv_tw), -0.5f), tyf = __fadd_rn(__fmul_rn((float)y, inv_th), -0.5f);
+    int tx1 = (int)floorf(txf), ty1 = (int)floorf(tyf);
+    int tx2 = tx1 + 1, ty2 = ty1 + 1;
+    const float xa = __fadd_rn(txf, -(float)tx1), xa1 = __fadd_rn(1.0f, -xa);
+    const float ya = __fadd_rn(tyf, -(float)ty1), ya1 = __fadd_rn(1.0f, -ya);
+    tx1 = max(tx1, 0); tx2 = min(tx2, kClaheTiles - 1); ty1 = max(ty1, 0); ty2 = min(ty2, kClaheTiles - 1);
+    const int v = src[(size_t)y * step + x];
+    const float a = (float)luts[(ty1 * kClaheTiles + tx1) * 256 + v], b = (float)luts[(ty1 * kClaheTiles + tx2) * 256 + v];
+    const float c = (float)luts[(ty2 * kClaheTiles + tx1) * 256 + v], d = (float)luts[(ty2 * kClaheTiles + tx2) * 256 + v];
+    const float top = __fadd_rn(__fmul_rn(a, xa1), __fmul_rn(b, xa)), bot = __fadd_rn(__fmul_rn(c, xa1), __fmul_rn(d, xa));
+    const int r = __float2int_rn(__fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya)));
+    dst[(size_t)y * dstep + x] = (uint8_t)min(max(r, 0), 255);
+}
+
+__global__ void __launch_bounds__(256)
+hist256_kernel(const uint8_t* __restrict__ src, size_t step, int rows, int cols, uint32_t* __restrict__ hist)
+{
+    __shared__ uint32_t sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (int y = blockIdx.x; y < rows; y += gridDim.x)
+        for (int x = threadIdx.x; x < cols; x += 256) atomicAdd(&sh[src[(size_t)y * step + x]], 1u);
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+// cv::equalizeHist's LUT from the page histogram (one CTA of 256 threads)
+__global__ void __launch_bounds__(256)
+equalize_lut_kernel(const uint32_t* __restrict__ hist, uint32_t total, uint8_t* __restrict__ lut)
+{
+    __shared__ uint32_t part[8];
+    __shared__ int first_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t h = hist[tid];
+    if (tid == 0) first_s = 256;
+    __syncthreads();
+    if (h) atomicMin(&first_s, tid);
+    __syncthreads();
+    const int first = first_s;
+    const uint32_t hf = hist[first];
+    if (hf == total) { lut[tid] = (uint8_t)first; return; }            // one grey level: dst.setTo(first)
+    const float scale = __fdiv_rn(255.0f, (float)(total - hf));
+    uint32_t v = tid > first ? h : 0u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t; }
+    if (lane == 31) part[wid] = v;
+    __syncthreads();
+    for (int k = 0; k < wid; ++k) v += part[k];
+    const int r = tid > first ? __float2int_rn(__fmul_rn((float)v, scale)) : 0;
+    lut[tid] = (uint8_t)min(max(r, 0), 255);
+}
+
+__global__ void __launch_bounds__(256)
+apply_lut_kernel(const uint8_t* __restrict__ src, size_t step, int rows, int cols, const uint8_t* __restrict__ lut, uint8_t* __restrict__ dst,
+                 size_t dstep)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x < cols) dst[(size_t)y * dstep + x] = lut[src[(size_t)y * step + x]];
+}
+
 inline size_t r16(size_t v) { return (v + 15) & ~(size_t)15; }
 inline size_t r256(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -444,6 +561,40 @@ int prl_k_external_rects(prl_cuda_ctx* ctx, const uint8_t* d_edges, int rows, in
     { prl_launch_scope ls(ctx, FAM_EDGES); ccl_vmerge_kernel<<<grid, 256, 0, ctx->stream>>>(d_edges, step, rows, cols, L); }
     { prl_launch_scope ls(ctx, FAM_EDGES); ccl_border_kernel<<<grid, 256, 0, ctx->stream>>>(d_edges, step, rows, cols, L, top, bx0, by0, bx1, by1); }
     { prl_launch_scope ls(ctx, FAM_EDGES); ccl_rects_kernel<<<grid, 256, 0, ctx->stream>>>(d_edges, step, rows, cols, L, top, bx0, by0, bx1, by1, d_count, d_xywh, cap); }
+    PRL_CUDA_TRY(ctx, cudaGetLastError());
+    return PRL_OK;
+}
+
+// EnhanceLocalContrastByCLAHE(src, dst, clip_limit, equalize) for one channel (imageLibCommon.cpp:326-346).
+// d_tmp: rows x dst_step bytes (the CLAHE output when equalize is set); scratch: 64 x 256 LUT bytes + 256 hist words + 256 LUT bytes
+int prl_k_clahe(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, double clip_limit, bool equalize,
+                uint8_t* d_dst, size_t dst_step, uint8_t* d_tmp, void* scratch)
+{
+    if (rows > 65535) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "grid too large");
+    uint8_t* luts = (uint8_t*)scratch;
+    uint32_t* hist = (uint32_t*)(luts + kClaheTiles * kClaheTiles * 256);
+    uint8_t* eq_lut = (uint8_t*)(hist + 256);
+    // tile grid over the image extended to a multiple of 8 (copyMakeBorder bottom / right, BORDER_REFLECT_101).  As
+    // OpenCV writes it: when EITHER dimension is not a multiple, BOTH are extended by 8 - (size % 8), i.e. a dimension
+    // that already is a multiple grows by a whole 8.
+    const bool exact = cols % kClaheTiles == 0 && rows % kClaheTiles == 0;
+    const int ext_w = exact ? cols : cols + kClaheTiles - cols % kClaheTiles;
+    const int ext_h = exact ? rows : rows + kClaheTiles - rows % kClaheTiles;
+    const int tw = ext_w / kClaheTiles, th = ext_h / kClaheTiles, area = tw * th;
+    int clip = 0;
+    if (clip_limit > 0.0) { clip = (int)(clip_limit * area / 256); clip = std::max(clip, 1); }
+    const float lut_scale = 255.0f / (float)area;
+    const float inv_tw = 1.0f / (float)tw, inv_th = 1.0f / (float)th;
+    dim3 grid((cols + 255) / 256, rows);
+    uint8_t* clahe_out = equalize ? d_tmp : d_dst;
+    { prl_launch_scope ls(ctx, FAM_EDGES); clahe_lut_kernel<<<kClaheTiles * kClaheTiles, 256, 0, ctx->stream>>>(d_src, step, rows, cols, tw, th, clip, lut_scale, luts); }
+    { prl_launch_scope ls(ctx, FAM_EDGES); clahe_interp_kernel<<<grid, 256, 0, ctx->stream>>>(d_src, step, rows, cols, inv_tw, inv_th, luts, clahe_out, dst_step); }
+    if (equalize) {
+        PRL_CUDA_TRY(ctx, cudaMemsetAsync(hist, 0, 256 * sizeof(uint32_t), ctx->stream));
+        { prl_launch_scope ls(ctx, FAM_EDGES); hist256_kernel<<<std::min(rows, 8 * ctx->num_sms), 256, 0, ctx->stream>>>(d_tmp, dst_step, rows, cols, hist); }
+        { prl_launch_scope ls(ctx, FAM_EDGES); equalize_lut_kernel<<<1, 256, 0, ctx->stream>>>(hist, (uint32_t)((size_t)rows * cols), eq_lut); }
+        { prl_launch_scope ls(ctx, FAM_EDGES); apply_lut_kernel<<<grid, 256, 0, ctx->stream>>>(d_tmp, dst_step, rows, cols, eq_lut, d_dst, dst_step); }
+    }
     PRL_CUDA_TRY(ctx, cudaGetLastError());
     return PRL_OK;
 }

@@ -507,18 +507,16 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 encode_tiled_fn get_encode_tiled()
 {
-    static encode_tiled_fn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // resolved once; function-local static initialisation is thread-safe (the page dispatcher calls from one thread per device)
+    static const encode_tiled_fn fn = []() -> encode_tiled_fn {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult qr;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
             qr == cudaDriverEntryPointSuccess)
-            fn = (encode_tiled_fn)p;
-        else
-            cudaGetLastError();
-    }
+            return (encode_tiled_fn)p;
+        cudaGetLastError();
+        return nullptr;
+    }();
     return fn;
 }
 

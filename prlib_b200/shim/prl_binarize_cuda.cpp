@@ -168,10 +168,6 @@ void prl::localOtsuEdges(const cv::Mat& imageToProc, cv::Mat& resultCanny, int G
     resultCanny = out;
 }
 
-#ifdef PRL_CUDA_HAVE_CLAHE
-#include "imageLibCommon.h"
-#endif
-
 void prl::binarizeLocalOtsu(cv::Mat& inputImage, cv::Mat& outputImage, double maxValue, double CLAHEClipLimit,
                             int GaussianBlurKernelSize, double CannyUpperThresholdCoeff, double CannyLowerThresholdCoeff,
                             int CannyMorphIters)
@@ -185,24 +181,10 @@ void prl::binarizeLocalOtsu(cv::Mat& inputImage, cv::Mat& outputImage, double ma
     prl_cuda_ctx* c = context();
     cv::Mat out(inputImage.rows, inputImage.cols, CV_8UC1);
     int n = 0;
-    if (CLAHEClipLimit > 0) {
-#ifdef PRL_CUDA_HAVE_CLAHE
-        // gray conversion on the host as the reference does, then its own CLAHE step, then the device path
-        cv::Mat gray;
-        if (inputImage.channels() != 1) cv::cvtColor(inputImage, gray, cv::COLOR_RGB2GRAY); else gray = inputImage.clone();
-        EnhanceLocalContrastByCLAHE(gray, gray, CLAHEClipLimit, true);
-        check(c, prl_cuda_binarize_local_otsu(c, gray.data, gray.rows, gray.cols, gray.step, 1, maxValue, GaussianBlurKernelSize,
-                                              CannyUpperThresholdCoeff, CannyLowerThresholdCoeff, CannyMorphIters, out.data,
-                                              out.step, &n, nullptr, 0));
-        outputImage = out;
-        return;
-#else
-        throw std::runtime_error("prl::binarizeLocalOtsu: CLAHEClipLimit > 0 needs PRL_CUDA_HAVE_CLAHE (EnhanceLocalContrastByCLAHE)");
-#endif
-    }
     check(c, prl_cuda_binarize_local_otsu(c, inputImage.data, inputImage.rows, inputImage.cols, inputImage.step,
-                                          inputImage.channels(), maxValue, GaussianBlurKernelSize, CannyUpperThresholdCoeff,
-                                          CannyLowerThresholdCoeff, CannyMorphIters, out.data, out.step, &n, nullptr, 0));
+                                          inputImage.channels(), maxValue, CLAHEClipLimit > 0 ? CLAHEClipLimit : 0.0,
+                                          GaussianBlurKernelSize, CannyUpperThresholdCoeff, CannyLowerThresholdCoeff,
+                                          CannyMorphIters, out.data, out.step, &n, nullptr, 0));
     outputImage = out;
 }
 

@@ -39,9 +39,8 @@ CV_EXPORTS void binarizeLocalOtsuRects(const cv::Mat& gray, const std::vector<in
 // returns the threshold like cv::threshold does.
 CV_EXPORTS double thresholdOtsu(const cv::Mat& src, cv::Mat& dst, double maxValue = 255);
 // prl::binarizeLocalOtsu with the reference's signature and defaults (binarizeLocalOtsu.h:50-57); blur, Otsu value, Canny,
-// morphology, top-level contour rectangles and the rectangle loop all run on the device.  CLAHEClipLimit > 0 (off by
-// default) needs the reference's EnhanceLocalContrastByCLAHE: define PRL_CUDA_HAVE_CLAHE when building inside PRLib
-// (imageLibCommon.h is then included and called first, binarizeLocalOtsu.cpp:79-82); without it the call throws.
+// morphology, top-level contour rectangles and the rectangle loop all run on the device, and so does the optional
+// CLAHE + equalizeHist pre-step (CLAHEClipLimit > 0, binarizeLocalOtsu.cpp:79-82).
 CV_EXPORTS void binarizeLocalOtsu(cv::Mat& inputImage, cv::Mat& outputImage, double maxValue = 255.0,
                                   double CLAHEClipLimit = 0.0, int GaussianBlurKernelSize = 19,
                                   double CannyUpperThresholdCoeff = 0.15, double CannyLowerThresholdCoeff = 0.01,

@@ -168,3 +168,20 @@ def test_external_rects_on_adversarial_topologies(ctx):
     for i, m in enumerate(masks):
         got = sorted(map(tuple, ctx.external_rects(m).tolist()))
         assert got == want(m), (i, m.shape)
+
+
+@pytest.mark.gpu
+def test_clahe_and_local_otsu_with_clahe(ctx, noise_page, real_crops):
+    """EnhanceLocalContrastByCLAHE (cv::CLAHE 8x8 tiles + equalizeHist) bit for bit, sizes that are and are not multiples
+    of the tile grid, a one-grey-level image; then prl::binarizeLocalOtsu with CLAHEClipLimit > 0."""
+    imgs = [noise_page, CO.synth_page(2, 701, 903), CO.synth_page(4, 160, 240), np.ascontiguousarray(noise_page[:37, :53]),
+            np.full((64, 80), 93, np.uint8)]
+    imgs += [np.ascontiguousarray(v) for k, v in real_crops.items() if getattr(v, "ndim", 0) == 2][:2]
+    for img in imgs:
+        for clip in (0.5, 2.0, 4.0, 40.0):
+            for eq in (False, True):
+                assert np.array_equal(ctx.clahe(img, clip, eq), O.enhance_local_contrast_clahe(img, clip, eq)), (img.shape, clip, eq)
+    page = CO.synth_page(3, 1000, 800)
+    assert np.array_equal(prlib_b200.binarizeLocalOtsu(page, 255.0, 2.0), O.binarizeLocalOtsu(page, 255.0, 2.0))
+    bgr = real_crops["bgr_0037"]
+    assert np.array_equal(prlib_b200.binarizeLocalOtsu(bgr, 255.0, 4.0), O.binarizeLocalOtsu(bgr, 255.0, 4.0))
