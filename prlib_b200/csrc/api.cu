@@ -296,7 +296,10 @@ static int planes_pages(prl_cuda_ctx* c, int method, int mode, const uint8_t* d_
         const int np = std::min(chunk, n_pages - p0);
         const uint8_t* src = d_src + (size_t)p0 * src_page_stride;
         uint8_t* dst = d_dst + (size_t)p0 * dst_page_stride;
-        rc = prl_k_integral(c, src, np, g.rows, g.cols, src_step, src_page_stride, g.h, S, Q, g.pitch, plane_elems, d_imin + p0);
+        // the page minimum (cv::minMaxLoc, binarizeWolfJolion.cpp:115-116 / binarizeFeng.cpp) is fused into kernel 1 only when needed
+        const bool need_min = method == PRL_WOLFJOLION || method == PRL_FENG;
+        rc = prl_k_integral(c, src, np, g.rows, g.cols, src_step, src_page_stride, g.h, S, Q, g.pitch, plane_elems,
+                            need_min ? d_imin + p0 : nullptr);
         if (rc) return rc;
         const bool with_morph = morph_iters != 0 && mode == 0;
         // with a morphology tail kernel 2 writes the raw mask into the scratch and the tail writes the final one

@@ -214,7 +214,7 @@ integral_tma_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int cols
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 const uint32_t w = fetch(buf + r * BOX, j);
-                if (yc + r < y1) mn4 = __vminu4(mn4, w);
+                if (imin != nullptr && yc + r < y1) mn4 = __vminu4(mn4, w);   // (byte-wise minimum is emulated: ~15 instructions)
                 s = __dp4a(w, 0x01010101u, s);       // sum of the 4 bytes
                 q = __dp4a(w, w, q);                 // sum of their squares
             }
