@@ -205,6 +205,21 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    numa_note = None
+    if world > 1:
+        # one process per GPU: run (and first-touch the pinned staging buffers) on the cores next to this GPU, otherwise
+        # every rank's host buffers land on one socket and the end-to-end path crosses the inter-socket link
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1} & os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                numa_note = f"rank pinned to the {len(cpus)} cores nearest its GPU (nvmlDeviceGetCpuAffinity)"
+        except Exception as ex:
+            numa_note = f"no CPU affinity set ({type(ex).__name__})"
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
 
@@ -382,7 +397,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": n_pages * ROWS * COLS,
                     "d2h_bytes_per_step": n_pages * g["out_rows"] * g["out_cols"], "ms_per_step": e2e_ms / e2e_steps,
                     "pages_per_sec": total_pages * e2e_steps / (e2e_ms / 1e3), "masks_match_device_path": same,
-                    "api": "prl_cuda_binarize_batch (pinned host pages -> H2D -> K1 -> K2 -> D2H -> host masks, 3-slot ring)"},
+                    "api": "prl_cuda_binarize_batch (pinned host pages -> H2D -> K1 -> K2 -> D2H -> host masks, 3-slot ring)",
+                    "host_affinity": numa_note},
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         }
