@@ -58,3 +58,26 @@ def _sweep(ctx, seed):
             continue
         got = ctx.binarize_local(img, method, window, params, morph)
         assert got.shape == want.shape and np.array_equal(got, want), tag
+
+
+@pytest.mark.gpu
+def test_random_otsu_tiles_rects_and_global(ctx):
+    """Random tile sizes (vector path, byte path, tiles larger than the image, area above 65535), random rectangles with
+    overlaps, random maxValue -- against cv2's THRESH_OTSU (IPP off)."""
+    from oracle import prl_oracle as O
+    rng = np.random.default_rng(77)
+    for case in range(16):
+        rows, cols = int(rng.integers(1, 300)), int(rng.integers(1, 500))
+        img = _image(rng, rows, cols, int(rng.integers(0, 4)))
+        tw = int(rng.choice([1, 3, 16, 17, 32, 48, 64, 100, 128, 256, 300, 512, 600]))
+        th = int(rng.choice([1, 2, 7, 16, 33, 64, 128, 130, 400]))
+        assert np.array_equal(ctx.otsu_tiles(img, tw, th), O.otsu_tiles(img, tw, th)), (case, rows, cols, tw, th)
+        mv = float(rng.choice([255.0, 255.0, 100.0, 0.0, 254.6]))
+        thr, mask = ctx.otsu_global(img, mv)
+        thr_w, mask_w = O.otsu_global(img, mv)
+        assert thr == thr_w and np.array_equal(mask, mask_w), (case, rows, cols, mv)
+        rects = []
+        for _ in range(int(rng.integers(0, 9))):
+            x, y = int(rng.integers(0, cols)), int(rng.integers(0, rows))
+            rects.append((x, y, int(rng.integers(1, cols - x + 1)), int(rng.integers(1, rows - y + 1))))
+        assert np.array_equal(ctx.otsu_rects(img, rects, mv), O.otsu_rects(img, rects, mv)), (case, rects, mv)
