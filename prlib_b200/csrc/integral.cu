@@ -458,11 +458,59 @@ band_colsum_kernel(const uint8_t* __restrict__ src, size_t src_step, size_t src_
         if (X + i < Wp) { out[X + i] = sb[i] + s[i]; out[pitch + X + i] = q[i]; }
 }
 
+// Same sums per SOURCE column (the carry kernel maps padded columns onto them), for 16-byte aligned pages: a thread owns
+// 16 adjacent columns (one 16-byte load per row, 8 rows in flight), a CTA 2048 columns of one slice of 128 rows of a
+// band; 32-bit partial sums (255^2 * 128 * (pad + 1) < 2^32 for pad < 515) are added to the band's 64-bit sums with atomics.
+__global__ void __launch_bounds__(128)
+band_colsum_vec_kernel(const uint8_t* __restrict__ src, size_t src_step, size_t src_page_stride, int rows, int cols,
+                       int pad, int rows_per_band, int slices, unsigned long long* __restrict__ colsum, size_t pitch)
+{
+    const int page = blockIdx.z, band = blockIdx.y / slices, slice = blockIdx.y - band * slices, bands = gridDim.y / slices;
+    const int x = (blockIdx.x * 128 + threadIdx.x) * 16;
+    if (x >= cols) return;
+    const int yb0 = band * rows_per_band, yb1 = min(yb0 + rows_per_band, rows);
+    const int y0 = yb0 + slice * 128, y1 = min(y0 + 128, yb1);
+    if (y0 >= y1) return;
+    src += (size_t)page * src_page_stride + x;
+    uint32_t s[16], q[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s[i] = q[i] = 0;
+    auto add = [&](const uint4& v, uint32_t mult) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t p = (w[k] >> (8 * i)) & 0xffu;
+                s[4 * k + i] += mult * p; q[4 * k + i] += mult * p * p;
+            }
+    };
+    int y = y0;
+    for (; y + 8 <= y1; y += 8) {
+        uint4 v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[r] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(y + r) * src_step));
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int yy = y + r;
+            add(v[r], 1u + ((yy == 0) ? pad : 0) + ((yy == rows - 1) ? pad : 0));      // replicated border rows count pad more times
+        }
+    }
+    for (; y < y1; ++y)
+        add(__ldg(reinterpret_cast<const uint4*>(src + (size_t)y * src_step)), 1u + ((y == 0) ? pad : 0) + ((y == rows - 1) ? pad : 0));
+    unsigned long long* out = colsum + ((size_t)page * bands + band) * 2 * pitch + x;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        if (x + i < cols) { atomicAdd(out + i, (unsigned long long)s[i]); atomicAdd(out + pitch + i, (unsigned long long)q[i]); }
+}
+
 // carry[page][band][plane][X] = sum_{b' < band} sum_{X' <= X} colsum[page][b'][plane][X']
 //                             = the integral row just above the band's first emitted padded row
 __global__ void __launch_bounds__(1024)
-band_carry_kernel(const unsigned long long* __restrict__ colsum, long long* __restrict__ carry, int Wp, size_t pitch)
+band_carry_kernel(const unsigned long long* __restrict__ colsum, long long* __restrict__ carry, int Wp, size_t pitch,
+                  int src_cols, int pad)
 {
+    // src_cols > 0: colsum is indexed by source column; padded column X reads source column clamp(X - pad)
     __shared__ unsigned long long wtot[2][32];
     const int page = blockIdx.y, band = blockIdx.x, bands = gridDim.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -472,11 +520,13 @@ band_carry_kernel(const unsigned long long* __restrict__ colsum, long long* __re
     for (int base = 0; base < Wp; base += 1024) {
         const int X = base + threadIdx.x;
         unsigned long long vs = 0, vq = 0;
-        if (X < Wp)
+        if (X < Wp) {
+            const int xi = src_cols > 0 ? min(max(X - pad, 0), src_cols - 1) : X;
             for (int b = 0; b < band; ++b) {
-                vs += in[(size_t)b * 2 * pitch + X];
-                vq += in[(size_t)b * 2 * pitch + pitch + X];
+                vs += in[(size_t)b * 2 * pitch + xi];
+                vq += in[(size_t)b * 2 * pitch + pitch + xi];
             }
+        }
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             unsigned long long ts = __shfl_up_sync(0xffffffffu, vs, d);
@@ -591,7 +641,15 @@ int prl_k_integral(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int row
         size_t need = (size_t)n_pages * bands * 2 * pitch * sizeof(int64_t);
         int rc = prl_ensure(ctx, &ctx->colsum, &ctx->colsum_bytes, need); if (rc) return rc;
         rc = prl_ensure(ctx, &ctx->carry, &ctx->carry_bytes, need); if (rc) return rc;
-        {
+        const bool vec_src = (((uintptr_t)d_src | src_step | src_page_stride) & 15) == 0 && pad < 512 &&
+                             src_step >= (size_t)((cols + 15) & ~15) && (size_t)bands * ((rpb + 127) / 128) <= 65535;
+        if (vec_src) {
+            const int slices = (rpb + 127) / 128;
+            PRL_CUDA_TRY(ctx, cudaMemsetAsync(ctx->colsum, 0, need, ctx->stream));
+            prl_launch_scope ls(ctx, FAM_BAND_CARRY);
+            band_colsum_vec_kernel<<<dim3((cols + 2047) / 2048, bands * slices, n_pages), 128, 0, ctx->stream>>>(
+                d_src, src_step, src_page_stride, rows, cols, pad, rpb, slices, (unsigned long long*)ctx->colsum, pitch);
+        } else {
             prl_launch_scope ls(ctx, FAM_BAND_CARRY);
             band_colsum_kernel<<<dim3((Wp + 1023) / 1024, bands, n_pages), 256, 0, ctx->stream>>>(
                 d_src, src_step, src_page_stride, rows, cols, pad, rpb, (unsigned long long*)ctx->colsum, pitch);
@@ -599,7 +657,7 @@ int prl_k_integral(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int row
         {
             prl_launch_scope ls(ctx, FAM_BAND_CARRY);
             band_carry_kernel<<<dim3(bands, n_pages), 1024, 0, ctx->stream>>>(
-                (const unsigned long long*)ctx->colsum, (long long*)ctx->carry, Wp, pitch);
+                (const unsigned long long*)ctx->colsum, (long long*)ctx->carry, Wp, pitch, vec_src ? cols : 0, pad);
         }
         d_carry = (const int64_t*)ctx->carry;
     }
