@@ -50,6 +50,7 @@ struct prl_cuda_ctx {
 
     bool force_exact = false;   // validation: kernel 2 runs the literal FP64 path for every pixel
     bool no_tma = false;        // validation: kernel 1 uses the generic (non-TMA) kernel
+    int thr_rows = 0;           // kernel 2: output rows per CTA (0 = automatic: 4, or 8 when the tap distance exceeds 64)
     int tile_prefetch = 0;      // tile Otsu: how many tiles ahead a warp pulls into L2 (0 = off)
     bool morph_bytes = false;   // validation: the morphology tail runs the byte kernels even on binary masks
     bool use_fused = false;     // opt-in: fused small-window strip kernel (integral planes never reach HBM)
