@@ -213,8 +213,8 @@ int prl_cuda_external_rects(prl_cuda_ctx* ctx, const uint8_t* mask, int rows, in
 
 /* ---- prl::removeLines (src/removeLines.cpp:30-77; a Global-Otsu caller) -------------
  * bw = cv::threshold(~gray, OTSU); horizontal / vertical = opening of bw by a 1 x cols/50 / rows/50 x 1 element;
- * out = ~(bw - horizontal - vertical).  channels 1, or 3 = BGR (cvtColor BGR2GRAY, :33-36).  Needs rows, cols >= 50
- * (PRL_E_UNSUPPORTED below that, where the reference's empty structuring element means OpenCV's default 3x3). */
+ * out = ~(bw - horizontal - vertical).  channels 1, or 3 = BGR (cvtColor BGR2GRAY, :33-36).  rows < 50 or cols < 50:
+ * PRL_E_EMPTY_ROI, the cv::Exception of the reference (a zero-sized structuring element fails cv::erode's anchor assertion). */
 int prl_cuda_remove_lines(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step, int channels,
                           uint8_t* dst, size_t dst_step);
 

@@ -152,8 +152,8 @@ int prl_k_remove_lines(prl_cuda_ctx* ctx, const uint8_t* d_gray, int rows, int c
     if (rows > 65535) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "grid too large");
     const int Lh = cols / 50, Lv = rows / 50;                // removeLines.cpp:51,61
     if (Lh < 1 || Lv < 1)
-        return prl_set_err(ctx, PRL_E_UNSUPPORTED, "removeLines needs at least 50 rows and 50 columns (smaller images make the "
-                                                   "reference fall back to OpenCV's default 3x3 element)");
+        return prl_set_err(ctx, PRL_E_EMPTY_ROI, "removeLines: rows / 50 or cols / 50 is 0 -- the reference's zero-sized structuring "
+                                                 "element makes cv::erode assert (cv::Exception)");
     const int wpr = (cols + 31) / 32;
     const size_t img = ((size_t)rows * wpr * 4 + 255) & ~(size_t)255;
     uint8_t* b = (uint8_t*)scratch;

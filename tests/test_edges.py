@@ -128,8 +128,13 @@ def test_remove_lines_equals_the_opencv_sequence(ctx, noise_page, real_crops):
     imgs += [np.ascontiguousarray(v) for k, v in real_crops.items() if getattr(v, "ndim", 0) == 2]
     for img in imgs:
         assert np.array_equal(prlib_b200.removeLines(img), O.removeLines(img)), img.shape
-    with pytest.raises(prlib_b200.PrlCudaError):
-        prlib_b200.removeLines(np.zeros((40, 200), np.uint8))
+    import cv2
+    small = np.zeros((40, 200), np.uint8)
+    with pytest.raises(cv2.error):                       # the reference: zero-sized structuring element -> cv::Exception
+        O.removeLines(small)
+    with pytest.raises(prlib_b200.PrlCudaError) as ei:   # here: PRL_E_EMPTY_ROI, which the shim rethrows as cv::Exception
+        prlib_b200.removeLines(small)
+    assert ei.value.code == prlib_b200.capi.PRL_E_EMPTY_ROI
 
 
 @pytest.mark.gpu
