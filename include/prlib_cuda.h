@@ -172,7 +172,7 @@ int prl_cuda_binarize_batch(const int* devices, int n_dev, int method, const uin
  * Otsu value of the blurred image, cv::Canny(lowerCoeff * upper, upper = upperCoeff * otsu), closing (morph_iters > 0)
  * or opening (< 0)) followed by `post_dilate` dilations (binarizeLocalOtsu.cpp:92 uses 3); single-channel u8 in,
  * 0/255 edge map out, bit-identical to OpenCV 4.x.  PRL_E_INVALID mirrors the reference's std::invalid_argument
- * checks (:248-272) and OpenCV's odd-kernel assertion.  The contour step (cv::findContours, :104-110) stays with the
+ * checks (:248-272), PRL_E_EMPTY_ROI OpenCV's odd-kernel assertion (a cv::Exception); sizes above 63: PRL_E_UNSUPPORTED.  The contour step (cv::findContours, :104-110) stays with the
  * caller; its rectangles go to prl_cuda_otsu_rects.  prl_cuda_gaussian_blur / prl_cuda_canny are the two building
  * blocks alone (cv::GaussianBlur on CV_8U with BORDER_DEFAULT; cv::Canny with aperture 3, L1 gradient). */
 /* the 8.8 fixed-point Gaussian coefficients cv::GaussianBlur uses on CV_8U (host-only helper; n odd, <= 63; k[n]) */

@@ -624,8 +624,10 @@ extern "C" int prl_cuda_canny_edge_detection_dev(prl_cuda_ctx* c, const uint8_t*
     if (!d_gray || !d_dst || rows <= 0 || cols <= 0 || step < (size_t)cols || dst_step < (size_t)cols)
         return prl_set_err(c, PRL_E_INVALID, "bad argument");
     // the reference's own argument checks (imageLibCommon.cpp:248-272); cv::GaussianBlur needs an odd size
-    if (gauss_ksize < 3 || (gauss_ksize & 1) == 0 || gauss_ksize > 63)
-        return prl_set_err(c, PRL_E_INVALID, "Gaussian blur kernel size must be odd and in [3, 63]");
+    if (gauss_ksize < 3) return prl_set_err(c, PRL_E_INVALID, "Gaussian blur kernel size is lesser than 3");     // :253-256
+    if ((gauss_ksize & 1) == 0)                                       // cv::GaussianBlur asserts an odd size: cv::Exception
+        return prl_set_err(c, PRL_E_EMPTY_ROI, "GaussianBlur: the kernel size must be odd");
+    if (gauss_ksize > 63) return prl_set_err(c, PRL_E_UNSUPPORTED, "Gaussian blur kernel sizes above 63 are not supported");
     if (!(upper_coeff >= 0 && upper_coeff <= 1) || !(lower_coeff >= 0 && lower_coeff <= 1) || lower_coeff > upper_coeff)
         return prl_set_err(c, PRL_E_INVALID, "Canny threshold coefficients must satisfy 0 <= lower <= upper <= 1");
     if (post_dilate < 0 || post_dilate > 15 || morph_iters > 15 || morph_iters < -15)

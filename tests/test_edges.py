@@ -66,9 +66,12 @@ def test_canny_edge_detection_chain(ctx, noise_page):
                                     (19, 1.0, 1.0, 2, 3)):
             want = O.local_otsu_edges(img, k, up, lo, it, post)
             assert np.array_equal(ctx.canny_edge_detection(img, k, up, lo, it, post), want), (img.shape, k, up, lo, it, post)
-    for bad in ((2, 0.15, 0.01), (4, 0.15, 0.01), (19, 1.5, 0.01), (19, 0.1, 0.2), (19, 0.15, -0.1)):
+    for bad in ((2, 0.15, 0.01), (19, 1.5, 0.01), (19, 0.1, 0.2), (19, 0.15, -0.1)):     # the reference's std::invalid_argument checks
         with pytest.raises(ValueError):
             ctx.canny_edge_detection(page, *bad)
+    with pytest.raises(prlib_b200.PrlCudaError) as ei:                                   # even size: cv::GaussianBlur's assertion
+        ctx.canny_edge_detection(page, 4, 0.15, 0.01)
+    assert ei.value.code == prlib_b200.capi.PRL_E_EMPTY_ROI
 
 
 @pytest.mark.gpu
