@@ -20,8 +20,16 @@
  * real OpenCV primitives through cv2 4.13.0 (tests/test_oracle.py), and against the SHA-1
  * digests in tests/golden/.
  *
- * Build: gcc -O2 -ffp-contract=off -fPIC -shared  (no FMA contraction: the reference's
+ * Build: gcc -O2 -ffp-contract=off -fPIC -shared  (no compiler FMA contraction: the reference's
  * direct-tap filter2D path rounds every product).
+ *
+ * Where OpenCV itself fuses: on every x86-64 build with the AVX2/FMA3 dispatch (the cv2 wheel here, any distro
+ * OpenCV >= 3.x on a CPU from 2013 on) Mat::convertTo(alpha, beta), cv::scaleAdd and cv::addWeighted evaluate their
+ * multiply-add with ONE rounding (v_fma / v_muladd in convert_scale.simd.hpp, matmul.simd.hpp, arithm.simd.hpp);
+ * measured on the wheel by tests/test_ref.py::test_wheel_multiply_add_is_fused, and what oracle/_ref (the reference's
+ * own C++ over that wheel) therefore computes.  The explicit fma() calls below restate exactly those three.
+ * (addWeighted's scalar tail -- the last cols % 8 columns -- is contracted by the compiler in a different order,
+ * fma(b, beta, a*alpha) + gamma; that is a <= 1 ulp difference in T on those columns and is NOT restated.)
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -116,26 +124,26 @@ static inline double threshold_value(const thr_ctx *c, double m, double s)
 {
     switch (c->method) {
     case PRL_SAUVOLA: {               /* binarizeSauvola.cpp:115-118 */
-        double t = s * c->p1 + c->p2; /* p1 = k*(1/128), p2 = 1-k */
+        double t = fma(s, c->p1, c->p2); /* Mat::convertTo(alpha = k*(1/128), beta = 1-k): ONE rounding (header note) */
         return m * t;
     }
     case PRL_NIBLACK:                 /* binarizeNiblack.cpp:108 */
-        return m + c->p0 * s;
+        return fma(s, c->p0, m);      /* MatExpr m + k*s -> cv::scaleAdd(s, k, m): ONE rounding (header note) */
     case PRL_WOLFJOLION: {            /* binarizeWolfJolion.cpp:128-130 */
-        double d = s * c->coeff + (-c->p0);
+        double d = fma(s, c->coeff, -c->p0);         /* convertTo(coeff, -k): ONE rounding */
         d = d * (m - c->imin);
         return m + d;
     }
     case PRL_NICK: {                  /* binarizeNICK.cpp:121-126 */
         double C = sqrt(m * m + s * s);
-        return m * 1.0 + C * c->p0 + 0.0;
+        return fma(m, 1.0, fma(C, c->p0, 0.0));      /* cv::addWeighted; == m + round(C*k) because alpha is 1 */
     }
     default: {                        /* binarizeFeng.cpp:118-142 */
         double t1 = s / s;            /* Rs aliases s (:118) -> 1, or NaN when s is 0/NaN */
         double t2 = (t1 == t1) ? 1.0 : t1;          /* cv::pow(1, gamma) == 1; NaN stays NaN */
         double alpha3 = c->p2 * t2;   /* k2 * tmpAlpha2 */
         double c2 = t2 * t1;
-        double c3 = alpha3 * c->imin + c2 * (-c->imin) + 0.0;
+        double c3 = fma(alpha3, c->imin, fma(c2, -c->imin, 0.0));   /* cv::addWeighted: fma(a, alpha, fma(b, beta, gamma)) */
         double T = c2 + (1.0 - c->p0);
         T = T * m;
         return T + c3;

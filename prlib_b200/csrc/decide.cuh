@@ -49,15 +49,18 @@ __device__ __forceinline__ double tap4(double kw, double nkw, long long a, long 
 
 // The reference's FP64 threshold formulas (binarizeSauvola.cpp:115-118, binarizeNiblack.cpp:108,
 // binarizeWolfJolion.cpp:128-130, binarizeNICK.cpp:121-126, binarizeFeng.cpp:118-142), operation order kept.
+// Roundings follow what OpenCV executes on an FMA-capable host (pinned by oracle/_ref, the reference's own C++ over the
+// cv2 wheel): Mat::convertTo(alpha, beta) and cv::scaleAdd fuse their multiply-add (one rounding), cv::addWeighted is
+// fma(a, alpha, fma(b, beta, gamma)); filter2D's taps, Mat::mul, add and subtract round every operation.
 template <int METHOD>
 __device__ __forceinline__ double thr_value_p(double m, double s, double p0, double p1, double p2, double imin, double coeff)
 {
     if (METHOD == PRL_SAUVOLA) {
-        return __dmul_rn(m, __dadd_rn(__dmul_rn(s, p1), p2));
+        return __dmul_rn(m, __fma_rn(s, p1, p2));                      // convertTo(k/128, 1-k), then mul
     } else if (METHOD == PRL_NIBLACK) {
-        return __dadd_rn(m, __dmul_rn(p0, s));
+        return __fma_rn(s, p0, m);                                     // scaleAdd(s, k, m)
     } else if (METHOD == PRL_WOLFJOLION) {
-        double dd = __dadd_rn(__dmul_rn(s, coeff), -p0);
+        double dd = __fma_rn(s, coeff, -p0);                           // convertTo(coeff, -k)
         dd = __dmul_rn(dd, __dadd_rn(m, -imin));
         return __dadd_rn(m, dd);
     } else if (METHOD == PRL_NICK) {
@@ -65,7 +68,7 @@ __device__ __forceinline__ double thr_value_p(double m, double s, double p0, dou
         return __dadd_rn(m, __dmul_rn(C, p0));
     } else {
         if (!(s == s) || s == 0.0) return __longlong_as_double(0x7ff8000000000000LL);
-        double c3 = __dadd_rn(__dmul_rn(p2, imin), -imin);
+        double c3 = __fma_rn(p2, imin, -imin);                         // addWeighted(alpha3, imin, c2, -imin, 0), c2 == 1
         return __dadd_rn(__dmul_rn(p1, m), c3);
     }
 }

@@ -42,26 +42,11 @@ struct ThrArgs {
     double kw, nkw, p0, p1, p2;
 };
 
+// one spelling of the reference's formulas for every kernel: decide.cuh:thr_value_p
 template <int METHOD>
 __device__ __forceinline__ double thr_value(double m, double s, const ThrArgs& A, double imin, double coeff)
 {
-    if (METHOD == PRL_SAUVOLA) {
-        return __dmul_rn(m, __dadd_rn(__dmul_rn(s, A.p1), A.p2));
-    } else if (METHOD == PRL_NIBLACK) {
-        return __dadd_rn(m, __dmul_rn(A.p0, s));
-    } else if (METHOD == PRL_WOLFJOLION) {
-        double dd = __dadd_rn(__dmul_rn(s, coeff), -A.p0);
-        dd = __dmul_rn(dd, __dadd_rn(m, -imin));
-        return __dadd_rn(m, dd);
-    } else if (METHOD == PRL_NICK) {
-        double C = __dsqrt_rn(__dadd_rn(__dmul_rn(m, m), __dmul_rn(s, s)));
-        return __dadd_rn(m, __dmul_rn(C, A.p0));
-    } else {
-        // Feng as written: s/Rs with Rs aliasing s is 1, or NaN when s is 0 or NaN
-        if (!(s == s) || s == 0.0) return __longlong_as_double(0x7ff8000000000000LL);
-        double c3 = __dadd_rn(__dmul_rn(A.p2, imin), -imin);
-        return __dadd_rn(__dmul_rn(A.p1, m), c3);   // p1 = 1 + (1 - alpha1), p2 = k2
-    }
+    return thr_value_p<METHOD>(m, s, A.p0, A.p1, A.p2, imin, coeff);
 }
 
 constexpr int kTR = 4;   // output rows per CTA (exact kernel)
