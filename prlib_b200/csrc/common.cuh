@@ -15,6 +15,35 @@
 // even columns are aligned.
 static inline size_t prl_plane_pitch(int padded_cols) { return ((size_t)padded_cols + 15) & ~(size_t)15; }
 
+// The integral planes of a chunk of pages, in one of two layouts:
+//   compact == 0  S, Q: int64 (what cv::integral(CV_64F) holds, exactly) -- the exported bit-exactness hook
+//                 (prl_cuda_integral_u8*), the literal-FP64 kernels, and any buffer the fast path cannot take;
+//   compact == 1  S, Q: the LOW 32-bit words only (window sums are < 2^32, so differences of low words are the exact
+//                 window sums) plus the HIGH words of every (1 << ashift)-th padded row in AS / AQ.  A full int64 tap --
+//                 needed only by the ~1e-3 of the pixels that evaluate the reference's FP64 formula -- is rebuilt as
+//                 full(Y, X) = (hi(Ya, X) << 32 | lo(Ya, X)) + u32(lo(Y, X) - lo(Ya, X)),  Ya = Y rounded down to an anchor row,
+//                 exact because a column grows by less than 2^32 over (1 << ashift) - 1 rows (prl_anchor_shift).
+//                 9 bytes per padded pixel instead of 16 on both sides of the kernel-1 / kernel-2 hand-over.
+struct prl_planes {
+    int compact = 0;
+    void* S = nullptr;          // int64_t* or uint32_t*
+    void* Q = nullptr;
+    size_t pitch = 0;           // elements per row (128-byte multiple in bytes)
+    size_t page_stride = 0;     // elements per page
+    uint32_t* AS = nullptr;     // compact: high words of the anchor rows, ceil(Hp / A) rows of `pitch` elements
+    uint32_t* AQ = nullptr;
+    int ashift = 0;
+    size_t a_page_stride = 0;   // elements per page in AS / AQ
+};
+static inline size_t prl_plane_pitch32(int padded_cols) { return ((size_t)padded_cols + 31) & ~(size_t)31; }
+// largest A = 1 << shift <= 8 with (A - 1) * 255^2 * Wp < 2^32: the growth of Q down a column over A - 1 rows fits 32 bits
+static inline int prl_anchor_shift(int padded_cols)
+{
+    int sh = 3;
+    while (sh > 0 && (double)((1 << sh) - 1) * 65025.0 * (double)padded_cols >= 4294967296.0) --sh;
+    return sh;
+}
+
 struct prl_timing_rec { cudaEvent_t a, b; int family; };
 
 struct prl_cuda_ctx {
@@ -49,6 +78,7 @@ struct prl_cuda_ctx {
     uint8_t* h_pin = nullptr;   size_t h_pin_bytes = 0;
 
     bool force_exact = false;   // validation: kernel 2 runs the literal FP64 path for every pixel
+    bool no_compact = false;    // validation: the two-kernel path keeps full int64 planes (16 B per padded pixel) instead of the compact layout
     bool no_tma = false;        // validation: kernel 1 uses the generic (non-TMA) kernel
     int thr_rows = 0;           // kernel 2: output rows per CTA (0 = automatic: 4, or 8 when the tap distance exceeds 64)
     int tile_prefetch = 0;      // tile Otsu: how many tiles ahead a warp pulls into L2 (0 = off)
@@ -98,10 +128,15 @@ int prl_make_geom(int method, int rows, int cols, int window, prl_geom* g);
 int prl_k_integral(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int rows, int cols, size_t src_step,
                    size_t src_page_stride, int pad, int64_t* d_S, int64_t* d_Q, size_t pitch,
                    size_t plane_page_stride, uint32_t* d_imin /*per page or null*/);
+// same, into either plane layout; the compact layout needs the TMA kernel (prl_integral_compact_ok)
+int prl_k_integral_planes(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int rows, int cols, size_t src_step,
+                          size_t src_page_stride, int pad, const prl_planes& P, uint32_t* d_imin);
+bool prl_integral_compact_ok(const prl_cuda_ctx* ctx, const uint8_t* d_src, size_t src_step, size_t src_page_stride);
+bool prl_threshold_fast_ok(const prl_cuda_ctx* ctx, int method, const double* params, const prl_geom& g,
+                           const uint8_t* d_src, size_t src_step, size_t src_page_stride);
 struct prl_thr_params { double kw, nkw, p0, p1, p2; };
 int prl_k_threshold(prl_cuda_ctx* ctx, int method, int mode /*0 mask, 1 T8*/, const uint8_t* d_src, int n_pages,
-                    const prl_geom& g, size_t src_step, size_t src_page_stride, const int64_t* d_S,
-                    const int64_t* d_Q, size_t plane_page_stride, const double* params,
+                    const prl_geom& g, size_t src_step, size_t src_page_stride, const prl_planes& P, const double* params,
                     const uint32_t* d_imin, long long* d_smax, uint8_t* d_dst, size_t dst_step,
                     size_t dst_page_stride);
 bool prl_fused_eligible(const prl_cuda_ctx* ctx, int method, int n_pages, const prl_geom& g, const double* params);

@@ -35,7 +35,8 @@ namespace {
 
 struct ThrArgs {
     const uint8_t* src; size_t src_step, src_page_stride;
-    const int64_t* S; const int64_t* Q; size_t pitch, plane_page_stride;
+    const int64_t* S; const int64_t* Q; size_t pitch, plane_page_stride;   // compact layout: really uint32_t* (low words)
+    const uint32_t* AS; const uint32_t* AQ; size_t a_page_stride; int ashift; // compact layout: high words of the anchor rows
     uint8_t* dst; size_t dst_step, dst_page_stride;
     const uint32_t* imin; long long* smax;
     int out_rows, out_cols, d;
@@ -147,10 +148,51 @@ __device__ __forceinline__ void ldg256(const int64_t* p, long long& a, long long
 {
     asm volatile("ld.global.nc.v4.s64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
 }
+__device__ __forceinline__ uint4 ldg128u(const uint32_t* p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// low words of 4 adjacent plane elements at element offset `e` of a page's plane, either layout
+template <bool COMPACT>
+__device__ __forceinline__ uint4 lo4(const int64_t* plane, size_t e)
+{
+    if (COMPACT) return ldg128u(reinterpret_cast<const uint32_t*>(plane) + e);
+    long long a, b, c, d;
+    ldg256(plane + e, a, b, c, d);
+    return make_uint4((unsigned int)a, (unsigned int)b, (unsigned int)c, (unsigned int)d);
+}
+
+// compact layout: the full int64 value at (Y, X) from the low-word plane L and the anchor high words H (common.cuh: prl_planes)
+__device__ __forceinline__ long long full_tap(const uint32_t* __restrict__ L, const uint32_t* __restrict__ H, size_t pitch,
+                                              int ashift, int Y, int X)
+{
+    const int ya = Y >> ashift;
+    const unsigned int lo_a = __ldg(L + ((size_t)ya << ashift) * pitch + X);
+    const unsigned int hi = __ldg(H + (size_t)ya * pitch + X);
+    const unsigned int lo = __ldg(L + (size_t)Y * pitch + X);
+    return (long long)((((unsigned long long)hi << 32) | lo_a) + (unsigned long long)(unsigned int)(lo - lo_a));
+}
+
+// the literal reference arithmetic for output pixel (y, x) from compact planes of one page
+template <int METHOD>
+__device__ __noinline__ int exact_t8_compact(const uint32_t* __restrict__ S, const uint32_t* __restrict__ Q,
+                                             const uint32_t* __restrict__ AS, const uint32_t* __restrict__ AQ, size_t pitch,
+                                             int ashift, int y, int x, int d, double kw, double p0, double p1, double p2,
+                                             double imin, double coeff)
+{
+    const long long sa = full_tap(S, AS, pitch, ashift, y, x), sb = full_tap(S, AS, pitch, ashift, y, x + d);
+    const long long sc = full_tap(S, AS, pitch, ashift, y + d, x), sd = full_tap(S, AS, pitch, ashift, y + d, x + d);
+    const long long qa = full_tap(Q, AQ, pitch, ashift, y, x), qb = full_tap(Q, AQ, pitch, ashift, y, x + d);
+    const long long qc = full_tap(Q, AQ, pitch, ashift, y + d, x), qd = full_tap(Q, AQ, pitch, ashift, y + d, x + d);
+    return exact_t8_from_taps<METHOD>(sa, sb, sc, sd, qa, qb, qc, qd, kw, p0, p1, p2, imin, coeff);
+}
 
 // NT threads per CTA: 128 (512 columns loaded per row) for small windows, 256 (1024 columns) when the tap
 // distance d would otherwise waste a large share of each CTA's loads on the column halo
-template <int METHOD, int NT>
+template <int METHOD, int NT, bool COMPACT>
 __global__ void __launch_bounds__(NT, 1024 / NT)     // <= 64 registers: 32 resident warps per SM
 threshold_fast_kernel(const ThrArgs A, const FastArgs F)
 {
@@ -163,8 +205,11 @@ threshold_fast_kernel(const ThrArgs A, const FastArgs F)
     const int x = X0 + 4 * threadIdx.x;              // this thread's first column (32-byte aligned in the planes)
     const int y_begin = blockIdx.y * F.rows_per_cta;
     const int y_end = min(y_begin + F.rows_per_cta, A.out_rows);
-    const int64_t* S = A.S + (size_t)page * A.plane_page_stride;
-    const int64_t* Q = A.Q + (size_t)page * A.plane_page_stride;
+    // (compact layout: the same expressions step through u32 elements, see lo4)
+    const int64_t* S = COMPACT ? reinterpret_cast<const int64_t*>(reinterpret_cast<const uint32_t*>(A.S) + (size_t)page * A.plane_page_stride)
+                               : A.S + (size_t)page * A.plane_page_stride;
+    const int64_t* Q = COMPACT ? reinterpret_cast<const int64_t*>(reinterpret_cast<const uint32_t*>(A.Q) + (size_t)page * A.plane_page_stride)
+                               : A.Q + (size_t)page * A.plane_page_stride;
     const uint8_t* src = A.src + (size_t)page * A.src_page_stride;
     uint8_t* dst = A.dst + (size_t)page * A.dst_page_stride;
 
@@ -186,6 +231,26 @@ threshold_fast_kernel(const ThrArgs A, const FastArgs F)
     for (int y = y_begin; y < y_end; y += kFR, buf ^= 1) {
         // ---- vertical differences of the low words -> shared memory (own copy stays in registers)
         unsigned int dsr[kFR][4], dqr[kFR][4];
+        if (COMPACT) {
+            // 16-byte loads: all eight of an iteration are in flight before the first difference is formed
+            uint4 ta[kFR], tb[kFR], ua[kFR], ub[kFR];
+#pragma unroll
+            for (int r = 0; r < kFR; ++r) {
+                ta[r] = tb[r] = ua[r] = ub[r] = make_uint4(0u, 0u, 0u, 0u);
+                if (in_plane && y + r < y_end) {
+                    const size_t e = (size_t)(y + r) * A.pitch + x, eb = e + (size_t)A.d * A.pitch;
+                    ta[r] = lo4<true>(S, e); tb[r] = lo4<true>(S, eb);
+                    ua[r] = lo4<true>(Q, e); ub[r] = lo4<true>(Q, eb);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kFR; ++r) {
+                dsr[r][0] = tb[r].x - ta[r].x; dsr[r][1] = tb[r].y - ta[r].y; dsr[r][2] = tb[r].z - ta[r].z; dsr[r][3] = tb[r].w - ta[r].w;
+                dqr[r][0] = ub[r].x - ua[r].x; dqr[r][1] = ub[r].y - ua[r].y; dqr[r][2] = ub[r].z - ua[r].z; dqr[r][3] = ub[r].w - ua[r].w;
+                *reinterpret_cast<uint4*>(&sD[buf][r][0][4 * threadIdx.x]) = make_uint4(dsr[r][0], dsr[r][1], dsr[r][2], dsr[r][3]);
+                *reinterpret_cast<uint4*>(&sD[buf][r][1][4 * threadIdx.x]) = make_uint4(dqr[r][0], dqr[r][1], dqr[r][2], dqr[r][3]);
+            }
+        } else {
 #pragma unroll
         for (int r = 0; r < kFR; ++r) {
             unsigned int (&ds)[4] = dsr[r];
@@ -204,6 +269,7 @@ threshold_fast_kernel(const ThrArgs A, const FastArgs F)
             }
             *reinterpret_cast<uint4*>(&sD[buf][r][0][4 * threadIdx.x]) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
             *reinterpret_cast<uint4*>(&sD[buf][r][1][4 * threadIdx.x]) = make_uint4(dq[0], dq[1], dq[2], dq[3]);
+        }
         }
         __syncthreads();
         // ---- horizontal differences, decision, store
@@ -236,10 +302,17 @@ threshold_fast_kernel(const ThrArgs A, const FastArgs F)
                     int o;
                     if (!fast_decide<METHOD, METHOD == PRL_SAUVOLA>(sw[i], qw[i], p, F, iminf, coefff, mu, o)) {
                         if (x + i < A.out_cols) {
-                            const size_t e0 = (size_t)yy * A.pitch + x + i;
-                            const int t8 = exact_t8_at<METHOD>(reinterpret_cast<const long long*>(S) + e0,
-                                                               reinterpret_cast<const long long*>(Q) + e0, (size_t)A.d * A.pitch,
-                                                               A.d, A.kw, A.p0, A.p1, A.p2, imin, coeff);
+                            int t8;
+                            if (COMPACT) {
+                                t8 = exact_t8_compact<METHOD>(reinterpret_cast<const uint32_t*>(S), reinterpret_cast<const uint32_t*>(Q),
+                                                              A.AS + (size_t)page * A.a_page_stride, A.AQ + (size_t)page * A.a_page_stride,
+                                                              A.pitch, A.ashift, yy, x + i, A.d, A.kw, A.p0, A.p1, A.p2, imin, coeff);
+                            } else {
+                                const size_t e0 = (size_t)yy * A.pitch + x + i;
+                                t8 = exact_t8_at<METHOD>(reinterpret_cast<const long long*>(S) + e0,
+                                                         reinterpret_cast<const long long*>(Q) + e0, (size_t)A.d * A.pitch,
+                                                         A.d, A.kw, A.p0, A.p1, A.p2, imin, coeff);
+                            }
                             o = (int)p > t8 ? 255 : 0;
                         } else o = 0;
                     }
@@ -284,6 +357,7 @@ void launch_exact(prl_cuda_ctx* ctx, int mode, const ThrArgs& A, dim3 grid)
 //   pass B (smax_candidates_kernel): only tiles whose maximum reaches N_max - margin are revisited, and only
 //   their pixels within the margin evaluate the literal FP64 s; the maximum over those is s_max, bit-exact.
 // ------------------------------------------------------------------------------------------------
+template <bool COMPACT>
 __global__ void __launch_bounds__(kFT)
 nmax_fast_kernel(const ThrArgs A, const FastArgs F, unsigned long long* __restrict__ nmax_page,
                  unsigned long long* __restrict__ nmax_tile)
@@ -296,8 +370,10 @@ nmax_fast_kernel(const ThrArgs A, const FastArgs F, unsigned long long* __restri
     const int x = X0 + 4 * threadIdx.x;
     const int y_begin = blockIdx.y * F.rows_per_cta;
     const int y_end = min(y_begin + F.rows_per_cta, A.out_rows);
-    const int64_t* S = A.S + (size_t)page * A.plane_page_stride;
-    const int64_t* Q = A.Q + (size_t)page * A.plane_page_stride;
+    const int64_t* S = COMPACT ? reinterpret_cast<const int64_t*>(reinterpret_cast<const uint32_t*>(A.S) + (size_t)page * A.plane_page_stride)
+                               : A.S + (size_t)page * A.plane_page_stride;
+    const int64_t* Q = COMPACT ? reinterpret_cast<const int64_t*>(reinterpret_cast<const uint32_t*>(A.Q) + (size_t)page * A.plane_page_stride)
+                               : A.Q + (size_t)page * A.plane_page_stride;
     const bool in_plane = x < (int)A.pitch;
     const bool has_out = (4 * threadIdx.x + 3 + A.d < kFC) && (4 * (int)threadIdx.x < oc) && x < A.out_cols;
     unsigned long long best = 0;
@@ -310,15 +386,10 @@ nmax_fast_kernel(const ThrArgs A, const FastArgs F, unsigned long long* __restri
             unsigned int (&dq)[4] = dqr[r];
             ds[0] = ds[1] = ds[2] = ds[3] = 0; dq[0] = dq[1] = dq[2] = dq[3] = 0;
             if (in_plane && y + r < y_end) {
-                long long a0, a1, a2, a3, b0, b1, b2, b3;
-                ldg256(S + (size_t)(y + r) * A.pitch + x, a0, a1, a2, a3);
-                ldg256(S + (size_t)(y + r + A.d) * A.pitch + x, b0, b1, b2, b3);
-                ds[0] = (unsigned int)b0 - (unsigned int)a0; ds[1] = (unsigned int)b1 - (unsigned int)a1;
-                ds[2] = (unsigned int)b2 - (unsigned int)a2; ds[3] = (unsigned int)b3 - (unsigned int)a3;
-                ldg256(Q + (size_t)(y + r) * A.pitch + x, a0, a1, a2, a3);
-                ldg256(Q + (size_t)(y + r + A.d) * A.pitch + x, b0, b1, b2, b3);
-                dq[0] = (unsigned int)b0 - (unsigned int)a0; dq[1] = (unsigned int)b1 - (unsigned int)a1;
-                dq[2] = (unsigned int)b2 - (unsigned int)a2; dq[3] = (unsigned int)b3 - (unsigned int)a3;
+                const size_t e = (size_t)(y + r) * A.pitch + x, eb = e + (size_t)A.d * A.pitch;
+                const uint4 sa = lo4<COMPACT>(S, e), sb = lo4<COMPACT>(S, eb), qa = lo4<COMPACT>(Q, e), qb = lo4<COMPACT>(Q, eb);
+                ds[0] = sb.x - sa.x; ds[1] = sb.y - sa.y; ds[2] = sb.z - sa.z; ds[3] = sb.w - sa.w;
+                dq[0] = qb.x - qa.x; dq[1] = qb.y - qa.y; dq[2] = qb.z - qa.z; dq[3] = qb.w - qa.w;
             }
             *reinterpret_cast<uint4*>(&sD[buf][r][0][4 * threadIdx.x]) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
             *reinterpret_cast<uint4*>(&sD[buf][r][1][4 * threadIdx.x]) = make_uint4(dq[0], dq[1], dq[2], dq[3]);
@@ -359,6 +430,7 @@ nmax_fast_kernel(const ThrArgs A, const FastArgs F, unsigned long long* __restri
 }
 
 // One CTA revisits up to 16 consecutive tiles of pass A (same tile geometry: oc columns x rows_per_cta rows).
+template <bool COMPACT>
 __global__ void __launch_bounds__(128)
 smax_candidates_kernel(const ThrArgs A, const FastArgs F, const unsigned long long* __restrict__ nmax_page,
                        const unsigned long long* __restrict__ nmax_tile, int tiles_x, int tiles_y,
@@ -371,6 +443,10 @@ smax_candidates_kernel(const ThrArgs A, const FastArgs F, const unsigned long lo
     const int oc = (kFC - A.d) & ~3;
     const long long* S = reinterpret_cast<const long long*>(A.S) + (size_t)page * A.plane_page_stride;
     const long long* Q = reinterpret_cast<const long long*>(A.Q) + (size_t)page * A.plane_page_stride;
+    const uint32_t* S32 = reinterpret_cast<const uint32_t*>(A.S) + (size_t)page * A.plane_page_stride;
+    const uint32_t* Q32 = reinterpret_cast<const uint32_t*>(A.Q) + (size_t)page * A.plane_page_stride;
+    const uint32_t* AS = COMPACT ? A.AS + (size_t)page * A.a_page_stride : nullptr;
+    const uint32_t* AQ = COMPACT ? A.AQ + (size_t)page * A.a_page_stride : nullptr;
     long long best = (long long)0xfff0000000000000LL;   // -inf
     const int tiles = tiles_x * tiles_y;
     for (int t = blockIdx.x * 16; t < min(tiles, blockIdx.x * 16 + 16); ++t) {
@@ -381,11 +457,26 @@ smax_candidates_kernel(const ThrArgs A, const FastArgs F, const unsigned long lo
         const int w = x_end - x_begin, n = w * (y_end - y_begin);
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const int y = y_begin + i / w, x = x_begin + i % w;
-            const long long* s0 = S + (size_t)y * A.pitch + x;
-            const long long* q0 = Q + (size_t)y * A.pitch + x;
+            long long sa, sb, sc, sd, qa, qb, qc, qd;
             const size_t dr = (size_t)A.d * A.pitch;
-            const long long sa = __ldg(s0), sb = __ldg(s0 + A.d), sc = __ldg(s0 + dr), sd = __ldg(s0 + dr + A.d);
-            const long long qa = __ldg(q0), qb = __ldg(q0 + A.d), qc = __ldg(q0 + dr), qd = __ldg(q0 + dr + A.d);
+            if (COMPACT) {
+                // the integer screen needs the low words only; the full taps are rebuilt for the few candidates
+                const uint32_t* s0 = S32 + (size_t)y * A.pitch + x;
+                const uint32_t* q0 = Q32 + (size_t)y * A.pitch + x;
+                const unsigned int swl = (__ldg(s0 + dr + A.d) - __ldg(s0 + dr)) - (__ldg(s0 + A.d) - __ldg(s0));
+                const unsigned int qwl = (__ldg(q0 + dr + A.d) - __ldg(q0 + dr)) - (__ldg(q0 + A.d) - __ldg(q0));
+                const unsigned long long Nl = (unsigned long long)F.w2 * qwl - (unsigned long long)swl * swl;
+                if (Nl < lo) continue;
+                sa = full_tap(S32, AS, A.pitch, A.ashift, y, x); sb = full_tap(S32, AS, A.pitch, A.ashift, y, x + A.d);
+                sc = full_tap(S32, AS, A.pitch, A.ashift, y + A.d, x); sd = full_tap(S32, AS, A.pitch, A.ashift, y + A.d, x + A.d);
+                qa = full_tap(Q32, AQ, A.pitch, A.ashift, y, x); qb = full_tap(Q32, AQ, A.pitch, A.ashift, y, x + A.d);
+                qc = full_tap(Q32, AQ, A.pitch, A.ashift, y + A.d, x); qd = full_tap(Q32, AQ, A.pitch, A.ashift, y + A.d, x + A.d);
+            } else {
+                const long long* s0 = S + (size_t)y * A.pitch + x;
+                const long long* q0 = Q + (size_t)y * A.pitch + x;
+                sa = __ldg(s0); sb = __ldg(s0 + A.d); sc = __ldg(s0 + dr); sd = __ldg(s0 + dr + A.d);
+                qa = __ldg(q0); qb = __ldg(q0 + A.d); qc = __ldg(q0 + dr); qd = __ldg(q0 + dr + A.d);
+            }
             const unsigned long long sw = (unsigned long long)((sd - sc) - (sb - sa));
             const unsigned long long qw = (unsigned long long)((qd - qc) - (qb - qa));
             const unsigned long long N = (unsigned long long)F.w2 * qw - sw * sw;
@@ -420,15 +511,28 @@ __global__ void init_smax_kernel(long long* smax, int n)
 
 }  // namespace
 
+// What kernel 2's fast path needs besides suitable planes: an even tap distance below 256, aligned pages, and margins the
+// host error analysis accepts.  The compact plane layout exists only for this path, so its callers ask first.
+bool prl_threshold_fast_ok(const prl_cuda_ctx* ctx, int method, const double* params, const prl_geom& g,
+                           const uint8_t* d_src, size_t src_step, size_t src_page_stride)
+{
+    FastArgs F;
+    return !ctx->force_exact && (g.d & 1) == 0 && g.d <= 254 && ((src_step | src_page_stride | (uintptr_t)d_src) & 3) == 0 &&
+           fast_margins(method, params, g, &F);
+}
+
 int prl_k_threshold(prl_cuda_ctx* ctx, int method, int mode, const uint8_t* d_src, int n_pages,
-                    const prl_geom& g, size_t src_step, size_t src_page_stride, const int64_t* d_S,
-                    const int64_t* d_Q, size_t plane_page_stride, const double* params,
+                    const prl_geom& g, size_t src_step, size_t src_page_stride, const prl_planes& P, const double* params,
                     const uint32_t* d_imin, long long* d_smax, uint8_t* d_dst, size_t dst_step,
                     size_t dst_page_stride)
 {
+    const int64_t* d_S = (const int64_t*)P.S;
+    const int64_t* d_Q = (const int64_t*)P.Q;
+    const size_t plane_page_stride = P.page_stride;
     ThrArgs A;
     A.src = d_src; A.src_step = src_step; A.src_page_stride = src_page_stride;
-    A.S = d_S; A.Q = d_Q; A.pitch = g.pitch; A.plane_page_stride = plane_page_stride;
+    A.S = d_S; A.Q = d_Q; A.pitch = P.pitch; A.plane_page_stride = plane_page_stride;
+    A.AS = P.AS; A.AQ = P.AQ; A.a_page_stride = P.a_page_stride; A.ashift = P.ashift;
     A.dst = d_dst; A.dst_step = dst_step; A.dst_page_stride = dst_page_stride;
     A.imin = d_imin; A.smax = d_smax;
     A.out_rows = g.out_rows; A.out_cols = g.out_cols; A.d = g.d;
@@ -445,8 +549,10 @@ int prl_k_threshold(prl_cuda_ctx* ctx, int method, int mode, const uint8_t* d_sr
     // fast path eligibility: mask output, even tap distance < 256, window sums < 2^32, 4/32-byte aligned buffers
     FastArgs F;
     const bool aligned = ((src_step | src_page_stride | (uintptr_t)d_src) & 3) == 0 &&
-                         ((((uintptr_t)d_S) | ((uintptr_t)d_Q)) & 31) == 0 && (plane_page_stride & 3) == 0 && (g.pitch & 3) == 0;
+                         ((((uintptr_t)d_S) | ((uintptr_t)d_Q)) & (P.compact ? 15 : 31)) == 0 && (plane_page_stride & 3) == 0 && (P.pitch & 3) == 0;
     const bool fast_ok = !ctx->force_exact && (g.d & 1) == 0 && g.d <= 254 && aligned && fast_margins(method, params, g, &F);
+    if (P.compact && !(fast_ok && mode == 0))
+        return prl_set_err(ctx, PRL_E_INVALID, "compact planes serve the fast mask path only");
     const int rpc = ctx->thr_rows > 0 ? ctx->thr_rows : (g.d > 64 ? 8 : 4);   // rows per CTA of the fast kernels, see below (8 measured 4 % faster for wide windows)
     F.rows_per_cta = rpc;
 
@@ -469,12 +575,17 @@ int prl_k_threshold(prl_cuda_ctx* ctx, int method, int mode, const uint8_t* d_sr
             const unsigned long long margin = (unsigned long long)(2.0 * dv * w2 * w2) + 2;
             {
                 prl_launch_scope ls(ctx, FAM_SMAX);
-                nmax_fast_kernel<<<dim3(tiles_x, tiles_y, n_pages), kFT, 0, ctx->stream>>>(A, F, nmax_page, nmax_tile);
+                if (P.compact) nmax_fast_kernel<true><<<dim3(tiles_x, tiles_y, n_pages), kFT, 0, ctx->stream>>>(A, F, nmax_page, nmax_tile);
+                else nmax_fast_kernel<false><<<dim3(tiles_x, tiles_y, n_pages), kFT, 0, ctx->stream>>>(A, F, nmax_page, nmax_tile);
             }
             {
                 prl_launch_scope ls(ctx, FAM_SMAX);
-                smax_candidates_kernel<<<dim3((tiles_x * tiles_y + 15) / 16, n_pages), 128, 0, ctx->stream>>>(
-                    A, F, nmax_page, nmax_tile, tiles_x, tiles_y, margin);
+                if (P.compact)
+                    smax_candidates_kernel<true><<<dim3((tiles_x * tiles_y + 15) / 16, n_pages), 128, 0, ctx->stream>>>(
+                        A, F, nmax_page, nmax_tile, tiles_x, tiles_y, margin);
+                else
+                    smax_candidates_kernel<false><<<dim3((tiles_x * tiles_y + 15) / 16, n_pages), 128, 0, ctx->stream>>>(
+                        A, F, nmax_page, nmax_tile, tiles_x, tiles_y, margin);
             }
         } else {
             prl_launch_scope ls(ctx, FAM_SMAX);
@@ -494,8 +605,10 @@ int prl_k_threshold(prl_cuda_ctx* ctx, int method, int mode, const uint8_t* d_sr
         const int oc = (nt * 4 - g.d) & ~3;
         dim3 fg((g.out_cols + oc - 1) / oc, (g.out_rows + rpc - 1) / rpc, n_pages);
 #define PRL_LAUNCH_FAST(M)                                                                            \
-        do { if (wide) threshold_fast_kernel<M, 256><<<fg, 256, 0, ctx->stream>>>(A, F);              \
-             else threshold_fast_kernel<M, 128><<<fg, 128, 0, ctx->stream>>>(A, F); } while (0)
+        do { if (P.compact) { if (wide) threshold_fast_kernel<M, 256, true><<<fg, 256, 0, ctx->stream>>>(A, F);     \
+                              else threshold_fast_kernel<M, 128, true><<<fg, 128, 0, ctx->stream>>>(A, F); }          \
+             else { if (wide) threshold_fast_kernel<M, 256, false><<<fg, 256, 0, ctx->stream>>>(A, F);               \
+                    else threshold_fast_kernel<M, 128, false><<<fg, 128, 0, ctx->stream>>>(A, F); } } while (0)
         switch (method) {
         case PRL_SAUVOLA:    PRL_LAUNCH_FAST(PRL_SAUVOLA); break;
         case PRL_NIBLACK:    PRL_LAUNCH_FAST(PRL_NIBLACK); break;
