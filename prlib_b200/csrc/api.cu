@@ -165,7 +165,7 @@ extern "C" void prl_cuda_destroy(prl_cuda_ctx* c)
     cudaStreamSynchronize(c->stream);
     for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto& ev : c->event_pool) cudaEventDestroy(ev);
-    cudaFree(c->planes); cudaFree(c->carry); cudaFree(c->colsum); cudaFree(c->scalars); cudaFree(c->fused_ws);
+    cudaFree(c->sched); cudaFree(c->planes); cudaFree(c->carry); cudaFree(c->colsum); cudaFree(c->scalars); cudaFree(c->fused_ws);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
     cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_tmp); cudaFree(c->d_misc); cudaFree(c->d_bgr); cudaFree(c->edges_ws); cudaFree(c->rects_ws); cudaFree(c->clahe_ws);
     if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -205,6 +205,10 @@ extern "C" int prl_cuda_set_option(prl_cuda_ctx* c, const char* name, long long 
     if (strcmp(name, "exact_threshold") == 0) c->force_exact = value != 0;
     else if (strcmp(name, "disable_tma") == 0) c->no_tma = value != 0;
     else if (strcmp(name, "disable_compact") == 0) c->no_compact = value != 0;
+    else if (strcmp(name, "thr_legacy") == 0) c->thr_legacy = value != 0;
+    else if (strcmp(name, "thr_no_tma") == 0) c->thr_no_tma = value != 0;
+    else if (strcmp(name, "dbg_skip_exact") == 0) c->dbg_skip_exact = value != 0;
+    else if (strcmp(name, "thr_stages") == 0) c->thr_stages = value == 2 ? 2 : 3;
     else if (strcmp(name, "enable_fused") == 0) c->use_fused = value != 0;
     else if (strcmp(name, "morph_bytes") == 0) c->morph_bytes = value != 0;
     else if (strcmp(name, "thr_rows") == 0) c->thr_rows = value <= 0 ? 0 : ((int)std::min<long long>(std::max<long long>(value, 2), 64) & ~1);
@@ -272,18 +276,19 @@ static int planes_pages(prl_cuda_ctx* c, int method, int mode, const uint8_t* d_
                         size_t src_step, size_t src_page_stride, const double* params, int morph_iters,
                         uint8_t* d_dst, size_t dst_step, size_t dst_page_stride)
 {
-    // Plane layout (common.cuh: prl_planes).  The mask path of aligned batches takes the compact one: low words + anchor
-    // high words, 9 instead of 16 bytes per padded pixel written by kernel 1 and 8 instead of 16 read by kernel 2.
+    // Plane layout (common.cuh: prl_planes).  The mask path of aligned batches takes the compact one: interleaved low words
+    // + sparse anchor high words, 8.5 instead of 16 bytes per padded pixel written by kernel 1 and read by kernel 2.
     const bool compact = mode == 0 && !c->no_compact && prl_threshold_fast_ok(c, method, params, g, d_src, src_step, src_page_stride) &&
-                         prl_integral_compact_ok(c, d_src, src_step, src_page_stride);
+                         prl_integral_compact_ok(c, d_src, src_step, src_page_stride, g.rows, g.cols, g.h);
     prl_planes P;
     P.compact = compact ? 1 : 0;
-    P.pitch = compact ? prl_plane_pitch32(g.Wp) : g.pitch;
-    P.ashift = compact ? prl_anchor_shift(g.Wp) : 0;
+    P.pitch = g.pitch;                                          // elements per row: int64, or uint2 {S lo, Q lo}
+    P.ashift = compact ? prl_anchor_shift(g.Hp, g.Wp) : 0;
     const size_t plane_elems = (size_t)g.Hp * P.pitch;          // one plane of one page
     const size_t anchor_rows = compact ? (((size_t)g.Hp + ((size_t)1 << P.ashift) - 1) >> P.ashift) : 0;
-    const size_t anchor_elems = anchor_rows * P.pitch;
-    const size_t per_page = compact ? 2 * (plane_elems + anchor_elems) * sizeof(uint32_t) : 2 * plane_elems * sizeof(int64_t);
+    P.a_pitch = compact ? P.pitch / 4 : 0;
+    const size_t anchor_elems = anchor_rows * P.a_pitch;
+    const size_t per_page = compact ? (plane_elems + anchor_elems) * sizeof(uint2) : 2 * plane_elems * sizeof(int64_t);
     const size_t budget = std::min(planes_budget(c, (size_t)n_pages * per_page), c->workspace_limit);
     int chunk = (int)std::min<size_t>((size_t)n_pages, std::max<size_t>(1, budget / per_page));
     int rc;
@@ -305,11 +310,8 @@ static int planes_pages(prl_cuda_ctx* c, int method, int mode, const uint8_t* d_
     P.page_stride = plane_elems;
     P.a_page_stride = anchor_elems;
     if (compact) {
-        uint32_t* base = (uint32_t*)c->planes;
-        P.S = base;
-        P.Q = base + (size_t)chunk * plane_elems;
-        P.AS = base + 2 * (size_t)chunk * plane_elems;
-        P.AQ = P.AS + (size_t)chunk * anchor_elems;
+        P.S = c->planes;
+        P.AS = (uint2*)c->planes + (size_t)chunk * plane_elems;
     } else {
         P.S = c->planes;
         P.Q = c->planes + (size_t)chunk * plane_elems;

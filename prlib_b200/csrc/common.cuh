@@ -18,30 +18,31 @@ static inline size_t prl_plane_pitch(int padded_cols) { return ((size_t)padded_c
 // The integral planes of a chunk of pages, in one of two layouts:
 //   compact == 0  S, Q: int64 (what cv::integral(CV_64F) holds, exactly) -- the exported bit-exactness hook
 //                 (prl_cuda_integral_u8*), the literal-FP64 kernels, and any buffer the fast path cannot take;
-//   compact == 1  S, Q: the LOW 32-bit words only (window sums are < 2^32, so differences of low words are the exact
-//                 window sums) plus the HIGH words of every (1 << ashift)-th padded row in AS / AQ.  A full int64 tap --
-//                 needed only by the ~1e-3 of the pixels that evaluate the reference's FP64 formula -- is rebuilt as
-//                 full(Y, X) = (hi(Ya, X) << 32 | lo(Ya, X)) + u32(lo(Y, X) - lo(Ya, X)),  Ya = Y rounded down to an anchor row,
-//                 exact because a column grows by less than 2^32 over (1 << ashift) - 1 rows (prl_anchor_shift).
-//                 9 bytes per padded pixel instead of 16 on both sides of the kernel-1 / kernel-2 hand-over.
+//   compact == 1  ONE plane of uint2 {S mod 2^32, Q mod 2^32} per padded pixel (S points to it, Q is unused): window sums
+//                 are < 2^32, so differences of the low words ARE the exact window sums.  The HIGH words are kept only at
+//                 anchor positions (Y % A == 0, X % 4 == 0), A = 1 << ashift, as uint2 {S >> 32, Q >> 32} in AS.  A full
+//                 int64 tap -- needed only by the ~1e-3 of the pixels that evaluate the reference's FP64 formula -- is
+//                     full(Y, X) = (hi(Ya, Xa) << 32 | lo(Ya, Xa)) + u32(lo(Y, X) - lo(Ya, Xa)),   Ya = Y & ~(A-1), Xa = X & ~3,
+//                 exact because an integral grows by less than 2^32 between an anchor and the (A-1) rows / 3 columns it
+//                 serves (prl_anchor_shift).  8.5 bytes per padded pixel on both sides of the kernel-1 / kernel-2 hand-over
+//                 instead of 16, and 32-byte vectors of 4 pixels for stores, loads and TMA boxes.
 struct prl_planes {
     int compact = 0;
-    void* S = nullptr;          // int64_t* or uint32_t*
-    void* Q = nullptr;
-    size_t pitch = 0;           // elements per row (128-byte multiple in bytes)
+    void* S = nullptr;          // int64_t* (compact: uint2*, low words of S and Q interleaved)
+    void* Q = nullptr;          // int64_t* (compact: unused)
+    size_t pitch = 0;           // elements per row (rows are 128-byte multiples)
     size_t page_stride = 0;     // elements per page
-    uint32_t* AS = nullptr;     // compact: high words of the anchor rows, ceil(Hp / A) rows of `pitch` elements
-    uint32_t* AQ = nullptr;
+    void* AS = nullptr;         // compact: uint2 high words at the anchors, ceil(Hp / A) rows of a_pitch = pitch / 4 elements
     int ashift = 0;
-    size_t a_page_stride = 0;   // elements per page in AS / AQ
+    size_t a_pitch = 0;
+    size_t a_page_stride = 0;   // elements per page in AS
 };
-static inline size_t prl_plane_pitch32(int padded_cols) { return ((size_t)padded_cols + 31) & ~(size_t)31; }
-// largest A = 1 << shift <= 8 with (A - 1) * 255^2 * Wp < 2^32: the growth of Q down a column over A - 1 rows fits 32 bits
-static inline int prl_anchor_shift(int padded_cols)
+// largest A = 1 << shift <= 8 with ((A-1) Wp + 3 Hp) * 255^2 < 2^32; -1: no anchor spacing works (Hp >= 22016): keep int64 planes
+static inline int prl_anchor_shift(int padded_rows, int padded_cols)
 {
-    int sh = 3;
-    while (sh > 0 && (double)((1 << sh) - 1) * 65025.0 * (double)padded_cols >= 4294967296.0) --sh;
-    return sh;
+    for (int sh = 3; sh >= 0; --sh)
+        if (((double)((1 << sh) - 1) * padded_cols + 3.0 * padded_rows) * 65025.0 < 4294967296.0) return sh;
+    return -1;
 }
 
 struct prl_timing_rec { cudaEvent_t a, b; int family; };
@@ -60,6 +61,7 @@ struct prl_cuda_ctx {
     void* carry = nullptr;      size_t carry_bytes = 0;
     void* colsum = nullptr;     size_t colsum_bytes = 0;
     void* scalars = nullptr;    size_t scalars_bytes = 0;
+    void* sched = nullptr;      size_t sched_bytes = 0;    // work counters of the persistent kernels
     void* fused_ws = nullptr;   size_t fused_ws_bytes = 0; // fused path: row sums per strip, fixup counters and lists
     uint32_t* h_cnt = nullptr;  size_t h_cnt_bytes = 0;    // pinned read-back of the fused path's per-page counters
     int fused_page_cap = 128;                              // undecided pixels per page the fused path finishes itself
@@ -78,6 +80,10 @@ struct prl_cuda_ctx {
     uint8_t* h_pin = nullptr;   size_t h_pin_bytes = 0;
 
     bool force_exact = false;   // validation: kernel 2 runs the literal FP64 path for every pixel
+    bool dbg_skip_exact = false; // DIAGNOSTIC ONLY: kernel 2 (TMA) leaves undecided pixels black; timing experiments, never a result
+    int thr_stages = 3;         // kernel 2 (TMA): ring stages per CTA (3: two CTAs per SM, 2: three CTAs per SM)
+    bool thr_no_tma = false;    // validation: kernel 2 on compact planes runs the register-staged streaming kernel instead of the TMA ring
+    bool thr_legacy = false;    // validation: kernel 2's mask path runs the round-1 two-tier kernel instead of the streaming kernel
     bool no_compact = false;    // validation: the two-kernel path keeps full int64 planes (16 B per padded pixel) instead of the compact layout
     bool no_tma = false;        // validation: kernel 1 uses the generic (non-TMA) kernel
     int thr_rows = 0;           // kernel 2: output rows per CTA (0 = automatic: 4, or 8 when the tap distance exceeds 64)
@@ -131,7 +137,13 @@ int prl_k_integral(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int row
 // same, into either plane layout; the compact layout needs the TMA kernel (prl_integral_compact_ok)
 int prl_k_integral_planes(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int rows, int cols, size_t src_step,
                           size_t src_page_stride, int pad, const prl_planes& P, uint32_t* d_imin);
-bool prl_integral_compact_ok(const prl_cuda_ctx* ctx, const uint8_t* d_src, size_t src_step, size_t src_page_stride);
+bool prl_integral_compact_ok(const prl_cuda_ctx* ctx, const uint8_t* d_src, size_t src_step, size_t src_page_stride, int rows, int cols, int pad);
+// the compact-layout kernel (integral_sq.cu) and the band pre-pass it shares with the int64 kernel (integral.cu)
+int prl_k_integral_sq(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int rows, int cols, size_t src_step,
+                      size_t src_page_stride, int pad, const prl_planes& P, uint32_t* d_imin);
+int prl_choose_bands(const prl_cuda_ctx* ctx, int n_pages, int rows, int ctas_per_sm);
+int prl_band_carries(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int rows, int cols, size_t src_step,
+                     size_t src_page_stride, int pad, int bands, int rpb, size_t pitch, const int64_t** d_carry);
 bool prl_threshold_fast_ok(const prl_cuda_ctx* ctx, int method, const double* params, const prl_geom& g,
                            const uint8_t* d_src, size_t src_step, size_t src_page_stride);
 struct prl_thr_params { double kw, nkw, p0, p1, p2; };

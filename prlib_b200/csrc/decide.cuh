@@ -22,6 +22,7 @@ struct FastArgs {
     unsigned int qfloor_u;       // integer form of q_floor
     double dv_ref;               // bound on |v_ref - v| of the reference's FP64 variance
     int n32;                     // w^2 * (w-1)^2 * 255^2 < 2^32: N fits 32 bits
+    int dbg_skip_exact;          // DIAGNOSTIC ONLY (wrong masks): undecided pixels are not evaluated -- measures what the exact path costs
 };
 
 __device__ __forceinline__ int to_u8(double T)
@@ -247,6 +248,7 @@ inline bool fast_margins(int method, const double* params, const prl_geom& g, Fa
     F->pb_hi = (float)(b0 > b1 ? b0 : b1); F->pb_lo = (float)(b0 > b1 ? b1 : b0);
     F->qfloor_u = (unsigned int)(nf * nf * 1.001 / (2.0 * g.w - 1.0)) + 2u;
     F->n32 = ((double)g.w * g.w * (double)g.d * g.d * 65025.0 < 4294967296.0) ? 1 : 0;
+    F->dbg_skip_exact = 0;
     return true;
 }
 

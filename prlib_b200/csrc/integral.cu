@@ -29,7 +29,7 @@
 // each band's top carry (weighted column sums of the rows above, row-scanned) so bands run
 // concurrently.  integral_generic_kernel is the any-alignment / any-pitch fallback (no TMA).
 #include "common.cuh"
-#include <cuda.h>
+#include "tma.cuh"
 #include <algorithm>
 
 namespace {
@@ -54,37 +54,8 @@ __device__ __forceinline__ void st_v4_s64(int64_t* p, long long a, long long b, 
 {
     asm volatile("st.global.v4.s64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }
-__device__ __forceinline__ void st_v4_u32(uint32_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
-{
-    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 
-// ---- mbarrier / TMA primitives ---------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
-}
+using namespace prl_tma;
 
 // ------------------------------------------------------------------------------------------------
 // TMA kernel.  Band b covers source rows [b*rows_per_band, ...); it emits padded row y+pad for each
@@ -95,15 +66,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
 template <int J> __host__ __device__ constexpr int box_bytes() { return 128 * J + 16; }   // 16-byte aligned origin
 template <int J, int R> __host__ __device__ constexpr int stage_bytes() { return (R * box_bytes<J>() + 127) / 128 * 128; }
 
-// COMPACT: the planes receive the low 32-bit words only (16-byte stores), and every (1 << ashift)-th padded row also
-// leaves its high words in the anchor planes AS / AQ (common.cuh: prl_planes).  The accumulators stay 64-bit.
-template <int MAXW, int MINB, int J, int R, int NS, bool MULTI, bool COMPACT>
+template <int MAXW, int MINB, int J, int R, int NS, bool MULTI>
 __global__ void __launch_bounds__(MAXW * 32, MINB)
-integral_tma_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int cols, int pad, void* __restrict__ Sv,
-                    void* __restrict__ Qv, size_t pitch, size_t page_stride, int rows_per_band,
+integral_tma_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int cols, int pad, int64_t* __restrict__ S,
+                    int64_t* __restrict__ Q, size_t pitch, size_t page_stride, int rows_per_band,
                     const int64_t* __restrict__ carry, uint32_t* __restrict__ imin, int col0,
-                    uint2* __restrict__ rowoff, int has_in, int has_out, uint32_t* __restrict__ AS,
-                    uint32_t* __restrict__ AQ, int ashift, size_t a_page_stride, size_t carry_pitch)
+                    uint2* __restrict__ rowoff, int has_in, int has_out)
 {
     // Wide pages are covered by several launches ("column passes") of at most MAXW strips each: pass p starts at
     // padded column col0 and takes, per source row, the row prefix accumulated by the passes to its left from
@@ -120,17 +88,8 @@ integral_tma_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int cols
     const int y0 = band * rows_per_band;
     const int y1 = min(y0 + rows_per_band, rows);
 
-    int64_t* S = reinterpret_cast<int64_t*>(Sv);
-    int64_t* Q = reinterpret_cast<int64_t*>(Qv);
-    uint32_t* S32 = reinterpret_cast<uint32_t*>(Sv);
-    uint32_t* Q32 = reinterpret_cast<uint32_t*>(Qv);
-    if (COMPACT) {
-        S32 += (size_t)page * page_stride; Q32 += (size_t)page * page_stride;
-        AS += (size_t)page * a_page_stride; AQ += (size_t)page * a_page_stride;
-    } else {
-        S += (size_t)page * page_stride; Q += (size_t)page * page_stride;
-    }
-    const int amask = (1 << ashift) - 1;
+    S += (size_t)page * page_stride;
+    Q += (size_t)page * page_stride;
 
     uint8_t* slot = smem_raw + (size_t)wid * (NS * STAGE);               // this warp's ring
     const int X0 = (MULTI ? col0 : 0) + wid * WC;
@@ -163,9 +122,9 @@ integral_tma_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int cols
 #pragma unroll
         for (int i = 0; i < 4; ++i) accS[j][i] = accQ[j][i] = 0;
         if (carry != nullptr && band > 0 && st[j]) {
-            const long long* c = reinterpret_cast<const long long*>(carry) + ((size_t)page * bands + band) * 2 * carry_pitch + Xl + 128 * j;
+            const long long* c = reinterpret_cast<const long long*>(carry) + ((size_t)page * bands + band) * 2 * pitch + Xl + 128 * j;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { accS[j][i] = c[i]; accQ[j][i] = c[carry_pitch + i]; }
+            for (int i = 0; i < 4; ++i) { accS[j][i] = c[i]; accQ[j][i] = c[pitch + i]; }
         }
     }
 
@@ -275,27 +234,15 @@ integral_tma_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int cols
                 if (y == 0) { Y = 0; rep += pad; }
                 if (y == rows - 1) rep += pad;
                 for (int k = 0; k < rep; ++k, ++Y) {
-                    const size_t ro = (size_t)Y * pitch + Xl;
-                    const bool anchor = COMPACT && (Y & amask) == 0;
-                    const size_t ao = (size_t)(Y >> ashift) * pitch + Xl;
+                    int64_t* Srow = S + (size_t)Y * pitch + Xl;
+                    int64_t* Qrow = Q + (size_t)Y * pitch + Xl;
 #pragma unroll
                     for (int j = 0; j < J; ++j) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) { accS[j][i] += (long long)rs[j][i]; accQ[j][i] += (long long)rq[j][i]; }
                         if (st[j]) {
-                            if (COMPACT) {
-                                st_v4_u32(S32 + ro + 128 * j, (uint32_t)accS[j][0], (uint32_t)accS[j][1], (uint32_t)accS[j][2], (uint32_t)accS[j][3]);
-                                st_v4_u32(Q32 + ro + 128 * j, (uint32_t)accQ[j][0], (uint32_t)accQ[j][1], (uint32_t)accQ[j][2], (uint32_t)accQ[j][3]);
-                                if (anchor) {
-                                    st_v4_u32(AS + ao + 128 * j, (uint32_t)(accS[j][0] >> 32), (uint32_t)(accS[j][1] >> 32),
-                                              (uint32_t)(accS[j][2] >> 32), (uint32_t)(accS[j][3] >> 32));
-                                    st_v4_u32(AQ + ao + 128 * j, (uint32_t)(accQ[j][0] >> 32), (uint32_t)(accQ[j][1] >> 32),
-                                              (uint32_t)(accQ[j][2] >> 32), (uint32_t)(accQ[j][3] >> 32));
-                                }
-                            } else {
-                                st_v4_s64(S + ro + 128 * j, accS[j][0], accS[j][1], accS[j][2], accS[j][3]);
-                                st_v4_s64(Q + ro + 128 * j, accQ[j][0], accQ[j][1], accQ[j][2], accQ[j][3]);
-                            }
+                            st_v4_s64(Srow + 128 * j, accS[j][0], accS[j][1], accS[j][2], accS[j][3]);
+                            st_v4_s64(Qrow + 128 * j, accQ[j][0], accQ[j][1], accQ[j][2], accQ[j][3]);
                         }
                     }
                 }
@@ -579,27 +526,10 @@ band_carry_kernel(const unsigned long long* __restrict__ colsum, long long* __re
 }
 
 // ---- host side ----------------------------------------------------------------------------------
-typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-encode_tiled_fn get_encode_tiled()
-{
-    // resolved once; function-local static initialisation is thread-safe (the page dispatcher calls from one thread per device)
-    static const encode_tiled_fn fn = []() -> encode_tiled_fn {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qr;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
-            qr == cudaDriverEntryPointSuccess)
-            return (encode_tiled_fn)p;
-        cudaGetLastError();
-        return nullptr;
-    }();
-    return fn;
-}
-
 // Number of row bands a page is cut into: 1 when the batch alone fills the machine.
-int choose_bands(const prl_cuda_ctx* ctx, int n_pages, int rows, int ctas_per_sm)
+}  // namespace
+
+int prl_choose_bands(const prl_cuda_ctx* ctx, int n_pages, int rows, int ctas_per_sm)
 {
     const int want = ctas_per_sm * ctx->num_sms;
     if (n_pages >= want - want / 4) return 1;   // >= 1.5 pages per SM: the batch alone fills the machine
@@ -610,10 +540,12 @@ int choose_bands(const prl_cuda_ctx* ctx, int n_pages, int rows, int ctas_per_sm
     return bands < 1 ? 1 : bands;
 }
 
-template <int MAXW, int MINB, int J, int R, int NS, bool MULTI, bool COMPACT>
+namespace {
+
+template <int MAXW, int MINB, int J, int R, int NS, bool MULTI>
 int launch_tma(prl_cuda_ctx* ctx, encode_tiled_fn enc, dim3 grid, int nwarps, const uint8_t* d_src, int n_pages,
-               size_t src_step, size_t src_page_stride, int rows, int cols, int pad, const prl_planes& P,
-               int rpb, const int64_t* d_carry, uint32_t* d_imin, bool* launched,
+               size_t src_step, size_t src_page_stride, int rows, int cols, int pad, int64_t* d_S, int64_t* d_Q,
+               size_t pitch, size_t plane_page_stride, int rpb, const int64_t* d_carry, uint32_t* d_imin, bool* launched,
                int col0 = 0, uint2* rowoff = nullptr, int has_in = 0, int has_out = 0)
 {
     *launched = false;
@@ -628,93 +560,68 @@ int launch_tma(prl_cuda_ctx* ctx, encode_tiled_fn enc, dim3 grid, int nwarps, co
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return PRL_OK;     // caller falls back to the generic kernel
     const size_t smem = (size_t)nwarps * NS * stage_bytes<J, R>();
-    auto kfn = integral_tma_kernel<MAXW, MINB, J, R, NS, MULTI, COMPACT>;
+    auto kfn = integral_tma_kernel<MAXW, MINB, J, R, NS, MULTI>;
     // (per device: the attribute lives in the current device's copy of the function, so no process-wide cache)
     PRL_CUDA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kfn<<<grid, nwarps * 32, smem, ctx->stream>>>(tmap, rows, cols, pad, P.S, P.Q, P.pitch, P.page_stride, rpb, d_carry, d_imin,
-                                                  col0, rowoff, has_in, has_out, P.AS, P.AQ, P.ashift, P.a_page_stride, P.pitch);
+    kfn<<<grid, nwarps * 32, smem, ctx->stream>>>(tmap, rows, cols, pad, d_S, d_Q, pitch, plane_page_stride, rpb, d_carry, d_imin,
+                                                  col0, rowoff, has_in, has_out);
     *launched = true;
     return PRL_OK;
 }
 
-// the three TMA configurations (A4-class, up to 3072 columns, wide pages in chained column passes) for one plane layout
-template <bool COMPACT>
-int launch_tma_any(prl_cuda_ctx* ctx, encode_tiled_fn enc, dim3 grid, const uint8_t* d_src, int n_pages, size_t src_step,
-                   size_t src_page_stride, int rows, int cols, int pad, const prl_planes& P, int rpb, const int64_t* d_carry,
-                   uint32_t* d_imin, bool* launched)
-{
-    constexpr int R = 8;
-    const int Wp = cols + 2 * pad;
-    const bool narrow = Wp <= 24 * 128;                   // 128 columns per warp, up to 24 warps, 2 CTAs per SM
-    int rc;
-    if (narrow && Wp <= 20 * 128) {
-        const int nw = (Wp + 127) / 128;          // A4-class widths: 51 registers available at 2 CTAs/SM
-        rc = launch_tma<20, 2, 1, R, 3, false, COMPACT>(ctx, enc, grid, nw, d_src, n_pages, src_step, src_page_stride, rows, cols, pad, P,
-                                                        rpb, d_carry, d_imin, launched);
-    } else if (narrow) {
-        const int nw = (Wp + 127) / 128;          // up to 3072 columns: still one pass (42 registers, small spills)
-        rc = launch_tma<24, 2, 1, R, 3, false, COMPACT>(ctx, enc, grid, nw, d_src, n_pages, src_step, src_page_stride, rows, cols, pad, P,
-                                                        rpb, d_carry, d_imin, launched);
-    } else {
-        // wide page: column passes of <= 20 strips of 128 columns each, chained through rowoff
-        const int nw_total = (Wp + 127) / 128;
-        const int npass = (nw_total + 19) / 20, wp = (nw_total + npass - 1) / npass;
-        rc = prl_ensure(ctx, &ctx->d_misc, &ctx->d_misc_bytes, (size_t)n_pages * rows * sizeof(uint2)); if (rc) return rc;
-        for (int p = 0; p < npass; ++p) {
-            const int nw = std::min(wp, nw_total - p * wp);
-            rc = launch_tma<20, 2, 1, R, 3, true, COMPACT>(ctx, enc, grid, nw, d_src, n_pages, src_step, src_page_stride, rows, cols, pad, P,
-                                                           rpb, d_carry, d_imin, launched, p * wp * 128,
-                                                           (uint2*)ctx->d_misc, p > 0, p + 1 < npass);
-            if (rc || !*launched) break;
-        }
-    }
-    return rc;
-}
-
 }  // namespace
 
-static bool tma_source_ok(const prl_cuda_ctx* ctx, const uint8_t* d_src, size_t src_step, size_t src_page_stride)
+// Latency mode pre-pass: the top carry of every band (the integral row just above its first emitted padded row),
+// carry[page][band][plane S/Q][pitch] int64.
+int prl_band_carries(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int rows, int cols, size_t src_step,
+                     size_t src_page_stride, int pad, int bands, int rpb, size_t pitch, const int64_t** d_carry)
 {
-    return get_encode_tiled() != nullptr && !ctx->no_tma && (((uintptr_t)d_src | src_step | src_page_stride) & 15) == 0;
-}
-
-bool prl_integral_compact_ok(const prl_cuda_ctx* ctx, const uint8_t* d_src, size_t src_step, size_t src_page_stride)
-{
-    return tma_source_ok(ctx, d_src, src_step, src_page_stride);
+    const int Wp = cols + 2 * pad;
+    size_t need = (size_t)n_pages * bands * 2 * pitch * sizeof(int64_t);
+    int rc = prl_ensure(ctx, &ctx->colsum, &ctx->colsum_bytes, need); if (rc) return rc;
+    rc = prl_ensure(ctx, &ctx->carry, &ctx->carry_bytes, need); if (rc) return rc;
+    const bool vec_src = (((uintptr_t)d_src | src_step | src_page_stride) & 15) == 0 && pad < 512 &&
+                         src_step >= (size_t)((cols + 15) & ~15) && (size_t)bands * ((rpb + 127) / 128) <= 65535;
+    if (vec_src) {
+        const int slices = (rpb + 127) / 128;
+        PRL_CUDA_TRY(ctx, cudaMemsetAsync(ctx->colsum, 0, need, ctx->stream));
+        prl_launch_scope ls(ctx, FAM_BAND_CARRY);
+        band_colsum_vec_kernel<<<dim3((cols + 2047) / 2048, bands * slices, n_pages), 128, 0, ctx->stream>>>(
+            d_src, src_step, src_page_stride, rows, cols, pad, rpb, slices, (unsigned long long*)ctx->colsum, pitch);
+    } else {
+        prl_launch_scope ls(ctx, FAM_BAND_CARRY);
+        band_colsum_kernel<<<dim3((Wp + 1023) / 1024, bands, n_pages), 256, 0, ctx->stream>>>(
+            d_src, src_step, src_page_stride, rows, cols, pad, rpb, (unsigned long long*)ctx->colsum, pitch);
+    }
+    {
+        prl_launch_scope ls(ctx, FAM_BAND_CARRY);
+        band_carry_kernel<<<dim3(bands, n_pages), 1024, 0, ctx->stream>>>(
+            (const unsigned long long*)ctx->colsum, (long long*)ctx->carry, Wp, pitch, vec_src ? cols : 0, pad);
+    }
+    *d_carry = (const int64_t*)ctx->carry;
+    PRL_CUDA_TRY(ctx, cudaGetLastError());
+    return PRL_OK;
 }
 
 int prl_k_integral(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int rows, int cols, size_t src_step,
                    size_t src_page_stride, int pad, int64_t* d_S, int64_t* d_Q, size_t pitch,
                    size_t plane_page_stride, uint32_t* d_imin)
 {
-    prl_planes P;
-    P.compact = 0; P.S = d_S; P.Q = d_Q; P.pitch = pitch; P.page_stride = plane_page_stride;
-    return prl_k_integral_planes(ctx, d_src, n_pages, rows, cols, src_step, src_page_stride, pad, P, d_imin);
-}
-
-int prl_k_integral_planes(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int rows, int cols, size_t src_step,
-                          size_t src_page_stride, int pad, const prl_planes& P, uint32_t* d_imin)
-{
     const int Wp = cols + 2 * pad;
-    const size_t pitch = P.pitch, plane_page_stride = P.page_stride;
-    int64_t* d_S = (int64_t*)P.S;
-    int64_t* d_Q = (int64_t*)P.Q;
     if (n_pages > 65535) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "more than 65535 pages per launch");
 
-    // TMA path: 16-byte aligned source rows, 32-byte aligned planes (16-byte for the compact layout), pitch % 4 == 0
+    // TMA path: 16-byte aligned source rows, 32-byte aligned planes, pitch % 4 == 0
     encode_tiled_fn enc = get_encode_tiled();
-    const uintptr_t plane_align = P.compact ? 15 : 31;
-    const bool tma_ok = tma_source_ok(ctx, d_src, src_step, src_page_stride) &&
-                        ((((uintptr_t)P.S) | ((uintptr_t)P.Q)) & plane_align) == 0 && (pitch & 3) == 0 && (plane_page_stride & 3) == 0 &&
-                        (!P.compact || (((((uintptr_t)P.AS) | ((uintptr_t)P.AQ)) & 15) == 0 && (P.a_page_stride & 3) == 0));
-    if (P.compact && !tma_ok) return prl_set_err(ctx, PRL_E_INVALID, "compact planes need the TMA kernel (aligned pages and planes)");
+    const bool tma_ok = enc != nullptr && !ctx->no_tma && (((uintptr_t)d_src | src_step | src_page_stride) & 15) == 0 &&
+                        ((((uintptr_t)d_S) | ((uintptr_t)d_Q)) & 31) == 0 && (pitch & 3) == 0 && (plane_page_stride & 3) == 0;
     const bool vec_ok = ((((uintptr_t)d_S) | ((uintptr_t)d_Q)) & 15) == 0 && (pitch & 1) == 0 && (plane_page_stride & 1) == 0;
+    const bool narrow = tma_ok && Wp <= 24 * 128;        // 128 columns per warp, up to 24 warps, 2 CTAs per SM
     // wider pages run as chained column passes on the TMA path (any width); the generic kernel covers one pass only
     if (Wp > 8192 && !tma_ok)
         return prl_set_err(ctx, PRL_E_UNSUPPORTED, "padded width > 8192 columns needs 16-byte aligned pages and 32-byte aligned planes");
 
     constexpr int R = 8;
-    int bands = choose_bands(ctx, n_pages, rows, 2);
+    int bands = prl_choose_bands(ctx, n_pages, rows, 2);
     int rpb = (rows + bands - 1) / bands;
     rpb = (rpb + R - 1) / R * R;
     bands = (rows + rpb - 1) / rpb;
@@ -723,43 +630,42 @@ int prl_k_integral_planes(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, 
 
     const int64_t* d_carry = nullptr;
     if (bands > 1) {
-        size_t need = (size_t)n_pages * bands * 2 * pitch * sizeof(int64_t);
-        int rc = prl_ensure(ctx, &ctx->colsum, &ctx->colsum_bytes, need); if (rc) return rc;
-        rc = prl_ensure(ctx, &ctx->carry, &ctx->carry_bytes, need); if (rc) return rc;
-        const bool vec_src = (((uintptr_t)d_src | src_step | src_page_stride) & 15) == 0 && pad < 512 &&
-                             src_step >= (size_t)((cols + 15) & ~15) && (size_t)bands * ((rpb + 127) / 128) <= 65535;
-        if (vec_src) {
-            const int slices = (rpb + 127) / 128;
-            PRL_CUDA_TRY(ctx, cudaMemsetAsync(ctx->colsum, 0, need, ctx->stream));
-            prl_launch_scope ls(ctx, FAM_BAND_CARRY);
-            band_colsum_vec_kernel<<<dim3((cols + 2047) / 2048, bands * slices, n_pages), 128, 0, ctx->stream>>>(
-                d_src, src_step, src_page_stride, rows, cols, pad, rpb, slices, (unsigned long long*)ctx->colsum, pitch);
-        } else {
-            prl_launch_scope ls(ctx, FAM_BAND_CARRY);
-            band_colsum_kernel<<<dim3((Wp + 1023) / 1024, bands, n_pages), 256, 0, ctx->stream>>>(
-                d_src, src_step, src_page_stride, rows, cols, pad, rpb, (unsigned long long*)ctx->colsum, pitch);
-        }
-        {
-            prl_launch_scope ls(ctx, FAM_BAND_CARRY);
-            band_carry_kernel<<<dim3(bands, n_pages), 1024, 0, ctx->stream>>>(
-                (const unsigned long long*)ctx->colsum, (long long*)ctx->carry, Wp, pitch, vec_src ? cols : 0, pad);
-        }
-        d_carry = (const int64_t*)ctx->carry;
+        int rc = prl_band_carries(ctx, d_src, n_pages, rows, cols, src_step, src_page_stride, pad, bands, rpb, pitch, &d_carry);
+        if (rc) return rc;
     }
 
     prl_launch_scope ls(ctx, FAM_INTEGRAL);
     dim3 grid(bands, n_pages);
     if (tma_ok) {
         bool launched = false;
-        int rc = P.compact ? launch_tma_any<true>(ctx, enc, grid, d_src, n_pages, src_step, src_page_stride, rows, cols, pad, P, rpb, d_carry, d_imin, &launched)
-                           : launch_tma_any<false>(ctx, enc, grid, d_src, n_pages, src_step, src_page_stride, rows, cols, pad, P, rpb, d_carry, d_imin, &launched);
+        int rc;
+        if (narrow && Wp <= 20 * 128) {
+            const int nw = (Wp + 127) / 128;          // A4-class widths: 51 registers available at 2 CTAs/SM
+            rc = launch_tma<20, 2, 1, R, 3, false>(ctx, enc, grid, nw, d_src, n_pages, src_step, src_page_stride, rows, cols, pad, d_S, d_Q,
+                                                   pitch, plane_page_stride, rpb, d_carry, d_imin, &launched);
+        } else if (narrow) {
+            const int nw = (Wp + 127) / 128;          // up to 3072 columns: still one pass (42 registers, small spills)
+            rc = launch_tma<24, 2, 1, R, 3, false>(ctx, enc, grid, nw, d_src, n_pages, src_step, src_page_stride, rows, cols, pad, d_S, d_Q,
+                                                   pitch, plane_page_stride, rpb, d_carry, d_imin, &launched);
+        } else {
+            // wide page: column passes of <= 20 strips of 128 columns each, chained through rowoff
+            const int nw_total = (Wp + 127) / 128;
+            const int npass = (nw_total + 19) / 20, wp = (nw_total + npass - 1) / npass;
+            rc = prl_ensure(ctx, &ctx->d_misc, &ctx->d_misc_bytes, (size_t)n_pages * rows * sizeof(uint2)); if (rc) return rc;
+            for (int p = 0; p < npass; ++p) {
+                const int nw = std::min(wp, nw_total - p * wp);
+                rc = launch_tma<20, 2, 1, R, 3, true>(ctx, enc, grid, nw, d_src, n_pages, src_step, src_page_stride, rows, cols, pad, d_S, d_Q,
+                                                pitch, plane_page_stride, rpb, d_carry, d_imin, &launched, p * wp * 128,
+                                                (uint2*)ctx->d_misc, p > 0, p + 1 < npass);
+                if (rc || !launched) break;
+            }
+        }
         if (rc) return rc;
         if (launched) {
             PRL_CUDA_TRY(ctx, cudaGetLastError());
             return PRL_OK;
         }
         // the driver rejected the tensor map (e.g. stride limits): fall through to the generic kernel
-        if (P.compact) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "tensor map rejected: the compact plane layout has no generic kernel");
     }
     const int nwarps = (Wp + kWarpCols - 1) / kWarpCols;
     if (nwarps > 32) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "padded width > 8192 columns: tensor map rejected, no generic path");
@@ -771,4 +677,18 @@ int prl_k_integral_planes(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, 
             d_src, src_step, src_page_stride, rows, cols, pad, d_S, d_Q, pitch, plane_page_stride, rpb, d_carry, d_imin, vec_ok);
     PRL_CUDA_TRY(ctx, cudaGetLastError());
     return PRL_OK;
+}
+
+bool prl_integral_compact_ok(const prl_cuda_ctx* ctx, const uint8_t* d_src, size_t src_step, size_t src_page_stride, int rows, int cols, int pad)
+{
+    return get_encode_tiled() != nullptr && !ctx->no_tma && (((uintptr_t)d_src | src_step | src_page_stride) & 15) == 0 &&
+           cols + 2 * pad <= 8192 && prl_anchor_shift(rows + 2 * pad, cols + 2 * pad) >= 0;
+}
+
+int prl_k_integral_planes(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int rows, int cols, size_t src_step,
+                          size_t src_page_stride, int pad, const prl_planes& P, uint32_t* d_imin)
+{
+    if (P.compact) return prl_k_integral_sq(ctx, d_src, n_pages, rows, cols, src_step, src_page_stride, pad, P, d_imin);
+    return prl_k_integral(ctx, d_src, n_pages, rows, cols, src_step, src_page_stride, pad, (int64_t*)P.S, (int64_t*)P.Q, P.pitch,
+                          P.page_stride, d_imin);
 }

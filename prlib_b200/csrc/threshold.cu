@@ -30,13 +30,15 @@
 //    re-read from L1/L2: 2 global loads per plane and pixel-quad instead of 4.
 #include "common.cuh"
 #include "decide.cuh"
+#include "tma.cuh"
+#include <algorithm>
 
 namespace {
 
 struct ThrArgs {
     const uint8_t* src; size_t src_step, src_page_stride;
-    const int64_t* S; const int64_t* Q; size_t pitch, plane_page_stride;   // compact layout: really uint32_t* (low words)
-    const uint32_t* AS; const uint32_t* AQ; size_t a_page_stride; int ashift; // compact layout: high words of the anchor rows
+    const int64_t* S; const int64_t* Q; size_t pitch, plane_page_stride;   // compact layout: S is the uint2 {S lo, Q lo} plane, Q unused
+    const uint2* AH; size_t a_pitch, a_page_stride; int ashift;            // compact layout: high words at the anchors (prl_planes)
     uint8_t* dst; size_t dst_step, dst_page_stride;
     const uint32_t* imin; long long* smax;
     int out_rows, out_cols, d;
@@ -148,51 +150,50 @@ __device__ __forceinline__ void ldg256(const int64_t* p, long long& a, long long
 {
     asm volatile("ld.global.nc.v4.s64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
 }
-__device__ __forceinline__ uint4 ldg128u(const uint32_t* p)
-{
-    uint4 v;
-    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-}
-
-// low words of 4 adjacent plane elements at element offset `e` of a page's plane, either layout
+// low words of S and of Q at 4 adjacent plane elements starting at element offset e (e % 4 == 0), either layout
 template <bool COMPACT>
-__device__ __forceinline__ uint4 lo4(const int64_t* plane, size_t e)
+__device__ __forceinline__ void lo4(const ThrArgs& A, size_t e, uint4& s, uint4& q)
 {
-    if (COMPACT) return ldg128u(reinterpret_cast<const uint32_t*>(plane) + e);
     long long a, b, c, d;
-    ldg256(plane + e, a, b, c, d);
-    return make_uint4((unsigned int)a, (unsigned int)b, (unsigned int)c, (unsigned int)d);
+    if (COMPACT) {                                   // one 32-byte load: 4 x {S lo, Q lo}
+        ldg256(A.S + e, a, b, c, d);
+        s = make_uint4((unsigned int)a, (unsigned int)b, (unsigned int)c, (unsigned int)d);
+        q = make_uint4((unsigned int)(a >> 32), (unsigned int)(b >> 32), (unsigned int)(c >> 32), (unsigned int)(d >> 32));
+    } else {
+        ldg256(A.S + e, a, b, c, d);
+        s = make_uint4((unsigned int)a, (unsigned int)b, (unsigned int)c, (unsigned int)d);
+        ldg256(A.Q + e, a, b, c, d);
+        q = make_uint4((unsigned int)a, (unsigned int)b, (unsigned int)c, (unsigned int)d);
+    }
 }
 
-// compact layout: the full int64 value at (Y, X) from the low-word plane L and the anchor high words H (common.cuh: prl_planes)
-__device__ __forceinline__ long long full_tap(const uint32_t* __restrict__ L, const uint32_t* __restrict__ H, size_t pitch,
-                                              int ashift, int Y, int X)
+// compact layout: the full int64 S and Q at (Y, X) of one page, rebuilt from the anchor that serves it (common.cuh: prl_planes)
+__device__ __forceinline__ void full_taps(const uint2* __restrict__ L, const uint2* __restrict__ H, size_t pitch, size_t a_pitch,
+                                          int ashift, int Y, int X, long long& s, long long& q)
 {
-    const int ya = Y >> ashift;
-    const unsigned int lo_a = __ldg(L + ((size_t)ya << ashift) * pitch + X);
-    const unsigned int hi = __ldg(H + (size_t)ya * pitch + X);
-    const unsigned int lo = __ldg(L + (size_t)Y * pitch + X);
-    return (long long)((((unsigned long long)hi << 32) | lo_a) + (unsigned long long)(unsigned int)(lo - lo_a));
+    const int ya = Y >> ashift, xa = X & ~3;
+    const uint2 lo_a = __ldg(L + ((size_t)ya << ashift) * pitch + xa);
+    const uint2 hi = __ldg(H + (size_t)ya * a_pitch + (xa >> 2));
+    const uint2 lo = __ldg(L + (size_t)Y * pitch + X);
+    s = (long long)((((unsigned long long)hi.x << 32) | lo_a.x) + (unsigned long long)(unsigned int)(lo.x - lo_a.x));
+    q = (long long)((((unsigned long long)hi.y << 32) | lo_a.y) + (unsigned long long)(unsigned int)(lo.y - lo_a.y));
 }
 
-// the literal reference arithmetic for output pixel (y, x) from compact planes of one page
+// the literal reference arithmetic for output pixel (y, x) from the compact planes of one page
 template <int METHOD>
-__device__ __noinline__ int exact_t8_compact(const uint32_t* __restrict__ S, const uint32_t* __restrict__ Q,
-                                             const uint32_t* __restrict__ AS, const uint32_t* __restrict__ AQ, size_t pitch,
+__device__ __noinline__ int exact_t8_compact(const uint2* __restrict__ L, const uint2* __restrict__ H, size_t pitch, size_t a_pitch,
                                              int ashift, int y, int x, int d, double kw, double p0, double p1, double p2,
                                              double imin, double coeff)
 {
-    const long long sa = full_tap(S, AS, pitch, ashift, y, x), sb = full_tap(S, AS, pitch, ashift, y, x + d);
-    const long long sc = full_tap(S, AS, pitch, ashift, y + d, x), sd = full_tap(S, AS, pitch, ashift, y + d, x + d);
-    const long long qa = full_tap(Q, AQ, pitch, ashift, y, x), qb = full_tap(Q, AQ, pitch, ashift, y, x + d);
-    const long long qc = full_tap(Q, AQ, pitch, ashift, y + d, x), qd = full_tap(Q, AQ, pitch, ashift, y + d, x + d);
+    long long sa, sb, sc, sd, qa, qb, qc, qd;
+    full_taps(L, H, pitch, a_pitch, ashift, y, x, sa, qa);
+    full_taps(L, H, pitch, a_pitch, ashift, y, x + d, sb, qb);
+    full_taps(L, H, pitch, a_pitch, ashift, y + d, x, sc, qc);
+    full_taps(L, H, pitch, a_pitch, ashift, y + d, x + d, sd, qd);
     return exact_t8_from_taps<METHOD>(sa, sb, sc, sd, qa, qb, qc, qd, kw, p0, p1, p2, imin, coeff);
 }
 
-// NT threads per CTA: 128 (512 columns loaded per row) for small windows, 256 (1024 columns) when the tap
-// distance d would otherwise waste a large share of each CTA's loads on the column halo
-template <int METHOD, int NT, bool COMPACT>
+template <int METHOD, int NT>
 __global__ void __launch_bounds__(NT, 1024 / NT)     // <= 64 registers: 32 resident warps per SM
 threshold_fast_kernel(const ThrArgs A, const FastArgs F)
 {
@@ -205,11 +206,8 @@ threshold_fast_kernel(const ThrArgs A, const FastArgs F)
     const int x = X0 + 4 * threadIdx.x;              // this thread's first column (32-byte aligned in the planes)
     const int y_begin = blockIdx.y * F.rows_per_cta;
     const int y_end = min(y_begin + F.rows_per_cta, A.out_rows);
-    // (compact layout: the same expressions step through u32 elements, see lo4)
-    const int64_t* S = COMPACT ? reinterpret_cast<const int64_t*>(reinterpret_cast<const uint32_t*>(A.S) + (size_t)page * A.plane_page_stride)
-                               : A.S + (size_t)page * A.plane_page_stride;
-    const int64_t* Q = COMPACT ? reinterpret_cast<const int64_t*>(reinterpret_cast<const uint32_t*>(A.Q) + (size_t)page * A.plane_page_stride)
-                               : A.Q + (size_t)page * A.plane_page_stride;
+    const int64_t* S = A.S + (size_t)page * A.plane_page_stride;
+    const int64_t* Q = A.Q + (size_t)page * A.plane_page_stride;
     const uint8_t* src = A.src + (size_t)page * A.src_page_stride;
     uint8_t* dst = A.dst + (size_t)page * A.dst_page_stride;
 
@@ -231,26 +229,6 @@ threshold_fast_kernel(const ThrArgs A, const FastArgs F)
     for (int y = y_begin; y < y_end; y += kFR, buf ^= 1) {
         // ---- vertical differences of the low words -> shared memory (own copy stays in registers)
         unsigned int dsr[kFR][4], dqr[kFR][4];
-        if (COMPACT) {
-            // 16-byte loads: all eight of an iteration are in flight before the first difference is formed
-            uint4 ta[kFR], tb[kFR], ua[kFR], ub[kFR];
-#pragma unroll
-            for (int r = 0; r < kFR; ++r) {
-                ta[r] = tb[r] = ua[r] = ub[r] = make_uint4(0u, 0u, 0u, 0u);
-                if (in_plane && y + r < y_end) {
-                    const size_t e = (size_t)(y + r) * A.pitch + x, eb = e + (size_t)A.d * A.pitch;
-                    ta[r] = lo4<true>(S, e); tb[r] = lo4<true>(S, eb);
-                    ua[r] = lo4<true>(Q, e); ub[r] = lo4<true>(Q, eb);
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < kFR; ++r) {
-                dsr[r][0] = tb[r].x - ta[r].x; dsr[r][1] = tb[r].y - ta[r].y; dsr[r][2] = tb[r].z - ta[r].z; dsr[r][3] = tb[r].w - ta[r].w;
-                dqr[r][0] = ub[r].x - ua[r].x; dqr[r][1] = ub[r].y - ua[r].y; dqr[r][2] = ub[r].z - ua[r].z; dqr[r][3] = ub[r].w - ua[r].w;
-                *reinterpret_cast<uint4*>(&sD[buf][r][0][4 * threadIdx.x]) = make_uint4(dsr[r][0], dsr[r][1], dsr[r][2], dsr[r][3]);
-                *reinterpret_cast<uint4*>(&sD[buf][r][1][4 * threadIdx.x]) = make_uint4(dqr[r][0], dqr[r][1], dqr[r][2], dqr[r][3]);
-            }
-        } else {
 #pragma unroll
         for (int r = 0; r < kFR; ++r) {
             unsigned int (&ds)[4] = dsr[r];
@@ -269,7 +247,6 @@ threshold_fast_kernel(const ThrArgs A, const FastArgs F)
             }
             *reinterpret_cast<uint4*>(&sD[buf][r][0][4 * threadIdx.x]) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
             *reinterpret_cast<uint4*>(&sD[buf][r][1][4 * threadIdx.x]) = make_uint4(dq[0], dq[1], dq[2], dq[3]);
-        }
         }
         __syncthreads();
         // ---- horizontal differences, decision, store
@@ -302,17 +279,10 @@ threshold_fast_kernel(const ThrArgs A, const FastArgs F)
                     int o;
                     if (!fast_decide<METHOD, METHOD == PRL_SAUVOLA>(sw[i], qw[i], p, F, iminf, coefff, mu, o)) {
                         if (x + i < A.out_cols) {
-                            int t8;
-                            if (COMPACT) {
-                                t8 = exact_t8_compact<METHOD>(reinterpret_cast<const uint32_t*>(S), reinterpret_cast<const uint32_t*>(Q),
-                                                              A.AS + (size_t)page * A.a_page_stride, A.AQ + (size_t)page * A.a_page_stride,
-                                                              A.pitch, A.ashift, yy, x + i, A.d, A.kw, A.p0, A.p1, A.p2, imin, coeff);
-                            } else {
-                                const size_t e0 = (size_t)yy * A.pitch + x + i;
-                                t8 = exact_t8_at<METHOD>(reinterpret_cast<const long long*>(S) + e0,
-                                                         reinterpret_cast<const long long*>(Q) + e0, (size_t)A.d * A.pitch,
-                                                         A.d, A.kw, A.p0, A.p1, A.p2, imin, coeff);
-                            }
+                            const size_t e0 = (size_t)yy * A.pitch + x + i;
+                            const int t8 = exact_t8_at<METHOD>(reinterpret_cast<const long long*>(S) + e0,
+                                                               reinterpret_cast<const long long*>(Q) + e0, (size_t)A.d * A.pitch,
+                                                               A.d, A.kw, A.p0, A.p1, A.p2, imin, coeff);
                             o = (int)p > t8 ? 255 : 0;
                         } else o = 0;
                     }
@@ -336,6 +306,417 @@ threshold_fast_kernel(const ThrArgs A, const FastArgs F)
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// streaming kernel (the default mask path).  Same data path and the same decision rule as threshold_fast_kernel above
+// -- exact integer window sums, FP32 estimate T~, decided unless within the proven margin mu, else the reference's FP64
+// formula -- restructured for instruction count, which is what bounded that kernel once the planes went compact
+// (ncu: 65 % issue-active, 76 thread-instructions per pixel, 45 % of them in the branchy two-tier decision):
+//   * persistent CTAs walk the tiles in raster order (grid = resident CTAs), so the per-tile prologue is a handful of
+//     integer updates and the second fetch of every plane row still finds it in L2;
+//   * the FP32 estimate is evaluated for all four pixels of a thread unconditionally and branch-free (no variance-free
+//     pre-test, no early-outs, hence no divergence); only pixels it cannot settle leave the straight line;
+//   * u8 -> float and S_win -> float go through the 2^23 magic-number trick on the ALU pipe instead of I2F on the XU
+//     pipe (exact for values < 2^23: S_win <= 255 (w-1)^2 needs w <= 181; wider windows convert with I2F).
+// The estimate is the expression fast_decide evaluates (same operations, same order), so fast_margins covers it as is.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float u8_to_float(unsigned int p4, int i)
+{
+    // byte i of p4 under the exponent of 2^23: 0x4B0000pp = 8388608 + pp exactly
+    return __uint_as_float(__byte_perm(p4, 0x4B000000u, 0x7540u | (unsigned int)i)) - 8388608.0f;
+}
+
+template <int METHOD, int NT, bool COMPACT>
+__global__ void __launch_bounds__(NT, 1024 / NT)
+threshold_stream_kernel(const ThrArgs A, const FastArgs F, int tiles_x, int tiles_y, int n_pages)
+{
+    constexpr int FC = NT * 4;                        // columns loaded per CTA row
+    __shared__ __align__(16) unsigned int sD[2][kFR][2][FC];   // [buffer][row][plane S/Q][column]
+
+    const int oc = (FC - A.d) & ~3;                  // output columns per tile
+    const int tid = threadIdx.x;
+    const bool col_out = (4 * tid + 3 + A.d < FC) && (4 * tid < oc);
+    const bool small_s = F.w2 <= 181u * 181u;        // S_win < 2^23: magic-number conversion is exact
+
+    // tile = (page, ty, tx), x fastest; this CTA takes tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+    int tx = blockIdx.x % tiles_x, t1 = blockIdx.x / tiles_x;
+    int ty = t1 % tiles_y, page = t1 / tiles_y;
+    const int sx = gridDim.x % tiles_x, s1 = gridDim.x / tiles_x;
+    const int sy = s1 % tiles_y, sp = s1 / tiles_y;
+
+    int buf = 0, cur_page = -1;
+    double imin = 0.0, coeff = 0.0;
+    float iminf = 0.f, coefff = 0.f, mu = F.mu0;
+    for (; page < n_pages;) {
+        if ((METHOD == PRL_WOLFJOLION || METHOD == PRL_FENG) && page != cur_page) {
+            cur_page = page;
+            imin = (double)A.imin[page]; iminf = (float)imin;
+            if (METHOD == PRL_WOLFJOLION) {
+                coeff = __ddiv_rn(A.p0, __longlong_as_double(A.smax[page]));
+                coefff = (float)coeff;
+                mu = F.mu0 + F.mu1 * fabsf(coefff);
+                if (!(mu < 0.25f)) mu = 1e30f;       // degenerate s_max: every pixel takes the exact path
+            }
+        }
+        const int x = tx * oc + 4 * tid;             // this thread's first column (16/32-byte aligned in the planes)
+        const int y_begin = ty * F.rows_per_cta;
+        const int y_end = min(y_begin + F.rows_per_cta, A.out_rows);
+        const bool in_plane = x < (int)A.pitch;
+        const bool has_out = col_out && x < A.out_cols;
+        const bool full4 = x + 3 < A.out_cols;
+        const size_t pbase = (size_t)page * A.plane_page_stride + x;
+        const uint8_t* srow = A.src + (size_t)page * A.src_page_stride + (size_t)y_begin * A.src_step + x;
+        uint8_t* orow = A.dst + (size_t)page * A.dst_page_stride + (size_t)y_begin * A.dst_step + x;
+
+        for (int y = y_begin; y < y_end; y += kFR, buf ^= 1) {
+            // ---- vertical differences of the low words -> shared memory (own copy stays in registers)
+            unsigned int dsr[kFR][4], dqr[kFR][4], pix[kFR];
+            {
+                uint4 ta[kFR], tb[kFR], ua[kFR], ub[kFR];
+#pragma unroll
+                for (int r = 0; r < kFR; ++r) {
+                    // the page pixels travel with the plane loads: fetched in the decision phase they were its longest stall
+                    pix[r] = 0u;
+                    if (has_out && y + r < y_end) {
+                        const uint8_t* prow = srow + (size_t)(y + r - y_begin) * A.src_step;
+                        if (full4) pix[r] = __ldg(reinterpret_cast<const unsigned int*>(prow));
+                        else for (int i = 0; i < 4; ++i) if (x + i < A.out_cols) pix[r] |= (unsigned int)prow[i] << (8 * i);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < kFR; ++r) {
+                    ta[r] = tb[r] = ua[r] = ub[r] = make_uint4(0u, 0u, 0u, 0u);
+                    if (in_plane && y + r < y_end) {
+                        const size_t e = pbase + (size_t)(y + r) * A.pitch, eb = e + (size_t)A.d * A.pitch;
+                        lo4<COMPACT>(A, e, ta[r], ua[r]);
+                        lo4<COMPACT>(A, eb, tb[r], ub[r]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < kFR; ++r) {
+                    dsr[r][0] = tb[r].x - ta[r].x; dsr[r][1] = tb[r].y - ta[r].y; dsr[r][2] = tb[r].z - ta[r].z; dsr[r][3] = tb[r].w - ta[r].w;
+                    dqr[r][0] = ub[r].x - ua[r].x; dqr[r][1] = ub[r].y - ua[r].y; dqr[r][2] = ub[r].z - ua[r].z; dqr[r][3] = ub[r].w - ua[r].w;
+                    *reinterpret_cast<uint4*>(&sD[buf][r][0][4 * tid]) = make_uint4(dsr[r][0], dsr[r][1], dsr[r][2], dsr[r][3]);
+                    *reinterpret_cast<uint4*>(&sD[buf][r][1][4 * tid]) = make_uint4(dqr[r][0], dqr[r][1], dqr[r][2], dqr[r][3]);
+                }
+            }
+            __syncthreads();
+            if (has_out) {
+#pragma unroll
+                for (int r = 0; r < kFR; ++r) {
+                    const int yy = y + r;
+                    if (yy >= y_end) break;
+                    const unsigned int* ls = &sD[buf][r][0][4 * tid + A.d];          // d even -> 8-byte aligned
+                    const unsigned int* lq = &sD[buf][r][1][4 * tid + A.d];
+                    const uint2 s_r0 = *reinterpret_cast<const uint2*>(ls), s_r1 = *reinterpret_cast<const uint2*>(ls + 2);
+                    const uint2 q_r0 = *reinterpret_cast<const uint2*>(lq), q_r1 = *reinterpret_cast<const uint2*>(lq + 2);
+                    const unsigned int sw[4] = {s_r0.x - dsr[r][0], s_r0.y - dsr[r][1], s_r1.x - dsr[r][2], s_r1.y - dsr[r][3]};
+                    const unsigned int qw[4] = {q_r0.x - dqr[r][0], q_r0.y - dqr[r][1], q_r1.x - dqr[r][2], q_r1.y - dqr[r][3]};
+                    const unsigned int p4 = pix[r];
+                    unsigned int o4 = 0, und = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float pm = u8_to_float(p4, i) - 0.5f;
+                        const float mf = small_s ? __uint_as_float(0x4B000000u + sw[i]) - 8388608.0f : (float)sw[i];
+                        const float m = mf * F.kwf;
+                        const float fn = n_to_float(F, sw[i], qw[i]);          // N = w^2 Q - S^2, exact and >= 0 before the conversion
+                        const float sd = (fn * rsqrtf(fn)) * F.inv_w2f;        // fn == 0 gives NaN -> undecided (or the all-zero window below)
+                        float T;
+                        if (METHOD == PRL_SAUVOLA) T = m * fmaf(sd, F.c1, F.c2);
+                        else if (METHOD == PRL_NIBLACK) T = fmaf(F.c0, sd, m);
+                        else if (METHOD == PRL_WOLFJOLION) T = fmaf(fmaf(sd, coefff, -F.c0), m - iminf, m);
+                        else if (METHOD == PRL_NICK) T = fmaf(F.c0, sqrtf(fmaf(m, m, sd * sd)), m);
+                        else T = fmaf(F.c1, m, fmaf(F.c2, iminf, -iminf));
+                        const float g = pm - fmaxf(T, 0.0f);
+                        const bool ok = fn >= F.n_floor;
+                        const bool white = ok && g > mu;
+                        const bool black = (ok && g < -mu) || qw[i] == 0u;     // all-zero window => p == 0 => (0 > T8) is false
+                        if (white) o4 |= 0xffu << (8 * i);
+                        if (!(white || black)) und |= 1u << i;
+                    }
+                    if (und) {                                                  // ~1e-3 of the pixels: the reference arithmetic, literally
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (((und >> i) & 1u) && x + i < A.out_cols) {
+                                const unsigned int p = (p4 >> (8 * i)) & 0xffu;
+                                int t8;
+                                if (COMPACT) {
+                                    t8 = exact_t8_compact<METHOD>(reinterpret_cast<const uint2*>(A.S) + (size_t)page * A.plane_page_stride,
+                                                                  A.AH + (size_t)page * A.a_page_stride, A.pitch, A.a_pitch, A.ashift, yy, x + i,
+                                                                  A.d, A.kw, A.p0, A.p1, A.p2, imin, coeff);
+                                } else {
+                                    const size_t e0 = pbase + (size_t)yy * A.pitch + i;
+                                    t8 = exact_t8_at<METHOD>(reinterpret_cast<const long long*>(A.S) + e0, reinterpret_cast<const long long*>(A.Q) + e0,
+                                                             (size_t)A.d * A.pitch, A.d, A.kw, A.p0, A.p1, A.p2, imin, coeff);
+                                }
+                                if ((int)p > t8) o4 |= 0xffu << (8 * i);
+                            }
+                        }
+                    }
+                    // dst may be dense (pitch == out_cols, odd): store with whatever alignment the row has
+                    uint8_t* op = orow + (size_t)(yy - y_begin) * A.dst_step;
+                    const unsigned int al = (unsigned int)(uintptr_t)op & 3u;
+                    if (!full4) {
+                        for (int i = 0; i < 4; ++i) if (x + i < A.out_cols) op[i] = (uint8_t)(o4 >> (8 * i));
+                    } else if (al == 0) {
+                        *reinterpret_cast<unsigned int*>(op) = o4;
+                    } else if (al == 2) {
+                        *reinterpret_cast<unsigned short*>(op) = (unsigned short)o4;
+                        *reinterpret_cast<unsigned short*>(op + 2) = (unsigned short)(o4 >> 16);
+                    } else {
+                        op[0] = (uint8_t)o4;
+                        *reinterpret_cast<unsigned short*>(op + 1) = (unsigned short)(o4 >> 8);
+                        op[3] = (uint8_t)(o4 >> 24);
+                    }
+                }
+            }
+        }
+        // next tile of this CTA
+        tx += sx; ty += sy; page += sp;
+        if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+        if (ty >= tiles_y) { ty -= tiles_y; ++page; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA kernel (the default mask path on compact planes).  The streaming kernel above is latency-bound: its loads live in
+// registers, a CTA alternates "issue 8 loads - wait - decide", and 8 CTAs per SM keep only ~60 KB in flight against a
+// loaded-DRAM latency of ~2 us (measured: the same 7.1 ms for every method, 43 % of DRAM peak, long_scoreboard on top).
+// Here a PRODUCER warp pulls the plane rows and the page pixels of one work unit after the other into a shared-memory
+// ring with TMA (cp.async.bulk.tensor, mbarrier completion) and eight CONSUMER warps decide the pixels; full / empty
+// mbarriers per stage, no block-wide barrier, no register held across the DRAM latency.
+//   unit   = R rows x FC columns (4 x 512, or 2 x 1024 for tap distances > 64).  Per unit and side (top taps = plane rows
+//            y.., bottom taps = rows y + d..) FC / 256 boxes of 256 pixels x R rows of uint2 {S lo, Q lo}, plus one box
+//            of page pixels: 34 KB per stage.
+//   order  = raster (x fastest), handed out through a global counter: CTAs that run ahead or behind still work on
+//            neighbouring units, so the rows a unit needs as top taps were pulled through L2 as bottom taps d rows
+//            earlier.  (Static striding let the CTAs drift apart and cost 35 % extra DRAM reads.)
+//   thread = two PAIRS of adjacent pixels 64 columns apart in two rows of the unit: every shared-memory access of a
+//            warp is 32 consecutive 16-byte words (conflict-free LDS.128).
+// Decision rule and arithmetic are those of the streaming kernel (fast_margins covers both).
+// ------------------------------------------------------------------------------------------------
+constexpr int kTmaConsumers = 256;
+constexpr int kTmaThreads = kTmaConsumers + 32;
+constexpr int kTmaPix = 2048;                                     // pixels per unit = R * FC
+constexpr int kTmaStageBytes = 2 * kTmaPix * 8 + kTmaPix;         // two sides of uint2 + the page pixels = 34816 (272 * 128)
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned int lds16(uint32_t addr)
+{
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(prl_tma::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float rsq_approx(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));     // MUFU.RSQ, 2 ulp (what the margin assumes); x == 0 -> +inf
+    return r;
+}
+
+template <int METHOD, bool WIDE, int NS>
+__global__ void __launch_bounds__(kTmaThreads, (NS == 2) ? 3 : 2)
+threshold_tma_kernel(const __grid_constant__ CUtensorMap tmSQ, const __grid_constant__ CUtensorMap tmP, const ThrArgs A,
+                     const FastArgs F, int tiles_x, int yblocks, int n_units, int* __restrict__ counter)
+{
+    constexpr int FC = WIDE ? 1024 : 512;
+    constexpr int R = kTmaPix / FC;                               // rows per unit (4 / 2)
+    constexpr int NBOX = FC / 256;                                // plane boxes per side
+    constexpr int RPP = kTmaConsumers / (FC / 4);                 // rows the consumers cover in one pass (2 / 1); two passes per unit
+    extern __shared__ __align__(128) uint8_t ring[];
+    __shared__ uint64_t full[NS], empty[NS];
+    __shared__ int4 info[NS];                                     // {page, yb, tx, -} of the unit in each stage; page < 0: no more units
+
+    const int tid = threadIdx.x;
+    const int oc = (FC - A.d) & ~15;                              // output columns per unit (16-byte aligned pixel boxes)
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) { prl_tma::mbar_init(&full[s], 1); prl_tma::mbar_init(&empty[s], kTmaConsumers / 32); }
+        prl_tma::mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (tid >= kTmaConsumers) {
+        // ---------------- producer: one lane ----------------
+        if (tid == kTmaConsumers) {
+            for (int k = 0;; ++k) {
+                const int stage = k % NS;
+                if (k >= NS) prl_tma::mbar_wait(&empty[stage], (uint32_t)(((k / NS) - 1) & 1));
+                const int u = atomicAdd(counter, 1);
+                if (u >= n_units) {
+                    info[stage] = make_int4(-1, 0, 0, 0);
+                    mbar_arrive(&full[stage]);
+                    break;
+                }
+                const int tx = u % tiles_x, t1 = u / tiles_x;
+                const int yb = t1 % yblocks, page = t1 / yblocks;
+                info[stage] = make_int4(page, yb, tx, 0);
+                uint8_t* dst = ring + (size_t)stage * kTmaStageBytes;
+                prl_tma::mbar_expect_tx(&full[stage], kTmaStageBytes);
+                const int x0 = tx * oc, y0 = yb * R;
+#pragma unroll
+                for (int b = 0; b < NBOX; ++b) {
+                    prl_tma::tma_load_3d(dst + (size_t)b * (R * 2048), &tmSQ, x0 + 256 * b, y0, page, &full[stage]);
+                    prl_tma::tma_load_3d(dst + kTmaPix * 8 + (size_t)b * (R * 2048), &tmSQ, x0 + 256 * b, y0 + A.d, page, &full[stage]);
+                }
+                prl_tma::tma_load_3d(dst + 2 * kTmaPix * 8, &tmP, x0 / (WIDE ? 4 : 2), y0, page, &full[stage]);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const bool small_s = F.w2 <= 181u * 181u;
+    const int rs = tid / (FC / 4);                                // row slot of the pass
+    const int j = tid % (FC / 4);
+    const int c0 = (j >> 5) * 128 + 2 * (j & 31);                 // first pixel of pair 0; pair 1 starts 64 columns further
+    // loop-invariant shared-memory offsets of the two pairs (own columns and columns + d), and whether they produce output
+    uint32_t off_a[2], off_b[2];
+    bool col_ok[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int c = c0 + 64 * h, cd = c + A.d;
+        off_a[h] = (uint32_t)((c >> 8) * (R << 11) + ((c & 255) << 3));
+        off_b[h] = (uint32_t)((cd >> 8) * (R << 11) + ((cd & 255) << 3));
+        col_ok[h] = c + 1 + A.d < FC && c < oc;
+    }
+    const uint32_t ring_u32 = prl_tma::smem_u32(ring);
+    const unsigned int dst_step = (unsigned int)A.dst_step;
+    const float mu_hi0 = 0.5f, kwf = F.kwf, inv_w2f = F.inv_w2f;
+
+    int cur_page = -1;
+    double imin = 0.0, coeff = 0.0;
+    float iminf = 0.f, coefff = 0.f, mu = F.mu0;
+    for (int k = 0;; ++k) {
+        const int stage = k % NS;
+        prl_tma::mbar_wait(&full[stage], (uint32_t)((k / NS) & 1));
+        const int4 ui = info[stage];
+        const int page = ui.x;
+        if (page < 0) break;
+        if ((METHOD == PRL_WOLFJOLION || METHOD == PRL_FENG) && page != cur_page) {
+            cur_page = page;
+            imin = (double)A.imin[page]; iminf = (float)imin;
+            if (METHOD == PRL_WOLFJOLION) {
+                coeff = __ddiv_rn(A.p0, __longlong_as_double(A.smax[page]));
+                coefff = (float)coeff;
+                mu = F.mu0 + F.mu1 * fabsf(coefff);
+                if (!(mu < 0.25f)) mu = 1e30f;       // degenerate s_max: every pixel takes the exact path
+            }
+        }
+        const uint32_t st = ring_u32 + (uint32_t)stage * kTmaStageBytes;
+        const int x0 = ui.z * oc, yu = ui.y * R;
+        uint8_t* obase = A.dst + (size_t)page * A.dst_page_stride + (size_t)yu * dst_step + x0;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const int rr = rs + pass * RPP;                       // row of the unit
+            const int y = yu + rr;
+            if (y >= A.out_rows) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = c0 + 64 * h;
+                const int x = x0 + c;
+                if (!(col_ok[h] && x < A.out_cols)) continue;
+                // taps: a = top[c], b = top[c + d], c = bottom[c], d = bottom[c + d]; each load = 2 pixels x {S lo, Q lo}
+                const uint32_t ra = st + (uint32_t)(rr << 11) + off_a[h], rb = st + (uint32_t)(rr << 11) + off_b[h];
+                const uint4 ta = lds128(ra), tb = lds128(rb), ba = lds128(ra + kTmaPix * 8), bb = lds128(rb + kTmaPix * 8);
+                const unsigned int p2 = lds16(st + 2 * kTmaPix * 8 + (uint32_t)(rr * FC + c));
+                const unsigned int sw[2] = {(bb.x - ba.x) - (tb.x - ta.x), (bb.z - ba.z) - (tb.z - ta.z)};
+                const unsigned int qw[2] = {(bb.y - ba.y) - (tb.y - ta.y), (bb.w - ba.w) - (tb.w - ta.w)};
+                unsigned int o2 = 0, und = 0;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float pm = u8_to_float(p2, i) - mu_hi0;
+                    const float mf = small_s ? __uint_as_float(0x4B000000u + sw[i]) - 8388608.0f : (float)sw[i];
+                    const float m = mf * kwf;
+                    const float fn = n_to_float(F, sw[i], qw[i]);          // N = w^2 Q - S^2, exact and >= 0 before the conversion
+                    const float sd = (fn * rsq_approx(fn)) * inv_w2f;      // fn == 0 gives NaN -> undecided (or the all-zero window below)
+                    float T;
+                    if (METHOD == PRL_SAUVOLA) T = m * fmaf(sd, F.c1, F.c2);
+                    else if (METHOD == PRL_NIBLACK) T = fmaf(F.c0, sd, m);
+                    else if (METHOD == PRL_WOLFJOLION) T = fmaf(fmaf(sd, coefff, -F.c0), m - iminf, m);
+                    else if (METHOD == PRL_NICK) T = fmaf(F.c0, sqrtf(fmaf(m, m, sd * sd)), m);
+                    else T = fmaf(F.c1, m, fmaf(F.c2, iminf, -iminf));
+                    const float g = pm - fmaxf(T, 0.0f);
+                    const bool ok = fn >= F.n_floor;
+                    const bool white = ok && g > mu;
+                    const bool black = (ok && g < -mu) || qw[i] == 0u;     // all-zero window => p == 0 => (0 > T8) is false
+                    if (white) o2 |= 0xffu << (8 * i);
+                    if (!(white || black)) und |= 1u << i;
+                }
+                if (und && !F.dbg_skip_exact) {                             // ~1e-3 of the pixels: the reference arithmetic, literally
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        if (((und >> i) & 1u) && x + i < A.out_cols) {
+                            const unsigned int p = (p2 >> (8 * i)) & 0xffu;
+                            const int t8 = exact_t8_compact<METHOD>(reinterpret_cast<const uint2*>(A.S) + (size_t)page * A.plane_page_stride,
+                                                                    A.AH + (size_t)page * A.a_page_stride, A.pitch, A.a_pitch, A.ashift, y, x + i,
+                                                                    A.d, A.kw, A.p0, A.p1, A.p2, imin, coeff);
+                            if ((int)p > t8) o2 |= 0xffu << (8 * i);
+                        }
+                    }
+                }
+                // dst may be dense (pitch == out_cols, odd): a pair goes out as one 16-bit store where its address allows
+                uint8_t* op = obase + (unsigned int)rr * dst_step + (unsigned int)c;
+                if (x + 1 < A.out_cols && (((uintptr_t)op) & 1u) == 0) {
+                    *reinterpret_cast<unsigned short*>(op) = (unsigned short)o2;
+                } else {
+                    op[0] = (uint8_t)o2;
+                    if (x + 1 < A.out_cols) op[1] = (uint8_t)(o2 >> 8);
+                }
+            }
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty[stage]);        // this warp is done with the stage
+    }
+}
+
+template <int METHOD>
+int launch_tma_threshold(prl_cuda_ctx* ctx, const ThrArgs& A, const FastArgs& F, const prl_geom& g, const prl_planes& P,
+                         const uint8_t* d_src, size_t src_step, size_t src_page_stride, int n_pages, bool* launched)
+{
+    *launched = false;
+    const bool wide = g.d > 64;
+    const int FC = wide ? 1024 : 512, R = kTmaPix / FC;
+    const int oc = (FC - g.d) & ~15;
+    if (oc <= 0 || A.dst_step >= ((size_t)1 << 32)) return PRL_OK;
+    const int tiles_x = (g.out_cols + oc - 1) / oc, yblocks = (g.out_rows + R - 1) / R;
+    const long long n_units = (long long)tiles_x * yblocks * n_pages;
+    if (n_units >= (1ll << 30)) return PRL_OK;
+    CUtensorMap tmSQ, tmP;
+    // planes: {pitch, Hp, pages} of 8-byte elements, boxes of 256 elements x R rows
+    if (!prl_tma::encode_3d(&tmSQ, CU_TENSOR_MAP_DATA_TYPE_UINT64, P.S, P.pitch, (uint64_t)g.Hp, (uint64_t)n_pages, P.pitch * 8,
+                            P.page_stride * 8, 256, R))
+        return PRL_OK;
+    // page pixels: rows of FC bytes described as 256 elements of 2 (4) bytes
+    const int eb = wide ? 4 : 2;
+    if (!prl_tma::encode_3d(&tmP, wide ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, d_src, src_step / eb,
+                            (uint64_t)g.rows, (uint64_t)n_pages, src_step, n_pages > 1 ? src_page_stride : src_step * g.rows, 256, R))
+        return PRL_OK;
+    int rc = prl_ensure(ctx, &ctx->sched, &ctx->sched_bytes, 256); if (rc) return rc;
+    PRL_CUDA_TRY(ctx, cudaMemsetAsync(ctx->sched, 0, sizeof(int), ctx->stream));
+    const int ns = ctx->thr_stages == 2 ? 2 : 3;
+    const size_t smem = (size_t)ns * kTmaStageBytes;
+    const int grid = (int)std::min<long long>(n_units, (long long)ctx->num_sms * (ns == 2 ? 3 : 2));
+#define PRL_LAUNCH_TMA(W, N)                                                                                          \
+    do { auto kfn = threshold_tma_kernel<METHOD, W, N>;                                                               \
+         PRL_CUDA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+         kfn<<<grid, kTmaThreads, smem, ctx->stream>>>(tmSQ, tmP, A, F, tiles_x, yblocks, (int)n_units, (int*)ctx->sched); } while (0)
+    if (wide) { if (ns == 2) PRL_LAUNCH_TMA(true, 2); else PRL_LAUNCH_TMA(true, 3); }
+    else { if (ns == 2) PRL_LAUNCH_TMA(false, 2); else PRL_LAUNCH_TMA(false, 3); }
+#undef PRL_LAUNCH_TMA
+    *launched = true;
+    return PRL_OK;
 }
 
 template <int METHOD>
@@ -370,10 +751,7 @@ nmax_fast_kernel(const ThrArgs A, const FastArgs F, unsigned long long* __restri
     const int x = X0 + 4 * threadIdx.x;
     const int y_begin = blockIdx.y * F.rows_per_cta;
     const int y_end = min(y_begin + F.rows_per_cta, A.out_rows);
-    const int64_t* S = COMPACT ? reinterpret_cast<const int64_t*>(reinterpret_cast<const uint32_t*>(A.S) + (size_t)page * A.plane_page_stride)
-                               : A.S + (size_t)page * A.plane_page_stride;
-    const int64_t* Q = COMPACT ? reinterpret_cast<const int64_t*>(reinterpret_cast<const uint32_t*>(A.Q) + (size_t)page * A.plane_page_stride)
-                               : A.Q + (size_t)page * A.plane_page_stride;
+    const size_t pbase = (size_t)page * A.plane_page_stride + x;
     const bool in_plane = x < (int)A.pitch;
     const bool has_out = (4 * threadIdx.x + 3 + A.d < kFC) && (4 * (int)threadIdx.x < oc) && x < A.out_cols;
     unsigned long long best = 0;
@@ -386,8 +764,10 @@ nmax_fast_kernel(const ThrArgs A, const FastArgs F, unsigned long long* __restri
             unsigned int (&dq)[4] = dqr[r];
             ds[0] = ds[1] = ds[2] = ds[3] = 0; dq[0] = dq[1] = dq[2] = dq[3] = 0;
             if (in_plane && y + r < y_end) {
-                const size_t e = (size_t)(y + r) * A.pitch + x, eb = e + (size_t)A.d * A.pitch;
-                const uint4 sa = lo4<COMPACT>(S, e), sb = lo4<COMPACT>(S, eb), qa = lo4<COMPACT>(Q, e), qb = lo4<COMPACT>(Q, eb);
+                const size_t e = pbase + (size_t)(y + r) * A.pitch, eb = e + (size_t)A.d * A.pitch;
+                uint4 sa, sb, qa, qb;
+                lo4<COMPACT>(A, e, sa, qa);
+                lo4<COMPACT>(A, eb, sb, qb);
                 ds[0] = sb.x - sa.x; ds[1] = sb.y - sa.y; ds[2] = sb.z - sa.z; ds[3] = sb.w - sa.w;
                 dq[0] = qb.x - qa.x; dq[1] = qb.y - qa.y; dq[2] = qb.z - qa.z; dq[3] = qb.w - qa.w;
             }
@@ -443,10 +823,8 @@ smax_candidates_kernel(const ThrArgs A, const FastArgs F, const unsigned long lo
     const int oc = (kFC - A.d) & ~3;
     const long long* S = reinterpret_cast<const long long*>(A.S) + (size_t)page * A.plane_page_stride;
     const long long* Q = reinterpret_cast<const long long*>(A.Q) + (size_t)page * A.plane_page_stride;
-    const uint32_t* S32 = reinterpret_cast<const uint32_t*>(A.S) + (size_t)page * A.plane_page_stride;
-    const uint32_t* Q32 = reinterpret_cast<const uint32_t*>(A.Q) + (size_t)page * A.plane_page_stride;
-    const uint32_t* AS = COMPACT ? A.AS + (size_t)page * A.a_page_stride : nullptr;
-    const uint32_t* AQ = COMPACT ? A.AQ + (size_t)page * A.a_page_stride : nullptr;
+    const uint2* L = reinterpret_cast<const uint2*>(A.S) + (size_t)page * A.plane_page_stride;
+    const uint2* H = COMPACT ? A.AH + (size_t)page * A.a_page_stride : nullptr;
     long long best = (long long)0xfff0000000000000LL;   // -inf
     const int tiles = tiles_x * tiles_y;
     for (int t = blockIdx.x * 16; t < min(tiles, blockIdx.x * 16 + 16); ++t) {
@@ -461,16 +839,15 @@ smax_candidates_kernel(const ThrArgs A, const FastArgs F, const unsigned long lo
             const size_t dr = (size_t)A.d * A.pitch;
             if (COMPACT) {
                 // the integer screen needs the low words only; the full taps are rebuilt for the few candidates
-                const uint32_t* s0 = S32 + (size_t)y * A.pitch + x;
-                const uint32_t* q0 = Q32 + (size_t)y * A.pitch + x;
-                const unsigned int swl = (__ldg(s0 + dr + A.d) - __ldg(s0 + dr)) - (__ldg(s0 + A.d) - __ldg(s0));
-                const unsigned int qwl = (__ldg(q0 + dr + A.d) - __ldg(q0 + dr)) - (__ldg(q0 + A.d) - __ldg(q0));
+                const uint2* l0 = L + (size_t)y * A.pitch + x;
+                const uint2 ta = __ldg(l0), tb = __ldg(l0 + A.d), tc = __ldg(l0 + dr), td = __ldg(l0 + dr + A.d);
+                const unsigned int swl = (td.x - tc.x) - (tb.x - ta.x), qwl = (td.y - tc.y) - (tb.y - ta.y);
                 const unsigned long long Nl = (unsigned long long)F.w2 * qwl - (unsigned long long)swl * swl;
                 if (Nl < lo) continue;
-                sa = full_tap(S32, AS, A.pitch, A.ashift, y, x); sb = full_tap(S32, AS, A.pitch, A.ashift, y, x + A.d);
-                sc = full_tap(S32, AS, A.pitch, A.ashift, y + A.d, x); sd = full_tap(S32, AS, A.pitch, A.ashift, y + A.d, x + A.d);
-                qa = full_tap(Q32, AQ, A.pitch, A.ashift, y, x); qb = full_tap(Q32, AQ, A.pitch, A.ashift, y, x + A.d);
-                qc = full_tap(Q32, AQ, A.pitch, A.ashift, y + A.d, x); qd = full_tap(Q32, AQ, A.pitch, A.ashift, y + A.d, x + A.d);
+                full_taps(L, H, A.pitch, A.a_pitch, A.ashift, y, x, sa, qa);
+                full_taps(L, H, A.pitch, A.a_pitch, A.ashift, y, x + A.d, sb, qb);
+                full_taps(L, H, A.pitch, A.a_pitch, A.ashift, y + A.d, x, sc, qc);
+                full_taps(L, H, A.pitch, A.a_pitch, A.ashift, y + A.d, x + A.d, sd, qd);
             } else {
                 const long long* s0 = S + (size_t)y * A.pitch + x;
                 const long long* q0 = Q + (size_t)y * A.pitch + x;
@@ -532,7 +909,7 @@ int prl_k_threshold(prl_cuda_ctx* ctx, int method, int mode, const uint8_t* d_sr
     ThrArgs A;
     A.src = d_src; A.src_step = src_step; A.src_page_stride = src_page_stride;
     A.S = d_S; A.Q = d_Q; A.pitch = P.pitch; A.plane_page_stride = plane_page_stride;
-    A.AS = P.AS; A.AQ = P.AQ; A.a_page_stride = P.a_page_stride; A.ashift = P.ashift;
+    A.AH = (const uint2*)P.AS; A.a_pitch = P.a_pitch; A.a_page_stride = P.a_page_stride; A.ashift = P.ashift;
     A.dst = d_dst; A.dst_step = dst_step; A.dst_page_stride = dst_page_stride;
     A.imin = d_imin; A.smax = d_smax;
     A.out_rows = g.out_rows; A.out_cols = g.out_cols; A.d = g.d;
@@ -549,7 +926,7 @@ int prl_k_threshold(prl_cuda_ctx* ctx, int method, int mode, const uint8_t* d_sr
     // fast path eligibility: mask output, even tap distance < 256, window sums < 2^32, 4/32-byte aligned buffers
     FastArgs F;
     const bool aligned = ((src_step | src_page_stride | (uintptr_t)d_src) & 3) == 0 &&
-                         ((((uintptr_t)d_S) | ((uintptr_t)d_Q)) & (P.compact ? 15 : 31)) == 0 && (plane_page_stride & 3) == 0 && (P.pitch & 3) == 0;
+                         ((((uintptr_t)d_S) | ((uintptr_t)d_Q)) & 31) == 0 && (plane_page_stride & 3) == 0 && (P.pitch & 3) == 0;
     const bool fast_ok = !ctx->force_exact && (g.d & 1) == 0 && g.d <= 254 && aligned && fast_margins(method, params, g, &F);
     if (P.compact && !(fast_ok && mode == 0))
         return prl_set_err(ctx, PRL_E_INVALID, "compact planes serve the fast mask path only");
@@ -594,7 +971,24 @@ int prl_k_threshold(prl_cuda_ctx* ctx, int method, int mode, const uint8_t* d_sr
     }
 
     const bool fast = mode == 0 && fast_ok;
+    F.dbg_skip_exact = ctx->dbg_skip_exact ? 1 : 0;
     prl_launch_scope ls(ctx, FAM_THRESHOLD);
+    if (fast && P.compact && !ctx->thr_no_tma && ((src_step | src_page_stride | (uintptr_t)d_src) & 15) == 0) {
+        bool launched = false;
+        int rc;
+        switch (method) {
+        case PRL_SAUVOLA:    rc = launch_tma_threshold<PRL_SAUVOLA>(ctx, A, F, g, P, d_src, src_step, src_page_stride, n_pages, &launched); break;
+        case PRL_NIBLACK:    rc = launch_tma_threshold<PRL_NIBLACK>(ctx, A, F, g, P, d_src, src_step, src_page_stride, n_pages, &launched); break;
+        case PRL_WOLFJOLION: rc = launch_tma_threshold<PRL_WOLFJOLION>(ctx, A, F, g, P, d_src, src_step, src_page_stride, n_pages, &launched); break;
+        case PRL_NICK:       rc = launch_tma_threshold<PRL_NICK>(ctx, A, F, g, P, d_src, src_step, src_page_stride, n_pages, &launched); break;
+        default:             rc = launch_tma_threshold<PRL_FENG>(ctx, A, F, g, P, d_src, src_step, src_page_stride, n_pages, &launched); break;
+        }
+        if (rc) return rc;
+        if (launched) {
+            PRL_CUDA_TRY(ctx, cudaGetLastError());
+            return PRL_OK;
+        }
+    }
     if (fast) {
         // Rows per CTA (rpc = 4).  Each S/Q row is fetched twice (as the bottom row of output row y-d, then as the
         // top row of y); the second fetch must hit L2, so the CTAs in flight have to cover a compact
@@ -604,11 +998,19 @@ int prl_k_threshold(prl_cuda_ctx* ctx, int method, int mode, const uint8_t* d_sr
         const int nt = wide ? 256 : 128;
         const int oc = (nt * 4 - g.d) & ~3;
         dim3 fg((g.out_cols + oc - 1) / oc, (g.out_rows + rpc - 1) / rpc, n_pages);
+        // streaming kernel: persistent CTAs (every resident slot of the device) over the same tiles in the same order
+        const long long n_tiles = (long long)fg.x * fg.y * n_pages;
+        const int slots = ctx->num_sms * (1024 / nt);
+        const int pg = (int)std::min<long long>(n_tiles, (long long)slots);
+        const bool stream_ok = (P.compact || !ctx->thr_legacy) && n_tiles < (1ll << 31);   // the round-1 kernel knows int64 planes only
 #define PRL_LAUNCH_FAST(M)                                                                            \
-        do { if (P.compact) { if (wide) threshold_fast_kernel<M, 256, true><<<fg, 256, 0, ctx->stream>>>(A, F);     \
-                              else threshold_fast_kernel<M, 128, true><<<fg, 128, 0, ctx->stream>>>(A, F); }          \
-             else { if (wide) threshold_fast_kernel<M, 256, false><<<fg, 256, 0, ctx->stream>>>(A, F);               \
-                    else threshold_fast_kernel<M, 128, false><<<fg, 128, 0, ctx->stream>>>(A, F); } } while (0)
+        do { if (stream_ok) {                                                                         \
+                 if (P.compact) { if (wide) threshold_stream_kernel<M, 256, true><<<pg, 256, 0, ctx->stream>>>(A, F, fg.x, fg.y, n_pages);    \
+                                  else threshold_stream_kernel<M, 128, true><<<pg, 128, 0, ctx->stream>>>(A, F, fg.x, fg.y, n_pages); }        \
+                 else { if (wide) threshold_stream_kernel<M, 256, false><<<pg, 256, 0, ctx->stream>>>(A, F, fg.x, fg.y, n_pages);             \
+                        else threshold_stream_kernel<M, 128, false><<<pg, 128, 0, ctx->stream>>>(A, F, fg.x, fg.y, n_pages); }                 \
+             } else { if (wide) threshold_fast_kernel<M, 256><<<fg, 256, 0, ctx->stream>>>(A, F);                    \
+                      else threshold_fast_kernel<M, 128><<<fg, 128, 0, ctx->stream>>>(A, F); } } while (0)
         switch (method) {
         case PRL_SAUVOLA:    PRL_LAUNCH_FAST(PRL_SAUVOLA); break;
         case PRL_NIBLACK:    PRL_LAUNCH_FAST(PRL_NIBLACK); break;

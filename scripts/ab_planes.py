@@ -35,14 +35,15 @@ def run(name, method, params, window, n, rows, cols, morph=0):
     rc, orow, ocol = ctx.output_shape(method, rows, cols, window)
     ostep = (ocol + 15) // 16 * 16
     outs = {}
-    for mode in ("int64", "compact"):
+    for mode in ("int64", "compact-noTMA-K2", "compact"):
         ctx.set_option("disable_compact", 1 if mode == "int64" else 0)
+        ctx.set_option("thr_no_tma", 1 if mode == "compact-noTMA-K2" else 0)
         out = torch.empty((n, orow, ostep), dtype=torch.uint8, device="cuda")
         ms, fam = timed(lambda: ctx.binarize_local_batch_dev(method, buf.data_ptr(), n, rows, cols, step, rows * step, window, params, morph,
                                                               out.data_ptr(), ostep, orow * ostep))
         outs[mode] = out[:, :, :ocol].clone()
         print(json.dumps({"config": name, "planes": mode, "ms_per_step": round(ms, 3), "pages_per_sec": round(n / ms * 1e3, 1), "kernels_ms": fam}), flush=True)
-    print(json.dumps({"config": name, "masks_equal": bool(torch.equal(outs["int64"], outs["compact"]))}), flush=True)
+    print(json.dumps({"config": name, "masks_equal": bool(torch.equal(outs["int64"], outs["compact"]) and torch.equal(outs["int64"], outs["compact-noTMA-K2"]))}), flush=True)
 
 
 A4 = (3508, 2480); A3 = (9921, 7016)
