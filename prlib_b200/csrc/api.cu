@@ -208,7 +208,8 @@ extern "C" int prl_cuda_set_option(prl_cuda_ctx* c, const char* name, long long 
     else if (strcmp(name, "thr_legacy") == 0) c->thr_legacy = value != 0;
     else if (strcmp(name, "thr_no_tma") == 0) c->thr_no_tma = value != 0;
     else if (strcmp(name, "dbg_skip_exact") == 0) c->dbg_skip_exact = value != 0;
-    else if (strcmp(name, "thr_stages") == 0) c->thr_stages = value == 2 ? 2 : 3;
+    else if (strcmp(name, "thr_stages") == 0) c->thr_stages = value == 3 ? 3 : 2;
+    else if (strcmp(name, "k1_bands") == 0) c->k1_bands = (int)std::min<long long>(std::max<long long>(value, 0), 64);
     else if (strcmp(name, "enable_fused") == 0) c->use_fused = value != 0;
     else if (strcmp(name, "morph_bytes") == 0) c->morph_bytes = value != 0;
     else if (strcmp(name, "thr_rows") == 0) c->thr_rows = value <= 0 ? 0 : ((int)std::min<long long>(std::max<long long>(value, 2), 64) & ~1);

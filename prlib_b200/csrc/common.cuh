@@ -81,7 +81,8 @@ struct prl_cuda_ctx {
 
     bool force_exact = false;   // validation: kernel 2 runs the literal FP64 path for every pixel
     bool dbg_skip_exact = false; // DIAGNOSTIC ONLY: kernel 2 (TMA) leaves undecided pixels black; timing experiments, never a result
-    int thr_stages = 3;         // kernel 2 (TMA): ring stages per CTA (3: two CTAs per SM, 2: three CTAs per SM)
+    int k1_bands = 0;           // kernel 1: row bands per page (0 = automatic)
+    int thr_stages = 2;         // kernel 2 (TMA): ring stages per CTA (2: three CTAs per SM -- measured 7 % faster; 3: two CTAs per SM)
     bool thr_no_tma = false;    // validation: kernel 2 on compact planes runs the register-staged streaming kernel instead of the TMA ring
     bool thr_legacy = false;    // validation: kernel 2's mask path runs the round-1 two-tier kernel instead of the streaming kernel
     bool no_compact = false;    // validation: the two-kernel path keeps full int64 planes (16 B per padded pixel) instead of the compact layout

@@ -531,6 +531,7 @@ band_carry_kernel(const unsigned long long* __restrict__ colsum, long long* __re
 
 int prl_choose_bands(const prl_cuda_ctx* ctx, int n_pages, int rows, int ctas_per_sm)
 {
+    if (ctx->k1_bands > 0) return std::max(1, std::min(ctx->k1_bands, rows / 32));   // tuning knob (set_option "k1_bands")
     const int want = ctas_per_sm * ctx->num_sms;
     if (n_pages >= want - want / 4) return 1;   // >= 1.5 pages per SM: the batch alone fills the machine
     int bands = want / n_pages;                 // floor: one full wave of CTAs, never a small second wave

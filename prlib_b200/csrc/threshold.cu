@@ -524,7 +524,8 @@ __device__ __forceinline__ float rsq_approx(float x)
     return r;
 }
 
-template <int METHOD, bool WIDE, int NS>
+// N32: the variance numerator N = w^2 Q - S^2 fits 32 bits (w <= 15); SMALLS: S_win < 2^23 (w <= 181, magic-number int -> float)
+template <int METHOD, bool WIDE, int NS, bool N32>
 __global__ void __launch_bounds__(kTmaThreads, (NS == 2) ? 3 : 2)
 threshold_tma_kernel(const __grid_constant__ CUtensorMap tmSQ, const __grid_constant__ CUtensorMap tmP, const ThrArgs A,
                      const FastArgs F, int tiles_x, int yblocks, int n_units, int* __restrict__ counter)
@@ -581,27 +582,41 @@ threshold_tma_kernel(const __grid_constant__ CUtensorMap tmSQ, const __grid_cons
     const int rs = tid / (FC / 4);                                // row slot of the pass
     const int j = tid % (FC / 4);
     const int c0 = (j >> 5) * 128 + 2 * (j & 31);                 // first pixel of pair 0; pair 1 starts 64 columns further
-    // loop-invariant shared-memory offsets of the two pairs (own columns and columns + d), and whether they produce output
+    // loop-invariant per pair: shared-memory offsets (own columns, columns + d, pixels) and the output columns left of it
     uint32_t off_a[2], off_b[2];
-    bool col_ok[2];
+    int cmax[2];                                                  // the pair produces output iff x0 < cmax (x0 = first column of the unit)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int c = c0 + 64 * h, cd = c + A.d;
         off_a[h] = (uint32_t)((c >> 8) * (R << 11) + ((c & 255) << 3));
         off_b[h] = (uint32_t)((cd >> 8) * (R << 11) + ((cd & 255) << 3));
-        col_ok[h] = c + 1 + A.d < FC && c < oc;
+        cmax[h] = (c + 1 + A.d < FC && c < oc) ? A.out_cols - c : -0x40000000;
     }
-    const uint32_t ring_u32 = prl_tma::smem_u32(ring);
+    const uint32_t ring_u32 = prl_tma::smem_u32(ring), full_u32 = prl_tma::smem_u32(full), empty_u32 = prl_tma::smem_u32(empty);
+    const uint32_t info_u32 = prl_tma::smem_u32(info);
     const unsigned int dst_step = (unsigned int)A.dst_step;
-    const float mu_hi0 = 0.5f, kwf = F.kwf, inv_w2f = F.inv_w2f;
+    // method constants with 1/w^2 folded in where the formula allows: sd always appears as (fn * rsqrt(fn)) * inv_w2
+    const float kwf = F.kwf, inv_w2f = F.inv_w2f, n_floor = F.n_floor;
+    const float c0f = F.c0, c1f = F.c1, c2f = F.c2;
+    const unsigned int w2 = F.w2;
 
     int cur_page = -1;
     double imin = 0.0, coeff = 0.0;
     float iminf = 0.f, coefff = 0.f, mu = F.mu0;
     for (int k = 0;; ++k) {
         const int stage = k % NS;
-        prl_tma::mbar_wait(&full[stage], (uint32_t)((k / NS) & 1));
-        const int4 ui = info[stage];
+        {   // wait for the stage (suspending try_wait: the hardware parks the warp instead of spinning)
+            const uint32_t bar = full_u32 + 8u * (uint32_t)stage, parity = (uint32_t)((k / NS) & 1);
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "WAITF_%=:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+                "@p bra DONEF_%=;\n\t"
+                "bra WAITF_%=;\n\t"
+                "DONEF_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+        }
+        int4 ui;
+        asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(ui.x), "=r"(ui.y), "=r"(ui.z), "=r"(ui.w) : "r"(info_u32 + 16u * (uint32_t)stage));
         const int page = ui.x;
         if (page < 0) break;
         if ((METHOD == PRL_WOLFJOLION || METHOD == PRL_FENG) && page != cur_page) {
@@ -614,70 +629,76 @@ threshold_tma_kernel(const __grid_constant__ CUtensorMap tmSQ, const __grid_cons
                 if (!(mu < 0.25f)) mu = 1e30f;       // degenerate s_max: every pixel takes the exact path
             }
         }
+        const float g_white = 0.5f + mu, g_black = 0.5f - mu;     // the -0.5 of (p - 0.5) - T rides in the comparison
         const uint32_t st = ring_u32 + (uint32_t)stage * kTmaStageBytes;
         const int x0 = ui.z * oc, yu = ui.y * R;
-        uint8_t* obase = A.dst + (size_t)page * A.dst_page_stride + (size_t)yu * dst_step + x0;
+        uint8_t* const obase = A.dst + (size_t)(unsigned int)page * A.dst_page_stride + (size_t)((unsigned int)yu * dst_step + (unsigned int)x0);
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
             const int rr = rs + pass * RPP;                       // row of the unit
             const int y = yu + rr;
-            if (y >= A.out_rows) continue;
+            if (y < A.out_rows) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c = c0 + 64 * h;
-                const int x = x0 + c;
-                if (!(col_ok[h] && x < A.out_cols)) continue;
-                // taps: a = top[c], b = top[c + d], c = bottom[c], d = bottom[c + d]; each load = 2 pixels x {S lo, Q lo}
-                const uint32_t ra = st + (uint32_t)(rr << 11) + off_a[h], rb = st + (uint32_t)(rr << 11) + off_b[h];
-                const uint4 ta = lds128(ra), tb = lds128(rb), ba = lds128(ra + kTmaPix * 8), bb = lds128(rb + kTmaPix * 8);
-                const unsigned int p2 = lds16(st + 2 * kTmaPix * 8 + (uint32_t)(rr * FC + c));
-                const unsigned int sw[2] = {(bb.x - ba.x) - (tb.x - ta.x), (bb.z - ba.z) - (tb.z - ta.z)};
-                const unsigned int qw[2] = {(bb.y - ba.y) - (tb.y - ta.y), (bb.w - ba.w) - (tb.w - ta.w)};
-                unsigned int o2 = 0, und = 0;
+                for (int h = 0; h < 2; ++h) {
+                    if (x0 < cmax[h]) {
+                        const int c = c0 + 64 * h;
+                        // taps: a = top[c], b = top[c + d], c = bottom[c], d = bottom[c + d]; each load = 2 pixels x {S lo, Q lo}
+                        const uint32_t ra = st + (uint32_t)(rr << 11) + off_a[h], rb = st + (uint32_t)(rr << 11) + off_b[h];
+                        const uint4 ta = lds128(ra), tb = lds128(rb), ba = lds128(ra + kTmaPix * 8), bb = lds128(rb + kTmaPix * 8);
+                        const unsigned int p2 = lds16(st + 2 * kTmaPix * 8 + (uint32_t)(rr * FC + c));
+                        const unsigned int sw[2] = {(bb.x - ba.x) - (tb.x - ta.x), (bb.z - ba.z) - (tb.z - ta.z)};
+                        const unsigned int qw[2] = {(bb.y - ba.y) - (tb.y - ta.y), (bb.w - ba.w) - (tb.w - ta.w)};
+                        unsigned int o2 = 0, und = 0;
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const float pm = u8_to_float(p2, i) - mu_hi0;
-                    const float mf = small_s ? __uint_as_float(0x4B000000u + sw[i]) - 8388608.0f : (float)sw[i];
-                    const float m = mf * kwf;
-                    const float fn = n_to_float(F, sw[i], qw[i]);          // N = w^2 Q - S^2, exact and >= 0 before the conversion
-                    const float sd = (fn * rsq_approx(fn)) * inv_w2f;      // fn == 0 gives NaN -> undecided (or the all-zero window below)
-                    float T;
-                    if (METHOD == PRL_SAUVOLA) T = m * fmaf(sd, F.c1, F.c2);
-                    else if (METHOD == PRL_NIBLACK) T = fmaf(F.c0, sd, m);
-                    else if (METHOD == PRL_WOLFJOLION) T = fmaf(fmaf(sd, coefff, -F.c0), m - iminf, m);
-                    else if (METHOD == PRL_NICK) T = fmaf(F.c0, sqrtf(fmaf(m, m, sd * sd)), m);
-                    else T = fmaf(F.c1, m, fmaf(F.c2, iminf, -iminf));
-                    const float g = pm - fmaxf(T, 0.0f);
-                    const bool ok = fn >= F.n_floor;
-                    const bool white = ok && g > mu;
-                    const bool black = (ok && g < -mu) || qw[i] == 0u;     // all-zero window => p == 0 => (0 > T8) is false
-                    if (white) o2 |= 0xffu << (8 * i);
-                    if (!(white || black)) und |= 1u << i;
-                }
-                if (und && !F.dbg_skip_exact) {                             // ~1e-3 of the pixels: the reference arithmetic, literally
+                        for (int i = 0; i < 2; ++i) {
+                            const float pf = u8_to_float(p2, i);
+                            const float mf = small_s ? __uint_as_float(0x4B000000u + sw[i]) - 8388608.0f : (float)sw[i];
+                            const float m = mf * kwf;
+                            float fn;                                              // N = w^2 Q - S^2, exact and >= 0 before the conversion
+                            if (N32) fn = (float)(w2 * qw[i] - sw[i] * sw[i]);
+                            else fn = n_to_float(F, sw[i], qw[i]);
+                            const float sd = (fn * rsq_approx(fn)) * inv_w2f;      // fn == 0 gives NaN -> undecided (or the all-zero window below)
+                            float T;
+                            if (METHOD == PRL_SAUVOLA) T = m * fmaf(sd, c1f, c2f);
+                            else if (METHOD == PRL_NIBLACK) T = fmaf(c0f, sd, m);
+                            else if (METHOD == PRL_WOLFJOLION) T = fmaf(fmaf(sd, coefff, -c0f), m - iminf, m);
+                            else if (METHOD == PRL_NICK) T = fmaf(c0f, sqrtf(fmaf(m, m, sd * sd)), m);
+                            else T = fmaf(c1f, m, fmaf(c2f, iminf, -iminf));
+                            const float g = pf - fmaxf(T, 0.0f);                   // (p - 0.5) - T  =  g - 0.5
+                            const bool ok = fn >= n_floor;
+                            const bool white = ok && g > g_white;
+                            const bool black = (ok && g < g_black) || qw[i] == 0u; // all-zero window => p == 0 => (0 > T8) is false
+                            o2 |= white ? (0xffu << (8 * i)) : 0u;
+                            und |= (white || black) ? 0u : (1u << i);
+                        }
+                        const int x = x0 + c;
+                        if (und && !F.dbg_skip_exact) {                             // ~1e-3 of the pixels: the reference arithmetic, literally
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        if (((und >> i) & 1u) && x + i < A.out_cols) {
-                            const unsigned int p = (p2 >> (8 * i)) & 0xffu;
-                            const int t8 = exact_t8_compact<METHOD>(reinterpret_cast<const uint2*>(A.S) + (size_t)page * A.plane_page_stride,
-                                                                    A.AH + (size_t)page * A.a_page_stride, A.pitch, A.a_pitch, A.ashift, y, x + i,
-                                                                    A.d, A.kw, A.p0, A.p1, A.p2, imin, coeff);
-                            if ((int)p > t8) o2 |= 0xffu << (8 * i);
+                            for (int i = 0; i < 2; ++i) {
+                                if (((und >> i) & 1u) && x + i < A.out_cols) {
+                                    const unsigned int p = (p2 >> (8 * i)) & 0xffu;
+                                    const int t8 = exact_t8_compact<METHOD>(reinterpret_cast<const uint2*>(A.S) + (size_t)page * A.plane_page_stride,
+                                                                            A.AH + (size_t)page * A.a_page_stride, A.pitch, A.a_pitch, A.ashift, y, x + i,
+                                                                            A.d, A.kw, A.p0, A.p1, A.p2, imin, coeff);
+                                    if ((int)p > t8) o2 |= 0xffu << (8 * i);
+                                }
+                            }
+                        }
+                        // dst may be dense (pitch == out_cols, odd): a pair goes out as one 16-bit store where its address allows
+                        uint8_t* op = obase + ((unsigned int)rr * dst_step + (unsigned int)c);
+                        if (x0 + 1 < cmax[h] && (((uintptr_t)op) & 1u) == 0) {
+                            *reinterpret_cast<unsigned short*>(op) = (unsigned short)o2;
+                        } else {
+                            op[0] = (uint8_t)o2;
+                            if (x0 + 1 < cmax[h]) op[1] = (uint8_t)(o2 >> 8);
                         }
                     }
-                }
-                // dst may be dense (pitch == out_cols, odd): a pair goes out as one 16-bit store where its address allows
-                uint8_t* op = obase + (unsigned int)rr * dst_step + (unsigned int)c;
-                if (x + 1 < A.out_cols && (((uintptr_t)op) & 1u) == 0) {
-                    *reinterpret_cast<unsigned short*>(op) = (unsigned short)o2;
-                } else {
-                    op[0] = (uint8_t)o2;
-                    if (x + 1 < A.out_cols) op[1] = (uint8_t)(o2 >> 8);
                 }
             }
         }
         __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&empty[stage]);        // this warp is done with the stage
+        if ((tid & 31) == 0)                                      // this warp is done with the stage
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_u32 + 8u * (uint32_t)stage) : "memory");
     }
 }
 
@@ -705,15 +726,16 @@ int launch_tma_threshold(prl_cuda_ctx* ctx, const ThrArgs& A, const FastArgs& F,
         return PRL_OK;
     int rc = prl_ensure(ctx, &ctx->sched, &ctx->sched_bytes, 256); if (rc) return rc;
     PRL_CUDA_TRY(ctx, cudaMemsetAsync(ctx->sched, 0, sizeof(int), ctx->stream));
-    const int ns = ctx->thr_stages == 2 ? 2 : 3;
+    const int ns = ctx->thr_stages == 3 ? 3 : 2;
     const size_t smem = (size_t)ns * kTmaStageBytes;
     const int grid = (int)std::min<long long>(n_units, (long long)ctx->num_sms * (ns == 2 ? 3 : 2));
-#define PRL_LAUNCH_TMA(W, N)                                                                                          \
-    do { auto kfn = threshold_tma_kernel<METHOD, W, N>;                                                               \
+#define PRL_LAUNCH_TMA(W, N, B)                                                                                       \
+    do { auto kfn = threshold_tma_kernel<METHOD, W, N, B>;                                                            \
          PRL_CUDA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
          kfn<<<grid, kTmaThreads, smem, ctx->stream>>>(tmSQ, tmP, A, F, tiles_x, yblocks, (int)n_units, (int*)ctx->sched); } while (0)
-    if (wide) { if (ns == 2) PRL_LAUNCH_TMA(true, 2); else PRL_LAUNCH_TMA(true, 3); }
-    else { if (ns == 2) PRL_LAUNCH_TMA(false, 2); else PRL_LAUNCH_TMA(false, 3); }
+    if (wide) { if (ns == 2) PRL_LAUNCH_TMA(true, 2, false); else PRL_LAUNCH_TMA(true, 3, false); }   // d > 64: N never fits 32 bits
+    else if (F.n32) { if (ns == 2) PRL_LAUNCH_TMA(false, 2, true); else PRL_LAUNCH_TMA(false, 3, true); }
+    else { if (ns == 2) PRL_LAUNCH_TMA(false, 2, false); else PRL_LAUNCH_TMA(false, 3, false); }
 #undef PRL_LAUNCH_TMA
     *launched = true;
     return PRL_OK;

@@ -21,12 +21,13 @@ def run(tag, method, params, window, **opts):
     torch.cuda.synchronize(); t = ctx.timing(); ctx.timing_enable(False)
     print(json.dumps({"tag": tag, **{k: round(v["ms"] / 5, 3) for k, v in t.items()}, "white": round(float((out[:4, :, :ocol] == 255).float().mean()), 5)}), flush=True)
     for k in opts: ctx.set_option(k, 0)
-run("sauvola tma ns3", capi.SAUVOLA, (0.2,), 15)
-run("sauvola tma ns2", capi.SAUVOLA, (0.2,), 15, thr_stages=2)
-ctx.set_option("thr_stages", 3)
-run("sauvola tma ns3 skip-exact", capi.SAUVOLA, (0.2,), 15, dbg_skip_exact=1)
-run("niblack tma ns3", capi.NIBLACK, (-0.2,), 15)
-run("wj tma ns3", capi.WOLFJOLION, (0.5,), 15)
-run("sauvola w=31 tma ns3", capi.SAUVOLA, (0.2,), 31)
-run("sauvola w=101 tma ns3", capi.SAUVOLA, (0.01,), 101)
-run("sauvola w=101 tma ns2", capi.SAUVOLA, (0.01,), 101, thr_stages=2)
+run("sauvola ns3", capi.SAUVOLA, (0.2,), 15)
+run("sauvola ns2", capi.SAUVOLA, (0.2,), 15, thr_stages=2)
+run("sauvola ns2 bands2", capi.SAUVOLA, (0.2,), 15, thr_stages=2, k1_bands=2)
+run("sauvola ns2 bands3", capi.SAUVOLA, (0.2,), 15, thr_stages=2, k1_bands=3)
+run("sauvola ns2 bands5", capi.SAUVOLA, (0.2,), 15, thr_stages=2, k1_bands=5)
+run("niblack ns2", capi.NIBLACK, (-0.2,), 15, thr_stages=2)
+run("wj ns2", capi.WOLFJOLION, (0.5,), 15, thr_stages=2)
+run("sauvola w=31 ns2", capi.SAUVOLA, (0.2,), 31, thr_stages=2)
+run("sauvola w=101 ns3", capi.SAUVOLA, (0.01,), 101)
+run("sauvola w=101 ns2", capi.SAUVOLA, (0.01,), 101, thr_stages=2)
