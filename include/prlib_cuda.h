@@ -160,12 +160,30 @@ int prl_cuda_synth_pages_dev(prl_cuda_ctx* ctx, uint8_t* d_dst, int n_pages, int
 
 /* ---- host batch + page dispatcher -------------------------------------------------------
  * n_pages contiguous rows x cols u8 pages in host memory -> n_pages contiguous out_rows x
- * out_cols masks.  Pages are sharded in contiguous ranges over `devices` (one host thread, one
- * context and a 3-deep pinned staging ring per device; no collective).  devices == NULL or
- * n_dev <= 0 means "every visible device". */
+ * out_cols masks.  Pages are sharded in contiguous ranges over `devices` (one host thread and one
+ * cached worker per device: a context, three streams and a 3-slot ring of DEVICE buffers so that the
+ * H2D copy of chunk i+1, the kernels of chunk i and the D2H copy of chunk i-1 overlap; no collective).
+ * devices == NULL or n_dev <= 0 means "every visible device".
+ * Host memory: page-locked buffers (prl_cuda_host_alloc, prl_cuda_host_register, cudaMallocHost, a torch
+ * pin_memory() tensor) go to the copy engines directly and are what the quoted end-to-end throughput needs.
+ * Pageable buffers are detected (cudaPointerGetAttributes) and staged through library-owned pinned bounce
+ * buffers with one memcpy per direction on the worker thread: correct overlap, bound by the host memcpy.
+ * Threading: the call takes no context and is re-entrant; concurrent callers that name the same device take
+ * turns on that device's worker (a mutex held for the caller's whole shard).  After an error nothing is left in
+ * flight on the caller's buffers and the worker is rebuilt on the next call. */
 int prl_cuda_binarize_batch(const int* devices, int n_dev, int method, const uint8_t* pages, int n_pages,
                             int rows, int cols, int window, const double* params, int morph_iters,
                             uint8_t* masks);
+/* Page-locked host memory for the batch loader ("pinned-memory batch loader" of the north star): alloc/free a
+ * portable pinned range, or pin/unpin a range the caller already owns (e.g. the data of a cv::Mat or an mmap). */
+int prl_cuda_host_alloc(size_t bytes, void** out);
+int prl_cuda_host_free(void* p);
+int prl_cuda_host_register(void* p, size_t bytes);
+int prl_cuda_host_unregister(void* p);
+/* Process-wide options of the ctx-less entry points: "batch_chunk_pages" (pages per ring slot, 0 = automatic,
+ * about 72 MiB of input), "batch_stage_pageable" (1 = bounce pageable memory through pinned buffers, default;
+ * 0 = hand it to the driver as it is).  PRL_E_INVALID for an unknown name. */
+int prl_cuda_set_global_option(const char* name, long long value);
 
 /* ---- edge front-end of prl::binarizeLocalOtsu -----------------------
  * prl_cuda_canny_edge_detection = CannyEdgeDetection (src/imageLibCommon.cpp:244-324: GaussianBlur k x k sigma 0,

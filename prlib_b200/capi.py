@@ -55,6 +55,11 @@ SIGNATURES = {
                                           C.c_void_p]),
     "prl_cuda_binarize_batch_packed": (C.c_int, [_intp, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, C.c_int,
                                                  C.c_void_p]),
+    "prl_cuda_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "prl_cuda_host_free": (C.c_int, [C.c_void_p]),
+    "prl_cuda_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "prl_cuda_host_unregister": (C.c_int, [C.c_void_p]),
+    "prl_cuda_set_global_option": (C.c_int, [C.c_char_p, C.c_longlong]),
     "prl_cuda_pack_mask_dev": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p]),
     "prl_cuda_clahe": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_double, C.c_int, C.c_void_p, C.c_size_t]),
     "prl_cuda_binarize_local_otsu": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,

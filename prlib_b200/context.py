@@ -330,6 +330,41 @@ def default_context(device: int = 0) -> Context:
     return d[device]
 
 
+class PinnedArray:
+    """A page-locked host buffer of the batch loader (prl_cuda_host_alloc) seen as a numpy array (`.array`).
+    Keep the object alive while the array is in use; close() (or garbage collection) frees the range."""
+
+    def __init__(self, shape, dtype=np.uint8):
+        L = capi.load()
+        self._n = max(1, int(np.prod(shape)) * np.dtype(dtype).itemsize)
+        p = C.c_void_p()
+        rc = L.prl_cuda_host_alloc(self._n, C.byref(p))
+        if rc != capi.PRL_OK:
+            raise PrlCudaError(rc, (L.prl_cuda_last_error(None) or b"").decode())
+        self._ptr = p.value
+        self.array = np.frombuffer((C.c_uint8 * self._n).from_address(self._ptr), dtype=dtype,
+                                   count=int(np.prod(shape))).reshape(shape)
+
+    def close(self):
+        if getattr(self, "_ptr", None):
+            self.array = None
+            capi.load().prl_cuda_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def set_global_option(name: str, value: int):
+    """prl_cuda_set_global_option: "batch_chunk_pages", "batch_stage_pageable"."""
+    rc = capi.load().prl_cuda_set_global_option(name.encode(), int(value))
+    if rc != capi.PRL_OK:
+        raise ValueError(f"unknown global option {name!r}")
+
+
 def unpack_lept1(bits: np.ndarray, cols: int) -> np.ndarray:
     """(..., rows, wpl) uint32 PIX words (pixel x at bit 31 - (x & 31) of word x >> 5, 1 = black) -> 0/255 u8 masks."""
     b = np.unpackbits(np.ascontiguousarray(bits).astype(">u4").view(np.uint8), axis=-1)[..., :cols]

@@ -10,7 +10,16 @@
 #include <memory>
 #include <algorithm>
 
+#include <atomic>
+#include <condition_variable>
+
 static thread_local std::string g_create_err;
+
+// process-wide knobs of the ctx-less batch entry points (prl_cuda_set_global_option)
+static std::atomic<long long> g_batch_chunk_pages{0};     // pages per ring slot, 0 = automatic (~72 MiB of input)
+static std::atomic<long long> g_batch_pageable{1};        // 1: pageable host buffers are staged through library-owned pinned
+                                                          //    bounce buffers (correct overlap, host-memcpy bound); 0: handed to the
+                                                          //    driver as they are (synchronous staged copies, no overlap)
 
 // ------------------------------------------------------------------------------------------------
 // plumbing
@@ -35,16 +44,6 @@ int prl_ensure(prl_cuda_ctx* ctx, void** ptr, size_t* have, size_t need)
     cudaError_t e = cudaMalloc(ptr, need);
     if (e != cudaSuccess) { *ptr = nullptr; return prl_set_err(ctx, PRL_E_NOMEM, "cudaMalloc", e); }
     *have = need;
-    return PRL_OK;
-}
-
-int prl_ensure_pinned(prl_cuda_ctx* ctx, size_t need)
-{
-    if (need <= ctx->h_pin_bytes && ctx->h_pin) return PRL_OK;
-    if (ctx->h_pin) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->h_pin); ctx->h_pin = nullptr; ctx->h_pin_bytes = 0; }
-    cudaError_t e = cudaMallocHost((void**)&ctx->h_pin, need);
-    if (e != cudaSuccess) { ctx->h_pin = nullptr; return prl_set_err(ctx, PRL_E_NOMEM, "cudaMallocHost", e); }
-    ctx->h_pin_bytes = need;
     return PRL_OK;
 }
 
@@ -168,7 +167,6 @@ extern "C" void prl_cuda_destroy(prl_cuda_ctx* c)
     cudaFree(c->sched); cudaFree(c->planes); cudaFree(c->carry); cudaFree(c->colsum); cudaFree(c->scalars); cudaFree(c->fused_ws);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
     cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_tmp); cudaFree(c->d_misc); cudaFree(c->d_bgr); cudaFree(c->edges_ws); cudaFree(c->rects_ws); cudaFree(c->clahe_ws);
-    if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -785,6 +783,17 @@ extern "C" int prl_cuda_binarize_local_otsu(prl_cuda_ctx* c, const uint8_t* src,
     if (n_rects) *n_rects = count;
     if (count == 0) return prl_set_err(c, PRL_E_INVALID, "Contours array is empty");                  // imageLibCommon.cpp:643-646
     if (count > kCap) return prl_set_err(c, PRL_E_UNSUPPORTED, "more than 65535 contours");
+    if (rows == 1 || cols == 1) {
+        // Every component of a one-pixel-wide image is a straight run: its CHAIN_APPROX_SIMPLE contour has 1 or 2
+        // points and CheckHierarhyLevelRecursively ignores contours with fewer than 3 (imageLibCommon.cpp:729-736), so
+        // no rectangle is thresholded and the result stays 255 (binarizeLocalOtsu.cpp:142).  With 2 or more rows and
+        // columns a component of the 3x-dilated edge map always holds a 2 x 2 block, i.e. at least 4 contour points.
+        if (n_rects) *n_rects = 0;
+        PRL_CUDA_TRY(c, cudaMemset2DAsync(c->d_out, o_step, 255, cols, rows, c->stream));
+        PRL_CUDA_TRY(c, cudaMemcpy2DAsync(dst, dst_step, c->d_out, o_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
+        PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        return PRL_OK;
+    }
     if (rects_out && rects_cap > 0)
         PRL_CUDA_TRY(c, cudaMemcpyAsync(rects_out, d_xywh, (size_t)std::min(count, rects_cap) * 16, cudaMemcpyDeviceToHost, c->stream));
     rc = prl_k_otsu_rects(c, d_proc, rows, cols, in_step, d_xywh, count, maxval, c->d_out, o_step, d_thr); if (rc) return rc;
@@ -944,55 +953,76 @@ namespace {
 
 struct DeviceWorker {
     prl_cuda_ctx* ctx = nullptr;
+    std::mutex busy;                                          // held for a whole shard: concurrent callers on one device take turns
     cudaStream_t s_in = nullptr, s_out = nullptr;
     static constexpr int NBUF = 3;
     uint8_t* d_in[NBUF] = {nullptr, nullptr, nullptr};
     uint8_t* d_out[NBUF] = {nullptr, nullptr, nullptr};
     uint32_t* d_bits[NBUF] = {nullptr, nullptr, nullptr};     // packed variant: 1 bit per pixel leaves the device
-    size_t in_bytes = 0, out_bytes = 0, bits_bytes = 0;
+    uint8_t* h_in[NBUF] = {nullptr, nullptr, nullptr};        // pinned bounce buffers, only for pageable caller memory
+    uint8_t* h_out[NBUF] = {nullptr, nullptr, nullptr};
+    size_t in_bytes = 0, out_bytes = 0, bits_bytes = 0, h_in_bytes = 0, h_out_bytes = 0;
     cudaEvent_t ev_in[NBUF], ev_comp[NBUF], ev_out[NBUF];
-    bool events = false;
+    int n_events = 0;
+    bool poisoned = false;                                    // a CUDA error occurred: the worker is rebuilt on the next call
     ~DeviceWorker()
     {
         if (!ctx) return;
         cudaSetDevice(ctx->device);
-        for (int i = 0; i < NBUF; ++i) { cudaFree(d_in[i]); cudaFree(d_out[i]); cudaFree(d_bits[i]); }
-        if (events) for (int i = 0; i < NBUF; ++i) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_comp[i]); cudaEventDestroy(ev_out[i]); }
+        cudaDeviceSynchronize();
+        for (int i = 0; i < NBUF; ++i) {
+            cudaFree(d_in[i]); cudaFree(d_out[i]); cudaFree(d_bits[i]);
+            if (h_in[i]) cudaFreeHost(h_in[i]);
+            if (h_out[i]) cudaFreeHost(h_out[i]);
+        }
+        for (int i = 0; i < n_events; ++i) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_comp[i]); cudaEventDestroy(ev_out[i]); }
         if (s_in) cudaStreamDestroy(s_in);
         if (s_out) cudaStreamDestroy(s_out);
         prl_cuda_destroy(ctx);
+        cudaGetLastError();
     }
 };
 
 std::mutex g_workers_mu;
 // cached per device across calls; leaked on purpose (no CUDA calls from static destructors at exit)
-auto& g_workers = *new std::map<int, std::unique_ptr<DeviceWorker>>();
+auto& g_workers = *new std::map<int, std::shared_ptr<DeviceWorker>>();
 
-DeviceWorker* get_worker(int device, std::string* err)
+std::shared_ptr<DeviceWorker> get_worker(int device, std::string* err)
 {
     std::lock_guard<std::mutex> lk(g_workers_mu);
     auto it = g_workers.find(device);
-    if (it != g_workers.end()) return it->second.get();
-    std::unique_ptr<DeviceWorker> w(new DeviceWorker());
+    if (it != g_workers.end()) {
+        if (!it->second->poisoned) return it->second;
+        g_workers.erase(it);                                  // the last user still holds a reference; it is destroyed when that ends
+    }
+    std::shared_ptr<DeviceWorker> w(new DeviceWorker());
     int rc = prl_cuda_create(device, &w->ctx);
     if (rc) { *err = prl_cuda_last_error(nullptr); w->ctx = nullptr; return nullptr; }
-    cudaStreamCreateWithFlags(&w->s_in, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&w->s_out, cudaStreamNonBlocking);
-    for (int i = 0; i < DeviceWorker::NBUF; ++i) {
-        cudaEventCreateWithFlags(&w->ev_in[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&w->ev_comp[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&w->ev_out[i], cudaEventDisableTiming);
+    cudaError_t e = cudaStreamCreateWithFlags(&w->s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->s_out, cudaStreamNonBlocking);
+    for (int i = 0; e == cudaSuccess && i < DeviceWorker::NBUF; ++i) {
+        e = cudaEventCreateWithFlags(&w->ev_in[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->ev_comp[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->ev_out[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) w->n_events = i + 1;
     }
-    w->events = true;
-    DeviceWorker* p = w.get();
-    g_workers[device] = std::move(w);
-    return p;
+    if (e != cudaSuccess) { *err = std::string("batch worker: ") + cudaGetErrorString(e); cudaGetLastError(); return nullptr; }
+    g_workers[device] = w;
+    return w;
+}
+
+// is this host range page-locked (cudaMallocHost / cudaHostRegister / prl_cuda_host_alloc)?
+bool host_range_pinned(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
 }
 
 // pages [p0, p1) of the batch on one device: 3-slot ring, H2D / kernels / D2H on three streams
-int run_shard(DeviceWorker* w, int method, const uint8_t* pages, int p0, int p1, int rows, int cols, int window,
-              const double* params, int morph_iters, uint8_t* masks, const prl_geom& g, std::string* err,
-              uint32_t* packed = nullptr)
+int run_shard_locked(DeviceWorker* w, int method, const uint8_t* pages, int p0, int p1, int rows, int cols, int window,
+                     const double* params, int morph_iters, uint8_t* masks, const prl_geom& g, std::string* err,
+                     uint32_t* packed)
 {
     prl_cuda_ctx* c = w->ctx;
 #define SHARD_TRY(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { *err = std::string(#call) + ": " + cudaGetErrorString(_e); return PRL_E_CUDA; } } while (0)
@@ -1001,40 +1031,72 @@ int run_shard(DeviceWorker* w, int method, const uint8_t* pages, int p0, int p1,
     const size_t in_step = round16(cols), o_step = packed ? round16((size_t)g.out_cols) : (size_t)g.out_cols;
     const size_t in_page = in_step * rows, out_page = o_step * g.out_rows;
     const size_t wpl = ((size_t)g.out_cols + 31) / 32, bits_page = wpl * g.out_rows * sizeof(uint32_t);
-    const size_t host_in_page = (size_t)rows * cols, host_out_page = (size_t)g.out_rows * g.out_cols;
+    const size_t host_in_page = (size_t)rows * cols, host_out_page = packed ? bits_page : (size_t)g.out_rows * g.out_cols;
     // chunk: about 64 MiB of input per slot (8 A4 pages; measured best of 4..64), at least 1 page
     int chunk = (int)std::max<size_t>(1, ((size_t)72 << 20) / in_page);
-    if (const char* e = getenv("PRL_BATCH_CHUNK_PAGES")) { int v = atoi(e); if (v > 0) chunk = v; }   // tuning knob
+    const long long forced = g_batch_chunk_pages.load();
+    if (forced > 0) chunk = (int)std::min<long long>(forced, 1 << 20);
     chunk = std::min(chunk, std::max(1, (p1 - p0 + 2) / 3));
     if (in_page * chunk > w->in_bytes || out_page * chunk > w->out_bytes) {
         SHARD_TRY(cudaDeviceSynchronize());
         for (int i = 0; i < DeviceWorker::NBUF; ++i) {
             cudaFree(w->d_in[i]); cudaFree(w->d_out[i]); w->d_in[i] = w->d_out[i] = nullptr;
         }
-        w->in_bytes = in_page * chunk; w->out_bytes = out_page * chunk;
+        w->in_bytes = w->out_bytes = 0;
         for (int i = 0; i < DeviceWorker::NBUF; ++i) {
-            SHARD_TRY(cudaMalloc((void**)&w->d_in[i], w->in_bytes));
-            SHARD_TRY(cudaMalloc((void**)&w->d_out[i], w->out_bytes + 16));
+            SHARD_TRY(cudaMalloc((void**)&w->d_in[i], in_page * chunk));
+            SHARD_TRY(cudaMalloc((void**)&w->d_out[i], out_page * chunk + 16));
         }
+        w->in_bytes = in_page * chunk; w->out_bytes = out_page * chunk;
     }
     if (packed && bits_page * chunk > w->bits_bytes) {
         SHARD_TRY(cudaDeviceSynchronize());
+        for (int i = 0; i < DeviceWorker::NBUF; ++i) { cudaFree(w->d_bits[i]); w->d_bits[i] = nullptr; }
+        w->bits_bytes = 0;
+        for (int i = 0; i < DeviceWorker::NBUF; ++i) SHARD_TRY(cudaMalloc((void**)&w->d_bits[i], bits_page * chunk));
         w->bits_bytes = bits_page * chunk;
-        for (int i = 0; i < DeviceWorker::NBUF; ++i) {
-            cudaFree(w->d_bits[i]); w->d_bits[i] = nullptr;
-            SHARD_TRY(cudaMalloc((void**)&w->d_bits[i], w->bits_bytes));
-        }
     }
+    // Pageable caller memory: cudaMemcpyAsync on it is a synchronous, driver-staged copy and the three-stream overlap is
+    // lost.  Stage through pinned bounce buffers instead (one memcpy per direction on this thread: host-memcpy bound,
+    // but the DMA and the kernels overlap it).  Page-locked memory (prl_cuda_host_alloc / prl_cuda_host_register /
+    // cudaMallocHost) goes to the copy engines directly and is what the quoted end-to-end throughput needs.
+    const bool stage_pageable = g_batch_pageable.load() != 0;
+    const bool bounce_in = stage_pageable && !host_range_pinned(pages);
+    const bool bounce_out = stage_pageable && !host_range_pinned(packed ? (const void*)packed : (const void*)masks);
+    if (bounce_in && host_in_page * chunk > w->h_in_bytes) {
+        SHARD_TRY(cudaDeviceSynchronize());
+        for (int i = 0; i < DeviceWorker::NBUF; ++i) { if (w->h_in[i]) cudaFreeHost(w->h_in[i]); w->h_in[i] = nullptr; }
+        w->h_in_bytes = 0;
+        for (int i = 0; i < DeviceWorker::NBUF; ++i) SHARD_TRY(cudaMallocHost((void**)&w->h_in[i], host_in_page * chunk));
+        w->h_in_bytes = host_in_page * chunk;
+    }
+    if (bounce_out && host_out_page * chunk > w->h_out_bytes) {
+        SHARD_TRY(cudaDeviceSynchronize());
+        for (int i = 0; i < DeviceWorker::NBUF; ++i) { if (w->h_out[i]) cudaFreeHost(w->h_out[i]); w->h_out[i] = nullptr; }
+        w->h_out_bytes = 0;
+        for (int i = 0; i < DeviceWorker::NBUF; ++i) SHARD_TRY(cudaMallocHost((void**)&w->h_out[i], host_out_page * chunk));
+        w->h_out_bytes = host_out_page * chunk;
+    }
+    uint8_t* host_out = packed ? reinterpret_cast<uint8_t*>(packed) : masks;
+    struct Pending { int p, np; };
+    Pending pend[DeviceWorker::NBUF] = {{0, 0}, {0, 0}, {0, 0}};           // bounce_out: chunks whose results sit in h_out[slot]
     int it = 0;
     for (int p = p0; p < p1; p += chunk, ++it) {
         const int np = std::min(chunk, p1 - p);
         const int slot = it % DeviceWorker::NBUF;
         if (it >= DeviceWorker::NBUF) {
+            if (bounce_in) SHARD_TRY(cudaEventSynchronize(w->ev_in[slot]));   // h_in[slot] has left the host
+            if (bounce_out && pend[slot].np) {                                // h_out[slot] arrived: hand it to the caller
+                SHARD_TRY(cudaEventSynchronize(w->ev_out[slot]));
+                memcpy(host_out + (size_t)pend[slot].p * host_out_page, w->h_out[slot], host_out_page * pend[slot].np);
+                pend[slot].np = 0;
+            }
             SHARD_TRY(cudaStreamWaitEvent(w->s_in, w->ev_comp[slot], 0));     // d_in[slot] consumed
             SHARD_TRY(cudaStreamWaitEvent(c->stream, w->ev_out[slot], 0));    // d_out[slot] drained
         }
-        SHARD_TRY(copy2d(w->d_in[slot], in_step, pages + (size_t)p * host_in_page, cols, cols,
-                         (size_t)rows * np, cudaMemcpyHostToDevice, w->s_in));
+        const uint8_t* hsrc = pages + (size_t)p * host_in_page;
+        if (bounce_in) { memcpy(w->h_in[slot], hsrc, host_in_page * np); hsrc = w->h_in[slot]; }
+        SHARD_TRY(copy2d(w->d_in[slot], in_step, hsrc, cols, cols, (size_t)rows * np, cudaMemcpyHostToDevice, w->s_in));
         SHARD_TRY(cudaEventRecord(w->ev_in[slot], w->s_in));
         SHARD_TRY(cudaStreamWaitEvent(c->stream, w->ev_in[slot], 0));
         int rc = prl_cuda_binarize_local_batch_dev(c, method, w->d_in[slot], np, rows, cols, in_step, in_page, window,
@@ -1046,19 +1108,39 @@ int run_shard(DeviceWorker* w, int method, const uint8_t* pages, int p0, int p1,
         }
         SHARD_TRY(cudaEventRecord(w->ev_comp[slot], c->stream));
         SHARD_TRY(cudaStreamWaitEvent(w->s_out, w->ev_comp[slot], 0));
+        uint8_t* hdst = bounce_out ? w->h_out[slot] : host_out + (size_t)p * host_out_page;
         if (packed)
-            SHARD_TRY(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(packed) + (size_t)p * bits_page, w->d_bits[slot], bits_page * np,
-                                      cudaMemcpyDeviceToHost, w->s_out));
+            SHARD_TRY(cudaMemcpyAsync(hdst, w->d_bits[slot], bits_page * np, cudaMemcpyDeviceToHost, w->s_out));
         else
-            SHARD_TRY(copy2d(masks + (size_t)p * host_out_page, g.out_cols, w->d_out[slot], o_step, g.out_cols,
-                             (size_t)g.out_rows * np, cudaMemcpyDeviceToHost, w->s_out));
+            SHARD_TRY(copy2d(hdst, g.out_cols, w->d_out[slot], o_step, g.out_cols, (size_t)g.out_rows * np, cudaMemcpyDeviceToHost, w->s_out));
         SHARD_TRY(cudaEventRecord(w->ev_out[slot], w->s_out));
+        if (bounce_out) pend[slot] = Pending{p, np};
     }
     SHARD_TRY(cudaStreamSynchronize(w->s_out));
     SHARD_TRY(cudaStreamSynchronize(c->stream));
     SHARD_TRY(cudaStreamSynchronize(w->s_in));
+    if (bounce_out)
+        for (int s2 = 0; s2 < DeviceWorker::NBUF; ++s2)
+            if (pend[s2].np) memcpy(host_out + (size_t)pend[s2].p * host_out_page, w->h_out[s2], host_out_page * pend[s2].np);
 #undef SHARD_TRY
     return PRL_OK;
+}
+
+// Serialises callers per device; after ANY failure nothing is left in flight on the caller's buffers (the copies are
+// drained before returning) and the worker is rebuilt on the next call.
+int run_shard(DeviceWorker* w, int method, const uint8_t* pages, int p0, int p1, int rows, int cols, int window,
+              const double* params, int morph_iters, uint8_t* masks, const prl_geom& g, std::string* err,
+              uint32_t* packed = nullptr)
+{
+    std::lock_guard<std::mutex> lk(w->busy);
+    const int rc = run_shard_locked(w, method, pages, p0, p1, rows, cols, window, params, morph_iters, masks, g, err, packed);
+    if (rc) {
+        cudaSetDevice(w->ctx->device);
+        cudaStreamSynchronize(w->s_in); cudaStreamSynchronize(w->ctx->stream); cudaStreamSynchronize(w->s_out);
+        cudaGetLastError();
+        w->poisoned = true;
+    }
+    return rc;
 }
 
 }  // namespace
@@ -1084,9 +1166,9 @@ static int binarize_batch_impl(const int* devices, int n_dev, int method, const 
         const int p0 = (int)((long long)gi * n_pages / G), p1 = (int)((long long)(gi + 1) * n_pages / G);
         if (p1 <= p0) continue;
         auto job = [&, gi, p0, p1]() {
-            DeviceWorker* w = get_worker(devs[gi], &errs[gi]);
+            std::shared_ptr<DeviceWorker> w = get_worker(devs[gi], &errs[gi]);
             if (!w) { rcs[gi] = PRL_E_CUDA; return; }
-            rcs[gi] = run_shard(w, method, pages, p0, p1, rows, cols, window, params, morph_iters, masks, g, &errs[gi], packed);
+            rcs[gi] = run_shard(w.get(), method, pages, p0, p1, rows, cols, window, params, morph_iters, masks, g, &errs[gi], packed);
         };
         if (G == 1) job(); else threads.emplace_back(job);
     }
@@ -1111,4 +1193,49 @@ extern "C" int prl_cuda_binarize_batch_packed(const int* devices, int n_dev, int
                                               uint32_t* bits)
 {
     return binarize_batch_impl(devices, n_dev, method, pages, n_pages, rows, cols, window, params, morph_iters, nullptr, bits);
+}
+
+// ------------------------------------------------------------------------------------------------
+// page-locked host memory for the batch loader, process-wide options
+// ------------------------------------------------------------------------------------------------
+extern "C" int prl_cuda_host_alloc(size_t bytes, void** out)
+{
+    if (!out || bytes == 0) return prl_set_err(nullptr, PRL_E_INVALID, "bad argument");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); *out = nullptr; return prl_set_err(nullptr, PRL_E_NOMEM, "cudaHostAlloc", e); }
+    return PRL_OK;
+}
+
+extern "C" int prl_cuda_host_free(void* p)
+{
+    if (!p) return PRL_OK;
+    cudaError_t e = cudaFreeHost(p);
+    if (e != cudaSuccess) { cudaGetLastError(); return prl_set_err(nullptr, PRL_E_CUDA, "cudaFreeHost", e); }
+    return PRL_OK;
+}
+
+extern "C" int prl_cuda_host_register(void* p, size_t bytes)
+{
+    if (!p || bytes == 0) return prl_set_err(nullptr, PRL_E_INVALID, "bad argument");
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return prl_set_err(nullptr, PRL_E_CUDA, "cudaHostRegister", e); }
+    return PRL_OK;
+}
+
+extern "C" int prl_cuda_host_unregister(void* p)
+{
+    if (!p) return PRL_OK;
+    cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) { cudaGetLastError(); return prl_set_err(nullptr, PRL_E_CUDA, "cudaHostUnregister", e); }
+    return PRL_OK;
+}
+
+extern "C" int prl_cuda_set_global_option(const char* name, long long value)
+{
+    if (!name) return PRL_E_INVALID;
+    if (strcmp(name, "batch_chunk_pages") == 0) g_batch_chunk_pages.store(value < 0 ? 0 : value);
+    else if (strcmp(name, "batch_stage_pageable") == 0) g_batch_pageable.store(value != 0);
+    else return prl_set_err(nullptr, PRL_E_INVALID, "unknown global option");
+    return PRL_OK;
 }

@@ -77,7 +77,6 @@ struct prl_cuda_ctx {
     void* rects_ws = nullptr;   size_t rects_ws_bytes = 0; // contour rectangles: count, list, thresholds, labels, boxes
     void* edges_ws = nullptr;   size_t edges_ws_bytes = 0; // edge front-end: blurred image, 8.8 rows, class map, labels, flags
     // pinned host staging
-    uint8_t* h_pin = nullptr;   size_t h_pin_bytes = 0;
 
     bool force_exact = false;   // validation: kernel 2 runs the literal FP64 path for every pixel
     bool dbg_skip_exact = false; // DIAGNOSTIC ONLY: kernel 2 (TMA) leaves undecided pixels black; timing experiments, never a result
@@ -107,7 +106,6 @@ enum prl_family {
 
 int  prl_set_err(prl_cuda_ctx* ctx, int code, const char* what, cudaError_t ce = cudaSuccess);
 int  prl_ensure(prl_cuda_ctx* ctx, void** ptr, size_t* have, size_t need);          // device scratch
-int  prl_ensure_pinned(prl_cuda_ctx* ctx, size_t need);
 void prl_launch_begin(prl_cuda_ctx* ctx, int family);
 void prl_launch_end(prl_cuda_ctx* ctx);
 

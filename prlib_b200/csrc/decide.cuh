@@ -50,7 +50,7 @@ __device__ __forceinline__ double tap4(double kw, double nkw, long long a, long 
 
 // The reference's FP64 threshold formulas (binarizeSauvola.cpp:115-118, binarizeNiblack.cpp:108,
 // binarizeWolfJolion.cpp:128-130, binarizeNICK.cpp:121-126, binarizeFeng.cpp:118-142), operation order kept.
-// Roundings follow what OpenCV executes on an FMA-capable host (pinned by oracle/_ref, the reference's own C++ over the
+// Roundings follow what OpenCV executes on an FMA-capable host (pinned by the compiled reference of the test tree, the reference's own C++ over the
 // cv2 wheel): Mat::convertTo(alpha, beta) and cv::scaleAdd fuse their multiply-add (one rounding), cv::addWeighted is
 // fma(a, alpha, fma(b, beta, gamma)); filter2D's taps, Mat::mul, add and subtract round every operation.
 template <int METHOD>

@@ -31,6 +31,15 @@ prl_cuda_ctx* context()
 // cv::Exception as OpenCV itself would raise it (CV_Assert -> code -215)
 cv::Exception cvError(const std::string& msg) { return cv::Exception(-215, msg, "prl (libprlib_cuda)", __FILE__, __LINE__); }
 
+// The reference ends in a cv::Exception for anything but 8-bit data (type mismatch at `gray > thresholds`, the
+// CV_8UC1 assertion of THRESH_OTSU, cvtColor's depth/channel checks); the device path reads bytes, so refuse here.
+void require8U(const cv::Mat& m, bool allow134 = true)
+{
+    if (m.depth() != CV_8U) throw cvError("expected an 8-bit image (depth() == CV_8U)");
+    const int ch = m.channels();
+    if (!(ch == 1 || (allow134 && (ch == 3 || ch == 4)))) throw cvError("cvtColor: unsupported number of channels");
+}
+
 void check(prl_cuda_ctx* c, int rc)
 {
     if (rc == PRL_OK) return;
@@ -62,9 +71,9 @@ void runLocal(int method, cv::Mat& imageInput, cv::Mat& outputImage, int windowS
     if (!((windowSize > 1) && ((windowSize % 2) == 1)))
         throw std::invalid_argument("Window size must satisfy the following condition: "
                                     "( (windowSize > 1) && ((windowSize % 2) == 1) ) ");
+    require8U(imageInput);
     prl_cuda_ctx* c = context();
     const int ch = imageInput.channels();
-    if (ch != 1 && ch != 3 && ch != 4) throw cvError("cvtColor: unsupported number of channels");
     int orows = 0, ocols = 0;
     check(c, prl_cuda_output_shape(method, imageInput.rows, imageInput.cols, windowSize, &orows, &ocols));
     cv::Mat out(orows, ocols, CV_8UC1);
@@ -86,7 +95,86 @@ void runLocal(int method, cv::Mat& imageInput, cv::Mat& outputImage, int windowS
 #endif
     outputImage = out;
 }
+
+// thread-local page-locked staging of the batch forms (prl_cuda_host_alloc), grown on demand
+struct PinnedBuf {
+    void* p = nullptr; size_t bytes = 0;
+    ~PinnedBuf() { prl_cuda_host_free(p); }
+    unsigned char* get(size_t need)
+    {
+        if (need > bytes) {
+            prl_cuda_host_free(p); p = nullptr; bytes = 0;
+            if (prl_cuda_host_alloc(need, &p) != PRL_OK) throw std::runtime_error(std::string("libprlib_cuda: ") + prl_cuda_last_error(nullptr));
+            bytes = need;
+        }
+        return static_cast<unsigned char*>(p);
+    }
+};
+
+void runLocalBatch(int method, const std::vector<cv::Mat>& inputs, std::vector<cv::Mat>& outputs, int windowSize,
+                   const double params[4], int morph)
+{
+    static thread_local PinnedBuf pin_in, pin_out;
+    std::vector<cv::Mat> result(inputs.size());
+    size_t i = 0;
+    while (i < inputs.size()) {
+        const cv::Mat& first = inputs[i];
+        if (first.empty()) throw std::invalid_argument("Input image for binarization is empty");
+        if (!((windowSize > 1) && ((windowSize % 2) == 1)))
+            throw std::invalid_argument("Window size must satisfy the following condition: "
+                                        "( (windowSize > 1) && ((windowSize % 2) == 1) ) ");
+        require8U(first);
+        if (first.channels() != 1) {                 // colour pages: single-image path (cvtColor on the device)
+            cv::Mat in = first, out;                 // header copy: runLocal re-seats `in`, the caller's Mat is untouched
+            runLocal(method, in, out, windowSize, params, morph);
+            result[i++] = out;
+            continue;
+        }
+        size_t j = i + 1;
+        while (j < inputs.size() && !inputs[j].empty() && inputs[j].depth() == CV_8U && inputs[j].channels() == 1 &&
+               inputs[j].rows == first.rows && inputs[j].cols == first.cols) ++j;
+        const int n = (int)(j - i), rows = first.rows, cols = first.cols;
+        int orows = 0, ocols = 0;
+        const int rc = prl_cuda_output_shape(method, rows, cols, windowSize, &orows, &ocols);
+        if (rc == PRL_E_EMPTY_ROI) throw cvError("empty processing rectangle: min(rows, cols) <= windowSize");
+        if (rc != PRL_OK) throw std::invalid_argument("bad geometry");
+        const size_t in_page = (size_t)rows * cols, out_page = (size_t)orows * ocols;
+        unsigned char* hin = pin_in.get(in_page * n);
+        unsigned char* hout = pin_out.get(out_page * n);
+        for (int p = 0; p < n; ++p)
+            for (int y = 0; y < rows; ++y) std::memcpy(hin + p * in_page + (size_t)y * cols, inputs[i + p].ptr(y), (size_t)cols);
+        check(nullptr, prl_cuda_binarize_batch(nullptr, 0, method, hin, n, rows, cols, windowSize, params, morph, hout));
+        for (int p = 0; p < n; ++p) {
+            cv::Mat out(orows, ocols, CV_8UC1);
+            for (int y = 0; y < orows; ++y) std::memcpy(out.ptr(y), hout + p * out_page + (size_t)y * ocols, (size_t)ocols);
+            result[i + p] = out;
+        }
+        i = j;
+    }
+    outputs.swap(result);
+}
 }  // namespace
+
+#define PRL_BATCH1(NAME, METHOD)                                                                                       \
+    void prl::NAME(const std::vector<cv::Mat>& inputs, std::vector<cv::Mat>& outputs, int windowSize,                 \
+                   double thresholdCoefficient, int morphIterationCount)                                              \
+    {                                                                                                                  \
+        const double p[4] = {thresholdCoefficient, 0, 0, 0};                                                          \
+        runLocalBatch(METHOD, inputs, outputs, windowSize, p, morphIterationCount);                                   \
+    }
+PRL_BATCH1(binarizeSauvolaBatch, PRL_SAUVOLA)
+PRL_BATCH1(binarizeNiblackBatch, PRL_NIBLACK)
+PRL_BATCH1(binarizeWolfJolionBatch, PRL_WOLFJOLION)
+PRL_BATCH1(binarizeNICKBatch, PRL_NICK)
+#undef PRL_BATCH1
+
+void prl::binarizeFengBatch(const std::vector<cv::Mat>& inputs, std::vector<cv::Mat>& outputs, int windowSize,
+                            double thresholdCoefficient_alpha1, double thresholdCoefficient_k1, double thresholdCoefficient_k2,
+                            double thresholdCoefficient_gamma, int morphIterationCount)
+{
+    const double p[4] = {thresholdCoefficient_alpha1, thresholdCoefficient_k1, thresholdCoefficient_k2, thresholdCoefficient_gamma};
+    runLocalBatch(PRL_FENG, inputs, outputs, windowSize, p, morphIterationCount);
+}
 
 void prl::binarizeSauvola(cv::Mat& imageInput, cv::Mat& outputImage, int windowSize, double thresholdCoefficient,
                           int morphIterationCount)
@@ -129,7 +217,8 @@ void prl::binarizeLocalOtsuRects(const cv::Mat& gray, const std::vector<int>& xy
 {
     if (gray.empty()) throw std::invalid_argument("Input image for binarization is empty");
     if (!(maxValue >= 0 && maxValue <= 255)) throw std::invalid_argument("Max value must be in range [0; 255]");
-    if (gray.channels() != 1 || xywh.size() % 4 != 0) throw std::invalid_argument("expected a gray image and x,y,w,h quadruples");
+    require8U(gray, false);
+    if (xywh.size() % 4 != 0) throw std::invalid_argument("expected x,y,w,h quadruples");
     prl_cuda_ctx* c = context();
     cv::Mat out(gray.rows, gray.cols, CV_8UC1);
     check(c, prl_cuda_otsu_rects(c, gray.data, gray.rows, gray.cols, gray.step, xywh.empty() ? nullptr : xywh.data(),
@@ -139,7 +228,8 @@ void prl::binarizeLocalOtsuRects(const cv::Mat& gray, const std::vector<int>& xy
 
 double prl::thresholdOtsu(const cv::Mat& src, cv::Mat& dst, double maxValue)
 {
-    if (src.empty() || src.channels() != 1) throw std::invalid_argument("expected a non-empty gray image");
+    if (src.empty()) throw cvError("threshold: empty image");
+    require8U(src, false);                                                  // THRESH_OTSU asserts CV_8UC1
     prl_cuda_ctx* c = context();
     cv::Mat out(src.rows, src.cols, CV_8UC1);
     int thr = 0;
@@ -159,7 +249,7 @@ void prl::localOtsuEdges(const cv::Mat& imageToProc, cv::Mat& resultCanny, int G
         throw std::invalid_argument("Canny lower threshold coefficient isn't in range [0;1]");                   // :263-266
     if (CannyLowerThresholdCoeff > CannyUpperThresholdCoeff)
         throw std::invalid_argument("Canny lower threshold coefficient is greater than Canny upper threshold coefficient");
-    if (imageToProc.channels() != 1) throw std::invalid_argument("expected a single-channel image");
+    require8U(imageToProc, false);
     prl_cuda_ctx* c = context();
     cv::Mat out(imageToProc.rows, imageToProc.cols, CV_8UC1);
     check(c, prl_cuda_canny_edge_detection(c, imageToProc.data, imageToProc.rows, imageToProc.cols, imageToProc.step,
@@ -178,6 +268,7 @@ void prl::binarizeLocalOtsu(cv::Mat& inputImage, cv::Mat& outputImage, double ma
     if (CannyUpperThresholdCoeff < 0 || CannyUpperThresholdCoeff > 1 || CannyLowerThresholdCoeff < 0 ||
         CannyLowerThresholdCoeff > 1 || CannyLowerThresholdCoeff > CannyUpperThresholdCoeff)
         throw std::invalid_argument("Canny threshold coefficients must satisfy 0 <= lower <= upper <= 1");
+    require8U(inputImage);
     prl_cuda_ctx* c = context();
     cv::Mat out(inputImage.rows, inputImage.cols, CV_8UC1);
     int n = 0;
@@ -191,6 +282,8 @@ void prl::binarizeLocalOtsu(cv::Mat& inputImage, cv::Mat& outputImage, double ma
 void prl::removeLines(const cv::Mat& inputImage, cv::Mat& outputImage)
 {
     if (inputImage.empty()) throw cvError("removeLines: empty image");     // (the reference would fail inside cv::threshold)
+    if (inputImage.depth() != CV_8U || (inputImage.channels() != 1 && inputImage.channels() != 3))
+        throw cvError("removeLines: expected an 8-bit image with 1 or 3 channels");   // cv::threshold's OTSU assertion
     prl_cuda_ctx* c = context();
     cv::Mat out(inputImage.rows, inputImage.cols, CV_8UC1);
     check(c, prl_cuda_remove_lines(c, inputImage.data, inputImage.rows, inputImage.cols, inputImage.step, inputImage.channels(),

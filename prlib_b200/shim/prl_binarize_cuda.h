@@ -31,6 +31,24 @@ CV_EXPORTS void binarizeFeng(cv::Mat& imageInput, cv::Mat& outputImage, int wind
                              double thresholdCoefficient_k2 = 0.03, double thresholdCoefficient_gamma = 2.0,
                              int morphIterationCount = 2);
 
+// Batch forms (no counterpart in the reference, whose API is one cv::Mat per call): the same five functions over a
+// vector of pages through the pinned-memory batch loader + page dispatcher of libprlib_cuda (prl_cuda_binarize_batch:
+// every visible GPU, H2D / kernels / D2H overlapped).  outputs[i] is what binarizeX(inputs[i], ...) returns; the inputs
+// are NOT modified (no padded-image side effect).  Runs of consecutive single-channel pages of one size go through the
+// batch loader together, anything else (3/4 channels) through the single-image path; exceptions as above.
+CV_EXPORTS void binarizeSauvolaBatch(const std::vector<cv::Mat>& inputs, std::vector<cv::Mat>& outputs, int windowSize = 101,
+                                     double thresholdCoefficient = 0.01, int morphIterationCount = 2);
+CV_EXPORTS void binarizeNiblackBatch(const std::vector<cv::Mat>& inputs, std::vector<cv::Mat>& outputs, int windowSize = 101,
+                                     double thresholdCoefficient = 0.01, int morphIterationCount = 2);
+CV_EXPORTS void binarizeWolfJolionBatch(const std::vector<cv::Mat>& inputs, std::vector<cv::Mat>& outputs, int windowSize = 101,
+                                        double thresholdCoefficient = 0.01, int morphIterationCount = 2);
+CV_EXPORTS void binarizeNICKBatch(const std::vector<cv::Mat>& inputs, std::vector<cv::Mat>& outputs, int windowSize = 21,
+                                  double thresholdCoefficient = -0.01, int morphIterationCount = 0);
+CV_EXPORTS void binarizeFengBatch(const std::vector<cv::Mat>& inputs, std::vector<cv::Mat>& outputs, int windowSize = 21,
+                                  double thresholdCoefficient_alpha1 = 0.75, double thresholdCoefficient_k1 = 0.2,
+                                  double thresholdCoefficient_k2 = 0.03, double thresholdCoefficient_gamma = 2.0,
+                                  int morphIterationCount = 2);
+
 // The per-contour-rectangle Otsu loop of prl::binarizeLocalOtsu (binarizeLocalOtsu.cpp:138-162):
 // `gray` is imageToProc, xywh holds cv::boundingRect(contour) as x, y, width, height quadruples.
 CV_EXPORTS void binarizeLocalOtsuRects(const cv::Mat& gray, const std::vector<int>& xywh, cv::Mat& binarized,

@@ -85,6 +85,48 @@ int main()
         try { prl::binarizeNICK(small, out, 101); } catch (const cv::Exception&) { t3 = true; }
         EXPECT(t1 && t2 && t3, "invalid_argument / cv::Exception like the reference");
     }
+    {   // 16-bit / float input: the reference ends in a cv::Exception, never in a mask of reinterpreted bytes
+        cv::Mat u16(64, 64, CV_16UC1), f32(64, 64, CV_32FC1), out;
+        std::memset(u16.data, 7, 64 * 64 * 2); std::memset(f32.data, 0, 64 * 64 * 4);
+        int thrown = 0;
+        try { prl::binarizeSauvola(u16, out, 15, 0.2, 0); } catch (const cv::Exception&) { ++thrown; }
+        try { prl::binarizeFeng(f32, out); } catch (const cv::Exception&) { ++thrown; }
+        try { prl::thresholdOtsu(u16, out); } catch (const cv::Exception&) { ++thrown; }
+        try { prl::binarizeLocalOtsu(f32, out); } catch (const cv::Exception&) { ++thrown; }
+        try { prl::removeLines(u16, out); } catch (const cv::Exception&) { ++thrown; }
+        cv::Mat c4(64, 64, CV_8UC4); std::memset(c4.data, 9, 64 * 64 * 4);
+        try { prl::removeLines(c4, out); } catch (const cv::Exception&) { ++thrown; }
+        EXPECT(thrown == 6 && u16.rows == 64 && u16.depth() == CV_16U, "non-8-bit input -> cv::Exception, input untouched");
+    }
+    {   // batch forms: pages of two sizes and one BGR page in one vector; outputs equal the single-image calls
+        std::vector<cv::Mat> in, out;
+        for (int p = 0; p < 5; ++p) { cv::Mat m(300, 421, CV_8UC1); oracle_synth_page(m.data, m.step, 300, 421, 2024, p); in.push_back(m); }
+        cv::Mat bgr(200, 300, CV_8UC3);
+        for (int y = 0; y < 200; ++y) for (int x = 0; x < 900; ++x) bgr.ptr(y)[x] = (unsigned char)((x * 7 + y * 13) & 255);
+        in.push_back(bgr);
+        for (int p = 0; p < 3; ++p) { cv::Mat m(220, 180, CV_8UC1); oracle_synth_page(m.data, m.step, 220, 180, 2024, 10 + p); in.push_back(m); }
+        const cv::Mat keep0 = in[0].clone();
+        prl::binarizeSauvolaBatch(in, out, 15, 0.2, 1);
+        bool ok = out.size() == in.size() && in[0].rows == 300 && std::memcmp(in[0].data, keep0.data, 300 * 421) == 0;
+        for (size_t i = 0; ok && i < in.size(); ++i) {
+            cv::Mat a = in[i].clone(), single;
+            prl::binarizeSauvola(a, single, 15, 0.2, 1);
+            ok = single.rows == out[i].rows && single.cols == out[i].cols;
+            for (int y = 0; ok && y < single.rows; ++y) ok = std::memcmp(single.ptr(y), out[i].ptr(y), (size_t)single.cols) == 0;
+        }
+        EXPECT(ok, "binarizeSauvolaBatch equals per-image binarizeSauvola, inputs untouched");
+        std::vector<cv::Mat> outw, outf;
+        prl::binarizeWolfJolionBatch(in, outw, 21, 0.5, 0);
+        prl::binarizeFengBatch(in, outf);
+        cv::Mat a = in[7].clone(), single;
+        prl::binarizeWolfJolion(a, single, 21, 0.5, 0);
+        bool okw = outw.size() == in.size() && single.rows == outw[7].rows && std::memcmp(single.data, outw[7].data, (size_t)single.rows * single.cols) == 0;
+        EXPECT(okw && outf.size() == in.size() && outf[0].rows == 300 - 21, "Wolf-Jolion / Feng batch forms");
+        bool thrown = false;
+        std::vector<cv::Mat> bad(2); bad[0] = in[0];
+        try { prl::binarizeNICKBatch(bad, out); } catch (const std::invalid_argument&) { thrown = true; }
+        EXPECT(thrown, "empty page inside a batch -> invalid_argument");
+    }
     {   // Otsu
         std::vector<uint8_t> want((size_t)rows * cols);
         int thr = oracle_otsu_global(page.data, rows, cols, page.step, 255, want.data(), cols);

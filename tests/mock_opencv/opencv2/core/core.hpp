@@ -13,10 +13,14 @@
 #define CV_EXPORTS
 #define CV_CN_SHIFT 3
 #define CV_8U 0
+#define CV_16U 2
+#define CV_32F 5
 #define CV_MAKETYPE(depth, cn) ((depth) + (((cn)-1) << CV_CN_SHIFT))
 #define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
 #define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
 #define CV_8UC4 CV_MAKETYPE(CV_8U, 4)
+#define CV_16UC1 CV_MAKETYPE(CV_16U, 1)
+#define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
 
 namespace cv {
 
@@ -38,23 +42,24 @@ public:
     Mat(int r, int c, int type) { create(r, c, type); }
     void create(int r, int c, int type)
     {
-        if (r == rows && c == cols && type == type_ && data && step == (size_t)c * channels()) return;
+        if (r == rows && c == cols && type == type_ && data) return;
         rows = r; cols = c; type_ = type;
-        step = (size_t)c * channels();
+        step = (size_t)c * channels() * elemSize1();
         buf_ = std::shared_ptr<unsigned char>(new unsigned char[step * (r > 0 ? r : 1) + 1], std::default_delete<unsigned char[]>());
         data = buf_.get();
     }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
     int type() const { return type_; }
     int depth() const { return type_ & 7; }
+    size_t elemSize1() const { return depth() < 2 ? 1 : (depth() < 4 ? 2 : (depth() < 6 ? 4 : 8)); }
     int channels() const { return (type_ >> CV_CN_SHIFT) + 1; }
-    bool isContinuous() const { return step == (size_t)cols * channels(); }
+    bool isContinuous() const { return step == (size_t)cols * channels() * elemSize1(); }
     unsigned char* ptr(int y = 0) { return data + (size_t)y * step; }
     const unsigned char* ptr(int y = 0) const { return data + (size_t)y * step; }
     Mat clone() const
     {
         Mat m(rows, cols, type_);
-        for (int y = 0; y < rows; ++y) std::memcpy(m.ptr(y), ptr(y), (size_t)cols * channels());
+        for (int y = 0; y < rows; ++y) std::memcpy(m.ptr(y), ptr(y), (size_t)cols * channels() * elemSize1());
         return m;
     }
 

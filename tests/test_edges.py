@@ -109,6 +109,24 @@ def test_binarize_local_otsu_end_to_end(ctx, real_crops):
         prlib_b200.binarizeLocalOtsu(np.full((80, 80), 200, np.uint8))      # no edges -> no contours -> invalid_argument
 
 
+@pytest.mark.gpu
+def test_binarize_local_otsu_one_pixel_wide_images(ctx):
+    """1 x N and N x 1 images: every contour is a straight run with fewer than 3 CHAIN_APPROX_SIMPLE points, which
+    CheckHierarhyLevelRecursively ignores (imageLibCommon.cpp:729-736) -> the result stays 255; 2 x N is
+    the first shape whose contours survive."""
+    rng = np.random.default_rng(3)
+    for shape in ((1, 200), (200, 1), (2, 200), (200, 2), (1, 37), (3, 64)):
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        img[..., :max(1, shape[1] // 2)] //= 4
+        img[:max(1, shape[0] // 2)] //= 2
+        want = O.binarizeLocalOtsu(img)
+        got = prlib_b200.binarizeLocalOtsu(img)
+        assert np.array_equal(got, want), shape
+    for shape in ((1, 1), (3, 3)):
+        with pytest.raises(ValueError):
+            prlib_b200.binarizeLocalOtsu(rng.integers(0, 256, shape, dtype=np.uint8))
+
+
 def _page_with_rules(rows, cols, seed):
     page = CO.synth_page(seed, rows, cols).copy()
     rng = np.random.default_rng(seed)

@@ -308,3 +308,50 @@ def test_every_device_of_the_box_and_the_page_dispatcher():
     assert np.array_equal(prlib_b200.binarize_batch(pages, 0, 15, (0.2,), 0, devices=list(range(n_dev))), want)
     assert np.array_equal(prlib_b200.binarize_batch(pages, 2, 15, (0.5,), 1, devices=None),
                           prlib_b200.binarize_batch(pages, 2, 15, (0.5,), 1, devices=[0]))
+
+
+@pytest.mark.gpu
+def test_batch_loader_pinned_pageable_and_concurrent_callers():
+    """The ctx-less batch entry point: page-locked buffers from prl_cuda_host_alloc, pageable buffers (bounced through
+    library-owned pinned memory, or handed to the driver as they are), forced chunk sizes, and two host threads on
+    the same device at once (the cached per-device worker is now taken in turns) all give the same masks."""
+    import threading
+    n, rows, cols = 9, 500, 731
+    pages = np.stack([CO.synth_page(p, rows, cols) for p in range(n)])
+    want = np.stack([CO.binarize_local(pages[p], 0, 15, (0.2,), 0) for p in range(n)])
+    assert np.array_equal(prlib_b200.binarize_batch(pages, 0, 15, (0.2,), 0, devices=[0]), want)       # pageable, bounced
+    pin_in = prlib_b200.PinnedArray(pages.shape); pin_out = prlib_b200.PinnedArray(want.shape)
+    pin_in.array[...] = pages
+    got = prlib_b200.binarize_batch(pin_in.array, 0, 15, (0.2,), 0, devices=[0], out=pin_out.array)
+    assert np.array_equal(got, want)
+    try:
+        prlib_b200.set_global_option("batch_stage_pageable", 0)
+        assert np.array_equal(prlib_b200.binarize_batch(pages, 0, 15, (0.2,), 0, devices=[0]), want)
+        prlib_b200.set_global_option("batch_stage_pageable", 1)
+        for chunk in (1, 2, 100):
+            prlib_b200.set_global_option("batch_chunk_pages", chunk)
+            assert np.array_equal(prlib_b200.binarize_batch(pages, 0, 15, (0.2,), 0, devices=[0]), want), chunk
+            assert np.array_equal(prlib_b200.unpack_lept1(
+                prlib_b200.binarize_batch(pages, 0, 15, (0.2,), 0, devices=[0], packed=True), want.shape[2]), want), chunk
+    finally:
+        prlib_b200.set_global_option("batch_chunk_pages", 0)
+        prlib_b200.set_global_option("batch_stage_pageable", 1)
+    with pytest.raises(ValueError):
+        prlib_b200.set_global_option("no_such_option", 1)
+    # concurrent callers, same device, different methods and shapes
+    jobs = [(0, 15, (0.2,), 0, pages), (3, 21, (-0.1,), 1, pages[:5, :300, :400].copy()), (2, 15, (0.5,), 0, pages),
+            (1, 31, (-0.2,), 0, pages[:, :411, :].copy())]
+    results = [None] * len(jobs)
+
+    def run(i):
+        m, w, prm, mo, pg = jobs[i]
+        for _ in range(3):
+            results[i] = prlib_b200.binarize_batch(pg, m, w, prm, mo, devices=[0])
+
+    threads = [threading.Thread(target=run, args=(i,)) for i in range(len(jobs))]
+    for t in threads: t.start()
+    for t in threads: t.join()
+    for i, (m, w, prm, mo, pg) in enumerate(jobs):
+        for p in range(pg.shape[0]):
+            assert np.array_equal(results[i][p], CO.binarize_local(pg[p], m, w, prm, mo)), (i, p)
+    pin_in.close(); pin_out.close()
