@@ -58,13 +58,16 @@ int         prl_cuda_synchronize(prl_cuda_ctx* ctx);
 /* Upper bound (bytes) for the S/Q scratch planes of one in-flight chunk of pages (default 48 GiB,
  * clipped to 70 % of free HBM at first use). */
 int         prl_cuda_set_workspace_limit(prl_cuda_ctx* ctx, size_t bytes);
-/* Validation switches (masks and planes are bit-identical either way; only the speed differs):
+/* Path selection and validation switches (masks and planes are bit-identical either way; only the speed differs):
+ *   "enable_fused"    = 0  : DEFAULT 1.  With 1, windows <= 31 (Sauvola/Niblack/NICK/Feng, padded width <= 8192) run the
+ *                            fused strip kernel that never materialises the integral planes in HBM; the rare page it cannot
+ *                            finish is handed to kernel 1 + kernel 2 through a page list kept in device memory (no host
+ *                            read-back: the *_dev calls stay asynchronous).  0 forces kernel 1 + kernel 2 for every window;
  *   "exact_threshold" != 0 : kernel 2 evaluates the reference's FP64 formula for EVERY pixel instead
  *                            of only for the pixels its exact-integer/FP32 decision cannot settle;
  *   "disable_tma"     != 0 : kernel 1 uses its generic byte-load kernel instead of the TMA-staged one;
- *   "enable_fused"    != 0 : windows <= 31 (Sauvola/Niblack/NICK/Feng) run the fused strip kernel that never
- *                            materialises the int64 integral planes in HBM.  The batch call then returns only after
- *                            the fused kernels finished (it reads a per-page counter back);
+ *   "disable_compact" != 0 : kernel 1 writes / kernel 2 reads full int64 planes (16 B per padded pixel) instead of the
+ *                            compact layout (low words + sparse high-word anchors, 8.25 B);
  *   "fused_page_cap"  = n  : undecided pixels per page (0..128, default 128) the fused path finishes itself by
  *                            brute force; a page with more is redone by kernel 1 + kernel 2 (test hook: 0);
  *   "fused_no_tier2"  != 0 : the fused path skips its FP64 estimate, so every pixel its FP32 estimate cannot settle
@@ -257,8 +260,9 @@ int  prl_cuda_timing_enable(prl_cuda_ctx* ctx, int on);
 int  prl_cuda_timing_reset(prl_cuda_ctx* ctx);
 int  prl_cuda_timing_get(prl_cuda_ctx* ctx, const char* family, double* total_ms, long long* launches);
 long long prl_cuda_launch_count(const prl_cuda_ctx* ctx);   /* kernels launched since create/reset */
-/* pages the fused small-window path ("enable_fused") handed back to the two-kernel path since create */
-long long prl_cuda_fused_redo_count(const prl_cuda_ctx* ctx);
+/* pages the fused small-window path handed back to the two-kernel path since create (a device-side counter:
+ * this call synchronises the context's stream) */
+long long prl_cuda_fused_redo_count(prl_cuda_ctx* ctx);
 
 #ifdef __cplusplus
 }

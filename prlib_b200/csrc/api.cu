@@ -165,7 +165,7 @@ extern "C" void prl_cuda_destroy(prl_cuda_ctx* c)
     for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto& ev : c->event_pool) cudaEventDestroy(ev);
     cudaFree(c->sched); cudaFree(c->planes); cudaFree(c->carry); cudaFree(c->colsum); cudaFree(c->scalars); cudaFree(c->fused_ws);
-    if (c->h_cnt) cudaFreeHost(c->h_cnt);
+    cudaFree(c->d_redo_total);
     cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_tmp); cudaFree(c->d_misc); cudaFree(c->d_bgr); cudaFree(c->edges_ws); cudaFree(c->rects_ws); cudaFree(c->clahe_ws);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -250,7 +250,15 @@ extern "C" int prl_cuda_timing_get(prl_cuda_ctx* c, const char* family, double* 
     return prl_set_err(c, PRL_E_INVALID, "unknown kernel family");
 }
 extern "C" long long prl_cuda_launch_count(const prl_cuda_ctx* c) { return c ? c->launches : 0; }
-extern "C" long long prl_cuda_fused_redo_count(const prl_cuda_ctx* c) { return c ? c->fused_redo_pages : 0; }
+// pages the fused path handed back to the two-kernel path so far: a device counter, so this call synchronises the stream
+extern "C" long long prl_cuda_fused_redo_count(prl_cuda_ctx* c)
+{
+    if (!c || !c->d_redo_total) return 0;
+    unsigned long long v = 0;
+    if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess ||
+        cudaMemcpy(&v, c->d_redo_total, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return (long long)v;
+}
 
 // ------------------------------------------------------------------------------------------------
 // device-resident batch entry points
@@ -338,6 +346,41 @@ static int planes_pages(prl_cuda_ctx* c, int method, int mode, const uint8_t* d_
     return PRL_OK;
 }
 
+// Hand-back of the fused path, without the host: the pages whose undecided-pixel list overflowed (rare: large exactly
+// flat areas whose threshold sits on a rounding boundary) are listed in device memory (fused.cu: overflow_list_kernel);
+// kernel 1 (generic, int64 planes) and kernel 2 (literal FP64 for every pixel) are launched OVER THAT LIST -- grid slot z
+// works on page map[z], slots beyond the list's length leave at once -- in rounds of as many plane slots as the scratch
+// holds (at most 32: 4.5 GB for A4), enough rounds to cover the case that every page overflowed.  Nothing is read back,
+// so the *_dev entry points stay asynchronous and the batch loader keeps its three streams overlapped; the price is two
+// near-empty launches per 32 pages (~3 us each).
+static int fused_hand_back(prl_cuda_ctx* c, int method, const uint8_t* d_src, int n_pages, const prl_geom& g, size_t src_step,
+                           size_t src_page_stride, const double* params, const uint32_t* d_imin, uint8_t* d_dst, size_t dst_step,
+                           size_t dst_page_stride, const int* d_map, const int* d_cnt)
+{
+    const size_t plane_elems = (size_t)g.Hp * g.pitch;
+    const size_t per_page = 2 * plane_elems * sizeof(int64_t);
+    const size_t want = (size_t)std::min(n_pages, 32) * per_page;
+    const size_t budget = std::min(planes_budget(c, want), c->workspace_limit);
+    const int slots = (int)std::min<size_t>((size_t)std::min(n_pages, 32), std::max<size_t>(1, budget / per_page));
+    if ((size_t)slots * per_page > c->planes_bytes || !c->planes) {
+        int rc = prl_ensure(c, (void**)&c->planes, &c->planes_bytes, (size_t)slots * per_page);
+        if (rc) return rc;
+    }
+    prl_planes P;
+    P.compact = 0; P.pitch = g.pitch; P.page_stride = plane_elems;
+    P.S = c->planes; P.Q = c->planes + (size_t)slots * plane_elems;
+    for (int base = 0; base < n_pages; base += slots) {
+        const int ns = std::min(slots, n_pages - base);
+        int rc = prl_k_integral_indirect(c, d_src, ns, g.rows, g.cols, src_step, src_page_stride, g.h, (int64_t*)P.S, (int64_t*)P.Q, P.pitch,
+                                         P.page_stride, d_map, d_cnt, base);
+        if (rc) return rc;
+        rc = prl_k_threshold_exact_indirect(c, method, d_src, ns, g, src_step, src_page_stride, P, params, d_imin, d_dst, dst_step,
+                                            dst_page_stride, d_map, d_cnt, base);
+        if (rc) return rc;
+    }
+    return PRL_OK;
+}
+
 static int local_batch_dev(prl_cuda_ctx* c, int method, int mode, const uint8_t* d_src, int n_pages, int rows, int cols,
                            size_t src_step, size_t src_page_stride, int window, const double* params, int morph_iters,
                            uint8_t* d_dst, size_t dst_step, size_t dst_page_stride)
@@ -365,18 +408,11 @@ static int local_batch_dev(prl_cuda_ctx* c, int method, int mode, const uint8_t*
         }
         uint8_t* raw = with_morph ? c->d_tmp : d_dst;
         const size_t raw_step = with_morph ? t_step : dst_step, raw_page = with_morph ? t_page : dst_page_stride;
-        std::vector<int> redo;
-        rc = prl_k_fused(c, method, d_src, n_pages, g, src_step, src_page_stride, params, imin, raw, raw_step, raw_page, &redo);
+        const int* d_map = nullptr; const int* d_cnt = nullptr;
+        rc = prl_k_fused(c, method, d_src, n_pages, g, src_step, src_page_stride, params, imin, raw, raw_step, raw_page, &d_map, &d_cnt);
         if (rc) return rc;
-        for (size_t i = 0; i < redo.size();) {                    // runs of consecutive pages
-            size_t j = i + 1;
-            while (j < redo.size() && redo[j] == redo[j - 1] + 1) ++j;
-            const int p0 = redo[i], np = (int)(j - i);
-            rc = planes_pages(c, method, 0, d_src + (size_t)p0 * src_page_stride, np, g, src_step, src_page_stride, params, 0,
-                              raw + (size_t)p0 * raw_page, raw_step, raw_page);
-            if (rc) return rc;
-            i = j;
-        }
+        rc = fused_hand_back(c, method, d_src, n_pages, g, src_step, src_page_stride, params, imin, raw, raw_step, raw_page, d_map, d_cnt);
+        if (rc) return rc;
         if (with_morph)
             rc = prl_k_morph(c, c->d_tmp, d_dst, n_pages, g.out_rows, g.out_cols, t_step, t_page, dst_step, dst_page_stride,
                              morph_iters, true);

@@ -63,10 +63,9 @@ struct prl_cuda_ctx {
     void* scalars = nullptr;    size_t scalars_bytes = 0;
     void* sched = nullptr;      size_t sched_bytes = 0;    // work counters of the persistent kernels
     void* fused_ws = nullptr;   size_t fused_ws_bytes = 0; // fused path: row sums per strip, fixup counters and lists
-    uint32_t* h_cnt = nullptr;  size_t h_cnt_bytes = 0;    // pinned read-back of the fused path's per-page counters
+    unsigned long long* d_redo_total = nullptr;            // pages the fused path handed back so far (device counter)
     int fused_page_cap = 128;                              // undecided pixels per page the fused path finishes itself
     bool fused_no_tier2 = false;                           // validation: fused path without its FP64 estimate tier
-    long long fused_redo_pages = 0;                        // pages the fused path handed back to the two-kernel path
     // device staging for host-pointer entry points
     uint8_t* d_in = nullptr;    size_t d_in_bytes = 0;
     uint8_t* d_out = nullptr;   size_t d_out_bytes = 0;
@@ -89,7 +88,8 @@ struct prl_cuda_ctx {
     int thr_rows = 0;           // kernel 2: output rows per CTA (0 = automatic: 4, or 8 when the tap distance exceeds 64)
     int tile_prefetch = 0;      // tile Otsu: how many tiles ahead a warp pulls into L2 (0 = off)
     bool morph_bytes = false;   // validation: the morphology tail runs the byte kernels even on binary masks
-    bool use_fused = false;     // opt-in: fused small-window strip kernel (integral planes never reach HBM)
+    bool use_fused = true;      // windows <= 31 take the fused small-window strip kernel (integral planes never reach HBM);
+                                // set_option("enable_fused", 0) forces kernel 1 + kernel 2
 
     // instrumentation
     bool timing = false;
@@ -153,7 +153,15 @@ int prl_k_threshold(prl_cuda_ctx* ctx, int method, int mode /*0 mask, 1 T8*/, co
 bool prl_fused_eligible(const prl_cuda_ctx* ctx, int method, int n_pages, const prl_geom& g, const double* params);
 int prl_k_fused(prl_cuda_ctx* ctx, int method, const uint8_t* d_src, int n_pages, const prl_geom& g, size_t src_step,
                 size_t src_page_stride, const double* params, uint32_t* d_imin, uint8_t* d_dst, size_t dst_step,
-                size_t dst_page_stride, std::vector<int>* redo_pages);
+                size_t dst_page_stride, const int** d_redo_map, const int** d_redo_count);
+// indirect launches over a device-resident page list (hand-back of the fused path)
+int prl_k_integral_indirect(prl_cuda_ctx* ctx, const uint8_t* d_src, int slots, int rows, int cols, size_t src_step,
+                            size_t src_page_stride, int pad, int64_t* d_S, int64_t* d_Q, size_t pitch, size_t plane_page_stride,
+                            const int* d_map, const int* d_count, int slot_base);
+int prl_k_threshold_exact_indirect(prl_cuda_ctx* ctx, int method, const uint8_t* d_src, int slots, const prl_geom& g, size_t src_step,
+                                   size_t src_page_stride, const prl_planes& P, const double* params, const uint32_t* d_imin,
+                                   uint8_t* d_dst, size_t dst_step, size_t dst_page_stride, const int* d_map, const int* d_count,
+                                   int slot_base);
 int prl_k_morph(prl_cuda_ctx* ctx, uint8_t* d_in, uint8_t* d_out, int n_pages, int rows, int cols, size_t in_step,
                 size_t in_page_stride, size_t out_step, size_t out_page_stride, int iters, bool binary);
 int prl_k_morph_single(prl_cuda_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int n_pages, int rows, int cols, size_t in_step,

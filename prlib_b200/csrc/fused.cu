@@ -371,6 +371,31 @@ fixup_kernel(const FusedArgs A)
     }
 }
 
+// ---- hand-back, decided on the device: the pages whose list overflowed, in page order, for the indirect two-kernel
+// launches that follow (api.cu: fused_hand_back).  One CTA; total[0] accumulates over the life of the context.
+__global__ void __launch_bounds__(256)
+overflow_list_kernel(const uint32_t* __restrict__ scount, int n_pages, uint32_t cap, int* __restrict__ map, int* __restrict__ count,
+                     unsigned long long* __restrict__ total)
+{
+    __shared__ int part[256];
+    const int t = threadIdx.x;
+    const int per = (n_pages + 255) / 256, p0 = t * per, p1 = min(p0 + per, n_pages);
+    int n = 0;
+    for (int p = p0; p < p1; ++p) n += scount[p] > cap ? 1 : 0;
+    part[t] = n;
+    __syncthreads();
+    if (t == 0) {
+        int run = 0;
+        for (int i = 0; i < 256; ++i) { const int v = part[i]; part[i] = run; run += v; }
+        *count = run;
+        if (run) atomicAdd(total, (unsigned long long)run);
+    }
+    __syncthreads();
+    int o = part[t];
+    for (int p = p0; p < p1; ++p)
+        if (scount[p] > cap) map[o++] = p;
+}
+
 template <int METHOD, int RR>
 void launch_fused_t(prl_cuda_ctx* ctx, const FusedArgs& A, const FastArgs& F)
 {
@@ -391,8 +416,9 @@ void launch_fused_m(prl_cuda_ctx* ctx, const FusedArgs& A, const FastArgs& F)
 // Can this call take the fused path?  (mask output only; Wolf-Jolion needs s_max first -> planes path)
 bool prl_fused_eligible(const prl_cuda_ctx* ctx, int method, int n_pages, const prl_geom& g, const double* params)
 {
-    if (!ctx->use_fused || ctx->force_exact) return false;   // opt-in: see DESIGN.md section 4 (F2)
+    if (!ctx->use_fused || ctx->force_exact) return false;   // default on; set_option("enable_fused", 0) forces the two-kernel path
     if (method == PRL_WOLFJOLION) return false;
+    if (g.Wp > 8192) return false;                            // width limit of the hand-back's generic integral kernel
     if ((g.d & 1) || g.d + 1 > 32 || g.d < 2) return false;
     if (g.rows > 65535 || g.cols > 65535) return false;   // fixup list packs (y, x) into 32 bits
     (void)n_pages;
@@ -402,7 +428,7 @@ bool prl_fused_eligible(const prl_cuda_ctx* ctx, int method, int n_pages, const 
 
 int prl_k_fused(prl_cuda_ctx* ctx, int method, const uint8_t* d_src, int n_pages, const prl_geom& g, size_t src_step,
                 size_t src_page_stride, const double* params, uint32_t* d_imin, uint8_t* d_dst, size_t dst_step,
-                size_t dst_page_stride, std::vector<int>* redo_pages)
+                size_t dst_page_stride, const int** d_redo_map, const int** d_redo_count)
 {
     FastArgs F;
     if (!fast_margins(method, params, g, &F)) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "fused path not eligible");
@@ -431,14 +457,22 @@ int prl_k_fused(prl_cuda_ctx* ctx, int method, const uint8_t* d_src, int n_pages
     }
     A.nblk = (g.Hp + 31) / 32;
     A.no_tier2 = ctx->fused_no_tier2 ? 1 : 0;
-    // workspace: [scount: n_pages u32][slist: n_pages * kPageCap u32][blocksum]  (counters and block sums start at zero)
+    // workspace: [scount: n_pages u32][redo count + map: 64 + n_pages i32][slist: n_pages * kPageCap u32][blocksum]
+    // (counters and block sums start at zero)
     const size_t cnt_bytes = ((size_t)n_pages * 4 + 255) & ~(size_t)255;
+    const size_t map_bytes = (256 + (size_t)n_pages * 4 + 255) & ~(size_t)255;
     const size_t list_bytes = (size_t)n_pages * kPageCap * 4;
     const size_t bsum_bytes = (size_t)n_pages * A.nblk * A.ns * 2 * sizeof(uint32_t);
-    int rc = prl_ensure(ctx, &ctx->fused_ws, &ctx->fused_ws_bytes, cnt_bytes + list_bytes + bsum_bytes); if (rc) return rc;
+    int rc = prl_ensure(ctx, &ctx->fused_ws, &ctx->fused_ws_bytes, cnt_bytes + map_bytes + list_bytes + bsum_bytes); if (rc) return rc;
+    if (!ctx->d_redo_total) {
+        PRL_CUDA_TRY(ctx, cudaMalloc((void**)&ctx->d_redo_total, 256));
+        PRL_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_redo_total, 0, 256, ctx->stream));
+    }
     A.scount = (uint32_t*)ctx->fused_ws;
-    A.slist = (uint32_t*)((uint8_t*)ctx->fused_ws + cnt_bytes);
-    A.blocksum = (uint32_t*)((uint8_t*)ctx->fused_ws + cnt_bytes + list_bytes);
+    int* redo_count = (int*)((uint8_t*)ctx->fused_ws + cnt_bytes);
+    int* redo_map = redo_count + 64;
+    A.slist = (uint32_t*)((uint8_t*)ctx->fused_ws + cnt_bytes + map_bytes);
+    A.blocksum = (uint32_t*)((uint8_t*)ctx->fused_ws + cnt_bytes + map_bytes + list_bytes);
     PRL_CUDA_TRY(ctx, cudaMemsetAsync(A.scount, 0, cnt_bytes, ctx->stream));
     PRL_CUDA_TRY(ctx, cudaMemsetAsync(A.blocksum, 0, bsum_bytes, ctx->stream));
     if (method == PRL_FENG) {
@@ -466,17 +500,13 @@ int prl_k_fused(prl_cuda_ctx* ctx, int method, const uint8_t* d_src, int n_pages
         default:          fixup_kernel<PRL_FENG><<<grid, 128, 0, ctx->stream>>>(A); break;
         }
     }
-    PRL_CUDA_TRY(ctx, cudaGetLastError());
-    // read the per-page counters back: a page whose list overflowed is redone by the caller (two-kernel path)
-    if (ctx->h_cnt_bytes < (size_t)n_pages * 4) {
-        if (ctx->h_cnt) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->h_cnt); ctx->h_cnt = nullptr; ctx->h_cnt_bytes = 0; }
-        const size_t need = std::max<size_t>((size_t)n_pages * 4, 4096);
-        PRL_CUDA_TRY(ctx, cudaMallocHost((void**)&ctx->h_cnt, need));
-        ctx->h_cnt_bytes = need;
+    {
+        // which pages overflowed their list: decided and listed on the device, no host read-back (the call stays asynchronous)
+        prl_launch_scope ls(ctx, FAM_FUSED_FIX);
+        overflow_list_kernel<<<1, 256, 0, ctx->stream>>>(A.scount, n_pages, A.cap, redo_map, redo_count, ctx->d_redo_total);
     }
-    PRL_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_cnt, A.scount, (size_t)n_pages * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PRL_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int p = 0; p < n_pages; ++p)
-        if (ctx->h_cnt[p] > A.cap) { redo_pages->push_back(p); ++ctx->fused_redo_pages; }
+    PRL_CUDA_TRY(ctx, cudaGetLastError());
+    *d_redo_map = redo_map;
+    *d_redo_count = redo_count;
     return PRL_OK;
 }

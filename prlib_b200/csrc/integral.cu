@@ -266,20 +266,29 @@ template <int MAXW, int R>
 __global__ void __launch_bounds__(MAXW * 32)
 integral_generic_kernel(const uint8_t* __restrict__ src, size_t src_step, size_t src_page_stride, int rows, int cols,
                         int pad, int64_t* __restrict__ S, int64_t* __restrict__ Q, size_t pitch, size_t page_stride,
-                        int rows_per_band, const int64_t* __restrict__ carry, uint32_t* __restrict__ imin, int vec_ok)
+                        int rows_per_band, const int64_t* __restrict__ carry, uint32_t* __restrict__ imin, int vec_ok,
+                        const int* __restrict__ page_map = nullptr, const int* __restrict__ page_count = nullptr, int slot_base = 0)
 {
     constexpr int kSub = 4;
     __shared__ uint2 tot[2][R][MAXW];
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int page = blockIdx.y, band = blockIdx.x, bands = gridDim.x;
+    const int band = blockIdx.x, bands = gridDim.x;
+    // indirect launch (hand-back of the fused path): plane slot blockIdx.y holds page page_map[slot_base + blockIdx.y] of the
+    // batch; the list and its length live in device memory, CTAs beyond it leave at once
+    int page = blockIdx.y;
+    const int slot = blockIdx.y;
+    if (page_map != nullptr) {
+        if (slot_base + slot >= *page_count) return;
+        page = page_map[slot_base + slot];
+    }
     const int Wp = cols + 2 * pad;
     const int y0 = band * rows_per_band;
     const int y1 = min(y0 + rows_per_band, rows);
 
     src += (size_t)page * src_page_stride;
-    S += (size_t)page * page_stride;
-    Q += (size_t)page * page_stride;
+    S += (size_t)slot * page_stride;
+    Q += (size_t)slot * page_stride;
 
     const int Xb = wid * kWarpCols + 2 * lane;
     int xs[kSub][2];
@@ -676,6 +685,31 @@ int prl_k_integral(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int row
     else
         integral_generic_kernel<32, 4><<<grid, nwarps * 32, 0, ctx->stream>>>(
             d_src, src_step, src_page_stride, rows, cols, pad, d_S, d_Q, pitch, plane_page_stride, rpb, d_carry, d_imin, vec_ok);
+    PRL_CUDA_TRY(ctx, cudaGetLastError());
+    return PRL_OK;
+}
+
+// int64 planes of the pages page_map[slot_base .. slot_base + slots) (as many as *page_count says exist) into plane
+// slots 0 .. slots-1: the generic kernel, one CTA per page.  Serves the device-side hand-back of the fused path.
+int prl_k_integral_indirect(prl_cuda_ctx* ctx, const uint8_t* d_src, int slots, int rows, int cols, size_t src_step,
+                            size_t src_page_stride, int pad, int64_t* d_S, int64_t* d_Q, size_t pitch, size_t plane_page_stride,
+                            const int* d_map, const int* d_count, int slot_base)
+{
+    const int Wp = cols + 2 * pad;
+    const int nwarps = (Wp + kWarpCols - 1) / kWarpCols;
+    if (nwarps > 32 || slots > 65535) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "indirect integral: page too wide or too many slots");
+    const bool vec_ok = ((((uintptr_t)d_S) | ((uintptr_t)d_Q)) & 15) == 0 && (pitch & 1) == 0 && (plane_page_stride & 1) == 0;
+    int rpb = (rows + 3) / 4 * 4;
+    prl_launch_scope ls(ctx, FAM_INTEGRAL);
+    dim3 grid(1, slots);
+    if (nwarps <= 16)
+        integral_generic_kernel<16, 4><<<grid, nwarps * 32, 0, ctx->stream>>>(
+            d_src, src_step, src_page_stride, rows, cols, pad, d_S, d_Q, pitch, plane_page_stride, rpb, nullptr, nullptr, vec_ok,
+            d_map, d_count, slot_base);
+    else
+        integral_generic_kernel<32, 4><<<grid, nwarps * 32, 0, ctx->stream>>>(
+            d_src, src_step, src_page_stride, rows, cols, pad, d_S, d_Q, pitch, plane_page_stride, rpb, nullptr, nullptr, vec_ok,
+            d_map, d_count, slot_base);
     PRL_CUDA_TRY(ctx, cudaGetLastError());
     return PRL_OK;
 }

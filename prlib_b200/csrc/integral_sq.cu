@@ -55,17 +55,28 @@ __device__ __forceinline__ void st_v4_u32(void* p, uint32_t a, uint32_t b, uint3
     asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// the replicated border, for the one or two warps of a CTA whose strip touches it (kept out of line: rare, register-hungry)
-__device__ __noinline__ uint2 fix_edge(uint2 w, int x_first, int cols, uint32_t lv, uint32_t rv)
+// The replicated border, for the one or two warps of a CTA whose strip touches it.  Which of a lane's 8 bytes lie left of
+// source column 0 / right of column cols-1 never changes from row to row, so the byte masks are built once per kernel
+// (edge_masks) and a row costs two multiplies and four LOP3 -- the first version rebuilt them byte by byte in every row,
+// which made the two edge warps ~30 % slower than the other eight and everybody wait for them at the chunk barrier
+// (ncu round 2: 29 % of the warp samples on that barrier).
+// edge_counts packs nl = bytes [0, nl) that replicate column 0 and nr = bytes [8 - nr, 8) that replicate column cols - 1.
+__device__ __forceinline__ uint32_t edge_counts(int x_first, int cols)
 {
-    uint32_t v[2] = {w.x, w.y};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int xi = x_first + i;
-        if (xi < 0) v[i >> 2] = (v[i >> 2] & ~(0xffu << (8 * (i & 3)))) | (lv << (8 * (i & 3)));
-        else if (xi >= cols) v[i >> 2] = (v[i >> 2] & ~(0xffu << (8 * (i & 3)))) | (rv << (8 * (i & 3)));
-    }
-    return make_uint2(v[0], v[1]);
+    const int nl = min(max(-x_first, 0), 8), nr = min(max(x_first + 8 - cols, 0), 8);
+    return (uint32_t)(64 - 8 * nl) | ((uint32_t)(64 - 8 * nr) << 8);          // as shift counts; shr/shl.b64 clamp at 64 -> 0
+}
+__device__ __forceinline__ uint2 fix_edge(uint2 w, uint32_t counts, uint32_t lv, uint32_t rv)
+{
+    unsigned long long ml, mr;
+    asm("shr.b64 %0, %1, %2;" : "=l"(ml) : "l"(~0ull), "r"(counts & 0xffu));
+    asm("shl.b64 %0, %1, %2;" : "=l"(mr) : "l"(~0ull), "r"(counts >> 8));
+    mr &= ~ml;
+    const uint32_t lx = (uint32_t)ml, ly = (uint32_t)(ml >> 32), rx = (uint32_t)mr, ry = (uint32_t)(mr >> 32);
+    const uint32_t l4 = lv * 0x01010101u, r4 = rv * 0x01010101u;
+    w.x = (w.x & ~(lx | rx)) | (l4 & lx) | (r4 & rx);
+    w.y = (w.y & ~(ly | ry)) | (l4 & ly) | (r4 & ry);
+    return w;
 }
 
 template <int MAXW, int MINB, bool WITH_MIN>
@@ -101,6 +112,7 @@ integral_sq_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int cols,
     const bool edge = (X0 < pad) || (X0 + kWC > pad + cols);             // strip touches a replicated column
     const int lcol = -xb;                                                // box offset of source column 0 (valid when X0 < pad)
     const int rcol = cols - 1 - xb;                                      // box offset of source column cols-1
+    const uint32_t em = edge_counts(Xl - pad, cols);
 
     if (lane == 0) {
 #pragma unroll
@@ -164,7 +176,7 @@ integral_sq_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int cols,
                 }
                 if (edge) {
                     const uint32_t lv = (X0 < pad) ? row[lcol] : 0u, rv = (rcol >= 0 && rcol < kBox) ? row[rcol] : 0u;
-                    w = fix_edge(w, Xl - pad, cols, lv, rv);
+                    w = fix_edge(w, em, lv, rv);
                 }
             }
             if (WITH_MIN && yc + r < y1) mn4 = __vminu4(__vminu4(mn4, w.x), w.y);

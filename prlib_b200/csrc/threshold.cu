@@ -43,6 +43,8 @@ struct ThrArgs {
     const uint32_t* imin; long long* smax;
     int out_rows, out_cols, d;
     double kw, nkw, p0, p1, p2;
+    // indirect launch of the exact kernel (hand-back of the fused path): plane slot z holds page page_map[slot_base + z]
+    const int* page_map = nullptr; const int* page_count = nullptr; int slot_base = 0;
 };
 
 // one spelling of the reference's formulas for every kernel: decide.cuh:thr_value_p
@@ -68,11 +70,15 @@ template <int METHOD, int MODE>
 __global__ void __launch_bounds__(256)
 threshold_exact_kernel(const ThrArgs A)
 {
-    const int page = blockIdx.z;
+    int page = blockIdx.z;
+    const int slot = blockIdx.z;
+    if (A.page_map != nullptr) {
+        if (A.slot_base + slot >= *A.page_count) return;
+        page = A.page_map[A.slot_base + slot];
+    }
     const int x = (blockIdx.x * 256 + threadIdx.x) * 2;
-    const int y0 = blockIdx.y * kTR;
-    const int64_t* S = A.S + (size_t)page * A.plane_page_stride;
-    const int64_t* Q = A.Q + (size_t)page * A.plane_page_stride;
+    const int64_t* S = A.S + (size_t)slot * A.plane_page_stride;
+    const int64_t* Q = A.Q + (size_t)slot * A.plane_page_stride;
     const uint8_t* src = A.src + (size_t)page * A.src_page_stride;
 
     double imin = 0.0, coeff = 0.0;
@@ -81,7 +87,10 @@ threshold_exact_kernel(const ThrArgs A)
         coeff = __ddiv_rn(A.p0, __longlong_as_double(A.smax[page]));   // coeff = k / devianceMax
 
     double smax_local = __longlong_as_double(0xfff0000000000000LL);   // -inf
-    if (x < A.out_cols) {
+    // (direct launches have one CTA per block of kTR rows; the indirect hand-back launches a short grid that strides, so
+    // that a launch over an empty page list costs a few thousand CTAs, not a million)
+    if (x < A.out_cols)
+    for (int y0 = blockIdx.y * kTR; y0 < A.out_rows; y0 += gridDim.y * kTR) {
 #pragma unroll
         for (int r = 0; r < kTR; ++r) {
             const int y = y0 + r;
@@ -920,17 +929,13 @@ bool prl_threshold_fast_ok(const prl_cuda_ctx* ctx, int method, const double* pa
            fast_margins(method, params, g, &F);
 }
 
-int prl_k_threshold(prl_cuda_ctx* ctx, int method, int mode, const uint8_t* d_src, int n_pages,
-                    const prl_geom& g, size_t src_step, size_t src_page_stride, const prl_planes& P, const double* params,
-                    const uint32_t* d_imin, long long* d_smax, uint8_t* d_dst, size_t dst_step,
-                    size_t dst_page_stride)
+static ThrArgs make_thr_args(int method, const uint8_t* d_src, const prl_geom& g, size_t src_step, size_t src_page_stride,
+                             const prl_planes& P, const double* params, const uint32_t* d_imin, long long* d_smax,
+                             uint8_t* d_dst, size_t dst_step, size_t dst_page_stride)
 {
-    const int64_t* d_S = (const int64_t*)P.S;
-    const int64_t* d_Q = (const int64_t*)P.Q;
-    const size_t plane_page_stride = P.page_stride;
     ThrArgs A;
     A.src = d_src; A.src_step = src_step; A.src_page_stride = src_page_stride;
-    A.S = d_S; A.Q = d_Q; A.pitch = P.pitch; A.plane_page_stride = plane_page_stride;
+    A.S = (const int64_t*)P.S; A.Q = (const int64_t*)P.Q; A.pitch = P.pitch; A.plane_page_stride = P.page_stride;
     A.AH = (const uint2*)P.AS; A.a_pitch = P.a_pitch; A.a_page_stride = P.a_page_stride; A.ashift = P.ashift;
     A.dst = d_dst; A.dst_step = dst_step; A.dst_page_stride = dst_page_stride;
     A.imin = d_imin; A.smax = d_smax;
@@ -940,6 +945,43 @@ int prl_k_threshold(prl_cuda_ctx* ctx, int method, int mode, const uint8_t* d_sr
     A.p0 = params[0]; A.p1 = 0; A.p2 = 0;
     if (method == PRL_SAUVOLA) { A.p1 = params[0] * (1.0 / 128.0); A.p2 = 1.0 - params[0]; }   // (k*RBack), (1-k) :115-117
     if (method == PRL_FENG) { A.p1 = 1.0 + (1.0 - params[0]); A.p2 = params[2]; }              // c2 + c1, k2
+    return A;
+}
+
+// Masks of the pages page_map[slot_base .. slot_base + slots) (as many as *page_count says exist) from the int64 planes in
+// slots 0 .. slots-1, every pixel through the literal FP64 path.  Serves the device-side hand-back of the fused path
+// (never Wolf-Jolion: that method does not take the fused path).
+int prl_k_threshold_exact_indirect(prl_cuda_ctx* ctx, int method, const uint8_t* d_src, int slots, const prl_geom& g, size_t src_step,
+                                   size_t src_page_stride, const prl_planes& P, const double* params, const uint32_t* d_imin,
+                                   uint8_t* d_dst, size_t dst_step, size_t dst_page_stride, const int* d_map, const int* d_count,
+                                   int slot_base)
+{
+    if (P.compact || method == PRL_WOLFJOLION || method < PRL_SAUVOLA || method > PRL_FENG)
+        return prl_set_err(ctx, PRL_E_INVALID, "indirect exact threshold: int64 planes, not Wolf-Jolion");
+    ThrArgs A = make_thr_args(method, d_src, g, src_step, src_page_stride, P, params, d_imin, nullptr, d_dst, dst_step, dst_page_stride);
+    A.page_map = d_map; A.page_count = d_count; A.slot_base = slot_base;
+    dim3 grid((g.out_cols + 511) / 512, std::min((g.out_rows + kTR - 1) / kTR, 64), slots);
+    if (slots > 65535) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "grid too large");
+    prl_launch_scope ls(ctx, FAM_THRESHOLD);
+    switch (method) {
+    case PRL_SAUVOLA: launch_exact<PRL_SAUVOLA>(ctx, 0, A, grid); break;
+    case PRL_NIBLACK: launch_exact<PRL_NIBLACK>(ctx, 0, A, grid); break;
+    case PRL_NICK:    launch_exact<PRL_NICK>(ctx, 0, A, grid); break;
+    default:          launch_exact<PRL_FENG>(ctx, 0, A, grid); break;
+    }
+    PRL_CUDA_TRY(ctx, cudaGetLastError());
+    return PRL_OK;
+}
+
+int prl_k_threshold(prl_cuda_ctx* ctx, int method, int mode, const uint8_t* d_src, int n_pages,
+                    const prl_geom& g, size_t src_step, size_t src_page_stride, const prl_planes& P, const double* params,
+                    const uint32_t* d_imin, long long* d_smax, uint8_t* d_dst, size_t dst_step,
+                    size_t dst_page_stride)
+{
+    const int64_t* d_S = (const int64_t*)P.S;
+    const int64_t* d_Q = (const int64_t*)P.Q;
+    const size_t plane_page_stride = P.page_stride;
+    ThrArgs A = make_thr_args(method, d_src, g, src_step, src_page_stride, P, params, d_imin, d_smax, d_dst, dst_step, dst_page_stride);
     if (method < PRL_SAUVOLA || method > PRL_FENG) return prl_set_err(ctx, PRL_E_INVALID, "unknown method");
 
     dim3 grid((g.out_cols + 511) / 512, (g.out_rows + kTR - 1) / kTR, n_pages);

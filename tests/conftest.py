@@ -22,11 +22,6 @@ def _has_gpu():
         return False
 
 
-def pytest_collection_modifyitems(config, items):
-    # -m gpu on a box without a GPU must FAIL loudly, not skip: only skip when gpu tests were not asked for
-    pass
-
-
 @pytest.fixture(scope="session")
 def golden():
     with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as f:
@@ -38,12 +33,28 @@ def real_crops():
     return dict(np.load(os.path.join(ROOT, "tests", "golden", "real_crops.npz")))
 
 
-@pytest.fixture(scope="session")
-def ctx():
+# Every GPU test that takes `ctx` runs twice: with the library's defaults (windows <= 31 take the fused small-window
+# kernel) and with that kernel switched off (kernel 1 + kernel 2 for every window) -- both must equal the oracle.
+@pytest.fixture(scope="session", params=["default_paths", "two_kernel_path"])
+def ctx(request):
     import prlib_b200
     c = prlib_b200.Context(0)     # raises PrlCudaError when there is no GPU: gpu tests fail loudly
+    c.fused_default = 1 if request.param == "default_paths" else 0
     yield c
     c.close()
+
+
+@pytest.fixture(autouse=True)
+def _path_options(request):
+    """(re)apply the path selection before every test that uses `ctx`: to it and to the package's own default context"""
+    if "ctx" in request.fixturenames:
+        import prlib_b200
+        c = request.getfixturevalue("ctx")
+        for k in (c, prlib_b200.default_context(0)):
+            k.set_option("enable_fused", c.fused_default)
+            k.set_option("fused_page_cap", 128)
+            k.set_option("fused_no_tier2", 0)
+    yield
 
 
 @pytest.fixture(scope="session")

@@ -241,12 +241,21 @@ def test_host_batch_dispatcher(golden):
 
 def test_timing_hooks_count_launches(ctx):
     img = CO.synth_page(0, 300, 400)
+    ctx.set_option("enable_fused", 0)
     ctx.timing_reset(); ctx.timing_enable(True)
     ctx.binarize_local(img, 0, 15, (0.2,), 0)
     t = ctx.timing()
     ctx.timing_enable(False)
     assert t["integral"]["launches"] == 1 and t["threshold"]["launches"] == 1
     assert t["integral"]["ms"] > 0 and ctx.launch_count() >= 2
+    # default path for this window: the fused kernel, its fixup, the device-side overflow list and one (empty) hand-back round
+    ctx.set_option("enable_fused", 1)
+    ctx.timing_reset(); ctx.timing_enable(True)
+    ctx.binarize_local(img, 0, 15, (0.2,), 0)
+    t = ctx.timing()
+    ctx.timing_enable(False)
+    assert t["fused"]["launches"] == 1 and t["fused_fix"]["launches"] == 2
+    assert t["integral"]["launches"] == 1 and t["threshold"]["launches"] == 1      # the indirect hand-back launches
 
 
 def lept1_words(mask):

@@ -43,11 +43,11 @@ def test_cuda_equals_reference_outputs(key, ctx):
         assert sha(prlib_b200.binarizeLocalOtsu(img, 255.0, 2.0)) == e["localOtsu_clahe2"], key
 
 
-@pytest.mark.parametrize("opt", ["exact_threshold", "enable_fused"])
-def test_cuda_validation_paths_equal_reference_outputs(ctx, opt):
-    """the literal-FP64 kernel and the fused small-window kernel against the same reference digests"""
+@pytest.mark.parametrize("opt,val", [("exact_threshold", 1), ("enable_fused", 0), ("enable_fused", 1), ("disable_compact", 1)])
+def test_cuda_validation_paths_equal_reference_outputs(ctx, opt, val):
+    """the literal-FP64 kernel, the two-kernel path (compact and int64 planes) and the fused small-window kernel against the same reference digests"""
     d = prlib_b200.default_context(0)
-    d.set_option(opt, 1)
+    d.set_option(opt, val)
     try:
         for key in ("noise_512x640", "halfblack_140x150", "sparse_150x160", "page_0001", "page_0099"):
             img, e = image(key), REF["images"][key]
@@ -55,7 +55,7 @@ def test_cuda_validation_paths_equal_reference_outputs(ctx, opt):
                 fn, args = REF["calls"][name]
                 assert sha(FN[fn](img, *args)) == want["sha1"], (opt, key, name)
     finally:
-        d.set_option(opt, 0)
+        d.set_option(opt, ctx.fused_default if opt == "enable_fused" else 0)
 
 
 @pytest.mark.skipif(not R.available(), reason="oracle/_ref/_prl_ref.so did not travel to this box")
