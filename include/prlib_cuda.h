@@ -239,6 +239,36 @@ int prl_cuda_external_rects(prl_cuda_ctx* ctx, const uint8_t* mask, int rows, in
 int prl_cuda_remove_lines(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step, int channels,
                           uint8_t* dst, size_t dst_step);
 
+/* ---- the adaptive-mean family: binarizeNativeAdaptive.cpp:34-140, binarizeAT.cpp:33-67,
+ * binarizeAGT.cpp:33-58, binarizePureAdaptiveGaussian.cpp:31-71 ------------------------------------------------
+ * cv::medianBlur (u8; 1, 3 or 4 interleaved channels; odd ksize 3..63; ksize <= 1 copies; even ksize: PRL_E_EMPTY_ROI, the
+ * cv::Exception of OpenCV) and cv::adaptiveThreshold (method 0 = ADAPTIVE_THRESH_MEAN_C, 1 = ADAPTIVE_THRESH_GAUSSIAN_C;
+ * type 0 = THRESH_BINARY, 1 = THRESH_BINARY_INV; odd block_size 3..255, else PRL_E_EMPTY_ROI) on one image, byte-identical
+ * to OpenCV 4.x; prl_cuda_gauss_kernel_float = cv::getGaussianKernel(n, 0, CV_32F), the coefficients of GAUSSIAN_C. */
+int prl_cuda_median_blur(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step, int channels, int ksize,
+                         uint8_t* dst, size_t dst_step);
+int prl_cuda_adaptive_threshold(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step, double maxval,
+                                int method, int type, int block_size, double delta, uint8_t* dst, size_t dst_step);
+int prl_cuda_gauss_kernel_float(int n, float* k);
+/* The whole call sequence of one family member in one call (the image crosses PCIe once each way).  The C++ shim fills
+ * the structure per reference function; 1 channel in = used as it is, 3 / 4 = BGR / BGRA. */
+typedef struct prl_adaptive_params {
+    int gray_first;      /* 1: cvtColor(BGR2GRAY), then the blur (NativeAdaptive :58-61); 0: blur the colour image, then gray (AT, AGT) */
+    int blur;            /* 0 none, 1 cv::medianBlur(blur_ksize), 2 cv::GaussianBlur(blur_ksize x blur_ksize, blur_sigma) */
+    int blur_ksize;
+    double blur_sigma;
+    int assert_ksize;    /* 1: CV_Assert(medianBlurKernelSize >= 3) of NativeAdaptive :65 */
+    int method, type;    /* as prl_cuda_adaptive_threshold */
+    double maxval;
+    int check_maxval;    /* 1: maxval outside [0, 255] is PRL_E_INVALID (NativeAdaptive :53-56) */
+    int block_size;
+    int auto_block;      /* 1: block_size < 3 means int(diagonal / 333 + 7) (NativeAdaptive :86-93) */
+    double delta;
+    int invert_if_dark;  /* 1: 255 - image when cv::mean(image)[0] < 128 (NativeAdaptive :108-111) */
+} prl_adaptive_params;
+int prl_cuda_binarize_adaptive(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step, int channels,
+                               const prl_adaptive_params* params, uint8_t* dst, size_t dst_step);
+
 /* ---- 1 bit per pixel ---------------------------------------------
  * The masks in Leptonica's PIX layout, the reference's second image container (src/formatConvert.cpp:39-69
  * writes PIX words with SET_DATA_BIT): rows of wpl = (cols + 31) / 32 32-bit words, pixel x of a row in word
@@ -254,7 +284,7 @@ int prl_cuda_binarize_batch_packed(const int* devices, int n_dev, int method, co
 /* ---- instrumentation ---------------------------------------------------------------------
  * With timing enabled every kernel launch is bracketed by CUDA events on the launching stream.
  * prl_cuda_timing_get sums them per kernel family ("integral", "threshold", "smax", "morph",
- * "otsu_hist", "otsu_search", "otsu_apply", "otsu_tiles", "synth", "bgr2gray", "band_carry", "fused", "fused_pre", "fused_fix");
+ * "otsu_hist", "otsu_search", "otsu_apply", "otsu_tiles", "synth", "bgr2gray", "band_carry", "fused", "fused_pre", "fused_fix", "pack", "edges", "lines", "adaptive");
  * it synchronizes the stream. */
 int  prl_cuda_timing_enable(prl_cuda_ctx* ctx, int on);
 int  prl_cuda_timing_reset(prl_cuda_ctx* ctx);

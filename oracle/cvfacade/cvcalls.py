@@ -239,6 +239,14 @@ def medianBlur(a, k):
     return cv2.medianBlur(a, k)
 
 
+def bilateralFilter(a, d, sigma_color, sigma_space):
+    return cv2.bilateralFilter(a, d, sigma_color, sigma_space)
+
+
+def mean(a):
+    return tuple(float(v) for v in cv2.mean(a))
+
+
 def inRange(a, lo, hi):
     return cv2.inRange(a, lo, hi)
 

@@ -393,6 +393,13 @@ void minMaxLoc(const Mat& src, double* minVal, double* maxVal, Point* minLoc, Po
     if (minLoc) *minLoc = Point(x0, y0);
     if (maxLoc) *maxLoc = Point(x1, y1);
 }
+Scalar mean(const Mat& src) {
+    PyObject* r = call("mean", "(O)", py(src));
+    Scalar s;
+    if (!PyArg_ParseTuple(r, "dddd", &s.val[0], &s.val[1], &s.val[2], &s.val[3])) { Py_DECREF(r); cvfacade::throw_python_error(); }
+    Py_DECREF(r);
+    return s;
+}
 void add(const Mat& a, const Mat& b, Mat& dst) { dst.store(call("add", "(OO)", py(a), py(b))); }
 void subtract(const Mat& a, const Mat& b, Mat& dst) { dst.store(call("subtract", "(OO)", py(a), py(b))); }
 void multiply(const Mat& a, const Mat& b, Mat& dst, double scale) { dst.store(call("multiply", "(OOd)", py(a), py(b), scale)); }
@@ -479,6 +486,9 @@ void GaussianBlur(const Mat& src, Mat& dst, Size ksize, double sigmaX, double si
     dst.store(call("GaussianBlur", "(Oiidd)", py(src), ksize.width, ksize.height, sigmaX, sigmaY));
 }
 void medianBlur(const Mat& src, Mat& dst, int ksize) { dst.store(call("medianBlur", "(Oi)", py(src), ksize)); }
+void bilateralFilter(const Mat& src, Mat& dst, int d, double sigmaColor, double sigmaSpace, int) {
+    dst.store(call("bilateralFilter", "(Oidd)", py(src), d, sigmaColor, sigmaSpace));
+}
 void Canny(const Mat& image, Mat& edges, double t1, double t2, int aperture, bool l2) {
     CV_Assert(aperture == 3 && !l2);
     edges.store(call("Canny", "(Odd)", py(image), t1, t2));

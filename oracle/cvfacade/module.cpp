@@ -21,6 +21,12 @@
 #include "binarizeFeng.h"
 #include "binarizeLocalOtsu.h"
 #include "removeLines.h"
+#include "binarizeAT.h"
+#include "binarizeAGT.h"
+#include "binarizeGAT.h"
+#include "binarizePureAdaptive.h"
+#include "binarizePureAdaptiveGaussian.h"
+#include "binarizeNativeAdaptive.h"
 
 static PyObject* g_cv_error = 0;  // cv2.error, or NULL -> RuntimeError
 
@@ -120,6 +126,47 @@ static PyObject* py_removeLines(PyObject*, PyObject* args) {
     }
 }
 
+// the adaptive-mean family: (image, [kernel size,] maxValue, blockSize, shift)
+#define PRL_ATWRAP(NAME, FMT, DECL, PARSE, CALLARGS)                                            \
+    static PyObject* py_##NAME(PyObject*, PyObject* args) {                                     \
+        PyObject* image;                                                                        \
+        DECL;                                                                                   \
+        if (!PyArg_ParseTuple(args, FMT, &image, PARSE)) return 0;                              \
+        try {                                                                                   \
+            cv::Mat in, out;                                                                    \
+            bind_input(in, image);                                                              \
+            prl::NAME CALLARGS;                                                                 \
+            return result_pair(out, in);                                                        \
+        } catch (...) {                                                                         \
+            return translate_exception();                                                       \
+        }                                                                                       \
+    }
+#define PRL_COMMA ,
+PRL_ATWRAP(binarizeAT, "Oidii", int mk PRL_COMMA bs PRL_COMMA sh; double mv, &mk PRL_COMMA &mv PRL_COMMA &bs PRL_COMMA &sh, (in, out, mk, mv, bs, sh))
+PRL_ATWRAP(binarizeAGT, "Oidii", int mk PRL_COMMA bs PRL_COMMA sh; double mv, &mk PRL_COMMA &mv PRL_COMMA &bs PRL_COMMA &sh, (in, out, mk, mv, bs, sh))
+PRL_ATWRAP(binarizeGAT, "Oidddii", int gk PRL_COMMA bs PRL_COMMA sh; double sx PRL_COMMA sy PRL_COMMA mv,
+           &gk PRL_COMMA &sx PRL_COMMA &sy PRL_COMMA &mv PRL_COMMA &bs PRL_COMMA &sh, (in, out, gk, sx, sy, mv, bs, sh))
+PRL_ATWRAP(binarizePureAdaptive, "Odii", int bs PRL_COMMA sh; double mv, &mv PRL_COMMA &bs PRL_COMMA &sh, (in, out, mv, bs, sh))
+PRL_ATWRAP(binarizePureAdaptiveGaussian, "Odii", int bs PRL_COMMA sh; double mv, &mv PRL_COMMA &bs PRL_COMMA &sh, (in, out, mv, bs, sh))
+
+static PyObject* py_binarizeNativeAdaptive(PyObject*, PyObject* args) {
+    PyObject* image;
+    int gauss_blur, median_k, gauss_k, by_gaussian, block, bil_k;
+    double gauss_sigma, maxval, shift, bil_color, bil_space;
+    if (!PyArg_ParseTuple(args, "Oiiididididd", &image, &gauss_blur, &median_k, &gauss_k, &gauss_sigma, &by_gaussian, &maxval, &block, &shift,
+                          &bil_k, &bil_color, &bil_space))
+        return 0;
+    try {
+        cv::Mat in, out;
+        bind_input(in, image);
+        prl::binarizeNativeAdaptive(in, out, gauss_blur != 0, median_k, gauss_k, gauss_sigma, by_gaussian != 0, maxval, block, shift, bil_k,
+                                    bil_color, bil_space);
+        return result_pair(out, in);
+    } catch (...) {
+        return translate_exception();
+    }
+}
+
 static PyObject* py_register(PyObject*, PyObject* args) {
     PyObject *calls, *cv_error;
     if (!PyArg_ParseTuple(args, "OO", &calls, &cv_error)) return 0;
@@ -139,6 +186,13 @@ static PyMethodDef methods[] = {
     {"binarizeFeng", py_binarizeFeng, METH_VARARGS, "prl::binarizeFeng(image, windowSize, alpha1, k1, k2, gamma, morph)"},
     {"binarizeLocalOtsu", py_binarizeLocalOtsu, METH_VARARGS, "prl::binarizeLocalOtsu(image, maxValue, clahe, gauss, upper, lower, morph)"},
     {"removeLines", py_removeLines, METH_VARARGS, "prl::removeLines(image)"},
+    {"binarizeAT", py_binarizeAT, METH_VARARGS, "prl::binarizeAT(image, medianKernelSize, maxValue, blockSize, shift)"},
+    {"binarizeAGT", py_binarizeAGT, METH_VARARGS, "prl::binarizeAGT(image, medianKernelSize, maxValue, blockSize, shift)"},
+    {"binarizeGAT", py_binarizeGAT, METH_VARARGS, "prl::binarizeGAT(image, gaussianKernelSize, sigmaX, sigmaY, maxValue, blockSize, shift)"},
+    {"binarizePureAdaptive", py_binarizePureAdaptive, METH_VARARGS, "prl::binarizePureAdaptive(image, maxValue, blockSize, shift)"},
+    {"binarizePureAdaptiveGaussian", py_binarizePureAdaptiveGaussian, METH_VARARGS, "prl::binarizePureAdaptiveGaussian(image, maxValue, blockSize, shift)"},
+    {"binarizeNativeAdaptive", py_binarizeNativeAdaptive, METH_VARARGS,
+     "prl::binarizeNativeAdaptive(image, gaussBlur, medianK, gaussK, gaussSigma, byGaussian, maxValue, blockSize, shift, bilateralK, colorSigma, spaceSigma)"},
     {0, 0, 0, 0}};
 
 static struct PyModuleDef moduledef = {PyModuleDef_HEAD_INIT, "_prl_ref",

@@ -284,6 +284,7 @@ Mat& operator/=(Mat& a, double s);
 /* ---- core ---- */
 void copyMakeBorder(const Mat& src, Mat& dst, int top, int bottom, int left, int right, int borderType,
                     const Scalar& value = Scalar());
+Scalar mean(const Mat& src);
 void sqrt(const Mat& src, Mat& dst);
 void pow(const Mat& src, double power, Mat& dst);
 void minMaxLoc(const Mat& src, double* minVal, double* maxVal = 0, Point* minLoc = 0, Point* maxLoc = 0,

@@ -31,6 +31,7 @@ void adaptiveThreshold(const Mat& src, Mat& dst, double maxValue, int adaptiveMe
 Mat getStructuringElement(int shape, Size ksize, Point anchor = Point(-1, -1));
 void GaussianBlur(const Mat& src, Mat& dst, Size ksize, double sigmaX, double sigmaY = 0, int borderType = BORDER_DEFAULT);
 void medianBlur(const Mat& src, Mat& dst, int ksize);
+void bilateralFilter(const Mat& src, Mat& dst, int d, double sigmaColor, double sigmaSpace, int borderType = BORDER_DEFAULT);
 void Canny(const Mat& image, Mat& edges, double threshold1, double threshold2, int apertureSize = 3, bool L2gradient = false);
 void equalizeHist(const Mat& src, Mat& dst);
 void findContours(const Mat& image, std::vector<std::vector<Point> >& contours, std::vector<Vec4i>& hierarchy, int mode,

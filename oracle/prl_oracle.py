@@ -24,14 +24,12 @@ erode) is executed by the real OpenCV through cv2 with the same dtypes and in th
 
 Parity pinning status
 ---------------------
-The reference ships NO tests, NO golden outputs and cannot be compiled here (it needs the
-OpenCV C++ headers/libs and Leptonica, neither of which exists in this image) -> by the
-letter of the brief "parity unpinned" by reference fixtures.  What pins this oracle instead:
-it does not re-implement the arithmetic, it *calls* the third-party library in which the
-reference's arithmetic lives (OpenCV, un-vendored, un-pinned by the reference,
-CMakeLists.txt:17).  A second, independent plain-C restatement (oracle/prl_oracle.c) is
-checked bit-for-bit against this one in tests/test_oracle.py, and SHA-1 digests of both are
-committed under tests/golden/ (generated by tests/golden/make_golden.py).
+PINNED since round 2: oracle/_ref is the reference's OWN binarize*.cpp / removeLines.cpp / imageLibCommon.cpp compiled
+unmodified against a cv:: facade whose primitives run in the cv2 wheel (oracle/Makefile, oracle/ref.py).  This file must
+equal it output for output (tests/test_ref.py, digests in tests/golden/ref_golden.json); it stays because it also
+travels to places the compiled module cannot (it needs no /root/reference) and because it exposes intermediate
+results (integrals, T maps).  A second, independent plain-C restatement (oracle/prl_oracle.c) is checked bit for bit
+against this one in tests/test_oracle.py.  The reference itself ships no tests and no golden outputs.
 """
 from __future__ import annotations
 
@@ -575,3 +573,127 @@ def binarize_local_numpy(gray: np.ndarray, method: int, window: int, params) -> 
     T, pad, (x, y, rw, rh) = threshold_map_f64_numpy(gray, method, window, params)
     T8 = to_u8_numpy(T)
     return np.where(pad[y:y + rh, x:x + rw] > T8, 255, 0).astype(np.uint8)
+
+
+# ------------------------------------------------------------------------------------------------
+# The adaptive-mean family: the reference's call sequences on cv2, op for op.
+# cv2.error plays the role of cv::Exception.  (oracle/_ref runs the reference's own object code for the same functions.)
+# ------------------------------------------------------------------------------------------------
+def _empty_mat_adaptive():
+    """what cv::adaptiveThreshold does with the empty Mat these functions hand it: CV_Assert(src.type() == CV_8UC1) ..."""
+    raise cv2.error("adaptiveThreshold on an empty Mat (the reference never assigned it)")
+
+
+def binarizeAT(image, medianKernelSize, maxValue, blockSize, shift):          # binarizeAT.cpp:33-67
+    with _single_thread():
+        if image is None or image.size == 0:
+            raise ValueError("Input image for binarization is empty")
+        tmp = cv2.medianBlur(image, medianKernelSize)
+        if image.ndim == 2 or image.shape[2] == 1:
+            _empty_mat_adaptive()
+        g = cv2.cvtColor(tmp, cv2.COLOR_BGR2GRAY)
+        return cv2.adaptiveThreshold(g, maxValue, cv2.ADAPTIVE_THRESH_MEAN_C, cv2.THRESH_BINARY, blockSize, int(shift))
+
+
+def binarizeAGT(image, medianKernelSize, maxValue, blockSize, shift):         # binarizeAGT.cpp:33-58
+    with _single_thread():
+        if image is None or image.size == 0:
+            raise ValueError("Input image for binarization is empty")
+        tmp = cv2.medianBlur(image, medianKernelSize)
+        if image.ndim == 2 or image.shape[2] == 1:
+            _empty_mat_adaptive()
+        g = cv2.cvtColor(tmp, cv2.COLOR_BGR2GRAY)
+        return cv2.adaptiveThreshold(g, maxValue, cv2.ADAPTIVE_THRESH_GAUSSIAN_C, cv2.THRESH_BINARY, blockSize, int(shift))
+
+
+def binarizePureAdaptiveGaussian(image, maxValue, blockSize, shift):          # binarizePureAdaptiveGaussian.cpp:31-71
+    with _single_thread():
+        if image is None or image.size == 0:
+            raise ValueError("Input image for binarization is empty")
+        if image.ndim == 2 or image.shape[2] == 1:
+            _empty_mat_adaptive()
+        g = cv2.cvtColor(image, cv2.COLOR_BGR2GRAY)
+        return cv2.adaptiveThreshold(g, maxValue, cv2.ADAPTIVE_THRESH_GAUSSIAN_C, cv2.THRESH_BINARY, blockSize, int(shift))
+
+
+def binarizeNativeAdaptive(image, isGaussianBlurReqiured=False, medianBlurKernelSize=5, GaussianBlurKernelSize=7, GaussianBlurSigma=150.0,
+                           isAdaptiveThresholdCalculatedByGaussian=True, adaptiveThresholdingMaxValue=255.0,
+                           adaptiveThresholdingBlockSize=19, adaptiveThresholdingShift=9):     # binarizeNativeAdaptive.cpp:34-115
+    with _single_thread():
+        if image is None or image.size == 0:
+            raise ValueError("Input image for binarization is empty")
+        if not (0 <= adaptiveThresholdingMaxValue <= 255):
+            raise ValueError("Max value must be in range [0; 255]")
+        g = cv2.cvtColor(image, cv2.COLOR_BGR2GRAY) if image.ndim == 3 and image.shape[2] > 1 else image.reshape(image.shape[:2])
+        if not isGaussianBlurReqiured:
+            if medianBlurKernelSize < 3:
+                raise cv2.error("medianBlurKernelSize >= 3")
+            out = cv2.medianBlur(g, medianBlurKernelSize)
+        else:
+            if GaussianBlurKernelSize < 3 or not GaussianBlurSigma > 0:
+                raise cv2.error("GaussianBlurKernelSize >= 3, GaussianBlurSigma > 0")
+            out = cv2.GaussianBlur(g, (GaussianBlurKernelSize, GaussianBlurKernelSize), GaussianBlurSigma)
+        method = cv2.ADAPTIVE_THRESH_GAUSSIAN_C if isAdaptiveThresholdCalculatedByGaussian else cv2.ADAPTIVE_THRESH_MEAN_C
+        bs = adaptiveThresholdingBlockSize
+        if bs < 3:
+            bs = int(np.sqrt(float(out.shape[0] * out.shape[0] + out.shape[1] * out.shape[1])) / 333 + 7)
+        out = cv2.adaptiveThreshold(out, adaptiveThresholdingMaxValue, method, cv2.THRESH_BINARY_INV, bs, adaptiveThresholdingShift)
+        if cv2.mean(out)[0] < 128:
+            out = 255 - out
+        return out
+
+
+# ---- first-principles models of the two means cv::adaptiveThreshold uses (what csrc/adaptive.cu restates); checked
+# against the real cv2 calls in tests/test_adaptive.py
+def box_mean_model(gray: np.ndarray, bs: int) -> np.ndarray:
+    """boxFilter(normalize, BORDER_REPLICATE) of a u8 image: round(sum / bs^2), never a tie for odd bs"""
+    h = bs // 2
+    p = np.pad(gray.astype(np.int64), h, mode="edge")
+    I = np.zeros((p.shape[0] + 1, p.shape[1] + 1), np.int64)
+    I[1:, 1:] = p.cumsum(0).cumsum(1)
+    H, W = gray.shape
+    s = I[bs:bs + H, bs:bs + W] - I[0:H, bs:bs + W] - I[bs:bs + H, 0:W] + I[0:H, 0:W]
+    return ((2 * s + bs * bs) // (2 * bs * bs)).astype(np.uint8)
+
+
+def _fma32(a, b, c):
+    # exact fused multiply-add in float32: the 48-bit product and the sum are exact in 64-bit-mantissa long doubles
+    return (a.astype(np.longdouble) * b.astype(np.longdouble) + c.astype(np.longdouble)).astype(np.float32)
+
+
+def _mad32(a, b, c):
+    return (c + (a * b).astype(np.float32)).astype(np.float32)
+
+
+def gaussian_mean_model(gray: np.ndarray, bs: int, as_float: bool = False) -> np.ndarray:
+    """GaussianBlur(float32(gray), (bs, bs), 0, BORDER_REPLICATE) -> u8 as the cv2 wheel's AVX2 build evaluates it:
+    fused multiply-adds in the vector bodies (row pass: columns below cols & ~3, column pass: below cols & ~7), the
+    scalar tails as gcc compiled them (csrc/adaptive.cu header)."""
+    H, W = gray.shape
+    f = gray.astype(np.float32)
+    # cv::GaussianBlur: a one-pixel-wide / -high image is not filtered along that axis (ksize.width / .height := 1)
+    k = cv2.getGaussianKernel(bs if W > 1 else 1, 0, cv2.CV_32F).ravel().astype(np.float32)
+    bs_x = len(k)
+    h = bs_x // 2
+    p = np.pad(f, ((0, 0), (h, h)), mode="edge")
+    nu = 4 * ((bs_x - 1) // 4)
+    body = (p[:, 0:W] * k[0]).astype(np.float32)
+    tail = body.copy()
+    for i in range(1, bs_x):
+        x = p[:, i:i + W]
+        body = _fma32(x, np.float32(k[i]), body)
+        tail = (_mad32 if i <= nu else _fma32)(x, np.float32(k[i]), tail)
+    rowp = np.where(np.arange(W)[None, :] < (W & ~3), body, tail)
+    k = cv2.getGaussianKernel(bs if H > 1 else 1, 0, cv2.CV_32F).ravel().astype(np.float32)
+    h = len(k) // 2
+    r = np.pad(rowp, ((h, h), (0, 0)), mode="edge")
+    body = (r[h:h + H] * k[h]).astype(np.float32)
+    tail = body.copy()
+    for j in range(1, h + 1):
+        sm = (r[h + j:h + j + H] + r[h - j:h - j + H]).astype(np.float32)
+        body = _fma32(sm, np.float32(k[h + j]), body)
+        tail = _mad32(sm, np.float32(k[h + j]), tail)
+    out = np.where(np.arange(W)[None, :] < (W & ~7), body, tail)
+    if as_float:
+        return out
+    return np.clip(np.rint(out), 0, 255).astype(np.uint8)

@@ -97,6 +97,39 @@ def removeLines(image):
     return out
 
 
+# ---- the adaptive-mean family; no defaults in the reference headers except NativeAdaptive's
+def binarizeAT(image, medianKernelSize, maxValue, blockSize, shift):
+    return module().binarizeAT(_img(image), int(medianKernelSize), float(maxValue), int(blockSize), int(shift))[0]
+
+
+def binarizeAGT(image, medianKernelSize, maxValue, blockSize, shift):
+    return module().binarizeAGT(_img(image), int(medianKernelSize), float(maxValue), int(blockSize), int(shift))[0]
+
+
+def binarizeGAT(image, gaussianKernelSize, sigmaX, sigmaY, maxValue, blockSize, shift):
+    return module().binarizeGAT(_img(image), int(gaussianKernelSize), float(sigmaX), float(sigmaY), float(maxValue), int(blockSize), int(shift))[0]
+
+
+def binarizePureAdaptive(image, maxValue, blockSize, shift):
+    return module().binarizePureAdaptive(_img(image), float(maxValue), int(blockSize), int(shift))[0]
+
+
+def binarizePureAdaptiveGaussian(image, maxValue, blockSize, shift):
+    return module().binarizePureAdaptiveGaussian(_img(image), float(maxValue), int(blockSize), int(shift))[0]
+
+
+def binarizeNativeAdaptive(image, isGaussianBlurReqiured=False, medianBlurKernelSize=5, GaussianBlurKernelSize=7, GaussianBlurSigma=150.0,
+                           isAdaptiveThresholdCalculatedByGaussian=True, adaptiveThresholdingMaxValue=255.0,
+                           adaptiveThresholdingBlockSize=19, adaptiveThresholdingShift=9, bilateralFilterBlockSize=0,
+                           bilateralFilterColorSigma=150.0, bilateralFilterSpaceSigma=150.0, return_input=False):
+    out, after = module().binarizeNativeAdaptive(_img(image), int(bool(isGaussianBlurReqiured)), int(medianBlurKernelSize),
+                                                 int(GaussianBlurKernelSize), float(GaussianBlurSigma),
+                                                 int(bool(isAdaptiveThresholdCalculatedByGaussian)), float(adaptiveThresholdingMaxValue),
+                                                 int(adaptiveThresholdingBlockSize), float(adaptiveThresholdingShift),
+                                                 int(bilateralFilterBlockSize), float(bilateralFilterColorSigma), float(bilateralFilterSpaceSigma))
+    return (out, after) if return_input else out
+
+
 _BY_METHOD = {0: "binarizeSauvola", 1: "binarizeNiblack", 2: "binarizeWolfJolion", 3: "binarizeNICK", 4: "binarizeFeng"}
 
 

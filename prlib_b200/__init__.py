@@ -8,9 +8,11 @@ from . import capi
 from .capi import PrlCudaError, SAUVOLA, NIBLACK, WOLFJOLION, NICK, FENG
 from .context import Context, default_context, binarize_batch, unpack_lept1, PinnedArray, set_global_option
 from .binarize import (binarizeSauvola, binarizeNiblack, binarizeWolfJolion, binarizeNICK, binarizeFeng,
-                       padded_gray, otsuThreshold, binarizeLocalOtsuRects, binarizeLocalOtsuTiles, binarizeLocalOtsu, removeLines)
+                       padded_gray, otsuThreshold, binarizeLocalOtsuRects, binarizeLocalOtsuTiles, binarizeLocalOtsu, removeLines,
+                       binarizeAT, binarizeAGT, binarizeGAT, binarizePureAdaptive, binarizePureAdaptiveGaussian, binarizeNativeAdaptive)
 
 __all__ = ["capi", "PrlCudaError", "Context", "default_context", "binarize_batch", "unpack_lept1", "PinnedArray", "set_global_option", "SAUVOLA", "NIBLACK",
            "WOLFJOLION", "NICK", "FENG", "binarizeSauvola", "binarizeNiblack", "binarizeWolfJolion",
            "binarizeNICK", "binarizeFeng", "padded_gray", "otsuThreshold", "binarizeLocalOtsuRects",
-           "binarizeLocalOtsuTiles", "binarizeLocalOtsu", "removeLines"]
+           "binarizeLocalOtsuTiles", "binarizeLocalOtsu", "removeLines", "binarizeAT", "binarizeAGT", "binarizeGAT",
+           "binarizePureAdaptive", "binarizePureAdaptiveGaussian", "binarizeNativeAdaptive"]

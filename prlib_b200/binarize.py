@@ -130,3 +130,85 @@ def binarizeLocalOtsuTiles(image, tileWidth: int = 64, tileHeight: int = 64, max
         raise ValueError("Max value must be in range [0; 255]")
     ctx = default_context(device)
     return ctx.otsu_tiles(_gray(image, ctx), tileWidth, tileHeight, maxValue)
+
+
+# ---- the adaptive-mean family -----------------------------------------------------------
+# The reference's own quirks are part of the interface (tests/test_adaptive.py runs the reference's own object code and shows the same):
+#   * binarizeAT / binarizeAGT / binarizePureAdaptiveGaussian only assign the image adaptiveThreshold reads inside
+#     `if (channels != 1)`: a 1-channel input ends in the cv::Exception of cv::adaptiveThreshold on an empty Mat
+#     (binarizeAT.cpp:53-65, binarizeAGT.cpp:46-58, binarizePureAdaptiveGaussian.cpp:47-69);
+#   * binarizeGAT and binarizePureAdaptive convert to gray first, so that branch is never taken: they raise for EVERY
+#     non-empty input (binarizeGAT.cpp:37-64, binarizePureAdaptive.cpp:38-60).
+_CV_EMPTY = "adaptiveThreshold: src.type() == CV_8UC1 fails on the empty Mat the reference passes (cv::Exception)"
+
+
+def _nonempty(image):
+    im = np.asarray(image)
+    if im.size == 0:
+        raise ValueError("Input image for binarization is empty")
+    return im
+
+
+def _colour_only(im):
+    if im.ndim == 2 or im.shape[2] == 1:
+        raise capi.PrlCudaError(capi.PRL_E_EMPTY_ROI, _CV_EMPTY)
+    return im
+
+
+def binarizeAT(inputImage, medianKernelSize: int, maxValue: float, blockSize: int, shift: int, device: int = 0) -> np.ndarray:
+    """prl::binarizeAT (binarizeAT.h:33-34): medianBlur on the colour image -> BGR2GRAY -> adaptiveThreshold(MEAN_C, BINARY)."""
+    im = _colour_only(_nonempty(inputImage))
+    return default_context(device).binarize_adaptive(im, gray_first=0, blur=1, blur_ksize=int(medianKernelSize), method=0, type=0,
+                                                     maxval=float(maxValue), block_size=int(blockSize), delta=float(int(shift)))
+
+
+def binarizeAGT(inputImage, medianKernelSize: int, maxValue: float, blockSize: int, shift: int, device: int = 0) -> np.ndarray:
+    """prl::binarizeAGT (binarizeAGT.h:32-33): as binarizeAT with ADAPTIVE_THRESH_GAUSSIAN_C."""
+    im = _colour_only(_nonempty(inputImage))
+    return default_context(device).binarize_adaptive(im, gray_first=0, blur=1, blur_ksize=int(medianKernelSize), method=1, type=0,
+                                                     maxval=float(maxValue), block_size=int(blockSize), delta=float(int(shift)))
+
+
+def binarizePureAdaptiveGaussian(inputImage, maxValue: float, blockSize: int, shift: int, device: int = 0) -> np.ndarray:
+    """prl::binarizePureAdaptiveGaussian (binarizePureAdaptiveGaussian.h:33-34): BGR2GRAY -> adaptiveThreshold(GAUSSIAN_C, BINARY)."""
+    im = _colour_only(_nonempty(inputImage))
+    return default_context(device).binarize_adaptive(im, gray_first=1, blur=0, method=1, type=0, maxval=float(maxValue),
+                                                     block_size=int(blockSize), delta=float(int(shift)))
+
+
+def binarizeGAT(inputImage, gaussianKernelSize: int, sigmaX: float, sigmaY: float, maxValue: float, blockSize: int, shift: int,
+                device: int = 0):
+    """prl::binarizeGAT (binarizeGAT.h:33-35) raises for every non-empty input (see above)."""
+    _nonempty(inputImage)
+    raise capi.PrlCudaError(capi.PRL_E_EMPTY_ROI, _CV_EMPTY)
+
+
+def binarizePureAdaptive(inputImage, maxValue: float, blockSize: int, shift: int, device: int = 0):
+    """prl::binarizePureAdaptive (binarizePureAdaptive.h:33-34) raises for every non-empty input (see above)."""
+    _nonempty(inputImage)
+    raise capi.PrlCudaError(capi.PRL_E_EMPTY_ROI, _CV_EMPTY)
+
+
+def binarizeNativeAdaptive(inputImage, isGaussianBlurReqiured: bool = False, medianBlurKernelSize: int = 5,
+                           GaussianBlurKernelSize: int = 7, GaussianBlurSigma: float = 150.0,
+                           isAdaptiveThresholdCalculatedByGaussian: bool = True, adaptiveThresholdingMaxValue: float = 255.0,
+                           adaptiveThresholdingBlockSize: int = 19, adaptiveThresholdingShift: float = 9,
+                           bilateralFilterBlockSize: int = 0, bilateralFilterColorSigma: float = 150.0,
+                           bilateralFilterSpaceSigma: float = 150.0, device: int = 0) -> np.ndarray:
+    """prl::binarizeNativeAdaptive (binarizeNativeAdaptive.h:63-75, same defaults): gray -> median or Gaussian blur ->
+    adaptiveThreshold(BINARY_INV) -> 255 - image when its mean is below 128.  The optional bilateral filter of the result
+    (bilateralFilterBlockSize >= 3, off by default) is not implemented on the device: PRL_E_UNSUPPORTED."""
+    im = _nonempty(inputImage)
+    if not (0 <= adaptiveThresholdingMaxValue <= 255):
+        raise ValueError("Max value must be in range [0; 255]")                                    # :53-56
+    if bilateralFilterBlockSize >= 3:
+        if bilateralFilterColorSigma <= 0:
+            raise ValueError("Color sigma for bilateral filtration must be greater than 0")        # :123-126
+        if bilateralFilterSpaceSigma <= 0:
+            raise ValueError("Space sigma for bilateral filtration must be greater than 0")        # :128-131
+        raise capi.PrlCudaError(capi.PRL_E_UNSUPPORTED, "the bilateral filter step of binarizeNativeAdaptive is not implemented")
+    return default_context(device).binarize_adaptive(
+        im, gray_first=1, blur=2 if isGaussianBlurReqiured else 1,
+        blur_ksize=int(GaussianBlurKernelSize if isGaussianBlurReqiured else medianBlurKernelSize), blur_sigma=float(GaussianBlurSigma),
+        assert_ksize=1, method=1 if isAdaptiveThresholdCalculatedByGaussian else 0, type=1, maxval=float(adaptiveThresholdingMaxValue),
+        check_maxval=1, block_size=int(adaptiveThresholdingBlockSize), auto_block=1, delta=float(adaptiveThresholdingShift), invert_if_dark=1)

@@ -287,6 +287,37 @@ class Context:
                                                   out.ctypes.data, im.shape[1]))
         return out
 
+    # ---- the adaptive-mean family
+    def median_blur(self, image, ksize: int):
+        im = np.ascontiguousarray(image)
+        if im.dtype != np.uint8 or im.ndim not in (2, 3):
+            raise TypeError("image must be a uint8 HxW or HxWxC array")
+        r, c = im.shape[:2]
+        ch = 1 if im.ndim == 2 else im.shape[2]
+        out = np.empty_like(im)
+        self._check(self._L.prl_cuda_median_blur(self._h, im.ctypes.data, r, c, im.strides[0], ch, int(ksize), out.ctypes.data, out.strides[0]))
+        return out
+
+    def adaptive_threshold(self, gray, maxval: float, method: int, thresh_type: int, block_size: int, delta: float):
+        g = _as_u8_2d(gray)
+        r, c = g.shape
+        out = np.empty((r, c), np.uint8)
+        self._check(self._L.prl_cuda_adaptive_threshold(self._h, g.ctypes.data, r, c, g.strides[0], float(maxval), int(method),
+                                                        int(thresh_type), int(block_size), float(delta), out.ctypes.data, c))
+        return out
+
+    def binarize_adaptive(self, image, **kw):
+        """prl_cuda_binarize_adaptive; keyword arguments = the fields of struct prl_adaptive_params"""
+        im = np.ascontiguousarray(image)
+        if im.dtype != np.uint8 or im.ndim not in (2, 3):
+            raise TypeError("image must be a uint8 HxW or HxWxC array")
+        r, c = im.shape[:2]
+        ch = 1 if im.ndim == 2 else im.shape[2]
+        p = capi.AdaptiveParams(**kw)
+        out = np.empty((r, c), np.uint8)
+        self._check(self._L.prl_cuda_binarize_adaptive(self._h, im.ctypes.data, r, c, im.strides[0], ch, C.byref(p), out.ctypes.data, c))
+        return out
+
     # -- device-pointer entry points (raw addresses: torch .data_ptr() or cudaMalloc) ----------
     def binarize_local_batch_dev(self, method, d_src, n_pages, rows, cols, src_step, src_page_stride, window, params,
                                  morph_iters, d_dst, dst_step, dst_page_stride):

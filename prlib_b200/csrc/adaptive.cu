@@ -1,0 +1,322 @@
+// adaptive.cu -- the adaptive-mean family of src/binarizations: cv::medianBlur and
+// cv::adaptiveThreshold (MEAN_C / GAUSSIAN_C) on the device, bit-identical to OpenCV 4.x, behind
+//   prl::binarizeNativeAdaptive   binarizeNativeAdaptive.cpp:34-140   (median / Gaussian blur -> adaptiveThreshold(BINARY_INV)
+//                                                                       -> invert when the mean is below 128)
+//   prl::binarizeAT / AGT          binarizeAT.cpp:33-67, binarizeAGT.cpp:33-58  (medianBlur on the colour image -> BGR2GRAY ->
+//                                                                       adaptiveThreshold(MEAN_C / GAUSSIAN_C, BINARY))
+//   prl::binarizePureAdaptiveGaussian  binarizePureAdaptiveGaussian.cpp:31-71   (BGR2GRAY -> adaptiveThreshold(GAUSSIAN_C))
+// Third-party semantics restated here (pinned against the real cv2 calls by tests/test_adaptive.py):
+//   * medianBlur (u8, 1/3/4 channels, odd ksize): the exact median of the ksize x ksize window per channel, BORDER_REPLICATE.
+//     Whatever algorithm OpenCV picks (sorting network, O(1) histogram) the median is unique; here: an 8-step radix select.
+//   * adaptiveThreshold: mean = boxFilter(normalize, BORDER_REPLICATE) or GaussianBlur on CV_32F (sigma = 0 -> derived from
+//     the block size) converted back to u8; dst = tab[src - mean + 255], tab = (i - 255 > -ceil(delta)) ? maxval : 0 for
+//     THRESH_BINARY and (i - 255 <= -floor(delta)) ? maxval : 0 for THRESH_BINARY_INV, maxval = saturate_cast<uchar>.
+//       - box mean of u8: cvRound(sum / bs^2).  bs is odd, so sum / bs^2 is never a tie and round-half-even, the float32
+//         product of OpenCV's SIMD body and the double product of its scalar tail all give floor((2 sum + bs^2) / (2 bs^2))
+//         (proof for bs <= 69: the nearest tie is 1 / (2 bs^2) away, float32 rounding moves the product by < 255 * 2^-23).
+//       - GaussianBlur on CV_32F is sepFilter2D with float32 coefficients (getGaussianKernel: the tables for 1..9 taps,
+//         else exp() normalised in double and rounded to float).  The summation order and the fusing are those of OpenCV's
+//         AVX2 build, measured column by column against the cv2 wheel (scripts in DESIGN.md):
+//           row pass    s = x[0] k[0];  s = fma(x[i], k[i], s) for columns below (cols & ~3); the scalar tail adds the
+//                       first 4 * floor((n - 1) / 4) products unfused (gcc vectorises them) and fuses the rest;
+//           column pass s = r[c] k[c];  s = fma(r[c + j] + r[c - j], k[c + j], s) for columns below (cols & ~7), unfused
+//                       multiply-then-add in the scalar tail.
+#include "common.cuh"
+#include <algorithm>
+#include <cmath>
+
+namespace {
+
+inline size_t r16(size_t v) { return (v + 15) & ~(size_t)15; }
+inline size_t r256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// ------------------------------------------------------------------------------------------------
+// medianBlur
+// ------------------------------------------------------------------------------------------------
+constexpr int kMedTW = 32, kMedTH = 8;
+
+template <int CH>
+__global__ void __launch_bounds__(kMedTW * kMedTH)
+median_kernel(const uint8_t* __restrict__ src, size_t step, int rows, int cols, int ksize, uint8_t* __restrict__ dst, size_t dstep)
+{
+    extern __shared__ uint8_t tile[];                       // (kMedTH + ksize - 1) x (kMedTW + ksize - 1) x CH
+    const int h = ksize / 2, tw = kMedTW + ksize - 1, th = kMedTH + ksize - 1;
+    const int x0 = blockIdx.x * kMedTW - h, y0 = blockIdx.y * kMedTH - h;
+    for (int i = threadIdx.x; i < tw * th; i += kMedTW * kMedTH) {
+        const int ty = i / tw, tx = i - ty * tw;
+        const int sy = min(max(y0 + ty, 0), rows - 1), sx = min(max(x0 + tx, 0), cols - 1);     // BORDER_REPLICATE
+        const uint8_t* p = src + (size_t)sy * step + (size_t)sx * CH;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) tile[i * CH + c] = p[c];
+    }
+    __syncthreads();
+    const int lx = threadIdx.x % kMedTW, ly = threadIdx.x / kMedTW;
+    const int x = blockIdx.x * kMedTW + lx, y = blockIdx.y * kMedTH + ly;
+    if (x >= cols || y >= rows) return;
+    const int r = (ksize * ksize) / 2;                      // 0-based rank of the median
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        // the greatest t with #{v < t} <= r is the r-th smallest value: fix its bits from the top
+        int res = 0;
+        for (int bit = 7; bit >= 0; --bit) {
+            const int cand = res | (1 << bit);
+            int cnt = 0;
+            for (int dy = 0; dy < ksize; ++dy) {
+                const uint8_t* row = tile + ((ly + dy) * tw + lx) * CH + c;
+                for (int dx = 0; dx < ksize; ++dx) cnt += row[dx * CH] < cand ? 1 : 0;
+            }
+            if (cnt <= r) res = cand;
+        }
+        dst[(size_t)y * dstep + (size_t)x * CH + c] = (uint8_t)res;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// adaptiveThreshold
+// ------------------------------------------------------------------------------------------------
+struct TabArgs { int inv; int idelta; int maxv; };
+
+// dst = tab[src - mean + 255]; counts the pixels set (for the mean < 128 test of binarizeNativeAdaptive.cpp:108)
+__device__ __forceinline__ int tab_value(const TabArgs& T, int s, int m)
+{
+    const int i = s - m;
+    return T.inv ? (i <= -T.idelta ? T.maxv : 0) : (i > -T.idelta ? T.maxv : 0);
+}
+
+// MEAN_C: box sums by two sliding passes in shared memory, one CTA per tile of TW x TH output pixels
+__global__ void __launch_bounds__(256)
+box_threshold_kernel(const uint8_t* __restrict__ src, size_t step, int rows, int cols, int bs, int TW, int TH, TabArgs T,
+                     uint8_t* __restrict__ dst, size_t dstep, unsigned long long* __restrict__ nset)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int h = bs / 2, tw = TW + bs - 1, th = TH + bs - 1;
+    uint8_t* tile = smem;                                               // th x tw
+    unsigned short* hs = reinterpret_cast<unsigned short*>(smem + (((size_t)tw * th + 15) & ~(size_t)15));   // th x TW
+    const int x0 = blockIdx.x * TW - h, y0 = blockIdx.y * TH - h;
+    for (int i = threadIdx.x; i < tw * th; i += 256) {
+        const int ty = i / tw, tx = i - ty * tw;
+        tile[i] = src[(size_t)min(max(y0 + ty, 0), rows - 1) * step + min(max(x0 + tx, 0), cols - 1)];
+    }
+    __syncthreads();
+    // horizontal window sums: units of (row, 16 columns)
+    const int segs = TW / 16;
+    for (int u = threadIdx.x; u < th * segs; u += 256) {
+        const int ty = u / segs, sx = (u - ty * segs) * 16;
+        const uint8_t* row = tile + ty * tw + sx;
+        int s = 0;
+        for (int k = 0; k < bs; ++k) s += row[k];
+        unsigned short* o = hs + ty * TW + sx;
+        o[0] = (unsigned short)s;
+        for (int j = 1; j < 16; ++j) { s += row[j + bs - 1] - row[j - 1]; o[j] = (unsigned short)s; }
+    }
+    __syncthreads();
+    // vertical window sums: units of (column, 8 rows)
+    const int vsegs = TH / 8;
+    const unsigned int area = (unsigned int)bs * bs;
+    unsigned int set = 0;
+    for (int u = threadIdx.x; u < TW * vsegs; u += 256) {
+        const int lx = u % TW, sy = (u / TW) * 8;
+        const unsigned short* col = hs + sy * TW + lx;
+        unsigned int s = 0;
+        for (int k = 0; k < bs; ++k) s += col[k * TW];
+        const int x = blockIdx.x * TW + lx;
+        for (int j = 0; j < 8; ++j) {
+            if (j) s += col[(j + bs - 1) * TW] - col[(j - 1) * TW];
+            const int y = blockIdx.y * TH + sy + j;
+            if (x < cols && y < rows) {
+                const int mean = (int)((2u * s + area) / (2u * area));
+                const int v = tab_value(T, tile[(sy + j + h) * tw + lx + h], mean);
+                dst[(size_t)y * dstep + x] = (uint8_t)v;
+                set += v ? 1u : 0u;
+            }
+        }
+    }
+    if (nset != nullptr) {
+        set = __reduce_add_sync(0xffffffffu, set);
+        if ((threadIdx.x & 31) == 0 && set) atomicAdd(nset, (unsigned long long)set);
+    }
+}
+
+struct GaussF { int n; int n_unfused; float k[256]; };      // n_unfused: leading terms of the row pass's scalar tail that are not fused
+
+// GAUSSIAN_C, row pass: u8 -> float32 rows
+__global__ void __launch_bounds__(256)
+gaussf_rows_kernel(const uint8_t* __restrict__ src, size_t step, int rows, int cols, const __grid_constant__ GaussF K,
+                   float* __restrict__ tmp, size_t tstep)
+{
+    __shared__ float kk[256];
+    __shared__ uint8_t line[256 + 256];
+    const int n = K.n, h = n / 2;
+    for (int i = threadIdx.x; i < n; i += 256) kk[i] = K.k[i];
+    const int y = blockIdx.y, xb = blockIdx.x * 256;
+    const uint8_t* row = src + (size_t)y * step;
+    for (int i = threadIdx.x; i < 256 + n - 1; i += 256) line[i] = row[min(max(xb + i - h, 0), cols - 1)];
+    __syncthreads();
+    const int x = xb + threadIdx.x;
+    if (x >= cols) return;
+    const uint8_t* p = line + threadIdx.x;
+    float s = __fmul_rn((float)p[0], kk[0]);
+    if (x < (cols & ~3)) {
+        for (int i = 1; i < n; ++i) s = __fmaf_rn((float)p[i], kk[i], s);
+    } else {
+        const int nu = K.n_unfused;
+        for (int i = 1; i <= nu; ++i) s = __fadd_rn(s, __fmul_rn((float)p[i], kk[i]));
+        for (int i = nu + 1; i < n; ++i) s = __fmaf_rn((float)p[i], kk[i], s);
+    }
+    tmp[(size_t)y * tstep + x] = s;
+}
+
+// GAUSSIAN_C, column pass + convertTo(u8) + table
+__global__ void __launch_bounds__(256)
+gaussf_cols_threshold_kernel(const float* __restrict__ tmp, size_t tstep, const uint8_t* __restrict__ src, size_t step, int rows, int cols,
+                             const __grid_constant__ GaussF K, TabArgs T, uint8_t* __restrict__ dst, size_t dstep,
+                             unsigned long long* __restrict__ nset)
+{
+    __shared__ float kk[256];
+    const int n = K.n, h = n / 2;
+    for (int i = threadIdx.x; i < n; i += 256) kk[i] = K.k[i];
+    __syncthreads();
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+    unsigned int set = 0;
+    if (x < cols) {
+        const float* c = tmp + x;
+        float s = __fmul_rn(c[(size_t)y * tstep], kk[h]);
+        const bool fused = x < (cols & ~7);
+        for (int j = 1; j <= h; ++j) {
+            const float a = c[(size_t)min(y + j, rows - 1) * tstep], b = c[(size_t)max(y - j, 0) * tstep];
+            const float pr = __fadd_rn(a, b);
+            s = fused ? __fmaf_rn(pr, kk[h + j], s) : __fadd_rn(s, __fmul_rn(pr, kk[h + j]));
+        }
+        int mean = __float2int_rn(s);                                   // saturate_cast<uchar>(float): cvRound, then clamp
+        mean = min(max(mean, 0), 255);
+        const int v = tab_value(T, src[(size_t)y * step + x], mean);
+        dst[(size_t)y * dstep + x] = (uint8_t)v;
+        set = v ? 1u : 0u;
+    }
+    if (nset != nullptr) {
+        set = __reduce_add_sync(0xffffffffu, set);
+        if ((threadIdx.x & 31) == 0 && set) atomicAdd(nset, (unsigned long long)set);
+    }
+}
+
+// inputImageChannels[c] = 255 - inputImageChannels[c] when cv::mean(...)[0] < 128 (binarizeNativeAdaptive.cpp:108-111)
+__global__ void __launch_bounds__(256)
+invert_if_dark_kernel(uint8_t* __restrict__ img, size_t step, int rows, int cols, int maxv, const unsigned long long* __restrict__ nset)
+{
+    // mean = maxv * nset / (rows * cols) < 128  <=>  maxv * nset < 128 * rows * cols   (exact in 64-bit integers)
+    if ((unsigned long long)maxv * *nset >= 128ull * (unsigned long long)rows * (unsigned long long)cols) return;
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+    if (x < cols) img[(size_t)y * step + x] = (uint8_t)(255 - img[(size_t)y * step + x]);
+}
+
+}  // namespace
+
+// float32 Gaussian coefficients as cv::getGaussianKernel(n, sigma <= 0, CV_32F) returns them (tables for n <= 9)
+int prl_gauss_kernel_float(int n, float* k)
+{
+    if (n < 1 || n > 255 || (n & 1) == 0) return PRL_E_INVALID;
+    static const double t1[] = {1.0}, t3[] = {0.25, 0.5, 0.25}, t5[] = {0.0625, 0.25, 0.375, 0.25, 0.0625},
+                        t7[] = {0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125},
+                        t9[] = {4.0 / 256, 13.0 / 256, 30.0 / 256, 51.0 / 256, 60.0 / 256, 51.0 / 256, 30.0 / 256, 13.0 / 256, 4.0 / 256};
+    if (n <= 9) {
+        const double* t = n == 1 ? t1 : n == 3 ? t3 : n == 5 ? t5 : n == 7 ? t7 : t9;
+        for (int i = 0; i < n; ++i) k[i] = (float)t[i];
+        return PRL_OK;
+    }
+    const double s = ((n - 1) * 0.5 - 1) * 0.3 + 0.8, scale2 = -0.5 / (s * s);
+    double c[255], sum = 0;
+    for (int i = 0; i < n; ++i) { const double x = i - (n - 1) * 0.5; c[i] = exp(scale2 * x * x); sum += c[i]; }
+    sum = 1.0 / sum;
+    for (int i = 0; i < n; ++i) k[i] = (float)(c[i] * sum);
+    return PRL_OK;
+}
+
+size_t prl_adaptive_scratch_bytes(int rows, int cols)
+{
+    return r256(sizeof(unsigned long long) * 4) + r256((size_t)rows * r16((size_t)cols) * sizeof(float));
+}
+
+// cv::medianBlur on the device (d_src != d_dst)
+int prl_k_median_blur(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, int channels, int ksize,
+                      uint8_t* d_dst, size_t dst_step)
+{
+    if (ksize < 3 || (ksize & 1) == 0 || ksize > 63) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "median kernel size must be odd and in [3, 63]");
+    const size_t smem = (size_t)(kMedTW + ksize - 1) * (kMedTH + ksize - 1) * channels;
+    dim3 grid((cols + kMedTW - 1) / kMedTW, (rows + kMedTH - 1) / kMedTH);
+    if (grid.y > 65535) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "image too tall");
+    prl_launch_scope ls(ctx, FAM_ADAPTIVE);
+#define PRL_MEDIAN(C)                                                                                                              \
+    do { auto kfn = median_kernel<C>;                                                                                              \
+         PRL_CUDA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));  \
+         kfn<<<grid, kMedTW * kMedTH, smem, ctx->stream>>>(d_src, step, rows, cols, ksize, d_dst, dst_step); } while (0)
+    if (channels == 1) PRL_MEDIAN(1);
+    else if (channels == 3) PRL_MEDIAN(3);
+    else if (channels == 4) PRL_MEDIAN(4);
+    else return prl_set_err(ctx, PRL_E_INVALID, "channels must be 1, 3 or 4");
+#undef PRL_MEDIAN
+    PRL_CUDA_TRY(ctx, cudaGetLastError());
+    return PRL_OK;
+}
+
+// cv::adaptiveThreshold on the device (d_src != d_dst).  method 0 = MEAN_C, 1 = GAUSSIAN_C;
+// type 0 = THRESH_BINARY, 1 = THRESH_BINARY_INV.  scratch: prl_adaptive_scratch_bytes.  invert_if_dark: the
+// `mean < 128 -> 255 - image` step of prl::binarizeNativeAdaptive, decided on the device.
+int prl_k_adaptive_threshold(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, double maxval, int method, int type,
+                             int block_size, double delta, uint8_t* d_dst, size_t dst_step, void* scratch, bool invert_if_dark)
+{
+    if (block_size <= 1 || (block_size & 1) == 0 || block_size > 255)
+        return prl_set_err(ctx, PRL_E_UNSUPPORTED, "adaptive block size must be odd and in [3, 255]");
+    if (rows > 65535) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "image too tall");
+    unsigned long long* nset = (unsigned long long*)scratch;
+    float* tmp = (float*)((uint8_t*)scratch + r256(sizeof(unsigned long long) * 4));
+    const size_t tstep = r16((size_t)cols);
+    TabArgs T;
+    T.inv = type != 0;
+    T.idelta = (int)(type == 0 ? ceil(delta) : floor(delta));
+    double mv = nearbyint(maxval);                                  // saturate_cast<uchar>(double) = cvRound + clamp
+    T.maxv = (int)std::min(std::max(mv, 0.0), 255.0);
+    if (maxval < 0) {                                               // "if( maxValue < 0 ) { dst = Scalar(0); return; }"
+        PRL_CUDA_TRY(ctx, cudaMemset2DAsync(d_dst, dst_step, 0, cols, rows, ctx->stream));
+        T.maxv = 0;
+        PRL_CUDA_TRY(ctx, cudaMemsetAsync(nset, 0, sizeof(unsigned long long), ctx->stream));
+    } else {
+        PRL_CUDA_TRY(ctx, cudaMemsetAsync(nset, 0, sizeof(unsigned long long), ctx->stream));
+        if (method == 0) {
+            const int TW = block_size <= 63 ? 64 : 32, TH = 32;
+            const size_t tile = ((size_t)(TW + block_size - 1) * (TH + block_size - 1) + 15) & ~(size_t)15;
+            const size_t smem = tile + (size_t)(TH + block_size - 1) * TW * sizeof(unsigned short);
+            dim3 grid((cols + TW - 1) / TW, (rows + TH - 1) / TH);
+            if (grid.y > 65535) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "image too tall");
+            PRL_CUDA_TRY(ctx, cudaFuncSetAttribute(box_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            prl_launch_scope ls(ctx, FAM_ADAPTIVE);
+            box_threshold_kernel<<<grid, 256, smem, ctx->stream>>>(d_src, step, rows, cols, block_size, TW, TH, T, d_dst, dst_step, nset);
+        } else if (method == 1) {
+            // cv::GaussianBlur: a one-pixel-wide / -high image is not filtered along that axis (ksize.width / .height := 1)
+            GaussF K, K1;
+            K.n = block_size;
+            K.n_unfused = 4 * ((block_size - 1) / 4);
+            if (prl_gauss_kernel_float(block_size, K.k) != PRL_OK) return prl_set_err(ctx, PRL_E_INVALID, "bad Gaussian block size");
+            for (int i = block_size; i < 256; ++i) K.k[i] = 0.f;     // the coefficients travel as a kernel parameter (1 KB)
+            K1 = K; K1.n = 1; K1.n_unfused = 0; K1.k[0] = 1.f;
+            const GaussF& Kx = cols > 1 ? K : K1;
+            const GaussF& Ky = rows > 1 ? K : K1;
+            dim3 grid((cols + 255) / 256, rows);
+            {
+                prl_launch_scope ls(ctx, FAM_ADAPTIVE);
+                gaussf_rows_kernel<<<grid, 256, 0, ctx->stream>>>(d_src, step, rows, cols, Kx, tmp, tstep);
+            }
+            {
+                prl_launch_scope ls(ctx, FAM_ADAPTIVE);
+                gaussf_cols_threshold_kernel<<<grid, 256, 0, ctx->stream>>>(tmp, tstep, d_src, step, rows, cols, Ky, T, d_dst, dst_step, nset);
+            }
+        } else {
+            return prl_set_err(ctx, PRL_E_INVALID, "Unknown/unsupported adaptive threshold method");
+        }
+    }
+    if (invert_if_dark) {
+        prl_launch_scope ls(ctx, FAM_ADAPTIVE);
+        invert_if_dark_kernel<<<dim3((cols + 255) / 256, rows), 256, 0, ctx->stream>>>(d_dst, dst_step, rows, cols, T.maxv, nset);
+    }
+    PRL_CUDA_TRY(ctx, cudaGetLastError());
+    return PRL_OK;
+}

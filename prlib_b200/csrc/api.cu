@@ -84,7 +84,7 @@ static void timing_collect(prl_cuda_ctx* ctx)
 }
 
 static const char* kFamilyNames[FAM_COUNT] = {"integral", "threshold", "smax", "morph", "otsu_hist", "otsu_search",
-                                              "otsu_apply", "otsu_tiles", "synth", "bgr2gray", "band_carry", "fused", "fused_pre", "fused_fix", "pack", "edges", "lines"};
+                                              "otsu_apply", "otsu_tiles", "synth", "bgr2gray", "band_carry", "fused", "fused_pre", "fused_fix", "pack", "edges", "lines", "adaptive"};
 
 int prl_make_geom(int method, int rows, int cols, int window, prl_geom* g)
 {
@@ -166,7 +166,7 @@ extern "C" void prl_cuda_destroy(prl_cuda_ctx* c)
     for (auto& ev : c->event_pool) cudaEventDestroy(ev);
     cudaFree(c->sched); cudaFree(c->planes); cudaFree(c->carry); cudaFree(c->colsum); cudaFree(c->scalars); cudaFree(c->fused_ws);
     cudaFree(c->d_redo_total);
-    cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_tmp); cudaFree(c->d_misc); cudaFree(c->d_bgr); cudaFree(c->edges_ws); cudaFree(c->rects_ws); cudaFree(c->clahe_ws);
+    cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_tmp); cudaFree(c->d_misc); cudaFree(c->d_bgr); cudaFree(c->edges_ws); cudaFree(c->adaptive_ws); cudaFree(c->rects_ws); cudaFree(c->clahe_ws);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -891,6 +891,130 @@ extern "C" int prl_cuda_remove_lines(prl_cuda_ctx* c, const uint8_t* src, int ro
     rc = prl_ensure(c, &c->edges_ws, &c->edges_ws_bytes, prl_lines_scratch_bytes(rows, cols)); if (rc) return rc;
     rc = prl_k_remove_lines(c, c->d_in, rows, cols, in_step, c->d_out, o_step, c->edges_ws); if (rc) return rc;
     PRL_CUDA_TRY(c, cudaMemcpy2DAsync(dst, dst_step, c->d_out, o_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
+    PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return PRL_OK;
+}
+
+// ---- the adaptive-mean family ---------------------------------------------------
+extern "C" int prl_cuda_gauss_kernel_float(int n, float* k)
+{
+    if (!k) return PRL_E_INVALID;
+    return prl_gauss_kernel_float(n, k);
+}
+
+extern "C" int prl_cuda_median_blur(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step, int channels, int ksize,
+                                    uint8_t* dst, size_t dst_step)
+{
+    if (!c) return PRL_E_INVALID;
+    if (!src || !dst || rows <= 0 || cols <= 0 || (channels != 1 && channels != 3 && channels != 4) ||
+        step < (size_t)cols * channels || dst_step < (size_t)cols * channels)
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    if ((ksize & 1) == 0) return prl_set_err(c, PRL_E_EMPTY_ROI, "medianBlur: the kernel size must be odd");     // cv::Exception
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    size_t in_step;
+    int rc = stage_in(c, src, rows, (size_t)cols * channels, step, &in_step); if (rc) return rc;
+    const size_t o_step = round16((size_t)cols * channels);
+    rc = prl_ensure(c, (void**)&c->d_out, &c->d_out_bytes, o_step * rows); if (rc) return rc;
+    if (ksize <= 1) {                                                                                             // src.copyTo(dst)
+        PRL_CUDA_TRY(c, cudaMemcpy2DAsync(c->d_out, o_step, c->d_in, in_step, (size_t)cols * channels, rows, cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        rc = prl_k_median_blur(c, c->d_in, rows, cols, in_step, channels, ksize, c->d_out, o_step); if (rc) return rc;
+    }
+    PRL_CUDA_TRY(c, copy2d(dst, dst_step, c->d_out, o_step, (size_t)cols * channels, rows, cudaMemcpyDeviceToHost, c->stream));
+    PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return PRL_OK;
+}
+
+extern "C" int prl_cuda_adaptive_threshold(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step, double maxval,
+                                           int method, int type, int block_size, double delta, uint8_t* dst, size_t dst_step)
+{
+    if (!c) return PRL_E_INVALID;
+    if (!src || !dst || rows <= 0 || cols <= 0 || step < (size_t)cols || dst_step < (size_t)cols)
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    // cv::adaptiveThreshold's own assertions -> cv::Exception
+    if (block_size <= 1 || (block_size & 1) == 0) return prl_set_err(c, PRL_E_EMPTY_ROI, "adaptiveThreshold: blockSize % 2 == 1 && blockSize > 1");
+    if ((method != 0 && method != 1) || (type != 0 && type != 1)) return prl_set_err(c, PRL_E_EMPTY_ROI, "adaptiveThreshold: unknown method or threshold type");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    size_t in_step;
+    int rc = stage_in(c, src, rows, cols, step, &in_step); if (rc) return rc;
+    const size_t o_step = (dst_step == (size_t)cols) ? (size_t)cols : round16(cols);
+    rc = prl_ensure(c, (void**)&c->d_out, &c->d_out_bytes, o_step * rows + 16); if (rc) return rc;
+    rc = prl_ensure(c, &c->adaptive_ws, &c->adaptive_ws_bytes, prl_adaptive_scratch_bytes(rows, cols)); if (rc) return rc;
+    rc = prl_k_adaptive_threshold(c, c->d_in, rows, cols, in_step, maxval, method, type, block_size, delta, c->d_out, o_step,
+                                  c->adaptive_ws, false);
+    if (rc) return rc;
+    PRL_CUDA_TRY(c, copy2d(dst, dst_step, c->d_out, o_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
+    PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return PRL_OK;
+}
+
+// One call for prl::binarizeNativeAdaptive / binarizeAT / binarizeAGT / binarizePureAdaptiveGaussian: the image crosses
+// PCIe once each way; colour conversion, blur, threshold and the mean test all run on the device.
+extern "C" int prl_cuda_binarize_adaptive(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step, int channels,
+                                          const prl_adaptive_params* p, uint8_t* dst, size_t dst_step)
+{
+    if (!c) return PRL_E_INVALID;
+    if (!src || !dst || !p || rows <= 0 || cols <= 0 || (channels != 1 && channels != 3 && channels != 4) ||
+        step < (size_t)cols * channels || dst_step < (size_t)cols)
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    if (!(p->maxval >= 0 && p->maxval <= 255) && p->check_maxval)
+        return prl_set_err(c, PRL_E_INVALID, "Max value must be in range [0; 255]");                // binarizeNativeAdaptive.cpp:53-56
+    int bs = p->block_size;
+    if (p->auto_block && bs < 3) {                                                                  // :86-93
+        const double diagonal = std::sqrt((double)(rows * rows + cols * cols));
+        bs = (int)(diagonal / 333 + 7);
+    }
+    if (bs <= 1 || (bs & 1) == 0) return prl_set_err(c, PRL_E_EMPTY_ROI, "adaptiveThreshold: blockSize % 2 == 1 && blockSize > 1");
+    if (p->blur == 1 && p->blur_ksize < 3 && p->assert_ksize) return prl_set_err(c, PRL_E_EMPTY_ROI, "medianBlurKernelSize >= 3");   // CV_Assert :65
+    if (p->blur == 1 && (p->blur_ksize & 1) == 0) return prl_set_err(c, PRL_E_EMPTY_ROI, "medianBlur: the kernel size must be odd");
+    if (p->blur == 2) {
+        if (p->blur_ksize < 3 || !(p->blur_sigma > 0)) return prl_set_err(c, PRL_E_EMPTY_ROI, "GaussianBlurKernelSize >= 3 && GaussianBlurSigma > 0");   // :70-71
+        if ((p->blur_ksize & 1) == 0) return prl_set_err(c, PRL_E_EMPTY_ROI, "GaussianBlur: the kernel size must be odd");
+        if (p->blur_ksize > 63) return prl_set_err(c, PRL_E_UNSUPPORTED, "Gaussian blur kernel sizes above 63 are not supported");
+        if (channels != 1 && !p->gray_first) return prl_set_err(c, PRL_E_UNSUPPORTED, "Gaussian blur of a colour image is not supported");
+    }
+    if ((p->method != 0 && p->method != 1) || (p->type != 0 && p->type != 1)) return prl_set_err(c, PRL_E_INVALID, "unknown method or threshold type");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+
+    const size_t g_step = round16((size_t)cols), g_img = g_step * rows;
+    const size_t c_step = round16((size_t)cols * channels);
+    int rc = prl_ensure(c, (void**)&c->d_in, &c->d_in_bytes, g_img); if (rc) return rc;
+    rc = prl_ensure(c, (void**)&c->d_tmp, &c->d_tmp_bytes, g_img); if (rc) return rc;
+    rc = prl_ensure(c, &c->adaptive_ws, &c->adaptive_ws_bytes, prl_adaptive_scratch_bytes(rows, cols)); if (rc) return rc;
+    const uint8_t* gray = nullptr;          // what adaptiveThreshold reads
+    if (channels == 1) {
+        size_t in_step;
+        rc = stage_in(c, src, rows, cols, step, &in_step); if (rc) return rc;       // -> d_in (pitch g_step)
+        gray = c->d_in;
+    } else {
+        rc = prl_ensure(c, (void**)&c->d_bgr, &c->d_bgr_bytes, c_step * rows); if (rc) return rc;
+        PRL_CUDA_TRY(c, copy2d(c->d_bgr, c_step, src, step, (size_t)cols * channels, rows, cudaMemcpyHostToDevice, c->stream));
+        const uint8_t* colour = c->d_bgr;
+        if (!p->gray_first && p->blur == 1 && p->blur_ksize > 1) {                  // cv::medianBlur on the colour image (binarizeAT.cpp:53)
+            rc = prl_ensure(c, &c->d_misc, &c->d_misc_bytes, c_step * rows); if (rc) return rc;
+            rc = prl_k_median_blur(c, c->d_bgr, rows, cols, c_step, channels, p->blur_ksize, (uint8_t*)c->d_misc, c_step); if (rc) return rc;
+            colour = (const uint8_t*)c->d_misc;
+        }
+        rc = prl_k_bgr2gray(c, colour, rows, cols, c_step, channels, c->d_in, g_step, false); if (rc) return rc;   // COLOR_BGR2GRAY
+        gray = c->d_in;
+    }
+    if (p->blur != 0 && (channels == 1 || p->gray_first)) {
+        if (p->blur == 1 && p->blur_ksize > 1) {
+            rc = prl_k_median_blur(c, gray, rows, cols, g_step, 1, p->blur_ksize, c->d_tmp, g_step); if (rc) return rc;
+            gray = c->d_tmp;
+        } else if (p->blur == 2) {
+            rc = prl_ensure(c, &c->edges_ws, &c->edges_ws_bytes, g_img * 2 + 256); if (rc) return rc;
+            rc = prl_k_gaussian_blur(c, gray, rows, cols, g_step, p->blur_ksize, p->blur_sigma, c->d_tmp, g_step, (uint16_t*)c->edges_ws);
+            if (rc) return rc;
+            gray = c->d_tmp;
+        }
+    }
+    const size_t o_step = (dst_step == (size_t)cols) ? (size_t)cols : g_step;
+    rc = prl_ensure(c, (void**)&c->d_out, &c->d_out_bytes, o_step * rows + 16); if (rc) return rc;
+    rc = prl_k_adaptive_threshold(c, gray, rows, cols, g_step, p->maxval, p->method, p->type, bs, p->delta, c->d_out, o_step,
+                                  c->adaptive_ws, p->invert_if_dark != 0);
+    if (rc) return rc;
+    PRL_CUDA_TRY(c, copy2d(dst, dst_step, c->d_out, o_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
     PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return PRL_OK;
 }

@@ -74,6 +74,7 @@ struct prl_cuda_ctx {
     void* d_misc = nullptr;     size_t d_misc_bytes = 0;   // histograms, thresholds, rect lists
     void* clahe_ws = nullptr;   size_t clahe_ws_bytes = 0; // CLAHE: enhanced image, intermediate, LUTs
     void* rects_ws = nullptr;   size_t rects_ws_bytes = 0; // contour rectangles: count, list, thresholds, labels, boxes
+    void* adaptive_ws = nullptr; size_t adaptive_ws_bytes = 0; // adaptive family: pixel counter, float32 rows of the Gaussian mean
     void* edges_ws = nullptr;   size_t edges_ws_bytes = 0; // edge front-end: blurred image, 8.8 rows, class map, labels, flags
     // pinned host staging
 
@@ -101,7 +102,7 @@ struct prl_cuda_ctx {
 
 enum prl_family {
     FAM_INTEGRAL = 0, FAM_THRESHOLD, FAM_SMAX, FAM_MORPH, FAM_OTSU_HIST, FAM_OTSU_SEARCH,
-    FAM_OTSU_APPLY, FAM_OTSU_TILES, FAM_SYNTH, FAM_BGR2GRAY, FAM_BAND_CARRY, FAM_FUSED, FAM_FUSED_PRE, FAM_FUSED_FIX, FAM_PACK, FAM_EDGES, FAM_LINES, FAM_COUNT
+    FAM_OTSU_APPLY, FAM_OTSU_TILES, FAM_SYNTH, FAM_BGR2GRAY, FAM_BAND_CARRY, FAM_FUSED, FAM_FUSED_PRE, FAM_FUSED_FIX, FAM_PACK, FAM_EDGES, FAM_LINES, FAM_ADAPTIVE, FAM_COUNT
 };
 
 int  prl_set_err(prl_cuda_ctx* ctx, int code, const char* what, cudaError_t ce = cudaSuccess);
@@ -167,6 +168,13 @@ int prl_k_morph(prl_cuda_ctx* ctx, uint8_t* d_in, uint8_t* d_out, int n_pages, i
 int prl_k_morph_single(prl_cuda_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int n_pages, int rows, int cols, size_t in_step,
                        size_t in_page_stride, size_t out_step, size_t out_page_stride, int n, bool dilate);
 int prl_gauss_kernel_fixed(int n, double sigma, int* k);
+// the adaptive-mean family (adaptive.cu)
+int prl_gauss_kernel_float(int n, float* k);
+size_t prl_adaptive_scratch_bytes(int rows, int cols);
+int prl_k_median_blur(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, int channels, int ksize,
+                      uint8_t* d_dst, size_t dst_step);
+int prl_k_adaptive_threshold(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, double maxval, int method, int type,
+                             int block_size, double delta, uint8_t* d_dst, size_t dst_step, void* scratch, bool invert_if_dark);
 int prl_k_gaussian_blur(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, int ksize, double sigma,
                         uint8_t* d_dst, size_t dst_step, uint16_t* d_tmp);
 int prl_k_canny(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, const int32_t* d_otsu,

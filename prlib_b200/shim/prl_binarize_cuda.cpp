@@ -290,3 +290,100 @@ void prl::removeLines(const cv::Mat& inputImage, cv::Mat& outputImage)
                                    out.data, out.step));
     outputImage = out;
 }
+
+// ---- the adaptive-mean family ---------------------------------------------------------------------------------------
+namespace
+{
+void runAdaptive(const cv::Mat& in, cv::Mat& out, const prl_adaptive_params& p)
+{
+    require8U(in);
+    prl_cuda_ctx* c = context();
+    cv::Mat res(in.rows, in.cols, CV_8UC1);
+    check(c, prl_cuda_binarize_adaptive(c, in.data, in.rows, in.cols, in.step, in.channels(), &p, res.data, res.step));
+    out = res;
+}
+
+// binarizeAT / binarizeAGT / binarizePureAdaptiveGaussian assign the Mat cv::adaptiveThreshold reads only inside
+// `if (inputImageMat.channels() != 1)` (binarizeAT.cpp:55-58): a 1-channel image reaches adaptiveThreshold empty
+void colourOnly(const cv::Mat& in)
+{
+    if (in.empty()) throw std::invalid_argument("Input image for binarization is empty");
+    if (in.channels() == 1) throw cvError("adaptiveThreshold: src.type() == CV_8UC1 (the reference passes an empty Mat)");
+}
+}  // namespace
+
+void prl::binarizeAT(const cv::Mat& inputImage, cv::Mat& outputImage, const int medianKernelSize, const double maxValue,
+                     const int blockSize, const int shift)
+{
+    colourOnly(inputImage);
+    prl_adaptive_params p = prl_adaptive_params();
+    p.gray_first = 0; p.blur = 1; p.blur_ksize = medianKernelSize; p.method = 0; p.type = 0;
+    p.maxval = maxValue; p.block_size = blockSize; p.delta = shift;
+    runAdaptive(inputImage, outputImage, p);
+}
+
+void prl::binarizeAGT(const cv::Mat& inputImage, cv::Mat& outputImage, const int medianKernelSize, const double maxValue,
+                      const int blockSize, const int shift)
+{
+    colourOnly(inputImage);
+    prl_adaptive_params p = prl_adaptive_params();
+    p.gray_first = 0; p.blur = 1; p.blur_ksize = medianKernelSize; p.method = 1; p.type = 0;
+    p.maxval = maxValue; p.block_size = blockSize; p.delta = shift;
+    runAdaptive(inputImage, outputImage, p);
+}
+
+void prl::binarizePureAdaptiveGaussian(const cv::Mat& inputImage, cv::Mat& outputImage, const double maxValue, const int blockSize,
+                                       const int shift)
+{
+    colourOnly(inputImage);
+    prl_adaptive_params p = prl_adaptive_params();
+    p.gray_first = 1; p.blur = 0; p.method = 1; p.type = 0; p.maxval = maxValue; p.block_size = blockSize; p.delta = shift;
+    runAdaptive(inputImage, outputImage, p);
+}
+
+// binarizeGAT.cpp:37-64 and binarizePureAdaptive.cpp:38-60 convert to gray first, so their `channels() != 1` branch is
+// never taken and cv::adaptiveThreshold always sees an empty Mat
+void prl::binarizeGAT(const cv::Mat& inputImage, cv::Mat&, const int, const double, const double, const double, const int, const int)
+{
+    if (inputImage.empty()) throw std::invalid_argument("Input image for binarization is empty");
+    throw cvError("adaptiveThreshold: src.type() == CV_8UC1 (the reference passes an empty Mat)");
+}
+
+void prl::binarizePureAdaptive(const cv::Mat& inputImage, cv::Mat&, const double, const int, const int)
+{
+    if (inputImage.empty()) throw std::invalid_argument("Input image for binarization is empty");
+    throw cvError("adaptiveThreshold: src.type() == CV_8UC1 (the reference passes an empty Mat)");
+}
+
+void prl::binarizeNativeAdaptive(cv::Mat& inputImage, cv::Mat& outputImage, bool isGaussianBlurReqiured, int medianBlurKernelSize,
+                                 int GaussianBlurKernelSize, double GaussianBlurSigma, bool isAdaptiveThresholdCalculatedByGaussian,
+                                 double adaptiveThresholdingMaxValue, int adaptiveThresholdingBlockSize, double adaptiveThresholdingShift,
+                                 int bilateralFilterBlockSize, double bilateralFilterColorSigma, double bilateralFilterSpaceSigma)
+{
+    if (inputImage.empty()) throw std::invalid_argument("Input image for binarization is empty");
+    if (!(adaptiveThresholdingMaxValue >= 0 && adaptiveThresholdingMaxValue <= 255))
+        throw std::invalid_argument("Max value must be in range [0; 255]");
+    require8U(inputImage);
+    prl_cuda_ctx* c = context();
+    if (inputImage.channels() > 1) {                       // cv::cvtColor(inputImage, inputImage, COLOR_BGR2GRAY): observable
+        cv::Mat gray(inputImage.rows, inputImage.cols, CV_8UC1);
+        check(c, prl_cuda_bgr2gray(c, inputImage.data, inputImage.rows, inputImage.cols, inputImage.step, inputImage.channels(),
+                                   gray.data, gray.step));
+        inputImage = gray;
+    }
+    prl_adaptive_params p = prl_adaptive_params();
+    p.gray_first = 1; p.blur = isGaussianBlurReqiured ? 2 : 1;
+    p.blur_ksize = isGaussianBlurReqiured ? GaussianBlurKernelSize : medianBlurKernelSize;
+    p.blur_sigma = GaussianBlurSigma; p.assert_ksize = 1;
+    p.method = isAdaptiveThresholdCalculatedByGaussian ? 1 : 0; p.type = 1;
+    p.maxval = adaptiveThresholdingMaxValue; p.check_maxval = 1;
+    p.block_size = adaptiveThresholdingBlockSize; p.auto_block = 1; p.delta = adaptiveThresholdingShift; p.invert_if_dark = 1;
+    cv::Mat res;
+    runAdaptive(inputImage, res, p);
+    if (bilateralFilterBlockSize >= 3) {
+        if (bilateralFilterColorSigma <= 0) throw std::invalid_argument("Color sigma for bilateral filtration must be greater than 0");
+        if (bilateralFilterSpaceSigma <= 0) throw std::invalid_argument("Space sigma for bilateral filtration must be greater than 0");
+        throw std::runtime_error("libprlib_cuda: the bilateral filter step of binarizeNativeAdaptive is not implemented");
+    }
+    outputImage = res;
+}

@@ -71,6 +71,31 @@ CV_EXPORTS void removeLines(const cv::Mat& inputImage, cv::Mat& outputImage);
 CV_EXPORTS void localOtsuEdges(const cv::Mat& imageToProc, cv::Mat& resultCanny, int GaussianBlurKernelSize = 19,
                                double CannyUpperThresholdCoeff = 0.15, double CannyLowerThresholdCoeff = 0.01,
                                int CannyMorphIters = 1, int postDilate = 3);
+
+// ---- the adaptive-mean family (binarizeNativeAdaptive.h:63-75, binarizeAT.h:33-34, binarizeAGT.h:32-33, binarizeGAT.h:33-35,
+// binarizePureAdaptive.h:33-34, binarizePureAdaptiveGaussian.h:33-34): same signatures and defaults.  The reference's own
+// behaviour is kept, quirks included (tests/test_adaptive.py runs the reference's own object code and shows the same):
+//   * binarizeAT / binarizeAGT / binarizePureAdaptiveGaussian only work on 3/4-channel input; a 1-channel image ends in the
+//     cv::Exception of cv::adaptiveThreshold on the empty Mat the reference passes it;
+//   * binarizeGAT and binarizePureAdaptive end in that cv::Exception for every non-empty input;
+//   * binarizeNativeAdaptive converts its INPUT Mat to gray in place (binarizeNativeAdaptive.cpp:58-61); its optional
+//     bilateral filter (bilateralFilterBlockSize >= 3, off by default) is not implemented: std::runtime_error.
+CV_EXPORTS void binarizeNativeAdaptive(cv::Mat& inputImage, cv::Mat& outputImage, bool isGaussianBlurReqiured = 0,
+                                       int medianBlurKernelSize = 5, int GaussianBlurKernelSize = 7, double GaussianBlurSigma = 150.0,
+                                       bool isAdaptiveThresholdCalculatedByGaussian = true, double adaptiveThresholdingMaxValue = 255.0,
+                                       int adaptiveThresholdingBlockSize = 19, double adaptiveThresholdingShift = 9,
+                                       int bilateralFilterBlockSize = 0, double bilateralFilterColorSigma = 150.0,
+                                       double bilateralFilterSpaceSigma = 150.0);
+CV_EXPORTS void binarizeAT(const cv::Mat& inputImage, cv::Mat& outputImage, const int medianKernelSize, const double maxValue,
+                           const int blockSize, const int shift);
+CV_EXPORTS void binarizeAGT(const cv::Mat& inputImage, cv::Mat& outputImage, const int medianKernelSize, const double maxValue,
+                            const int blockSize, const int shift);
+CV_EXPORTS void binarizeGAT(const cv::Mat& inputImage, cv::Mat& outputImage, const int gaussianKernelSize, const double sigmaX,
+                            const double sigmaY, const double maxValue, const int blockSize, const int shift);
+CV_EXPORTS void binarizePureAdaptive(const cv::Mat& inputImage, cv::Mat& outputImage, const double maxValue, const int blockSize,
+                                     const int shift);
+CV_EXPORTS void binarizePureAdaptiveGaussian(const cv::Mat& inputImage, cv::Mat& outputImage, const double maxValue,
+                                             const int blockSize, const int shift);
 }  // namespace prl
 
 #endif  // PRL_BINARIZE_CUDA_H

@@ -127,6 +127,37 @@ int main()
         try { prl::binarizeNICKBatch(bad, out); } catch (const std::invalid_argument&) { thrown = true; }
         EXPECT(thrown, "empty page inside a batch -> invalid_argument");
     }
+    {   // the adaptive-mean family: reference signatures, the reference's quirks, properties of the result
+        cv::Mat bgr(200, 300, CV_8UC3), out, gout;
+        for (int y = 0; y < 200; ++y) for (int x = 0; x < 900; ++x) bgr.ptr(y)[x] = (unsigned char)((x * 7 + y * 13 + (x * y) % 31) & 255);
+        prl::binarizeAT(bgr, out, 5, 255, 19, 9);
+        bool ok = out.rows == 200 && out.cols == 300 && out.channels() == 1;
+        for (int y = 0; ok && y < 200; ++y) for (int x = 0; x < 300; ++x) ok = ok && (out.ptr(y)[x] == 0 || out.ptr(y)[x] == 255);
+        EXPECT(ok, "binarizeAT on a BGR image: 0/255 mask of the image size");
+        prl::binarizeAGT(bgr, out, 5, 255, 19, 9);
+        prl::binarizePureAdaptiveGaussian(bgr, out, 200, 15, 4);
+        EXPECT(out.rows == 200 && out.cols == 300, "binarizeAGT / binarizePureAdaptiveGaussian run on BGR");
+        int thrown = 0;
+        cv::Mat g = page.clone();
+        try { prl::binarizeAT(g, out, 5, 255, 19, 9); } catch (const cv::Exception&) { ++thrown; }
+        try { prl::binarizeAGT(g, out, 5, 255, 19, 9); } catch (const cv::Exception&) { ++thrown; }
+        try { prl::binarizePureAdaptiveGaussian(g, out, 255, 19, 9); } catch (const cv::Exception&) { ++thrown; }
+        try { prl::binarizeGAT(bgr, out, 7, 1.0, 1.0, 255, 19, 9); } catch (const cv::Exception&) { ++thrown; }
+        try { prl::binarizePureAdaptive(bgr, out, 255, 19, 9); } catch (const cv::Exception&) { ++thrown; }
+        try { prl::binarizeAT(cv::Mat(), out, 5, 255, 19, 9); } catch (const std::invalid_argument&) { ++thrown; }
+        EXPECT(thrown == 6, "the family's exceptions are the reference's (1-channel AT/AGT/PAG, GAT, PureAdaptive, empty input)");
+        cv::Mat in = bgr.clone();
+        prl::binarizeNativeAdaptive(in, out);
+        EXPECT(in.channels() == 1 && in.rows == 200 && out.rows == 200 && out.cols == 300, "binarizeNativeAdaptive: input converted to gray in place");
+        long white = 0;
+        for (int y = 0; y < 200; ++y) for (int x = 0; x < 300; ++x) white += out.ptr(y)[x] == 255;
+        EXPECT(white * 2 >= 200L * 300, "binarizeNativeAdaptive: mean >= 128 after the inversion rule");
+        thrown = 0;
+        try { prl::binarizeNativeAdaptive(in, out, false, 5, 7, 150.0, true, 300.0); } catch (const std::invalid_argument&) { ++thrown; }
+        try { prl::binarizeNativeAdaptive(in, out, false, 2); } catch (const cv::Exception&) { ++thrown; }
+        try { prl::binarizeNativeAdaptive(in, out, false, 5, 7, 150.0, true, 255.0, 20); } catch (const cv::Exception&) { ++thrown; }
+        EXPECT(thrown == 3, "binarizeNativeAdaptive argument errors");
+    }
     {   // Otsu
         std::vector<uint8_t> want((size_t)rows * cols);
         int thr = oracle_otsu_global(page.data, rows, cols, page.step, 255, want.data(), cols);

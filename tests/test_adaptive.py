@@ -1,0 +1,248 @@
+"""The adaptive-mean family: prl::binarizeNativeAdaptive / AT / AGT / GAT / PureAdaptive /
+PureAdaptiveGaussian.  Oracles: the reference's own object code (oracle/_ref), its cv2 call sequence
+(oracle/prl_oracle.py) and the real cv2 primitives for the two building blocks (medianBlur, adaptiveThreshold)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as CO
+from oracle import prl_oracle as O
+from oracle import ref as R
+
+cv2 = pytest.importorskip("cv2")
+HERE = os.path.dirname(os.path.abspath(__file__))
+needs_ref = pytest.mark.skipif(not R.available(), reason="oracle/_ref/_prl_ref.so not built (needs /root/reference)")
+REPL = cv2.BORDER_REPLICATE | cv2.BORDER_ISOLATED
+
+
+def _images():
+    rng = np.random.default_rng(11)
+    crops = dict(np.load(os.path.join(HERE, "golden", "real_crops.npz")))
+    out = {"noise_120x150": rng.integers(0, 256, (120, 150, 3), dtype=np.uint8),
+           "synth_300x421": np.repeat(CO.synth_page(3, 300, 421)[:, :, None], 3, axis=2),
+           "dark_90x131": (rng.integers(0, 256, (90, 131, 3)) // 6).astype(np.uint8),
+           "bgra_64x70": rng.integers(0, 256, (64, 70, 4), dtype=np.uint8)}
+    for k, v in crops.items():
+        if v.ndim == 3:
+            out["crop_" + k] = v
+            break
+    return out
+
+
+IMAGES = _images()
+
+import json  # noqa: E402
+with open(os.path.join(HERE, "golden", "ref_adaptive_golden.json")) as _f:
+    GOLD = json.load(_f)       # outputs of the reference's own code (tests/golden/make_ref_adaptive_golden.py)
+
+
+def gold_image(key):
+    rng = np.random.default_rng(11)
+    gen = {"noise_bgr_120x150": lambda: rng.integers(0, 256, (120, 150, 3), dtype=np.uint8)}
+    if key == "noise_bgr_120x150":
+        return gen[key]()
+    a = rng.integers(0, 256, (120, 150, 3), dtype=np.uint8)
+    if key == "dark_bgr_90x131":
+        return (rng.integers(0, 256, (90, 131, 3)) // 6).astype(np.uint8)
+    b = (rng.integers(0, 256, (90, 131, 3)) // 6).astype(np.uint8)
+    if key == "noise_bgra_64x70":
+        return rng.integers(0, 256, (64, 70, 4), dtype=np.uint8)
+    if key == "synth_gray_300x421":
+        return CO.synth_page(3, 300, 421)
+    if key == "a4_p2":
+        return CO.synth_page(2)
+    return dict(np.load(os.path.join(HERE, "golden", "real_pages.npz")))[key]
+
+
+def digest_or_class(fn):
+    from util import sha
+    o = outcome(fn)
+    return sha(o[1]) if o[0] == "ok" else o[0]
+
+
+def outcome(fn):
+    """('ok', array) or the exception class the call ends in: the auto block size int(diagonal / 333 + 7) of
+    binarizeNativeAdaptive can come out even, and then the REFERENCE itself ends in cv::adaptiveThreshold's assertion"""
+    from prlib_b200 import PrlCudaError
+    try:
+        return "ok", fn()
+    except ValueError:
+        return "invalid_argument", None
+    except (cv2.error, PrlCudaError):
+        return "cv::Exception", None
+
+
+def same_outcome(a, b):
+    return a[0] == b[0] and (a[1] is None or np.array_equal(a[1], b[1]))
+
+
+# ---------------------------------------------------------------------------------------------- CPU suite
+def test_float_gaussian_coefficients_equal_getGaussianKernel():
+    from prlib_b200 import capi
+    L = capi.load()
+    for n in range(1, 256, 2):
+        k = (C.c_float * 256)()
+        assert L.prl_cuda_gauss_kernel_float(n, k) == 0
+        assert np.array_equal(np.array(k[:n], np.float32), cv2.getGaussianKernel(n, 0, cv2.CV_32F).ravel()), n
+    k = (C.c_float * 256)()
+    assert L.prl_cuda_gauss_kernel_float(4, k) != 0 and L.prl_cuda_gauss_kernel_float(257, k) != 0
+
+
+def test_box_mean_model_is_what_boxFilter_computes():
+    rng = np.random.default_rng(0)
+    with O._single_thread():
+        for bs in list(range(3, 65, 4)) + [63, 99, 201, 255]:
+            for shape in ((67, 131), (40, 33), (9, 300)):
+                img = rng.integers(0, 256, shape, dtype=np.uint8)
+                ref = cv2.boxFilter(img, -1, (bs, bs), normalize=True, borderType=REPL)
+                assert np.array_equal(O.box_mean_model(img, bs), ref), (bs, shape)
+
+
+def test_gaussian_mean_model_is_what_GaussianBlur_32f_computes():
+    """the measured summation order of the wheel's sepFilter2D (vector bodies fused, scalar tails as compiled): float for float"""
+    rng = np.random.default_rng(7)
+    with O._single_thread():
+        for shape in ((97, 131), (50, 133), (40, 64), (33, 70), (20, 7), (64, 12), (5, 3), (1, 9), (9, 1), (120, 257)):
+            g = rng.integers(0, 256, shape, dtype=np.uint8)
+            for bs in (3, 5, 7, 9, 11, 13, 19, 21, 31, 35, 51):
+                ref = cv2.GaussianBlur(g.astype(np.float32), (bs, bs), 0, 0, borderType=REPL)
+                assert np.array_equal(O.gaussian_mean_model(g, bs, as_float=True), ref), (shape, bs)
+
+
+@needs_ref
+def test_reference_family_quirks_and_port_equals_reference():
+    """AT / AGT / PureAdaptiveGaussian only work on colour input; GAT / PureAdaptive raise for every non-empty input; the
+    cv2 restatement equals the reference's own object code where that returns."""
+    for name, img in IMAGES.items():
+        gray = np.ascontiguousarray(img[:, :, 0])
+        for fn, args in (("binarizeAT", (5, 255, 19, 9)), ("binarizeAGT", (3, 200, 11, -3)), ("binarizePureAdaptiveGaussian", (255, 15, 4))):
+            assert np.array_equal(getattr(R, fn)(img, *args), getattr(O, fn)(img, *args)), (name, fn)
+            with pytest.raises(cv2.error):
+                getattr(R, fn)(gray, *args)
+            with pytest.raises(ValueError):
+                getattr(R, fn)(np.zeros((0, 0), np.uint8), *args)
+        for im in (img, gray):
+            with pytest.raises(cv2.error):
+                R.binarizeGAT(im, 7, 1.5, 1.5, 255, 19, 9)
+            with pytest.raises(cv2.error):
+                R.binarizePureAdaptive(im, 255, 19, 9)
+            for kw in ({}, {"isGaussianBlurReqiured": True}, {"isAdaptiveThresholdCalculatedByGaussian": False},
+                       {"adaptiveThresholdingBlockSize": 0}, {"medianBlurKernelSize": 3, "adaptiveThresholdingShift": -2.5},
+                       {"adaptiveThresholdingMaxValue": 77.6}):
+                assert same_outcome(outcome(lambda: R.binarizeNativeAdaptive(im, **kw)), outcome(lambda: O.binarizeNativeAdaptive(im, **kw))), (name, kw)
+    with pytest.raises(ValueError):
+        R.binarizeNativeAdaptive(IMAGES["noise_120x150"], adaptiveThresholdingMaxValue=300)
+    with pytest.raises(cv2.error):
+        R.binarizeNativeAdaptive(IMAGES["noise_120x150"], medianBlurKernelSize=2)
+    with pytest.raises(cv2.error):
+        R.binarizeNativeAdaptive(IMAGES["noise_120x150"], adaptiveThresholdingBlockSize=20)
+
+
+def test_host_mirror_raises_like_the_reference_without_touching_a_gpu():
+    import prlib_b200
+    from prlib_b200 import PrlCudaError, capi
+    gray = np.zeros((40, 50), np.uint8)
+    for call in (lambda: prlib_b200.binarizeAT(gray, 5, 255, 19, 9), lambda: prlib_b200.binarizeAGT(gray, 5, 255, 19, 9),
+                 lambda: prlib_b200.binarizePureAdaptiveGaussian(gray, 255, 19, 9),
+                 lambda: prlib_b200.binarizeGAT(np.zeros((40, 50, 3), np.uint8), 7, 1.0, 1.0, 255, 19, 9),
+                 lambda: prlib_b200.binarizePureAdaptive(np.zeros((40, 50, 3), np.uint8), 255, 19, 9)):
+        with pytest.raises(PrlCudaError) as e:
+            call()
+        assert e.value.code == capi.PRL_E_EMPTY_ROI
+    for call in (lambda: prlib_b200.binarizeAT(np.zeros((0, 0, 3), np.uint8), 5, 255, 19, 9),
+                 lambda: prlib_b200.binarizeNativeAdaptive(np.zeros((0, 0), np.uint8)),
+                 lambda: prlib_b200.binarizeNativeAdaptive(gray, adaptiveThresholdingMaxValue=256),
+                 lambda: prlib_b200.binarizeNativeAdaptive(gray, bilateralFilterBlockSize=5, bilateralFilterColorSigma=0)):
+        with pytest.raises(ValueError):
+            call()
+
+
+@pytest.mark.parametrize("key", [k for k in GOLD["images"] if k != "a4_p2"])
+def test_cv2_restatement_reproduces_the_reference_digests(key):
+    from util import sha
+    img, e = gold_image(key), GOLD["images"][key]
+    assert sha(img) == e["sha1"], key
+    for name, want in e["out"].items():
+        fn, args, kw = GOLD["calls"][name]
+        assert digest_or_class(lambda: getattr(O, fn)(img, *args, **kw)) == want, (key, name)
+
+
+# ---------------------------------------------------------------------------------------------- GPU suite
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", list(GOLD["images"]))
+def test_cuda_reproduces_the_reference_digests(ctx, key):
+    import prlib_b200
+    from util import sha
+    img, e = gold_image(key), GOLD["images"][key]
+    assert sha(img) == e["sha1"], key
+    for name, want in e["out"].items():
+        fn, args, kw = GOLD["calls"][name]
+        assert digest_or_class(lambda: getattr(prlib_b200, fn)(img, *args, **kw)) == want, (key, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ksize", [3, 5, 7, 9, 15, 31])
+def test_median_blur_equals_cv2(ctx, ksize):
+    rng = np.random.default_rng(ksize)
+    with O._single_thread():
+        for shape in ((97, 131), (33, 70, 3), (64, 12, 4), (5, 3), (1, 40), (300, 257, 3)):
+            if ksize > 5 and len(shape) == 3 and shape[0] * shape[1] > 20000:
+                continue
+            img = rng.integers(0, 256, shape, dtype=np.uint8)
+            if len(shape) == 2:
+                img[::3, ::2] //= 8                                    # repeated values: ties inside the window
+            assert np.array_equal(ctx.median_blur(img, ksize), cv2.medianBlur(img, ksize)), (ksize, shape)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", [0, 1])
+def test_adaptive_threshold_equals_cv2(ctx, method):
+    rng = np.random.default_rng(20 + method)
+    cvm = cv2.ADAPTIVE_THRESH_GAUSSIAN_C if method else cv2.ADAPTIVE_THRESH_MEAN_C
+    with O._single_thread():
+        for shape in ((97, 131), (50, 133), (40, 64), (33, 70), (20, 7), (64, 12), (5, 3), (1, 9), (9, 1), (300, 421)):
+            g = rng.integers(0, 256, shape, dtype=np.uint8)
+            if shape == (300, 421):
+                g = CO.synth_page(1, 300, 421)
+            for bs in (3, 5, 9, 11, 19, 21, 35, 63, 65, 101):
+                for ttype, delta, maxval in ((0, 9, 255), (1, 9, 255), (0, -3.5, 200.4), (1, 2.5, 77.5), (0, 0, 255), (1, 300, 255)):
+                    want = cv2.adaptiveThreshold(g, maxval, cvm, cv2.THRESH_BINARY_INV if ttype else cv2.THRESH_BINARY, bs, delta)
+                    got = ctx.adaptive_threshold(g, maxval, method, ttype, bs, delta)
+                    assert np.array_equal(got, want), (shape, bs, ttype, delta, maxval, int((got != want).sum()))
+    assert not ctx.adaptive_threshold(np.full((20, 30), 9, np.uint8), -1.0, 0, 0, 5, 0).any()          # maxValue < 0 -> zeros
+
+
+@pytest.mark.gpu
+def test_family_equals_the_reference(ctx):
+    import prlib_b200
+    from prlib_b200 import PrlCudaError
+    use_ref = R.available()
+    W = R if use_ref else O
+    for name, img in IMAGES.items():
+        gray = np.ascontiguousarray(img[:, :, 1])
+        for fn, args in (("binarizeAT", (5, 255, 19, 9)), ("binarizeAT", (3, 180, 7, -2)), ("binarizeAGT", (5, 255, 19, 9)),
+                         ("binarizeAGT", (7, 255, 35, 3)), ("binarizePureAdaptiveGaussian", (255, 15, 4))):
+            assert np.array_equal(getattr(prlib_b200, fn)(img, *args), getattr(W, fn)(img, *args)), (name, fn, args)
+            with pytest.raises(PrlCudaError):
+                getattr(prlib_b200, fn)(gray, *args)
+        for im in (img, gray):
+            for kw in ({}, {"isGaussianBlurReqiured": True}, {"isAdaptiveThresholdCalculatedByGaussian": False},
+                       {"adaptiveThresholdingBlockSize": 0}, {"medianBlurKernelSize": 3, "adaptiveThresholdingShift": -2.5},
+                       {"isGaussianBlurReqiured": True, "GaussianBlurKernelSize": 11, "GaussianBlurSigma": 2.0,
+                        "isAdaptiveThresholdCalculatedByGaussian": False, "adaptiveThresholdingMaxValue": 77.6}):
+                assert same_outcome(outcome(lambda: prlib_b200.binarizeNativeAdaptive(im, **kw)), outcome(lambda: W.binarizeNativeAdaptive(im, **kw))), (name, kw)
+    with pytest.raises(PrlCudaError):
+        prlib_b200.binarizeNativeAdaptive(IMAGES["noise_120x150"], medianBlurKernelSize=2)
+    with pytest.raises(PrlCudaError):
+        prlib_b200.binarizeNativeAdaptive(IMAGES["noise_120x150"], adaptiveThresholdingBlockSize=20)
+
+
+@pytest.mark.gpu
+def test_native_adaptive_on_an_a4_page(ctx):
+    import prlib_b200
+    page = CO.synth_page(2)
+    assert np.array_equal(prlib_b200.binarizeNativeAdaptive(page), O.binarizeNativeAdaptive(page))
+    assert np.array_equal(prlib_b200.binarizeNativeAdaptive(page, isAdaptiveThresholdCalculatedByGaussian=False, adaptiveThresholdingBlockSize=0),
+                          O.binarizeNativeAdaptive(page, isAdaptiveThresholdCalculatedByGaussian=False, adaptiveThresholdingBlockSize=0))
