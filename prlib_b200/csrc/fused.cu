@@ -312,19 +312,25 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
     return v;
 }
 
+constexpr int kFixThreads = 256;
+
+// One CTA per listed pixel (a single warp per pixel took ~0.4 ms for its ~19 k dependent byte loads -- longer than the
+// whole two-kernel path needs for a small batch); the entries of all pages are dealt round-robin over the grid.
 template <int METHOD>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kFixThreads)
 fixup_kernel(const FusedArgs A)
 {
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    __shared__ unsigned long long red[kFixThreads / 32][12];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned int item = 0;
     for (int page = 0; page < A.n_pages; ++page) {
         const uint32_t cnt = A.scount[page];
         if (cnt == 0 || cnt > A.cap) continue;
         const uint8_t* img = A.src + (size_t)page * A.src_page_stride;
         const uint32_t* bs = A.blocksum + (size_t)page * A.nblk * A.ns * 2;
         const double imin = METHOD == PRL_FENG ? (double)A.imin[page] : 0.0;
-        for (uint32_t e = warp; e < cnt; e += nwarps) {
+        for (uint32_t e = 0; e < cnt; ++e, ++item) {
+            if (item % gridDim.x != blockIdx.x) continue;
             const uint32_t ent = A.slist[(size_t)page * kPageCap + e];
             const int y = (int)(ent >> 16), x = (int)(ent & 0xffffu);
             const int b = x / A.ow, xs = b * A.ow;                    // strip whose start is <= x
@@ -332,7 +338,7 @@ fixup_kernel(const FusedArgs A)
             const int blk_t = (y + 1) >> 5, blk_b = (Yb + 1) >> 5;    // whole blocks at or above the tap rows
             // (1) + (2): everything left of the strip start
             unsigned long long lts = 0, ltq = 0, lbs = 0, lbq = 0;
-            for (int i = lane; i < blk_b * b; i += 32) {
+            for (int i = tid; i < blk_b * b; i += kFixThreads) {
                 const int bk = i / b, bb = i - bk * b;
                 const uint32_t s = bs[((size_t)bk * A.ns + bb) * 2], q = bs[((size_t)bk * A.ns + bb) * 2 + 1];
                 lbs += s; lbq += q;
@@ -342,13 +348,13 @@ fixup_kernel(const FusedArgs A)
                 if (Yp > y && Yp < 32 * blk_b) { Yp = 32 * blk_b - 1; continue; }      // rows already inside whole blocks of the bottom tap
                 const uint8_t* row = img + (size_t)min(max(Yp - A.pad, 0), A.rows - 1) * A.src_step;
                 unsigned long long s = 0, q = 0;
-                for (int X = lane; X < xs; X += 32) { const unsigned long long p = row[min(max(X - A.pad, 0), A.cols - 1)]; s += p; q += p * p; }
+                for (int X = tid; X < xs; X += kFixThreads) { const unsigned long long p = row[min(max(X - A.pad, 0), A.cols - 1)]; s += p; q += p * p; }
                 if (Yp <= y && Yp >= 32 * blk_t) { lts += s; ltq += q; }
                 if (Yp >= 32 * blk_b) { lbs += s; lbq += q; }
             }
             // (3): from the strip start to the tap columns, every row
             unsigned long long ta = 0, tb = 0, tc = 0, td = 0, ua = 0, ub = 0, uc = 0, ud = 0;
-            for (int Yp = lane; Yp <= Yb; Yp += 32) {
+            for (int Yp = tid; Yp <= Yb; Yp += kFixThreads) {
                 const uint8_t* row = img + (size_t)min(max(Yp - A.pad, 0), A.rows - 1) * A.src_step;
                 unsigned long long r1s = 0, r1q = 0;
                 for (int X = xs; X <= x; ++X) { const unsigned long long p = row[min(max(X - A.pad, 0), A.cols - 1)]; r1s += p; r1q += p * p; }
@@ -357,12 +363,21 @@ fixup_kernel(const FusedArgs A)
                 if (Yp <= y) { ta += r1s; tb += r2s; ua += r1q; ub += r2q; }
                 tc += r1s; td += r2s; uc += r1q; ud += r2q;
             }
-            lts = warp_sum_u64(lts); ltq = warp_sum_u64(ltq); lbs = warp_sum_u64(lbs); lbq = warp_sum_u64(lbq);
-            ta = warp_sum_u64(ta) + lts; tb = warp_sum_u64(tb) + lts; tc = warp_sum_u64(tc) + lbs; td = warp_sum_u64(td) + lbs;
-            ua = warp_sum_u64(ua) + ltq; ub = warp_sum_u64(ub) + ltq; uc = warp_sum_u64(uc) + lbq; ud = warp_sum_u64(ud) + lbq;
+            unsigned long long v[12] = {lts, ltq, lbs, lbq, ta, tb, tc, td, ua, ub, uc, ud};
+#pragma unroll
+            for (int k = 0; k < 12; ++k) v[k] = warp_sum_u64(v[k]);
+            __syncthreads();                                          // the previous item's readers are done with red[]
             if (lane == 0) {
-                const int t8 = exact_t8_from_taps<METHOD>((long long)ta, (long long)tb, (long long)tc, (long long)td,
-                                                          (long long)ua, (long long)ub, (long long)uc, (long long)ud,
+#pragma unroll
+                for (int k = 0; k < 12; ++k) red[wid][k] = v[k];
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned long long t[12];
+#pragma unroll
+                for (int k = 0; k < 12; ++k) { t[k] = 0; for (int w = 0; w < kFixThreads / 32; ++w) t[k] += red[w][k]; }
+                const int t8 = exact_t8_from_taps<METHOD>((long long)(t[4] + t[0]), (long long)(t[5] + t[0]), (long long)(t[6] + t[2]), (long long)(t[7] + t[2]),
+                                                          (long long)(t[8] + t[1]), (long long)(t[9] + t[1]), (long long)(t[10] + t[3]), (long long)(t[11] + t[3]),
                                                           A.kw, A.p0, A.p1, A.p2, imin, 0.0);
                 const int p = img[(size_t)y * A.src_step + x];
                 A.dst[(size_t)page * A.dst_page_stride + (size_t)y * A.dst_step + x] = p > t8 ? 255 : 0;
@@ -447,10 +462,14 @@ int prl_k_fused(prl_cuda_ctx* ctx, int method, const uint8_t* d_src, int n_pages
     A.imin = d_imin;
     A.cap = (uint32_t)std::min(std::max(ctx->fused_page_cap, 0), kPageCap);
 
-    // row bands: enough warps for ~8 waves of 20 warps per SM, bands a multiple of 32 rows and at least 256
+    // row bands: enough warps for ~8 waves of 20 warps per SM, bands a multiple of 32 rows and at least 256 -- or at least
+    // 64 when the batch is so small that 256-row bands would leave SMs idle (one A4 page: 286 -> 1210 warps, 0.18 -> 0.07 ms;
+    // every band re-scans d rows above its first output row, 22 % extra work at 64 rows)
     {
         const long long want = 8LL * ctx->num_sms * 20;
-        int nb = (int)std::min<long long>((want + (long long)A.ns * n_pages - 1) / ((long long)A.ns * n_pages), (g.out_rows + 255) / 256);
+        int min_rows = 256;
+        if ((long long)A.ns * n_pages * ((g.out_rows + 255) / 256) < 16LL * ctx->num_sms) min_rows = 64;
+        int nb = (int)std::min<long long>((want + (long long)A.ns * n_pages - 1) / ((long long)A.ns * n_pages), (g.out_rows + min_rows - 1) / min_rows);
         nb = std::max(nb, 1);
         A.band_rows = (((g.out_rows + nb - 1) / nb) + 31) & ~31;
         A.nb = (g.out_rows + A.band_rows - 1) / A.band_rows;
@@ -492,12 +511,12 @@ int prl_k_fused(prl_cuda_ctx* ctx, int method, const uint8_t* d_src, int n_pages
     }
     {
         prl_launch_scope ls(ctx, FAM_FUSED_FIX);
-        const int grid = ctx->num_sms * 4;
+        const int grid = ctx->num_sms * 8;
         switch (method) {
-        case PRL_SAUVOLA: fixup_kernel<PRL_SAUVOLA><<<grid, 128, 0, ctx->stream>>>(A); break;
-        case PRL_NIBLACK: fixup_kernel<PRL_NIBLACK><<<grid, 128, 0, ctx->stream>>>(A); break;
-        case PRL_NICK:    fixup_kernel<PRL_NICK><<<grid, 128, 0, ctx->stream>>>(A); break;
-        default:          fixup_kernel<PRL_FENG><<<grid, 128, 0, ctx->stream>>>(A); break;
+        case PRL_SAUVOLA: fixup_kernel<PRL_SAUVOLA><<<grid, kFixThreads, 0, ctx->stream>>>(A); break;
+        case PRL_NIBLACK: fixup_kernel<PRL_NIBLACK><<<grid, kFixThreads, 0, ctx->stream>>>(A); break;
+        case PRL_NICK:    fixup_kernel<PRL_NICK><<<grid, kFixThreads, 0, ctx->stream>>>(A); break;
+        default:          fixup_kernel<PRL_FENG><<<grid, kFixThreads, 0, ctx->stream>>>(A); break;
         }
     }
     {

@@ -146,6 +146,9 @@ integral_sq_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int cols,
     if (lane == 0)
         for (int c = 0; c < kNS - 1 && c < n_chunks; ++c) PRL_ISSUE_TMA(c);
 
+    // (Measured and dropped, round 2: software-pipelining the two sweeps -- sweep 1 of chunk c + 1 before sweep 2 of chunk c,
+    // hand-over through a split mbarrier, four tot buffers -- removes the block-wide barrier but ran 29 % SLOWER (5.2 vs
+    // 4.03 ms per 256 A4 pages): the longer live ranges spill at 64 registers and the waits turn into mbarrier polling.)
     uint32_t mn4 = 0xffffffffu;
     int buf_sel = 0;
     for (int c = 0; c < n_chunks; ++c, buf_sel ^= 1) {

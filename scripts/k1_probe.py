@@ -6,6 +6,7 @@ from prlib_b200 import capi
 kv = dict(a.split("=") for a in sys.argv[1:])
 n = int(kv.get("pages", 256)); rows, cols = int(kv.get("rows", 3508)), int(kv.get("cols", 2480)); window = int(kv.get("window", 15))
 ctx = prlib_b200.Context(0)
+ctx.set_option("enable_fused", 0)      # kernel 1 + kernel 2, whatever the window
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); ctx.set_stream(stream.cuda_stream)
 step = (cols + 15) // 16 * 16
 buf = torch.empty((n, rows, step), dtype=torch.uint8, device="cuda")
