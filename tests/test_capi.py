@@ -104,3 +104,22 @@ def test_product_sources_never_touch_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, fn), errors="ignore").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace("oracle/prl_oracle.py:synth_page", ""), fn
+
+
+def test_committed_dram_traffic_agrees_with_the_byte_model():
+    """profiles/traffic.json (ncu dram__bytes of kernel 1, kernel 2 and the fused kernel, regenerated by
+    scripts/make_profiles.py with every kernel change) must stay within 3 % of the algorithmic bytes bench.py's roofline
+    uses: traffic above the model means wasted re-reads, traffic below it means the model counts bytes nobody moves."""
+    import json
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+        t = json.load(f)
+    k1, k2 = bench.algorithmic_bytes(bench.ROWS, bench.COLS, bench.WINDOW, "compact")
+    g = bench.geometry(bench.ROWS, bench.COLS, bench.WINDOW)
+    pmin = bench.ROWS * bench.COLS + g["out_rows"] * g["out_cols"]
+    for fam, per_page in (("integral", k1), ("threshold", k2), ("fused", pmin)):
+        model = per_page * t[fam]["pages_per_launch"]
+        assert abs(t[fam]["dram_bytes_per_launch"] / model - 1.0) < 0.03, (fam, t[fam]["dram_bytes_per_launch"], model)
+    assert t.get("commit")
