@@ -239,6 +239,20 @@ int prl_cuda_external_rects(prl_cuda_ctx* ctx, const uint8_t* mask, int rows, in
 int prl_cuda_remove_lines(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step, int channels,
                           uint8_t* dst, size_t dst_step);
 
+/* Batched forms over gray pages resident in HBM.  The per-page kernel sequences are
+ * dozens of small launches; the library runs 16 pages side by side on internal streams.  Both calls are SYNCHRONOUS (they
+ * first wait for the context's stream, and return when every page is done).  status[p] / n_rects[p] (host arrays of n_pages
+ * ints, optional): the page's own outcome -- PRL_OK, PRL_E_INVALID = "Contours array is empty" (the std::invalid_argument the
+ * reference throws for that image, imageLibCommon.cpp:643-646; its output page is left untouched), PRL_E_UNSUPPORTED = more than
+ * 65535 contours -- and its number of rectangles.  prl_cuda_remove_lines_batch_dev fails as a whole with PRL_E_EMPTY_ROI
+ * when rows < 50 or cols < 50 (the cv::Exception of the reference). */
+int prl_cuda_binarize_local_otsu_batch_dev(prl_cuda_ctx* ctx, const uint8_t* d_gray, int n_pages, int rows, int cols, size_t step,
+                                           size_t page_stride, double maxval, double clahe_clip_limit, int gauss_ksize,
+                                           double upper_coeff, double lower_coeff, int morph_iters, uint8_t* d_dst, size_t dst_step,
+                                           size_t dst_page_stride, int32_t* n_rects, int32_t* status);
+int prl_cuda_remove_lines_batch_dev(prl_cuda_ctx* ctx, const uint8_t* d_gray, int n_pages, int rows, int cols, size_t step,
+                                    size_t page_stride, uint8_t* d_dst, size_t dst_step, size_t dst_page_stride);
+
 /* ---- the adaptive-mean family: binarizeNativeAdaptive.cpp:34-140, binarizeAT.cpp:33-67,
  * binarizeAGT.cpp:33-58, binarizePureAdaptiveGaussian.cpp:31-71 ------------------------------------------------
  * cv::medianBlur (u8; 1, 3 or 4 interleaved channels; odd ksize 3..63; ksize <= 1 copies; even ksize: PRL_E_EMPTY_ROI, the

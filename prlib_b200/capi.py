@@ -91,6 +91,11 @@ class AdaptiveParams(C.Structure):
 
 
 SIGNATURES.update({
+    "prl_cuda_binarize_local_otsu_batch_dev": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_double, C.c_double,
+                                                         C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t,
+                                                         C.c_void_p, C.c_void_p]),
+    "prl_cuda_remove_lines_batch_dev": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t,
+                                                  C.c_size_t]),
     "prl_cuda_median_blur": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "prl_cuda_adaptive_threshold": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_double, C.c_int, C.c_int, C.c_int,
                                               C.c_double, C.c_void_p, C.c_size_t]),

@@ -344,6 +344,20 @@ class Context:
         self._check(self._L.prl_cuda_otsu_tiles_batch_dev(self._h, d_src, n_pages, rows, cols, src_step, src_page_stride,
                                                           tile_w, tile_h, float(maxval), d_dst, dst_step, dst_page_stride))
 
+    def binarize_local_otsu_batch_dev(self, d_gray, n_pages, rows, cols, step, page_stride, d_dst, dst_step, dst_page_stride,
+                                      maxval=255.0, clahe_clip_limit=0.0, ksize=19, upper_coeff=0.15, lower_coeff=0.01, morph_iters=1):
+        """-> (n_rects[n_pages], status[n_pages]) as numpy int32 arrays; synchronous"""
+        n_rects = np.zeros(n_pages, np.int32)
+        status = np.zeros(n_pages, np.int32)
+        self._check(self._L.prl_cuda_binarize_local_otsu_batch_dev(self._h, d_gray, n_pages, rows, cols, step, page_stride, float(maxval),
+                                                                   float(clahe_clip_limit), int(ksize), float(upper_coeff), float(lower_coeff),
+                                                                   int(morph_iters), d_dst, dst_step, dst_page_stride, n_rects.ctypes.data,
+                                                                   status.ctypes.data))
+        return n_rects, status
+
+    def remove_lines_batch_dev(self, d_gray, n_pages, rows, cols, step, page_stride, d_dst, dst_step, dst_page_stride):
+        self._check(self._L.prl_cuda_remove_lines_batch_dev(self._h, d_gray, n_pages, rows, cols, step, page_stride, d_dst, dst_step, dst_page_stride))
+
     def synth_pages_dev(self, d_dst, n_pages, rows, cols, step, page_stride, seed=2024, first_page=0):
         self._check(self._L.prl_cuda_synth_pages_dev(self._h, d_dst, n_pages, rows, cols, step, page_stride, seed, first_page))
 

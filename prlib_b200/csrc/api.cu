@@ -162,6 +162,9 @@ extern "C" void prl_cuda_destroy(prl_cuda_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (prl_cuda_ctx* l : c->lanes) prl_cuda_destroy(l);
+    c->lanes.clear();
+    if (c->h_lane_counts) cudaFreeHost(c->h_lane_counts);
     for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto& ev : c->event_pool) cudaEventDestroy(ev);
     cudaFree(c->sched); cudaFree(c->planes); cudaFree(c->carry); cudaFree(c->colsum); cudaFree(c->scalars); cudaFree(c->fused_ws);
@@ -250,7 +253,13 @@ extern "C" int prl_cuda_timing_get(prl_cuda_ctx* c, const char* family, double* 
         }
     return prl_set_err(c, PRL_E_INVALID, "unknown kernel family");
 }
-extern "C" long long prl_cuda_launch_count(const prl_cuda_ctx* c) { return c ? c->launches : 0; }
+extern "C" long long prl_cuda_launch_count(const prl_cuda_ctx* c)
+{
+    if (!c) return 0;
+    long long n = c->launches;
+    for (const prl_cuda_ctx* l : c->lanes) n += l->launches;
+    return n;
+}
 // pages the fused path handed back to the two-kernel path so far: a device counter, so this call synchronises the stream
 extern "C" long long prl_cuda_fused_redo_count(prl_cuda_ctx* c)
 {
@@ -768,6 +777,63 @@ extern "C" int prl_cuda_clahe(prl_cuda_ctx* c, const uint8_t* src, int rows, int
     return PRL_OK;
 }
 
+// ---- prl::binarizeLocalOtsu on a gray image resident in HBM, in two asynchronous halves around the one number the host
+// needs (how many contour rectangles there are: it sizes the rectangle loop and decides the reference's error cases).
+struct LocalOtsuJob {
+    const uint8_t* proc = nullptr;      // imageToProc: the gray image, or its CLAHE + equalizeHist enhancement (binarizeLocalOtsu.cpp:79-82)
+    size_t proc_step = 0;
+    int* d_count = nullptr; int32_t* d_xywh = nullptr; int32_t* d_thr = nullptr;
+};
+constexpr int kRectCap = 65535;
+
+// phase A: edge map (binarizeLocalOtsu.cpp:85-92) -> c->d_tmp, bounding rectangles of the top-level contours (:104-110,150);
+// the count is copied to *h_count (pinned, or any host word for a synchronous caller) on the context's stream
+static int local_otsu_phase_a(prl_cuda_ctx* c, const uint8_t* d_gray, int rows, int cols, size_t in_step, double clahe_clip_limit,
+                              int gauss_ksize, double upper_coeff, double lower_coeff, int morph_iters, LocalOtsuJob* J, int* h_count)
+{
+    const size_t o_step = round16(cols);
+    int rc = prl_ensure(c, (void**)&c->d_tmp, &c->d_tmp_bytes, o_step * rows); if (rc) return rc;
+    J->proc = d_gray; J->proc_step = in_step;
+    if (clahe_clip_limit > 0) {
+        uint8_t* enh = nullptr;
+        rc = clahe_dev(c, d_gray, rows, cols, in_step, clahe_clip_limit, true, &enh); if (rc) return rc;
+        J->proc = enh; J->proc_step = round16((size_t)cols);
+    }
+    rc = prl_cuda_canny_edge_detection_dev(c, J->proc, rows, cols, J->proc_step, gauss_ksize, upper_coeff, lower_coeff, morph_iters, 3,
+                                           c->d_tmp, o_step);
+    if (rc) return rc;
+    // the list never leaves the device on its way to the Otsu loop
+    const size_t list_bytes = (256 + (size_t)kRectCap * 16 + (size_t)kRectCap * 4 + 255) & ~(size_t)255;
+    rc = prl_ensure(c, &c->rects_ws, &c->rects_ws_bytes, list_bytes + prl_rects_scratch_bytes(rows, cols)); if (rc) return rc;
+    J->d_count = (int*)c->rects_ws;
+    J->d_xywh = (int32_t*)((uint8_t*)c->rects_ws + 256);
+    J->d_thr = J->d_xywh + (size_t)kRectCap * 4;
+    rc = prl_k_external_rects(c, c->d_tmp, rows, cols, o_step, J->d_count, J->d_xywh, kRectCap, (uint8_t*)c->rects_ws + list_bytes);
+    if (rc) return rc;
+    PRL_CUDA_TRY(c, cudaMemcpyAsync(h_count, J->d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    return PRL_OK;
+}
+
+// phase B: the rectangle loop (:138-162) into d_dst, or the reference's outcome for the degenerate counts.
+// returns PRL_OK, PRL_E_INVALID ("Contours array is empty", imageLibCommon.cpp:643-646) or PRL_E_UNSUPPORTED (> 65535 contours)
+static int local_otsu_phase_b(prl_cuda_ctx* c, const LocalOtsuJob& J, int rows, int cols, int count, double maxval, uint8_t* d_dst,
+                              size_t dst_step, int* n_rects)
+{
+    if (n_rects) *n_rects = count;
+    if (count == 0) return prl_set_err(c, PRL_E_INVALID, "Contours array is empty");
+    if (count > kRectCap) return prl_set_err(c, PRL_E_UNSUPPORTED, "more than 65535 contours");
+    if (rows == 1 || cols == 1) {
+        // Every component of a one-pixel-wide image is a straight run: its CHAIN_APPROX_SIMPLE contour has 1 or 2
+        // points and CheckHierarhyLevelRecursively ignores contours with fewer than 3 (imageLibCommon.cpp:729-736), so
+        // no rectangle is thresholded and the result stays 255 (binarizeLocalOtsu.cpp:142).  With 2 or more rows and
+        // columns a component of the 3x-dilated edge map always holds a 2 x 2 block, i.e. at least 4 contour points.
+        if (n_rects) *n_rects = 0;
+        PRL_CUDA_TRY(c, cudaMemset2DAsync(d_dst, dst_step, 255, cols, rows, c->stream));
+        return PRL_OK;
+    }
+    return prl_k_otsu_rects(c, J.proc, rows, cols, J.proc_step, J.d_xywh, count, maxval, d_dst, dst_step, J.d_thr);
+}
+
 extern "C" int prl_cuda_binarize_local_otsu(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step, int channels,
                                             double maxval, double clahe_clip_limit, int gauss_ksize, double upper_coeff, double lower_coeff, int morph_iters,
                                             uint8_t* dst, size_t dst_step, int* n_rects, int32_t* rects_out, int rects_cap)
@@ -793,50 +859,101 @@ extern "C" int prl_cuda_binarize_local_otsu(prl_cuda_ctx* c, const uint8_t* src,
     }
     const size_t o_step = round16(cols);
     rc = prl_ensure(c, (void**)&c->d_out, &c->d_out_bytes, o_step * rows); if (rc) return rc;
-    rc = prl_ensure(c, (void**)&c->d_tmp, &c->d_tmp_bytes, o_step * rows); if (rc) return rc;
-    // imageToProc: the gray image, or its CLAHE + equalizeHist enhancement (binarizeLocalOtsu.cpp:79-82)
-    const uint8_t* d_proc = c->d_in;
-    if (clahe_clip_limit > 0) {
-        uint8_t* enh = nullptr;
-        rc = clahe_dev(c, c->d_in, rows, cols, in_step, clahe_clip_limit, true, &enh); if (rc) return rc;
-        d_proc = enh; in_step = round16((size_t)cols);
-    }
-    // edge map (binarizeLocalOtsu.cpp:85-92) -> d_tmp
-    rc = prl_cuda_canny_edge_detection_dev(c, d_proc, rows, cols, in_step, gauss_ksize, upper_coeff, lower_coeff, morph_iters, 3,
-                                           c->d_tmp, o_step);
-    if (rc) return rc;
-    // rectangles (:104-110,150); the list never leaves the device on its way to the Otsu loop
-    constexpr int kCap = 65535;
-    const size_t list_bytes = (256 + (size_t)kCap * 16 + (size_t)kCap * 4 + 255) & ~(size_t)255;
-    rc = prl_ensure(c, &c->rects_ws, &c->rects_ws_bytes, list_bytes + prl_rects_scratch_bytes(rows, cols)); if (rc) return rc;
-    int* d_count = (int*)c->rects_ws;
-    int32_t* d_xywh = (int32_t*)((uint8_t*)c->rects_ws + 256);
-    int32_t* d_thr = d_xywh + (size_t)kCap * 4;
-    rc = prl_k_external_rects(c, c->d_tmp, rows, cols, o_step, d_count, d_xywh, kCap, (uint8_t*)c->rects_ws + list_bytes);
-    if (rc) return rc;
+    LocalOtsuJob J;
     int count = 0;
-    PRL_CUDA_TRY(c, cudaMemcpyAsync(&count, d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    rc = local_otsu_phase_a(c, c->d_in, rows, cols, in_step, clahe_clip_limit, gauss_ksize, upper_coeff, lower_coeff, morph_iters, &J, &count);
+    if (rc) return rc;
     PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    if (n_rects) *n_rects = count;
-    if (count == 0) return prl_set_err(c, PRL_E_INVALID, "Contours array is empty");                  // imageLibCommon.cpp:643-646
-    if (count > kCap) return prl_set_err(c, PRL_E_UNSUPPORTED, "more than 65535 contours");
-    if (rows == 1 || cols == 1) {
-        // Every component of a one-pixel-wide image is a straight run: its CHAIN_APPROX_SIMPLE contour has 1 or 2
-        // points and CheckHierarhyLevelRecursively ignores contours with fewer than 3 (imageLibCommon.cpp:729-736), so
-        // no rectangle is thresholded and the result stays 255 (binarizeLocalOtsu.cpp:142).  With 2 or more rows and
-        // columns a component of the 3x-dilated edge map always holds a 2 x 2 block, i.e. at least 4 contour points.
-        if (n_rects) *n_rects = 0;
-        PRL_CUDA_TRY(c, cudaMemset2DAsync(c->d_out, o_step, 255, cols, rows, c->stream));
-        PRL_CUDA_TRY(c, cudaMemcpy2DAsync(dst, dst_step, c->d_out, o_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
-        PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-        return PRL_OK;
-    }
-    if (rects_out && rects_cap > 0)
-        PRL_CUDA_TRY(c, cudaMemcpyAsync(rects_out, d_xywh, (size_t)std::min(count, rects_cap) * 16, cudaMemcpyDeviceToHost, c->stream));
-    rc = prl_k_otsu_rects(c, d_proc, rows, cols, in_step, d_xywh, count, maxval, c->d_out, o_step, d_thr); if (rc) return rc;
+    if (rects_out && rects_cap > 0 && count > 0 && count <= kRectCap && rows > 1 && cols > 1)
+        PRL_CUDA_TRY(c, cudaMemcpyAsync(rects_out, J.d_xywh, (size_t)std::min(count, rects_cap) * 16, cudaMemcpyDeviceToHost, c->stream));
+    rc = local_otsu_phase_b(c, J, rows, cols, count, maxval, c->d_out, o_step, n_rects);
+    if (rc) return rc;
     PRL_CUDA_TRY(c, cudaMemcpy2DAsync(dst, dst_step, c->d_out, o_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
     PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return PRL_OK;
+}
+
+// ---- batched F3 / F4 rows: pages resident in HBM, several pages side by side --------------------------------------------
+// The kernel sequences of these two functions are ~25 / ~50 small launches per page, each far too small to fill the
+// device.  Instead of re-writing every kernel over a page index, the batch runs kLanes pages CONCURRENTLY: each lane is a
+// sub-context with its own stream and scratch, so the launches of different pages overlap on the SMs.
+constexpr int kLanes = 16;
+
+static int ensure_lanes(prl_cuda_ctx* c, int n)
+{
+    while ((int)c->lanes.size() < n) {
+        prl_cuda_ctx* l = nullptr;
+        int rc = prl_cuda_create(c->device, &l);
+        if (rc) return prl_set_err(c, rc, prl_cuda_last_error(nullptr));
+        c->lanes.push_back(l);
+    }
+    if (!c->h_lane_counts) PRL_CUDA_TRY(c, cudaMallocHost((void**)&c->h_lane_counts, sizeof(int) * kLanes));
+    return PRL_OK;
+}
+
+static int sync_lanes(prl_cuda_ctx* c, int n)
+{
+    for (int i = 0; i < n; ++i) PRL_CUDA_TRY(c, cudaStreamSynchronize(c->lanes[i]->stream));
+    return PRL_OK;
+}
+
+// prl::binarizeLocalOtsu (binarizeLocalOtsu.cpp:38-163) over n_pages gray pages in HBM.  Synchronous.  status[p] (host,
+// optional) receives the page's own outcome: PRL_OK, PRL_E_INVALID = "Contours array is empty" (the std::invalid_argument of
+// the reference for that image; its output page is left untouched), PRL_E_UNSUPPORTED = more than 65535 contours.
+extern "C" int prl_cuda_binarize_local_otsu_batch_dev(prl_cuda_ctx* c, const uint8_t* d_gray, int n_pages, int rows, int cols, size_t step,
+                                                      size_t page_stride, double maxval, double clahe_clip_limit, int gauss_ksize,
+                                                      double upper_coeff, double lower_coeff, int morph_iters, uint8_t* d_dst, size_t dst_step,
+                                                      size_t dst_page_stride, int32_t* n_rects, int32_t* status)
+{
+    if (!c) return PRL_E_INVALID;
+    if (!d_gray || !d_dst || n_pages <= 0 || rows <= 0 || cols <= 0 || step < (size_t)cols || dst_step < (size_t)cols)
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    if (!(maxval >= 0 && maxval <= 255)) return prl_set_err(c, PRL_E_INVALID, "Max value must be in range [0; 255]");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    const int nl = std::min(kLanes, n_pages);
+    int rc = ensure_lanes(c, nl); if (rc) return rc;
+    PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));               // the pages may have been produced on the caller's stream
+    LocalOtsuJob jobs[kLanes];
+    for (int p0 = 0; p0 < n_pages; p0 += nl) {
+        const int np = std::min(nl, n_pages - p0);
+        for (int i = 0; i < np; ++i) {
+            prl_cuda_ctx* l = c->lanes[i];
+            rc = local_otsu_phase_a(l, d_gray + (size_t)(p0 + i) * page_stride, rows, cols, step, clahe_clip_limit, gauss_ksize, upper_coeff,
+                                    lower_coeff, morph_iters, &jobs[i], c->h_lane_counts + i);
+            if (rc) { c->err = l->err; sync_lanes(c, nl); return rc; }
+        }
+        rc = sync_lanes(c, np); if (rc) return rc;
+        for (int i = 0; i < np; ++i) {
+            prl_cuda_ctx* l = c->lanes[i];
+            int nr = 0;
+            const int prc = local_otsu_phase_b(l, jobs[i], rows, cols, c->h_lane_counts[i], maxval, d_dst + (size_t)(p0 + i) * dst_page_stride,
+                                               dst_step, &nr);
+            if (prc == PRL_E_CUDA || prc == PRL_E_NOMEM) { c->err = l->err; sync_lanes(c, nl); return prc; }
+            if (n_rects) n_rects[p0 + i] = nr;
+            if (status) status[p0 + i] = prc;
+        }
+    }
+    return sync_lanes(c, nl);
+}
+
+// prl::removeLines (removeLines.cpp:30-77) over n_pages gray pages in HBM.  Synchronous.
+extern "C" int prl_cuda_remove_lines_batch_dev(prl_cuda_ctx* c, const uint8_t* d_gray, int n_pages, int rows, int cols, size_t step,
+                                               size_t page_stride, uint8_t* d_dst, size_t dst_step, size_t dst_page_stride)
+{
+    if (!c) return PRL_E_INVALID;
+    if (!d_gray || !d_dst || n_pages <= 0 || rows <= 0 || cols <= 0 || step < (size_t)cols || dst_step < (size_t)cols)
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    const int nl = std::min(kLanes, n_pages);
+    int rc = ensure_lanes(c, nl); if (rc) return rc;
+    PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (int p = 0; p < n_pages; ++p) {
+        prl_cuda_ctx* l = c->lanes[p % nl];
+        rc = prl_ensure(l, &l->edges_ws, &l->edges_ws_bytes, prl_lines_scratch_bytes(rows, cols));
+        if (!rc) rc = prl_k_remove_lines(l, d_gray + (size_t)p * page_stride, rows, cols, step, d_dst + (size_t)p * dst_page_stride, dst_step, l->edges_ws);
+        if (rc) { c->err = l->err; sync_lanes(c, nl); return rc; }
+    }
+    return sync_lanes(c, nl);
 }
 
 // bounding rectangles of the top-level contours of a binary image (non-zero = foreground): the set

@@ -93,6 +93,11 @@ struct prl_cuda_ctx {
     bool use_fused = true;      // windows <= 31 take the fused small-window strip kernel (integral planes never reach HBM);
                                 // set_option("enable_fused", 0) forces kernel 1 + kernel 2
 
+    // page lanes of the batched F3 / F4 entry points: sub-contexts (own stream, own scratch) that run the single-image
+    // kernel sequences of several pages side by side
+    std::vector<prl_cuda_ctx*> lanes;
+    int* h_lane_counts = nullptr;                          // pinned: contour counts of the pages in flight
+
     // instrumentation
     bool timing = false;
     long long launches = 0;

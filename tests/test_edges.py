@@ -211,3 +211,46 @@ def test_clahe_and_local_otsu_with_clahe(ctx, noise_page, real_crops):
     assert np.array_equal(prlib_b200.binarizeLocalOtsu(page, 255.0, 2.0), O.binarizeLocalOtsu(page, 255.0, 2.0))
     bgr = real_crops["bgr_0037"]
     assert np.array_equal(prlib_b200.binarizeLocalOtsu(bgr, 255.0, 4.0), O.binarizeLocalOtsu(bgr, 255.0, 4.0))
+
+
+@pytest.mark.gpu
+def test_batched_local_otsu_and_remove_lines_equal_the_per_image_oracle(ctx):
+    """prl_cuda_binarize_local_otsu_batch_dev / prl_cuda_remove_lines_batch_dev: pages resident in HBM, 16 page lanes side by
+    side; every page must equal the OpenCV call sequence of the reference for that page, a page without contours reports
+    the reference's std::invalid_argument through its status word and leaves the others alone."""
+    import torch
+    from prlib_b200 import capi
+    n, rows, cols = 37, 420, 610                       # more pages than lanes, odd pitch-free sizes
+    host = np.stack([CO.synth_page(60 + p, rows, cols) for p in range(n)])
+    host[5] = 200                                      # flat page: no edges -> "Contours array is empty"
+    host[9] = np.random.default_rng(9).integers(0, 256, (rows, cols), dtype=np.uint8)
+    step = (cols + 15) // 16 * 16
+    buf = torch.zeros((n, rows, step), dtype=torch.uint8, device="cuda:0")
+    buf[:, :, :cols] = torch.from_numpy(host).to("cuda:0")
+    out = torch.full((n, rows, step), 7, dtype=torch.uint8, device="cuda:0")
+    torch.cuda.synchronize()
+    n_rects, status = ctx.binarize_local_otsu_batch_dev(buf.data_ptr(), n, rows, cols, step, rows * step, out.data_ptr(), step, rows * step)
+    got = out.cpu().numpy()[:, :, :cols]
+    for p in range(n):
+        if p == 5:
+            assert status[p] == capi.PRL_E_INVALID and n_rects[p] == 0 and (got[p] == 7).all()
+            with pytest.raises(ValueError):
+                O.binarizeLocalOtsu(host[p])
+            continue
+        assert status[p] == 0 and n_rects[p] > 0, p
+        assert np.array_equal(got[p], O.binarizeLocalOtsu(host[p])), p
+    # with the CLAHE pre-step and a maxValue below 255 (the whole rectangle turns black, binarizeLocalOtsu.cpp:159)
+    n2 = 5
+    ctx.binarize_local_otsu_batch_dev(buf.data_ptr(), n2, rows, cols, step, rows * step, out.data_ptr(), step, rows * step,
+                                      maxval=200.0, clahe_clip_limit=2.0, ksize=11, morph_iters=2)
+    got = out.cpu().numpy()[:, :, :cols]
+    for p in range(n2):
+        assert np.array_equal(got[p], O.binarizeLocalOtsu(host[p], 200.0, 2.0, 11, 0.15, 0.01, 2)), p
+    out.fill_(7)
+    ctx.remove_lines_batch_dev(buf.data_ptr(), n, rows, cols, step, rows * step, out.data_ptr(), step, rows * step)
+    got = out.cpu().numpy()[:, :, :cols]
+    for p in range(n):
+        assert np.array_equal(got[p], O.removeLines(host[p])), p
+    with pytest.raises(prlib_b200.PrlCudaError) as e:
+        ctx.remove_lines_batch_dev(buf.data_ptr(), 2, 40, cols, step, rows * step, out.data_ptr(), step, rows * step)
+    assert e.value.code == capi.PRL_E_EMPTY_ROI
