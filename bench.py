@@ -376,9 +376,9 @@ def run_ours(args):
         default_path = {"error": str(ex)}
 
     # ---- end to end through the host C-ABI (pinned host buffers; H2D + D2H inside the timed region), library defaults
-    host_pages = torch.empty((n_pages, ROWS, COLS), dtype=torch.uint8).pin_memory()
+    host_pages = torch.empty((n_pages, ROWS, COLS), dtype=torch.uint8, pin_memory=True)
     host_pages.copy_(pages[:, :, :COLS])
-    host_masks = torch.empty((n_pages, g["out_rows"], g["out_cols"]), dtype=torch.uint8).pin_memory()
+    host_masks = torch.empty((n_pages, g["out_rows"], g["out_cols"]), dtype=torch.uint8, pin_memory=True)
     hp, hm = host_pages.numpy(), host_masks.numpy()
     ctx.set_stream(None)
     e2e_warm = max(1, min(args.warmup, 2))
@@ -396,7 +396,7 @@ def run_ours(args):
         bool(torch.equal(host_masks[-1:].to(dev), masks[-1:, :, :g["out_cols"]]))
     # extra: the same call with 1-bit-per-pixel output (prl_cuda_binarize_batch_packed, PIX layout): D2H is 8x smaller
     wpl = (g["out_cols"] + 31) // 32
-    host_bits = torch.empty((n_pages, g["out_rows"], wpl), dtype=torch.int32).pin_memory()
+    host_bits = torch.empty((n_pages, g["out_rows"], wpl), dtype=torch.int32, pin_memory=True)
     hb = host_bits.numpy().view(np.uint32)
     prlib_b200.binarize_batch(hp, capi.SAUVOLA, WINDOW, (K_COEF,), 0, devices=[local_rank], out=hb, packed=True)
     barrier()
@@ -465,8 +465,8 @@ def run_ours(args):
         if rank == 0:
             try:
                 big_n, calls = 1024, 8
-                big_in = torch.empty((big_n, ROWS, COLS), dtype=torch.uint8).pin_memory()
-                big_out = torch.empty((big_n, g["out_rows"], g["out_cols"]), dtype=torch.uint8).pin_memory()
+                big_in = torch.empty((big_n, ROWS, COLS), dtype=torch.uint8, pin_memory=True)
+                big_out = torch.empty((big_n, g["out_rows"], g["out_cols"]), dtype=torch.uint8, pin_memory=True)
                 for r in range(big_n // n_pages):
                     big_in[r * n_pages:(r + 1) * n_pages].copy_(host_pages)
                 bi, bo = big_in.numpy(), big_out.numpy()
