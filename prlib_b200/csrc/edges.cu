@@ -29,38 +29,72 @@ __device__ __forceinline__ int reflect101(int i, int n)
     return i;
 }
 
-// row pass: u8 -> 8.8 fixed point (exact: the coefficients sum to 256)
+// row pass: u8 -> 8.8 fixed point (exact: the coefficients sum to 256).  A CTA stages 1024 + n - 1 pixels of one row in
+// shared memory (reflected at the image border); a thread produces 4 adjacent outputs, so a staged pixel is read once per
+// thread instead of once per output.
+constexpr int kGRowOut = 4;
+
 __global__ void __launch_bounds__(256)
-gauss_rows_kernel(const uint8_t* __restrict__ src, size_t step, int rows, int cols, GaussK K, uint16_t* __restrict__ tmp, size_t tstep)
+gauss_rows_kernel(const uint8_t* __restrict__ src, size_t step, int rows, int cols, const __grid_constant__ GaussK K, uint16_t* __restrict__ tmp,
+                  size_t tstep)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= cols) return;
+    __shared__ uint8_t line[256 * kGRowOut + kMaxGauss + 1];
+    __shared__ int kk[kMaxGauss + 1];
+    const int y = blockIdx.y, xb = blockIdx.x * 256 * kGRowOut, r = K.n >> 1;
     const uint8_t* row = src + (size_t)y * step;
-    const int r = K.n >> 1;
-    uint32_t acc = 0;
-    if (x >= r && x + r < cols) {
-        for (int t = 0; t < K.n; ++t) acc += (uint32_t)row[x + t - r] * (uint32_t)K.k[t];
-    } else {
-        for (int t = 0; t < K.n; ++t) acc += (uint32_t)row[reflect101(x + t - r, cols)] * (uint32_t)K.k[t];
+    for (int i = threadIdx.x; i < K.n; i += 256) kk[i] = K.k[i];
+    const int span = min(256 * kGRowOut, cols - xb) + K.n - 1;
+    for (int i = threadIdx.x; i < span; i += 256) line[i] = row[reflect101(xb + i - r, cols)];
+    __syncthreads();
+    const int x = xb + threadIdx.x * kGRowOut;
+    if (x >= cols) return;
+    uint32_t acc[kGRowOut] = {0, 0, 0, 0};
+    const uint8_t* p = line + threadIdx.x * kGRowOut;
+    for (int j = 0; j < K.n + kGRowOut - 1; ++j) {
+        const uint32_t v = p[j];
+#pragma unroll
+        for (int o = 0; o < kGRowOut; ++o) {
+            const int t = j - o;
+            if (t >= 0 && t < K.n) acc[o] += v * (uint32_t)kk[t];
+        }
     }
-    tmp[(size_t)y * tstep + x] = (uint16_t)acc;
+    uint16_t* out = tmp + (size_t)y * tstep + x;
+#pragma unroll
+    for (int o = 0; o < kGRowOut; ++o) if (x + o < cols) out[o] = (uint16_t)acc[o];
 }
 
-// column pass: 8.8 -> 16.16 -> u8
+// column pass: 8.8 -> 16.16 -> u8.  A thread produces 8 vertically adjacent outputs of one column: n + 7 loads instead of 8 n.
+constexpr int kGColOut = 8;
+
 __global__ void __launch_bounds__(256)
-gauss_cols_kernel(const uint16_t* __restrict__ tmp, size_t tstep, int rows, int cols, GaussK K, uint8_t* __restrict__ dst, size_t dstep)
+gauss_cols_kernel(const uint16_t* __restrict__ tmp, size_t tstep, int rows, int cols, const __grid_constant__ GaussK K, uint8_t* __restrict__ dst,
+                  size_t dstep)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    __shared__ int kk[kMaxGauss + 1];
+    for (int i = threadIdx.x; i < K.n; i += 256) kk[i] = K.k[i];
+    __syncthreads();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y0 = blockIdx.y * kGColOut;
     if (x >= cols) return;
     const int r = K.n >> 1;
-    uint32_t acc = 0;
-    if (y >= r && y + r < rows) {
-        for (int t = 0; t < K.n; ++t) acc += (uint32_t)tmp[(size_t)(y + t - r) * tstep + x] * (uint32_t)K.k[t];
-    } else {
-        for (int t = 0; t < K.n; ++t) acc += (uint32_t)tmp[(size_t)reflect101(y + t - r, rows) * tstep + x] * (uint32_t)K.k[t];
+    uint32_t acc[kGColOut];
+#pragma unroll
+    for (int o = 0; o < kGColOut; ++o) acc[o] = 0;
+    const bool inner = y0 >= r && y0 + kGColOut - 1 + r < rows;
+    for (int j = 0; j < K.n + kGColOut - 1; ++j) {
+        const int yy = y0 + j - r;
+        const uint32_t v = tmp[(size_t)(inner ? yy : reflect101(yy, rows)) * tstep + x];
+#pragma unroll
+        for (int o = 0; o < kGColOut; ++o) {
+            const int t = j - o;
+            if (t >= 0 && t < K.n) acc[o] += v * (uint32_t)kk[t];
+        }
     }
-    const uint32_t v = (acc + 0x8000u) >> 16;
-    dst[(size_t)y * dstep + x] = (uint8_t)min(v, 255u);
+#pragma unroll
+    for (int o = 0; o < kGColOut; ++o)
+        if (y0 + o < rows) {
+            const uint32_t v = (acc[o] + 0x8000u) >> 16;
+            dst[(size_t)(y0 + o) * dstep + x] = (uint8_t)min(v, 255u);
+        }
 }
 
 // ---- Canny: Sobel + magnitude + non-maximum suppression -> class map (0 none, 1 weak, 2 strong) --------
@@ -68,7 +102,8 @@ constexpr int kCT = 32, kCH = 16;         // output tile
 
 __global__ void __launch_bounds__(kCT * kCH)
 canny_nms_kernel(const uint8_t* __restrict__ src, size_t step, int rows, int cols, const int32_t* __restrict__ otsu_thr,
-                 double upper_coeff, double lower_coeff, double fixed_low, double fixed_high, uint8_t* __restrict__ cls, size_t cstep)
+                 double upper_coeff, double lower_coeff, double fixed_low, double fixed_high, uint8_t* __restrict__ cls, size_t cstep,
+                 int* __restrict__ L, uint8_t* __restrict__ flag, int* __restrict__ list, int* __restrict__ count)
 {
     __shared__ uint8_t sp[kCH + 4][kCT + 4];          // pixels, halo 2 (replicated at the image border)
     __shared__ int smag[kCH + 2][kCT + 2];            // magnitudes, halo 1 (zero outside the image)
@@ -105,10 +140,10 @@ canny_nms_kernel(const uint8_t* __restrict__ src, size_t step, int rows, int col
     }
     __syncthreads();
     const int gx = x0 + tx, gy = y0 + ty;
-    if (gx >= cols || gy >= rows) return;
-    const int m = smag[ty + 1][tx + 1];
+    const bool inside = gx < cols && gy < rows;
+    const int m = inside ? smag[ty + 1][tx + 1] : 0;
     uint8_t out = 0;
-    if (m > low) {
+    if (inside && m > low) {
         const int xs = sdx[ty][tx], ys = sdy[ty][tx];
         const int x = abs(xs), y = abs(ys) << 15;
         const int tg22x = x * 13573;
@@ -122,83 +157,29 @@ canny_nms_kernel(const uint8_t* __restrict__ src, size_t step, int rows, int col
         }
         if (is_max) out = m > high ? 2 : 1;
     }
-    cls[(size_t)gy * cstep + gx] = out;
+    if (inside) cls[(size_t)gy * cstep + gx] = out;
+    // Labels and component flags exist only for surviving pixels, and those pixels (~2 % of a page) are LISTED: the
+    // hysteresis passes run one thread per listed pixel instead of one per pixel of the page (24 + 149 + 49 + 77 us per
+    // A4 page before).  One atomic per warp (ballot + prefix).
+    __shared__ int wcount[kCT * kCH / 32 + 1];
+    const uint32_t alive = __ballot_sync(0xffffffffu, out != 0);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) wcount[wid] = __popc(alive);
+    __syncthreads();
+    if (threadIdx.x == 0) {                                   // one atomic per CTA
+        int tot = 0;
+        for (int k = 0; k < kCT * kCH / 32; ++k) { const int c = wcount[k]; wcount[k] = tot; tot += c; }
+        wcount[kCT * kCH / 32] = tot ? atomicAdd(count, tot) : 0;
+    }
+    __syncthreads();
+    if (out) {
+        const int p = gy * cols + gx;
+        L[p] = p; flag[p] = 0;
+        list[wcount[kCT * kCH / 32] + wcount[wid] + __popc(alive & ((1u << lane) - 1u))] = p;
+    }
 }
 
 // ---- hysteresis: union-find over the surviving pixels, 8-connectivity --------------------------------
-__device__ __forceinline__ int uf_find(const int* __restrict__ L, int x)
-{
-    int p = L[x];
-    while (p != x) { x = p; p = L[x]; }
-    return x;
-}
-__device__ __forceinline__ void uf_union(int* L, int a, int b)
-{
-    for (;;) {
-        a = uf_find(L, a); b = uf_find(L, b);
-        if (a == b) return;
-        if (a < b) { const int t = a; a = b; b = t; }      // a > b: hang a under b
-        const int old = atomicMin(&L[a], b);
-        if (old == a) return;
-        a = old;                                             // somebody re-rooted a meanwhile: merge that root too
-    }
-}
-
-__global__ void __launch_bounds__(256)
-ccl_init_kernel(const uint8_t* __restrict__ cls, size_t cstep, int rows, int cols, int* __restrict__ L)
-{
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= cols) return;
-    const int p = y * cols + x;
-    L[p] = cls[(size_t)y * cstep + x] ? p : -1;
-}
-
-__global__ void __launch_bounds__(256)
-ccl_merge_kernel(const uint8_t* __restrict__ cls, size_t cstep, int rows, int cols, int* __restrict__ L)
-{
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= cols) return;
-    const uint8_t* row = cls + (size_t)y * cstep;
-    if (!row[x]) return;
-    const int p = y * cols + x;
-    if (x > 0 && row[x - 1]) uf_union(L, p, p - 1);
-    if (y > 0) {
-        const uint8_t* up = row - cstep;
-        if (up[x]) uf_union(L, p, p - cols);
-        if (x > 0 && up[x - 1]) uf_union(L, p, p - cols - 1);
-        if (x + 1 < cols && up[x + 1]) uf_union(L, p, p - cols + 1);
-    }
-}
-
-// flag[root] = 1 for every component that holds a strong pixel
-__global__ void __launch_bounds__(256)
-ccl_mark_kernel(const uint8_t* __restrict__ cls, size_t cstep, int rows, int cols, const int* __restrict__ L, uint8_t* __restrict__ flag)
-{
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= cols) return;
-    if (cls[(size_t)y * cstep + x] == 2) flag[uf_find(L, y * cols + x)] = 1;
-}
-
-__global__ void __launch_bounds__(256)
-ccl_emit_kernel(const uint8_t* __restrict__ cls, size_t cstep, int rows, int cols, const int* __restrict__ L,
-                const uint8_t* __restrict__ flag, uint8_t* __restrict__ dst, size_t dstep)
-{
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= cols) return;
-    uint8_t out = 0;
-    if (cls[(size_t)y * cstep + x]) out = flag[uf_find(L, y * cols + x)] ? 255 : 0;
-    dst[(size_t)y * dstep + x] = out;
-}
-
-// ---- contours -> rectangles: cv::findContours(RETR_EXTERNAL) + cv::boundingRect without the contours ------------
-// RETR_EXTERNAL keeps one outer border per 8-connected component of non-zero pixels that does not lie inside a hole
-// of another component; the rectangle loop only needs its bounding box.  Topologically (Suzuki-Abe, 8-connected
-// 1-pixels / 4-connected 0-pixels): a component is top-level iff one of its pixels has, in its 4-neighbourhood, a
-// 0-pixel of the background component that reaches the image frame (or the frame itself).  So: label 1-pixels with
-// 8-connectivity and 0-pixels with 4-connectivity in ONE union-find forest (plus a node for the frame), then every
-// border pixel of a component votes "top-level" and stretches its root's bounding box.
-// Rows are labelled by runs first (no atomics: every pixel points at the start of its horizontal run), so the
-// atomicMin unions only happen once per vertically overlapping pair of runs.
 __device__ __forceinline__ int uf_find_c(int* L, int x)
 {
     for (;;) {
@@ -221,9 +202,70 @@ __device__ __forceinline__ void uf_union_c(int* L, int a, int b)
     }
 }
 
-// one CTA per row: L[y * cols + x] = y * cols + (start of the horizontal run of equal class that holds x)
+// The hysteresis passes: one thread per LISTED (surviving) pixel, grid-stride over the list whose length lives in device memory
 __global__ void __launch_bounds__(256)
-ccl_runs_kernel(const uint8_t* __restrict__ E, size_t estep, int rows, int cols, int* __restrict__ L)
+ccl_merge_kernel(const uint8_t* __restrict__ cls, size_t cstep, int rows, int cols, int* __restrict__ L, const int* __restrict__ list,
+                 const int* __restrict__ count)
+{
+    const int n = *count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int p = list[i], y = p / cols, x = p - y * cols;
+        const uint8_t* row = cls + (size_t)y * cstep;
+        // 8-connectivity with the fewest unions: the diagonal ones only where no 4-neighbour already bridges them
+        // (NW is joined through N or W, NE through N or E, by those pixels' own unions)
+        const bool w = x > 0 && row[x - 1];
+        if (w) uf_union_c(L, p, p - 1);
+        if (y > 0) {
+            const uint8_t* up = row - cstep;
+            const bool n = up[x] != 0;
+            if (n) uf_union_c(L, p, p - cols);
+            else {
+                if (!w && x > 0 && up[x - 1]) uf_union_c(L, p, p - cols - 1);
+                if (x + 1 < cols && up[x + 1] && !row[x + 1]) uf_union_c(L, p, p - cols + 1);
+            }
+        }
+    }
+}
+
+// flag[root] = 1 for every component that holds a strong pixel
+__global__ void __launch_bounds__(256)
+ccl_mark_kernel(const uint8_t* __restrict__ cls, size_t cstep, int rows, int cols, int* __restrict__ L, uint8_t* __restrict__ flag,
+                const int* __restrict__ list, const int* __restrict__ count)
+{
+    const int n = *count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int p = list[i], y = p / cols, x = p - y * cols;
+        if (cls[(size_t)y * cstep + x] == 2) flag[uf_find_c(L, p)] = 1;
+    }
+}
+
+// dst was cleared; the pixels of the kept components are set
+__global__ void __launch_bounds__(256)
+ccl_emit_kernel(int rows, int cols, int* __restrict__ L, const uint8_t* __restrict__ flag, uint8_t* __restrict__ dst, size_t dstep,
+                const int* __restrict__ list, const int* __restrict__ count)
+{
+    const int n = *count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int p = list[i], y = p / cols, x = p - y * cols;
+        if (flag[uf_find_c(L, p)]) dst[(size_t)y * dstep + x] = 255;
+    }
+}
+
+// ---- contours -> rectangles: cv::findContours(RETR_EXTERNAL) + cv::boundingRect without the contours ------------
+// RETR_EXTERNAL keeps one outer border per 8-connected component of non-zero pixels that does not lie inside a hole
+// of another component; the rectangle loop only needs its bounding box.  Topologically (Suzuki-Abe, 8-connected
+// 1-pixels / 4-connected 0-pixels): a component is top-level iff one of its pixels has, in its 4-neighbourhood, a
+// 0-pixel of the background component that reaches the image frame (or the frame itself).  So: label 1-pixels with
+// 8-connectivity and 0-pixels with 4-connectivity in ONE union-find forest (plus a node for the frame), then every
+// border pixel of a component votes "top-level" and stretches its root's bounding box.
+// Rows are labelled by runs first (no atomics: every pixel points at the start of its horizontal run), so the
+// atomicMin unions only happen once per vertically overlapping pair of runs.
+// one CTA per row: L[y * cols + x] = y * cols + (start of the horizontal run of equal class that holds x).
+// A component's root is its smallest label, i.e. always the start of a run: the per-root state (top-level vote, bounding
+// box) is initialised here, at the starts of the 1-runs only -- no full-page memsets (17 bytes per pixel before).
+__global__ void __launch_bounds__(256)
+ccl_runs_kernel(const uint8_t* __restrict__ E, size_t estep, int rows, int cols, int* __restrict__ L, uint8_t* __restrict__ top,
+                int* __restrict__ bx0, int* __restrict__ by0, int* __restrict__ bx1, int* __restrict__ by1)
 {
     __shared__ int wmax[8];
     const int y = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -244,17 +286,41 @@ ccl_runs_kernel(const uint8_t* __restrict__ E, size_t estep, int rows, int cols,
     if (lane == 0) prev = -1;
     int cur = max(carry, prev);
     for (int x = x0; x < x1; ++x) {
-        if (x == 0 || (row[x] != 0) != (row[x - 1] != 0)) cur = x;
+        if (x == 0 || (row[x] != 0) != (row[x - 1] != 0)) {
+            cur = x;
+            if (row[x]) {
+                const int p = y * cols + x;
+                top[p] = 0; bx0[p] = 0x7f7f7f7f; by0[p] = 0x7f7f7f7f; bx1[p] = -1; by1[p] = -1;
+            }
+        }
         L[y * cols + x] = y * cols + cur;
     }
     if (y == 0 && tid == 0) L[rows * cols] = rows * cols;     // the frame node
 }
 
-__global__ void __launch_bounds__(256)
-ccl_vmerge_kernel(const uint8_t* __restrict__ E, size_t estep, int rows, int cols, int* __restrict__ L)
+// 16 pixels per thread: bit i of the result = pixel x0 + i is non-zero (bytes at or beyond `cols` read as 0; vec = the row
+// is 16-byte aligned)
+__device__ __forceinline__ uint32_t nz16(const uint8_t* __restrict__ row, int x0, int cols, bool vec)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= cols) return;
+    uint32_t m = 0;
+    if (vec && x0 + 16 <= cols) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(row + x0));
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t t = ((((w[k] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w[k]) & 0x80808080u) >> 7;      // 1 per non-zero byte
+            t = (t | (t >> 7) | (t >> 14) | (t >> 21)) & 0xfu;
+            m |= t << (4 * k);
+        }
+    } else {
+        for (int i = 0; i < 16 && x0 + i < cols; ++i) m |= (row[x0 + i] != 0 ? 1u : 0u) << i;
+    }
+    return m;
+}
+
+// the unions of one pixel (what every pixel did in the one-thread-per-pixel version; now the image frame and ragged ends)
+__device__ __forceinline__ void vmerge_pixel(const uint8_t* __restrict__ E, size_t estep, int rows, int cols, int* __restrict__ L, int x, int y)
+{
     const uint8_t* row = E + (size_t)y * estep;
     const bool c = row[x] != 0;
     const bool cw = x > 0 ? row[x - 1] != 0 : !c;             // "different class" at the row start
@@ -278,12 +344,35 @@ ccl_vmerge_kernel(const uint8_t* __restrict__ E, size_t estep, int rows, int col
     }
 }
 
+// Vertical (and diagonal) unions, 16 pixels per thread.  Interior groups work on bit masks of the two rows: the positions
+// that need a union are the set bits of three expressions, everything else costs two 16-byte loads.
 __global__ void __launch_bounds__(256)
-ccl_border_kernel(const uint8_t* __restrict__ E, size_t estep, int rows, int cols, int* __restrict__ L, uint8_t* __restrict__ top,
-                  int* __restrict__ bx0, int* __restrict__ by0, int* __restrict__ bx1, int* __restrict__ by1)
+ccl_vmerge_kernel(const uint8_t* __restrict__ E, size_t estep, int rows, int cols, int* __restrict__ L, int vec)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= cols) return;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16, y = blockIdx.y;
+    if (x0 >= cols) return;
+    if (y == 0 || y == rows - 1 || x0 == 0 || x0 + 17 > cols) {         // touches the frame, or has no right neighbour column
+        for (int i = 0; i < 16 && x0 + i < cols; ++i) vmerge_pixel(E, estep, rows, cols, L, x0 + i, y);
+        return;
+    }
+    const uint8_t* row = E + (size_t)y * estep;
+    const uint8_t* up = row - estep;
+    const uint32_t C = nz16(row, x0, cols, vec != 0), CN = nz16(up, x0, cols, vec != 0);
+    const uint32_t cl = row[x0 - 1] != 0, ul = up[x0 - 1] != 0, ur = up[x0 + 16] != 0;
+    const uint32_t CW = ((C << 1) | cl) & 0xffffu, CNW = ((CN << 1) | ul) & 0xffffu, CNE = (CN >> 1) | (ur << 15);
+    uint32_t A = ~(C ^ CN) & ((CW ^ C) | (CNW ^ CN)) & 0xffffu;         // same class above, first column of the overlap
+    uint32_t B = C & ~CN & CNW & ~CW & 0xffffu;                        // 1-pixel, 0 above, 1 at north-west, 0 at west
+    uint32_t D = C & ~CN & CNE & 0xffffu;                              // 1-pixel, 0 above, 1 at north-east
+    const int p0 = y * cols + x0;
+    while (A) { const int i = __ffs(A) - 1; A &= A - 1; uf_union_c(L, p0 + i, p0 + i - cols); }
+    while (B) { const int i = __ffs(B) - 1; B &= B - 1; uf_union_c(L, p0 + i, p0 + i - cols - 1); }
+    while (D) { const int i = __ffs(D) - 1; D &= D - 1; uf_union_c(L, p0 + i, p0 + i - cols + 1); }
+}
+
+__device__ __forceinline__ void border_pixel(const uint8_t* __restrict__ E, size_t estep, int rows, int cols, int* __restrict__ L,
+                                             uint8_t* __restrict__ top, int* __restrict__ bx0, int* __restrict__ by0, int* __restrict__ bx1,
+                                             int* __restrict__ by1, int x, int y)
+{
     const uint8_t* row = E + (size_t)y * estep;
     if (!row[x]) return;
     // 4-neighbours: outside the image (= frame), 0-pixel, or 1-pixel
@@ -307,19 +396,79 @@ ccl_border_kernel(const uint8_t* __restrict__ E, size_t estep, int rows, int col
     if (y > by1[root]) atomicMax(&by1[root], y);
 }
 
+// Every 1-pixel with a 0 (or the frame) in its 4-neighbourhood votes and stretches its root's box.  Pass 1 (16 pixels per
+// thread, bit masks of three rows) LISTS those pixels -- the candidates of an interior group are the set bits of
+// C & ~(W & E & N & S) -- with one atomic per CTA; pass 2 runs one thread per listed pixel.
+__global__ void __launch_bounds__(256)
+ccl_border_list_kernel(const uint8_t* __restrict__ E, size_t estep, int rows, int cols, int vec, int* __restrict__ list, int* __restrict__ count)
+{
+    __shared__ int wcount[9];
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16, y = blockIdx.y;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t cand = 0;
+    if (x0 < cols) {
+        const uint8_t* row = E + (size_t)y * estep;
+        const uint32_t C = nz16(row, x0, cols, vec != 0);
+        cand = C;
+        if (C && y > 0 && y < rows - 1 && x0 > 0 && x0 + 17 <= cols) {
+            const uint32_t N = nz16(row - estep, x0, cols, vec != 0), S = nz16(row + estep, x0, cols, vec != 0);
+            const uint32_t cl = row[x0 - 1] != 0, cr = row[x0 + 16] != 0;
+            const uint32_t W = ((C << 1) | cl) & 0xffffu, Eb = (C >> 1) | (cr << 15);
+            cand = C & ~(W & Eb & N & S);
+        }
+    }
+    // exclusive prefix of the candidate counts over the CTA
+    const int mine = __popc(cand);
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) wcount[wid] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int k = 0; k < 8; ++k) { const int c = wcount[k]; wcount[k] = tot; tot += c; }
+        wcount[8] = tot ? atomicAdd(count, tot) : 0;
+    }
+    __syncthreads();
+    int o = wcount[8] + wcount[wid] + incl - mine;
+    const int p0 = y * cols + x0;
+    while (cand) { const int i = __ffs(cand) - 1; cand &= cand - 1; list[o++] = p0 + i; }
+}
+
+__global__ void __launch_bounds__(256)
+ccl_border_kernel(const uint8_t* __restrict__ E, size_t estep, int rows, int cols, int* __restrict__ L, uint8_t* __restrict__ top,
+                  int* __restrict__ bx0, int* __restrict__ by0, int* __restrict__ bx1, int* __restrict__ by1, const int* __restrict__ list,
+                  const int* __restrict__ count)
+{
+    const int n = *count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int p = list[i], y = p / cols;
+        border_pixel(E, estep, rows, cols, L, top, bx0, by0, bx1, by1, p - y * cols, y);
+    }
+}
+
+// roots are starts of 1-runs: only those positions are looked at
 __global__ void __launch_bounds__(256)
 ccl_rects_kernel(const uint8_t* __restrict__ E, size_t estep, int rows, int cols, const int* __restrict__ L, const uint8_t* __restrict__ top,
                  const int* __restrict__ bx0, const int* __restrict__ by0, const int* __restrict__ bx1, const int* __restrict__ by1,
-                 int* __restrict__ count, int32_t* __restrict__ xywh, int cap)
+                 int* __restrict__ count, int32_t* __restrict__ xywh, int cap, int vec)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= cols) return;
-    const int p = y * cols + x;
-    if (!E[(size_t)y * estep + x] || L[p] != p || !top[p]) return;
-    const int slot = atomicAdd(count, 1);
-    if (slot < cap) {
-        xywh[4 * slot] = bx0[p]; xywh[4 * slot + 1] = by0[p];
-        xywh[4 * slot + 2] = bx1[p] - bx0[p] + 1; xywh[4 * slot + 3] = by1[p] - by0[p] + 1;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16, y = blockIdx.y;
+    if (x0 >= cols) return;
+    const uint8_t* row = E + (size_t)y * estep;
+    const uint32_t C = nz16(row, x0, cols, vec != 0);
+    if (!C) return;
+    const uint32_t cl = x0 > 0 ? (row[x0 - 1] != 0) : 0u;
+    uint32_t starts = C & ~(((C << 1) | cl) & 0xffffu);
+    while (starts) {
+        const int i = __ffs(starts) - 1; starts &= starts - 1;
+        const int p = y * cols + x0 + i;
+        if (L[p] != p || !top[p]) continue;
+        const int slot = atomicAdd(count, 1);
+        if (slot < cap) {
+            xywh[4 * slot] = bx0[p]; xywh[4 * slot + 1] = by0[p];
+            xywh[4 * slot + 2] = bx1[p] - bx0[p] + 1; xywh[4 * slot + 3] = by1[p] - by0[p] + 1;
+        }
     }
 }
 
@@ -487,14 +636,13 @@ int prl_k_gaussian_blur(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int c
     if (prl_gauss_kernel_fixed(ksize, sigma, K.k) != PRL_OK)
         return prl_set_err(ctx, PRL_E_INVALID, "Gaussian kernel size must be odd and in [1, 63]");
     const size_t tstep = r16((size_t)cols);
-    dim3 grid((cols + 255) / 256, rows);
     {
         prl_launch_scope ls(ctx, FAM_EDGES);
-        gauss_rows_kernel<<<grid, 256, 0, ctx->stream>>>(d_src, step, rows, cols, K, d_tmp, tstep);
+        gauss_rows_kernel<<<dim3((cols + 256 * kGRowOut - 1) / (256 * kGRowOut), rows), 256, 0, ctx->stream>>>(d_src, step, rows, cols, K, d_tmp, tstep);
     }
     {
         prl_launch_scope ls(ctx, FAM_EDGES);
-        gauss_cols_kernel<<<grid, 256, 0, ctx->stream>>>(d_tmp, tstep, rows, cols, K, d_dst, dst_step);
+        gauss_cols_kernel<<<dim3((cols + 255) / 256, (rows + kGColOut - 1) / kGColOut), 256, 0, ctx->stream>>>(d_tmp, tstep, rows, cols, K, d_dst, dst_step);
     }
     PRL_CUDA_TRY(ctx, cudaGetLastError());
     return PRL_OK;
@@ -502,7 +650,7 @@ int prl_k_gaussian_blur(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int c
 
 // cv::Canny(src, edges, low, high) (aperture 3, L2gradient = false).  d_otsu != nullptr: thresholds derived on the
 // device from the Otsu value there (upper = upper_coeff * otsu, lower = lower_coeff * upper).
-// scratch: cls rows x r16(cols) bytes | labels rows*cols int32 | flags rows*cols bytes
+// scratch: cls rows x r16(cols) bytes | labels rows*cols int32 | flags rows*cols bytes | list rows*cols + 1 int32
 int prl_k_canny(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, const int32_t* d_otsu,
                 double upper_coeff, double lower_coeff, double low, double high, uint8_t* d_dst, size_t dst_step, void* scratch)
 {
@@ -511,33 +659,37 @@ int prl_k_canny(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, siz
     uint8_t* cls = (uint8_t*)scratch;
     int* L = (int*)((uint8_t*)scratch + r256(cstep * rows));
     uint8_t* flag = (uint8_t*)L + r256((size_t)rows * cols * sizeof(int));
-    PRL_CUDA_TRY(ctx, cudaMemsetAsync(flag, 0, (size_t)rows * cols, ctx->stream));
-    dim3 grid((cols + 255) / 256, rows);
+    int* list = (int*)(flag + r256((size_t)rows * cols));
+    int* count = list + (size_t)rows * cols;
+    PRL_CUDA_TRY(ctx, cudaMemsetAsync(count, 0, sizeof(int), ctx->stream));
+    PRL_CUDA_TRY(ctx, cudaMemset2DAsync(d_dst, dst_step, 0, cols, rows, ctx->stream));
+    const int lgrid = ctx->num_sms * 8;
     {
         prl_launch_scope ls(ctx, FAM_EDGES);
         canny_nms_kernel<<<dim3((cols + kCT - 1) / kCT, (rows + kCH - 1) / kCH), kCT * kCH, 0, ctx->stream>>>(
-            d_src, step, rows, cols, d_otsu, upper_coeff, lower_coeff, low, high, cls, cstep);
+            d_src, step, rows, cols, d_otsu, upper_coeff, lower_coeff, low, high, cls, cstep, L, flag, list, count);
     }
-    { prl_launch_scope ls(ctx, FAM_EDGES); ccl_init_kernel<<<grid, 256, 0, ctx->stream>>>(cls, cstep, rows, cols, L); }
-    { prl_launch_scope ls(ctx, FAM_EDGES); ccl_merge_kernel<<<grid, 256, 0, ctx->stream>>>(cls, cstep, rows, cols, L); }
-    { prl_launch_scope ls(ctx, FAM_EDGES); ccl_mark_kernel<<<grid, 256, 0, ctx->stream>>>(cls, cstep, rows, cols, L, flag); }
-    { prl_launch_scope ls(ctx, FAM_EDGES); ccl_emit_kernel<<<grid, 256, 0, ctx->stream>>>(cls, cstep, rows, cols, L, flag, d_dst, dst_step); }
+    { prl_launch_scope ls(ctx, FAM_EDGES); ccl_merge_kernel<<<lgrid, 256, 0, ctx->stream>>>(cls, cstep, rows, cols, L, list, count); }
+    { prl_launch_scope ls(ctx, FAM_EDGES); ccl_mark_kernel<<<lgrid, 256, 0, ctx->stream>>>(cls, cstep, rows, cols, L, flag, list, count); }
+    { prl_launch_scope ls(ctx, FAM_EDGES); ccl_emit_kernel<<<lgrid, 256, 0, ctx->stream>>>(rows, cols, L, flag, d_dst, dst_step, list, count); }
     PRL_CUDA_TRY(ctx, cudaGetLastError());
     return PRL_OK;
 }
 
 size_t prl_canny_scratch_bytes(int rows, int cols)
 {
-    return r256(r16((size_t)cols) * rows) + r256((size_t)rows * cols * sizeof(int)) + r256((size_t)rows * cols);
+    // class map | labels | flags | list of surviving pixels + its length
+    return r256(r16((size_t)cols) * rows) + r256((size_t)rows * cols * sizeof(int)) + r256((size_t)rows * cols) +
+           r256(((size_t)rows * cols + 1) * sizeof(int));
 }
 
 // Bounding rectangles of the top-level components of a 0/255 map (what cv::findContours(RETR_EXTERNAL) +
 // cv::boundingRect give, binarizeLocalOtsu.cpp:104-105,150).  d_count: one int; d_xywh: cap x 4 ints.
-// scratch: labels (rows*cols + 1) int32 | top rows*cols bytes | 4 x rows*cols int32 boxes
+// scratch: labels (rows*cols + 1) int32 | top rows*cols bytes | 4 x rows*cols int32 boxes | border-pixel list (rows*cols + 1) int32
 size_t prl_rects_scratch_bytes(int rows, int cols)
 {
     const size_t n = (size_t)rows * cols;
-    return r256((n + 1) * sizeof(int)) + r256(n) + 4 * r256(n * sizeof(int));
+    return r256((n + 1) * sizeof(int)) + r256(n) + 4 * r256(n * sizeof(int)) + r256((n + 1) * sizeof(int));     // + list of border pixels
 }
 
 int prl_k_external_rects(prl_cuda_ctx* ctx, const uint8_t* d_edges, int rows, int cols, size_t step, int* d_count,
@@ -552,15 +704,17 @@ int prl_k_external_rects(prl_cuda_ctx* ctx, const uint8_t* d_edges, int rows, in
     int* by0 = (int*)b; b += r256(n * sizeof(int));
     int* bx1 = (int*)b; b += r256(n * sizeof(int));
     int* by1 = (int*)b;
-    PRL_CUDA_TRY(ctx, cudaMemsetAsync(top, 0, n, ctx->stream));
-    PRL_CUDA_TRY(ctx, cudaMemsetAsync(bx0, 0x7f, 2 * r256(n * sizeof(int)), ctx->stream));      // x0, y0 = 0x7f7f7f7f
-    PRL_CUDA_TRY(ctx, cudaMemsetAsync(bx1, 0xff, 2 * r256(n * sizeof(int)), ctx->stream));      // x1, y1 = -1
+    int* blist = (int*)((uint8_t*)by1 + r256(n * sizeof(int)));
+    int* bcount = blist + n;
     PRL_CUDA_TRY(ctx, cudaMemsetAsync(d_count, 0, sizeof(int), ctx->stream));
-    dim3 grid((cols + 255) / 256, rows);
-    { prl_launch_scope ls(ctx, FAM_EDGES); ccl_runs_kernel<<<rows, 256, 0, ctx->stream>>>(d_edges, step, rows, cols, L); }
-    { prl_launch_scope ls(ctx, FAM_EDGES); ccl_vmerge_kernel<<<grid, 256, 0, ctx->stream>>>(d_edges, step, rows, cols, L); }
-    { prl_launch_scope ls(ctx, FAM_EDGES); ccl_border_kernel<<<grid, 256, 0, ctx->stream>>>(d_edges, step, rows, cols, L, top, bx0, by0, bx1, by1); }
-    { prl_launch_scope ls(ctx, FAM_EDGES); ccl_rects_kernel<<<grid, 256, 0, ctx->stream>>>(d_edges, step, rows, cols, L, top, bx0, by0, bx1, by1, d_count, d_xywh, cap); }
+    PRL_CUDA_TRY(ctx, cudaMemsetAsync(bcount, 0, sizeof(int), ctx->stream));
+    const int vec = ((((uintptr_t)d_edges) | step) & 15) == 0;
+    dim3 grid16((cols + 16 * 256 - 1) / (16 * 256), rows);            // 16 pixels per thread
+    { prl_launch_scope ls(ctx, FAM_EDGES); ccl_runs_kernel<<<rows, 256, 0, ctx->stream>>>(d_edges, step, rows, cols, L, top, bx0, by0, bx1, by1); }
+    { prl_launch_scope ls(ctx, FAM_EDGES); ccl_vmerge_kernel<<<grid16, 256, 0, ctx->stream>>>(d_edges, step, rows, cols, L, vec); }
+    { prl_launch_scope ls(ctx, FAM_EDGES); ccl_border_list_kernel<<<grid16, 256, 0, ctx->stream>>>(d_edges, step, rows, cols, vec, blist, bcount); }
+    { prl_launch_scope ls(ctx, FAM_EDGES); ccl_border_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(d_edges, step, rows, cols, L, top, bx0, by0, bx1, by1, blist, bcount); }
+    { prl_launch_scope ls(ctx, FAM_EDGES); ccl_rects_kernel<<<grid16, 256, 0, ctx->stream>>>(d_edges, step, rows, cols, L, top, bx0, by0, bx1, by1, d_count, d_xywh, cap, vec); }
     PRL_CUDA_TRY(ctx, cudaGetLastError());
     return PRL_OK;
 }
