@@ -151,6 +151,8 @@ int prl_cuda_binarize_local_batch_dev(prl_cuda_ctx* ctx, int method, const uint8
 int prl_cuda_integral_u8_batch_dev(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int rows, int cols,
                                    size_t src_step, size_t src_page_stride, int pad,
                                    int64_t* d_sum, int64_t* d_sqsum, size_t plane_pitch, size_t plane_page_stride);
+/* (batches of 64 pages or more run in groups that alternate between two internal streams, so that one group's histogram
+ * pass -- bound by shared-memory atomics -- overlaps the other's apply pass -- bound by HBM; stream-ordered like every *_dev call) */
 int prl_cuda_otsu_global_batch_dev(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int rows, int cols,
                                    size_t src_step, size_t src_page_stride, double maxval,
                                    uint8_t* d_dst, size_t dst_step, size_t dst_page_stride, int32_t* d_thr);

@@ -97,6 +97,8 @@ struct prl_cuda_ctx {
     // kernel sequences of several pages side by side
     std::vector<prl_cuda_ctx*> lanes;
     int* h_lane_counts = nullptr;                          // pinned: contour counts of the pages in flight
+    cudaEvent_t lane_ev[3] = {nullptr, nullptr, nullptr};  // lane 0 / lane 1 done, context stream reached the call
+    int otsu_group = -1;                                   // Global Otsu batches: pages per group of the two-lane overlap (-1 = n/4 in [16, 256], 0 = off)
 
     // instrumentation
     bool timing = false;
