@@ -19,6 +19,12 @@
 //          fixup_kernel, which rebuilds the four true int64 taps by brute force (row prefixes at the strip start
 //          come from the pre-pass strip_rowsum_kernel) and evaluates the reference's FP64 formula literally.
 //   Strips overlap by d columns (a strip emits 128 - d outputs): ~12 % redundant work at w = 15.
+//
+// Measured and dropped (B200, 256 A4 pages, w = 15, masks identical in every case):
+//   * 8 columns per lane over strips of 256 columns (half the scans / exchanges / overlap per pixel): 138 registers at
+//     3 CTAs per SM 8.25 ms, squeezed to 128 registers at 4 CTAs per SM 7.20 ms -- against 7.31 ms for this kernel, and
+//     slower for w = 7, 31 and small pages.  The per-row fixed cost is not what bounds the kernel; the per-pixel decision is.
+//   * a per-warp queue of undecided pixels handled after the row loop: 8 % slower (divergence moved, not removed).
 #include "common.cuh"
 #include "decide.cuh"
 #include <algorithm>
