@@ -281,9 +281,17 @@ typedef struct prl_adaptive_params {
     int auto_block;      /* 1: block_size < 3 means int(diagonal / 333 + 7) (NativeAdaptive :86-93) */
     double delta;
     int invert_if_dark;  /* 1: 255 - image when cv::mean(image)[0] < 128 (NativeAdaptive :108-111) */
+    int bilateral_d;     /* >= 3: cv::bilateralFilter(result, d, sigma_color, sigma_space) as the last step (NativeAdaptive :116-134);
+                            a sigma <= 0 is then PRL_E_INVALID, raised after the threshold's own checks like the reference does */
+    double bilateral_sigma_color, bilateral_sigma_space;
 } prl_adaptive_params;
 int prl_cuda_binarize_adaptive(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step, int channels,
                                const prl_adaptive_params* params, uint8_t* dst, size_t dst_step);
+/* cv::bilateralFilter(src, dst, d, sigmaColor, sigmaSpace) for CV_8UC1, BORDER_DEFAULT -- OpenCV's own C++ arithmetic (float32
+ * weights from its SIMD exponential, taps in raster order; csrc/adaptive.cu spells it out).  The reference applies it to the
+ * 0 / maxval mask of binarizeNativeAdaptive (binarizeNativeAdaptive.cpp:129-133).  d <= 0 derives the radius from sigmaSpace. */
+int prl_cuda_bilateral_filter(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step, int d, double sigma_color,
+                              double sigma_space, uint8_t* dst, size_t dst_step);
 
 /* ---- 1 bit per pixel ---------------------------------------------
  * The masks in Leptonica's PIX layout, the reference's second image container (src/formatConvert.cpp:39-69

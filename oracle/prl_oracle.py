@@ -618,7 +618,8 @@ def binarizePureAdaptiveGaussian(image, maxValue, blockSize, shift):          # 
 
 def binarizeNativeAdaptive(image, isGaussianBlurReqiured=False, medianBlurKernelSize=5, GaussianBlurKernelSize=7, GaussianBlurSigma=150.0,
                            isAdaptiveThresholdCalculatedByGaussian=True, adaptiveThresholdingMaxValue=255.0,
-                           adaptiveThresholdingBlockSize=19, adaptiveThresholdingShift=9):     # binarizeNativeAdaptive.cpp:34-115
+                           adaptiveThresholdingBlockSize=19, adaptiveThresholdingShift=9, bilateralFilterBlockSize=0,
+                           bilateralFilterColorSigma=150.0, bilateralFilterSpaceSigma=150.0):     # binarizeNativeAdaptive.cpp:34-135
     with _single_thread():
         if image is None or image.size == 0:
             raise ValueError("Input image for binarization is empty")
@@ -640,6 +641,12 @@ def binarizeNativeAdaptive(image, isGaussianBlurReqiured=False, medianBlurKernel
         out = cv2.adaptiveThreshold(out, adaptiveThresholdingMaxValue, method, cv2.THRESH_BINARY_INV, bs, adaptiveThresholdingShift)
         if cv2.mean(out)[0] < 128:
             out = 255 - out
+        if bilateralFilterBlockSize >= 3:                                                          # :116-134
+            if bilateralFilterColorSigma <= 0:
+                raise ValueError("Color sigma for bilateral filtration must be greater than 0")
+            if bilateralFilterSpaceSigma <= 0:
+                raise ValueError("Space sigma for bilateral filtration must be greater than 0")
+            out = cv2.bilateralFilter(out, bilateralFilterBlockSize, bilateralFilterColorSigma, bilateralFilterSpaceSigma)   # IPP off, see _no_ipp
         return out
 
 
@@ -654,6 +661,62 @@ def box_mean_model(gray: np.ndarray, bs: int) -> np.ndarray:
     H, W = gray.shape
     s = I[bs:bs + H, bs:bs + W] - I[0:H, bs:bs + W] - I[bs:bs + H, 0:W] + I[0:H, 0:W]
     return ((2 * s + bs * bs) // (2 * bs * bs)).astype(np.uint8)
+
+
+def _vexp32(x):
+    """OpenCV's v_exp for float32 (the Cephes expf: two-piece ln 2 reduction, degree-5 polynomial) with every multiply-add
+    unfused, as the baseline (SSE) build that fills bilateralFilter's colour table evaluates it.  x: float32 array."""
+    f = np.float32
+    madd = lambda a, b, c: (a * b).astype(f) + c
+    x = np.minimum(np.maximum(x.astype(f), f(-88.3762626647949)), f(89.0))
+    fx = madd(x, f(1.44269504088896341), f(0.5)).astype(f)
+    mm = np.floor(fx)
+    fx = mm.astype(f)
+    x = madd(fx, f(-6.93359375E-1), x).astype(f)
+    x = madd(fx, f(2.12194440E-4), x).astype(f)
+    xx = (x * x).astype(f)
+    y = madd(x, f(1.9875691500E-4), f(1.3981999507E-3)).astype(f)
+    for c in (8.3334519073E-3, 4.1665795894E-2, 1.6666665459E-1, 5.0000001201E-1):
+        y = madd(y, x, f(c)).astype(f)
+    y = madd(y, xx, x).astype(f)
+    y = (y + f(1)).astype(f)
+    return (y * np.exp2(mm).astype(f)).astype(f)
+
+
+def bilateral_tables(d: int, sigma_color: float, sigma_space: float):
+    """(radius, colour weights[256], [(dy, dx, space weight)]) of cv::bilateralFilter for CV_8UC1 as OpenCV 4.13 builds them
+    (measured against the cv2 wheel, IPP off; what csrc/adaptive.cu restates)."""
+    if sigma_color <= 0:
+        sigma_color = 1
+    if sigma_space <= 0:
+        sigma_space = 1
+    gc = np.float32(-0.5 / (sigma_color * sigma_color))
+    gs = np.float32(-0.5 / (sigma_space * sigma_space))
+    radius = d // 2 if d > 0 else int(np.rint(sigma_space * 1.5))
+    radius = max(radius, 1)
+    i = np.arange(256)
+    cw = _vexp32((i * i).astype(np.float32) * gc)
+    taps = [(dy, dx, np.float32(np.exp(float(dy * dy + dx * dx) * float(gs))))
+            for dy in range(-radius, radius + 1) for dx in range(-radius, radius + 1) if dy * dy + dx * dx <= radius * radius]
+    return radius, cw, taps
+
+
+def bilateral_model(gray: np.ndarray, d: int, sigma_color: float, sigma_space: float) -> np.ndarray:
+    """cv::bilateralFilter(gray, d, sigmaColor, sigmaSpace), CV_8UC1, BORDER_REFLECT_101: taps in raster order,
+    w = sw * cw[|v - centre|], wsum += w, sum = fma(v, w, sum) in float32, dst = cvRound(sum / wsum).  Identical to the wheel
+    for radius != 2 and, for radius 2, on two-level images (all the reference feeds it); see csrc/adaptive.cu."""
+    radius, cw, taps = bilateral_tables(d, sigma_color, sigma_space)
+    t = cv2.copyMakeBorder(gray, radius, radius, radius, radius, cv2.BORDER_REFLECT_101)
+    H, W = gray.shape
+    c = gray.astype(np.int32)
+    s = np.zeros((H, W), np.float32)
+    ws = np.zeros((H, W), np.float32)
+    for dy, dx, sw in taps:
+        v = t[radius + dy:radius + dy + H, radius + dx:radius + dx + W].astype(np.int32)
+        w = (sw * cw[np.abs(v - c)]).astype(np.float32)
+        ws = (ws + w).astype(np.float32)
+        s = _fma32(v.astype(np.float32), w, s)
+    return np.rint((s / ws).astype(np.float32)).astype(np.uint8)
 
 
 def _fma32(a, b, c):

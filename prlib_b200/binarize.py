@@ -196,19 +196,16 @@ def binarizeNativeAdaptive(inputImage, isGaussianBlurReqiured: bool = False, med
                            bilateralFilterBlockSize: int = 0, bilateralFilterColorSigma: float = 150.0,
                            bilateralFilterSpaceSigma: float = 150.0, device: int = 0) -> np.ndarray:
     """prl::binarizeNativeAdaptive (binarizeNativeAdaptive.h:63-75, same defaults): gray -> median or Gaussian blur ->
-    adaptiveThreshold(BINARY_INV) -> 255 - image when its mean is below 128.  The optional bilateral filter of the result
-    (bilateralFilterBlockSize >= 3, off by default) is not implemented on the device: PRL_E_UNSUPPORTED."""
+    adaptiveThreshold(BINARY_INV) -> 255 - image when its mean is below 128 -> cv::bilateralFilter of the result when
+    bilateralFilterBlockSize >= 3 (off by default; its sigma checks come last, :116-127, so a cv::Exception of the steps before
+    wins, as in the reference)."""
     im = _nonempty(inputImage)
     if not (0 <= adaptiveThresholdingMaxValue <= 255):
         raise ValueError("Max value must be in range [0; 255]")                                    # :53-56
-    if bilateralFilterBlockSize >= 3:
-        if bilateralFilterColorSigma <= 0:
-            raise ValueError("Color sigma for bilateral filtration must be greater than 0")        # :123-126
-        if bilateralFilterSpaceSigma <= 0:
-            raise ValueError("Space sigma for bilateral filtration must be greater than 0")        # :128-131
-        raise capi.PrlCudaError(capi.PRL_E_UNSUPPORTED, "the bilateral filter step of binarizeNativeAdaptive is not implemented")
     return default_context(device).binarize_adaptive(
         im, gray_first=1, blur=2 if isGaussianBlurReqiured else 1,
         blur_ksize=int(GaussianBlurKernelSize if isGaussianBlurReqiured else medianBlurKernelSize), blur_sigma=float(GaussianBlurSigma),
         assert_ksize=1, method=1 if isAdaptiveThresholdCalculatedByGaussian else 0, type=1, maxval=float(adaptiveThresholdingMaxValue),
-        check_maxval=1, block_size=int(adaptiveThresholdingBlockSize), auto_block=1, delta=float(adaptiveThresholdingShift), invert_if_dark=1)
+        check_maxval=1, block_size=int(adaptiveThresholdingBlockSize), auto_block=1, delta=float(adaptiveThresholdingShift), invert_if_dark=1,
+        bilateral_d=int(bilateralFilterBlockSize) if bilateralFilterBlockSize >= 3 else 0,
+        bilateral_sigma_color=float(bilateralFilterColorSigma), bilateral_sigma_space=float(bilateralFilterSpaceSigma))

@@ -87,7 +87,8 @@ class AdaptiveParams(C.Structure):
     _fields_ = [("gray_first", C.c_int), ("blur", C.c_int), ("blur_ksize", C.c_int), ("blur_sigma", C.c_double),
                 ("assert_ksize", C.c_int), ("method", C.c_int), ("type", C.c_int), ("maxval", C.c_double),
                 ("check_maxval", C.c_int), ("block_size", C.c_int), ("auto_block", C.c_int), ("delta", C.c_double),
-                ("invert_if_dark", C.c_int)]
+                ("invert_if_dark", C.c_int), ("bilateral_d", C.c_int), ("bilateral_sigma_color", C.c_double),
+                ("bilateral_sigma_space", C.c_double)]
 
 
 SIGNATURES.update({
@@ -100,6 +101,8 @@ SIGNATURES.update({
     "prl_cuda_adaptive_threshold": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_double, C.c_int, C.c_int, C.c_int,
                                               C.c_double, C.c_void_p, C.c_size_t]),
     "prl_cuda_gauss_kernel_float": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
+    "prl_cuda_bilateral_filter": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_double, C.c_double, C.c_void_p,
+                                            C.c_size_t]),
     "prl_cuda_binarize_adaptive": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.POINTER(AdaptiveParams),
                                              C.c_void_p, C.c_size_t]),
 })

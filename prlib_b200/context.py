@@ -306,6 +306,15 @@ class Context:
                                                         int(thresh_type), int(block_size), float(delta), out.ctypes.data, c))
         return out
 
+    def bilateral_filter(self, gray, d: int, sigma_color: float, sigma_space: float):
+        """cv::bilateralFilter(gray, d, sigmaColor, sigmaSpace) for CV_8UC1 (prl_cuda_bilateral_filter)."""
+        g = _as_u8_2d(gray)
+        r, c = g.shape
+        out = np.empty((r, c), np.uint8)
+        self._check(self._L.prl_cuda_bilateral_filter(self._h, g.ctypes.data, r, c, g.strides[0], int(d), float(sigma_color), float(sigma_space),
+                                                      out.ctypes.data, c))
+        return out
+
     def binarize_adaptive(self, image, **kw):
         """prl_cuda_binarize_adaptive; keyword arguments = the fields of struct prl_adaptive_params"""
         im = np.ascontiguousarray(image)

@@ -21,9 +21,22 @@
 //                       first 4 * floor((n - 1) / 4) products unfused (gcc vectorises them) and fuses the rest;
 //           column pass s = r[c] k[c];  s = fma(r[c + j] + r[c - j], k[c + j], s) for columns below (cols & ~7), unfused
 //                       multiply-then-add in the scalar tail.
+//   * bilateralFilter (u8, 1 channel; the optional last step of binarizeNativeAdaptive.cpp:116-134, applied to the 0 / maxval
+//     mask): OpenCV 4.13's own C++ path (the wheel's closed IPP routine switched off, like for Otsu), measured against the cv2 wheel:
+//       radius = d / 2 (d <= 0: cvRound(1.5 sigmaSpace)), at least 1; BORDER_REFLECT_101; taps (dy, dx) with dy^2 + dx^2 <= radius^2
+//       in raster order, the centre among them;
+//       colour weight  cw[i] = v_exp(float(i * i) * float(-0.5 / sigmaColor^2)), OpenCV's float32 SIMD exponential (Cephes expf:
+//                      range reduction by ln 2 in two pieces, degree-5 polynomial) with unfused multiply-adds (baseline SSE build);
+//       space weight   sw = float(exp(double(dy^2 + dx^2) * double(float(-0.5 / sigmaSpace^2))));
+//       per tap        w = sw * cw[|v - centre|];  wsum += w;  sum = fma(v, w, sum);      dst = cvRound(sum / wsum), all float32.
+//     Identical to the wheel on every input tried for radius != 2, and for radius 2 (d = 4, 5) on every two-level image -- all
+//     2^13 neighbourhoods checked, which is everything the reference can feed it; on full-range gray input the wheel's radius-2
+//     special case (ring sums, and itself dependent on the CPU dispatch: AVX-512 and baseline builds differ) rounds ~1e-5 of
+//     the pixels the other way.
 #include "common.cuh"
 #include <algorithm>
 #include <cmath>
+#include <vector>
 
 namespace {
 
@@ -209,6 +222,73 @@ invert_if_dark_kernel(uint8_t* __restrict__ img, size_t step, int rows, int cols
     if (x < cols) img[(size_t)y * step + x] = (uint8_t)(255 - img[(size_t)y * step + x]);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// bilateralFilter (u8, one channel)
+// ------------------------------------------------------------------------------------------------
+constexpr int kBilTW = 32, kBilTH = 8;
+struct BilTap { short dy, dx; float sw; };
+
+__device__ __forceinline__ int reflect101(int p, int len)
+{
+    if (len == 1) return 0;
+    while ((unsigned)p >= (unsigned)len) p = p < 0 ? -p : 2 * len - 2 - p;
+    return p;
+}
+
+__global__ void __launch_bounds__(kBilTW * kBilTH)
+bilateral_kernel(const uint8_t* __restrict__ src, size_t step, int rows, int cols, int radius, const BilTap* __restrict__ taps, int n_taps,
+                 const float* __restrict__ color_weight, uint8_t* __restrict__ dst, size_t dstep)
+{
+    extern __shared__ __align__(16) uint8_t bil_sm[];
+    float* cw = reinterpret_cast<float*>(bil_sm);                       // 256 colour weights
+    uint8_t* tile = bil_sm + 256 * sizeof(float);                       // (kBilTH + 2 radius) x (kBilTW + 2 radius) pixels
+    const int tw = kBilTW + 2 * radius, th = kBilTH + 2 * radius;
+    const int tid = threadIdx.y * kBilTW + threadIdx.x;
+    const int x0 = blockIdx.x * kBilTW - radius, y0 = blockIdx.y * kBilTH - radius;
+    for (int i = tid; i < 256; i += kBilTW * kBilTH) cw[i] = color_weight[i];
+    for (int i = tid; i < tw * th; i += kBilTW * kBilTH) {
+        const int ty = i / tw, tx = i - ty * tw;
+        tile[i] = src[(size_t)reflect101(y0 + ty, rows) * step + reflect101(x0 + tx, cols)];
+    }
+    __syncthreads();
+    const int x = blockIdx.x * kBilTW + threadIdx.x, y = blockIdx.y * kBilTH + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    const uint8_t* c = tile + (threadIdx.y + radius) * tw + threadIdx.x + radius;
+    const int v0 = *c;
+    float sum = 0.f, wsum = 0.f;
+    for (int k = 0; k < n_taps; ++k) {
+        const BilTap t = taps[k];
+        const int v = c[t.dy * tw + t.dx];
+        const float w = __fmul_rn(t.sw, cw[abs(v - v0)]);
+        wsum = __fadd_rn(wsum, w);
+        sum = __fmaf_rn((float)v, w, sum);
+    }
+    dst[(size_t)y * dstep + x] = (uint8_t)__float2int_rn(__fdiv_rn(sum, wsum));
+}
+
+// OpenCV's v_exp for float32 (Cephes expf), every multiply-add unfused as in the baseline build that fills the table.
+// `volatile` keeps the host compiler from contracting a product into the following sum whatever -march it is given.
+float vexp_unfused(float x)
+{
+    auto madd = [](float a, float b, float c) { volatile float p = a * b; return p + c; };
+    x = std::min(std::max(x, -88.3762626647949f), 89.f);
+    float fx = madd(x, 1.44269504088896341f, 0.5f);
+    const int mm = (int)std::floor(fx);
+    fx = (float)mm;
+    x = madd(fx, -6.93359375E-1f, x);
+    x = madd(fx, 2.12194440E-4f, x);
+    volatile float xx = x * x;
+    float y = madd(x, 1.9875691500E-4f, 1.3981999507E-3f);
+    y = madd(y, x, 8.3334519073E-3f);
+    y = madd(y, x, 4.1665795894E-2f);
+    y = madd(y, x, 1.6666665459E-1f);
+    y = madd(y, x, 5.0000001201E-1f);
+    y = madd(y, xx, x);
+    volatile float y1 = y + 1.f;
+    return y1 * std::ldexp(1.f, mm);
+}
+
 }  // namespace
 
 // float32 Gaussian coefficients as cv::getGaussianKernel(n, sigma <= 0, CV_32F) returns them (tables for n <= 9)
@@ -317,6 +397,47 @@ int prl_k_adaptive_threshold(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, 
         prl_launch_scope ls(ctx, FAM_ADAPTIVE);
         invert_if_dark_kernel<<<dim3((cols + 255) / 256, rows), 256, 0, ctx->stream>>>(d_dst, dst_step, rows, cols, T.maxv, nset);
     }
+    PRL_CUDA_TRY(ctx, cudaGetLastError());
+    return PRL_OK;
+}
+
+size_t prl_bilateral_scratch_bytes(int d, double sigma_space)
+{
+    int radius = d > 0 ? d / 2 : (int)std::nearbyint(sigma_space * 1.5);
+    radius = std::max(radius, 1);
+    return r256(256 * sizeof(float)) + r256((size_t)(2 * radius + 1) * (2 * radius + 1) * sizeof(BilTap));
+}
+
+// cv::bilateralFilter(src, dst, d, sigmaColor, sigmaSpace) on the device, u8, one channel (d_src != d_dst).
+// scratch: prl_bilateral_scratch_bytes (receives the two weight tables).
+int prl_k_bilateral(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, int d, double sigma_color, double sigma_space,
+                    uint8_t* d_dst, size_t dst_step, void* scratch)
+{
+    if (sigma_color <= 0) sigma_color = 1;
+    if (sigma_space <= 0) sigma_space = 1;
+    int radius = d > 0 ? d / 2 : (int)std::nearbyint(sigma_space * 1.5);             // cvRound
+    radius = std::max(radius, 1);
+    if (radius > 32) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "bilateral filter diameters above 65 are not supported");
+    if ((rows + kBilTH - 1) / kBilTH > 65535) return prl_set_err(ctx, PRL_E_UNSUPPORTED, "image too tall");
+    const float gc = (float)(-0.5 / (sigma_color * sigma_color)), gs = (float)(-0.5 / (sigma_space * sigma_space));
+    float cw[256];
+    for (int i = 0; i < 256; ++i) { volatile float a = (float)(i * i) * gc; cw[i] = vexp_unfused(a); }
+    std::vector<BilTap> taps;
+    for (int dy = -radius; dy <= radius; ++dy)
+        for (int dx = -radius; dx <= radius; ++dx) {
+            const int r2 = dy * dy + dx * dx;
+            if (r2 > radius * radius) continue;
+            taps.push_back(BilTap{(short)dy, (short)dx, (float)std::exp((double)r2 * (double)gs)});
+        }
+    float* d_cw = (float*)scratch;
+    BilTap* d_taps = (BilTap*)((char*)scratch + r256(256 * sizeof(float)));
+    // the tables are a few KB of pageable memory: the copies return once staged, so the locals may go out of scope
+    PRL_CUDA_TRY(ctx, cudaMemcpyAsync(d_cw, cw, sizeof(cw), cudaMemcpyHostToDevice, ctx->stream));
+    PRL_CUDA_TRY(ctx, cudaMemcpyAsync(d_taps, taps.data(), taps.size() * sizeof(BilTap), cudaMemcpyHostToDevice, ctx->stream));
+    const size_t smem = 256 * sizeof(float) + (size_t)(kBilTW + 2 * radius) * (kBilTH + 2 * radius);
+    prl_launch_scope ls(ctx, FAM_ADAPTIVE);
+    bilateral_kernel<<<dim3((cols + kBilTW - 1) / kBilTW, (rows + kBilTH - 1) / kBilTH), dim3(kBilTW, kBilTH), smem, ctx->stream>>>(
+        d_src, step, rows, cols, radius, d_taps, (int)taps.size(), d_cw, d_dst, dst_step);
     PRL_CUDA_TRY(ctx, cudaGetLastError());
     return PRL_OK;
 }

@@ -1146,7 +1146,9 @@ extern "C" int prl_cuda_binarize_adaptive(prl_cuda_ctx* c, const uint8_t* src, i
     const size_t c_step = round16((size_t)cols * channels);
     int rc = prl_ensure(c, (void**)&c->d_in, &c->d_in_bytes, g_img); if (rc) return rc;
     rc = prl_ensure(c, (void**)&c->d_tmp, &c->d_tmp_bytes, g_img); if (rc) return rc;
-    rc = prl_ensure(c, &c->adaptive_ws, &c->adaptive_ws_bytes, prl_adaptive_scratch_bytes(rows, cols)); if (rc) return rc;
+    rc = prl_ensure(c, &c->adaptive_ws, &c->adaptive_ws_bytes,
+                    prl_adaptive_scratch_bytes(rows, cols) + (p->bilateral_d >= 3 ? prl_bilateral_scratch_bytes(p->bilateral_d, p->bilateral_sigma_space) : 0));
+    if (rc) return rc;
     const uint8_t* gray = nullptr;          // what adaptiveThreshold reads
     if (channels == 1) {
         size_t in_step;
@@ -1180,6 +1182,35 @@ extern "C" int prl_cuda_binarize_adaptive(prl_cuda_ctx* c, const uint8_t* src, i
     rc = prl_k_adaptive_threshold(c, gray, rows, cols, g_step, p->maxval, p->method, p->type, bs, p->delta, c->d_out, o_step,
                                   c->adaptive_ws, p->invert_if_dark != 0);
     if (rc) return rc;
+    const uint8_t* result = c->d_out;
+    size_t r_step = o_step;
+    if (p->bilateral_d >= 3) {                                                                      // binarizeNativeAdaptive.cpp:116-134
+        // the reference reaches these checks after the threshold, so its cv::Exceptions above come first
+        if (p->bilateral_sigma_color <= 0) return prl_set_err(c, PRL_E_INVALID, "Color sigma for bilateral filtration must be greater than 0");
+        if (p->bilateral_sigma_space <= 0) return prl_set_err(c, PRL_E_INVALID, "Space sigma for bilateral filtration must be greater than 0");
+        rc = prl_k_bilateral(c, c->d_out, rows, cols, o_step, p->bilateral_d, p->bilateral_sigma_color, p->bilateral_sigma_space,
+                             c->d_tmp, g_step, (char*)c->adaptive_ws + prl_adaptive_scratch_bytes(rows, cols));
+        if (rc) return rc;
+        result = c->d_tmp; r_step = g_step;
+    }
+    PRL_CUDA_TRY(c, copy2d(dst, dst_step, result, r_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
+    PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return PRL_OK;
+}
+
+extern "C" int prl_cuda_bilateral_filter(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step, int d, double sigma_color,
+                                         double sigma_space, uint8_t* dst, size_t dst_step)
+{
+    if (!c) return PRL_E_INVALID;
+    if (!src || !dst || rows <= 0 || cols <= 0 || step < (size_t)cols || dst_step < (size_t)cols)
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    size_t in_step;
+    int rc = stage_in(c, src, rows, cols, step, &in_step); if (rc) return rc;
+    const size_t o_step = round16(cols);
+    rc = prl_ensure(c, (void**)&c->d_out, &c->d_out_bytes, o_step * rows); if (rc) return rc;
+    rc = prl_ensure(c, &c->adaptive_ws, &c->adaptive_ws_bytes, prl_bilateral_scratch_bytes(d, sigma_space)); if (rc) return rc;
+    rc = prl_k_bilateral(c, c->d_in, rows, cols, in_step, d, sigma_color, sigma_space, c->d_out, o_step, c->adaptive_ws); if (rc) return rc;
     PRL_CUDA_TRY(c, copy2d(dst, dst_step, c->d_out, o_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
     PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return PRL_OK;

@@ -181,6 +181,9 @@ int prl_gauss_kernel_float(int n, float* k);
 size_t prl_adaptive_scratch_bytes(int rows, int cols);
 int prl_k_median_blur(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, int channels, int ksize,
                       uint8_t* d_dst, size_t dst_step);
+size_t prl_bilateral_scratch_bytes(int d, double sigma_space);
+int prl_k_bilateral(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, int d, double sigma_color, double sigma_space,
+                    uint8_t* d_dst, size_t dst_step, void* scratch);
 int prl_k_adaptive_threshold(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, double maxval, int method, int type,
                              int block_size, double delta, uint8_t* d_dst, size_t dst_step, void* scratch, bool invert_if_dark);
 int prl_k_gaussian_blur(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols, size_t step, int ksize, double sigma,

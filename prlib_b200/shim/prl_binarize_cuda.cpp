@@ -378,12 +378,11 @@ void prl::binarizeNativeAdaptive(cv::Mat& inputImage, cv::Mat& outputImage, bool
     p.method = isAdaptiveThresholdCalculatedByGaussian ? 1 : 0; p.type = 1;
     p.maxval = adaptiveThresholdingMaxValue; p.check_maxval = 1;
     p.block_size = adaptiveThresholdingBlockSize; p.auto_block = 1; p.delta = adaptiveThresholdingShift; p.invert_if_dark = 1;
+    // cv::bilateralFilter of the result (binarizeNativeAdaptive.cpp:116-134); a sigma <= 0 comes back as PRL_E_INVALID after the
+    // threshold's own checks, i.e. as std::invalid_argument in the reference's order
+    p.bilateral_d = bilateralFilterBlockSize >= 3 ? bilateralFilterBlockSize : 0;
+    p.bilateral_sigma_color = bilateralFilterColorSigma; p.bilateral_sigma_space = bilateralFilterSpaceSigma;
     cv::Mat res;
     runAdaptive(inputImage, res, p);
-    if (bilateralFilterBlockSize >= 3) {
-        if (bilateralFilterColorSigma <= 0) throw std::invalid_argument("Color sigma for bilateral filtration must be greater than 0");
-        if (bilateralFilterSpaceSigma <= 0) throw std::invalid_argument("Space sigma for bilateral filtration must be greater than 0");
-        throw std::runtime_error("libprlib_cuda: the bilateral filter step of binarizeNativeAdaptive is not implemented");
-    }
     outputImage = res;
 }

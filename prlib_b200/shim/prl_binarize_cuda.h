@@ -79,7 +79,7 @@ CV_EXPORTS void localOtsuEdges(const cv::Mat& imageToProc, cv::Mat& resultCanny,
 //     cv::Exception of cv::adaptiveThreshold on the empty Mat the reference passes it;
 //   * binarizeGAT and binarizePureAdaptive end in that cv::Exception for every non-empty input;
 //   * binarizeNativeAdaptive converts its INPUT Mat to gray in place (binarizeNativeAdaptive.cpp:58-61); its optional
-//     bilateral filter (bilateralFilterBlockSize >= 3, off by default) is not implemented: std::runtime_error.
+//     bilateral filter of the mask (bilateralFilterBlockSize >= 3, off by default) runs on the device too.
 CV_EXPORTS void binarizeNativeAdaptive(cv::Mat& inputImage, cv::Mat& outputImage, bool isGaussianBlurReqiured = 0,
                                        int medianBlurKernelSize = 5, int GaussianBlurKernelSize = 7, double GaussianBlurSigma = 150.0,
                                        bool isAdaptiveThresholdCalculatedByGaussian = true, double adaptiveThresholdingMaxValue = 255.0,

@@ -157,6 +157,23 @@ int main()
         try { prl::binarizeNativeAdaptive(in, out, false, 2); } catch (const cv::Exception&) { ++thrown; }
         try { prl::binarizeNativeAdaptive(in, out, false, 5, 7, 150.0, true, 255.0, 20); } catch (const cv::Exception&) { ++thrown; }
         EXPECT(thrown == 3, "binarizeNativeAdaptive argument errors");
+        // the optional bilateral filter of the mask (binarizeNativeAdaptive.cpp:116-134): a mask in, a gray-level image out;
+        // a sigma <= 0 is std::invalid_argument, but only after the threshold's own cv::Exception
+        cv::Mat plain, smoothed;
+        prl::binarizeNativeAdaptive(in, plain);
+        prl::binarizeNativeAdaptive(in, smoothed, false, 5, 7, 150.0, true, 255.0, 19, 9, 5);
+        long levels = 0, moved = 0;
+        for (int y = 0; y < 200; ++y) for (int x = 0; x < 300; ++x) {
+            const int v = smoothed.ptr(y)[x];
+            levels += v != 0 && v != 255;
+            moved += v != plain.ptr(y)[x];
+        }
+        EXPECT(smoothed.rows == 200 && smoothed.cols == 300 && levels > 0 && moved > 0, "binarizeNativeAdaptive: bilateral filter applied to the mask");
+        thrown = 0;
+        try { prl::binarizeNativeAdaptive(in, out, false, 5, 7, 150.0, true, 255.0, 19, 9, 7, 0.0); } catch (const std::invalid_argument&) { ++thrown; }
+        try { prl::binarizeNativeAdaptive(in, out, false, 5, 7, 150.0, true, 255.0, 19, 9, 7, 150.0, -1.0); } catch (const std::invalid_argument&) { ++thrown; }
+        try { prl::binarizeNativeAdaptive(in, out, false, 5, 7, 150.0, true, 255.0, 20, 9, 7, 0.0); } catch (const cv::Exception&) { ++thrown; }
+        EXPECT(thrown == 3, "binarizeNativeAdaptive bilateral argument errors in the reference's order");
     }
     {   // Otsu
         std::vector<uint8_t> want((size_t)rows * cols);

@@ -31,6 +31,15 @@ CALLS = {
     "native_meanC_autoblock": ("binarizeNativeAdaptive", (), {"isAdaptiveThresholdCalculatedByGaussian": False, "adaptiveThresholdingBlockSize": 0}),
     "native_m3_shift-2.5_max77.6": ("binarizeNativeAdaptive", (), {"medianBlurKernelSize": 3, "adaptiveThresholdingShift": -2.5,
                                                                      "adaptiveThresholdingMaxValue": 77.6}),
+    # the optional last step: cv::bilateralFilter of the mask (binarizeNativeAdaptive.cpp:116-134)
+    "native_bilateral5": ("binarizeNativeAdaptive", (), {"bilateralFilterBlockSize": 5}),
+    "native_bilateral9_c40_s3_max180": ("binarizeNativeAdaptive", (), {"bilateralFilterBlockSize": 9, "bilateralFilterColorSigma": 40.0,
+                                                                         "bilateralFilterSpaceSigma": 3.0, "adaptiveThresholdingMaxValue": 180}),
+    "native_bilateral3_meanC": ("binarizeNativeAdaptive", (), {"bilateralFilterBlockSize": 3, "isAdaptiveThresholdCalculatedByGaussian": False,
+                                                                 "bilateralFilterColorSigma": 25.0, "bilateralFilterSpaceSigma": 0.9}),
+    "native_bilateral_sigma0": ("binarizeNativeAdaptive", (), {"bilateralFilterBlockSize": 7, "bilateralFilterSpaceSigma": 0.0}),
+    "native_bilateral_evenblock": ("binarizeNativeAdaptive", (), {"bilateralFilterBlockSize": 7, "bilateralFilterColorSigma": -1.0,
+                                                                    "adaptiveThresholdingBlockSize": 20}),
 }
 GRAY_OK = [k for k in CALLS if k.startswith("native")]
 
@@ -70,7 +79,7 @@ def main():
     G = {"generator": "oracle/_ref (reference C++ compiled unmodified; OpenCV = cv2 wheel)", "cv2": cv2.__version__,
          "calls": {k: [v[0], list(v[1]), v[2]] for k, v in CALLS.items()}, "images": {}}
     for key, img in images().items():
-        names = list(CALLS) if key != "a4_p2" else ["native_defaults", "native_meanC_autoblock"]
+        names = list(CALLS) if key != "a4_p2" else ["native_defaults", "native_meanC_autoblock", "native_bilateral5"]
         G["images"][key] = {"shape": list(img.shape), "sha1": sha(img),
                             "out": {n: outcome(CALLS[n][0], img, CALLS[n][1], CALLS[n][2]) for n in names}}
     with open(os.path.join(HERE, "ref_adaptive_golden.json"), "w") as f:

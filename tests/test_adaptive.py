@@ -153,10 +153,44 @@ def test_host_mirror_raises_like_the_reference_without_touching_a_gpu():
         assert e.value.code == capi.PRL_E_EMPTY_ROI
     for call in (lambda: prlib_b200.binarizeAT(np.zeros((0, 0, 3), np.uint8), 5, 255, 19, 9),
                  lambda: prlib_b200.binarizeNativeAdaptive(np.zeros((0, 0), np.uint8)),
-                 lambda: prlib_b200.binarizeNativeAdaptive(gray, adaptiveThresholdingMaxValue=256),
-                 lambda: prlib_b200.binarizeNativeAdaptive(gray, bilateralFilterBlockSize=5, bilateralFilterColorSigma=0)):
+                 lambda: prlib_b200.binarizeNativeAdaptive(gray, adaptiveThresholdingMaxValue=256)):
         with pytest.raises(ValueError):
             call()
+
+
+def _two_level_neighbourhoods(radius, maxv, rng):
+    """one (2 radius + 1)^2 block per subset of the taps of the disc (and per centre value): every neighbourhood a two-level
+    image can show the filter; the corners outside the disc are random"""
+    n = 2 * radius + 1
+    taps = [(i, j) for i in range(-radius, radius + 1) for j in range(-radius, radius + 1) if i * i + j * j <= radius * radius]
+    npat = 1 << len(taps)
+    side = int(np.ceil(np.sqrt(npat)))
+    img = ((rng.random((side * n, side * n)) < 0.5) * maxv).astype(np.uint8)
+    p = np.arange(npat)
+    by, bx = p // side, p % side
+    for k, (i, j) in enumerate(taps):
+        img[by * n + radius + i, bx * n + radius + j] = np.where((p >> k) & 1, maxv, 0)
+    return img
+
+
+BILATERAL_CASES = ((3, 150.0, 150.0), (7, 30.0, 4.0), (9, 100.0, 2.5), (11, 60.0, 2.2), (0, 40.0, 2.0), (3, 10.0, 0.5), (15, 150.0, 150.0))
+
+
+def test_bilateral_model_is_what_cv2_computes():
+    """the restatement csrc/adaptive.cu follows (float32 tables from OpenCV's SIMD exponential, taps in raster order) against
+    the wheel's own C++ path: full-range gray for every radius but 2, and for radius 2 (where the wheel runs a special case that
+    rounds ~1e-5 of full-range pixels the other way) every neighbourhood of a two-level image -- what the reference feeds it"""
+    rng = np.random.default_rng(77)
+    gray = rng.integers(0, 256, (400, 523), dtype=np.uint8)
+    smooth = cv2.GaussianBlur(gray, (0, 0), 2.0)
+    with O._single_thread():
+        for d, sc, ss in BILATERAL_CASES:
+            for img in (gray, smooth, gray[:1], gray[:, :1], gray[:3, :2]):
+                assert np.array_equal(O.bilateral_model(img, d, sc, ss), cv2.bilateralFilter(img, d, sc, ss)), (d, sc, ss, img.shape)
+        for maxv in (255, 180, 1):
+            for d, sc, ss in ((5, 150.0, 150.0), (5, 20.0, 1.5), (4, 300.0, 0.8), (0, 75.0, 1.4)):
+                img = _two_level_neighbourhoods(2, maxv, rng)
+                assert np.array_equal(O.bilateral_model(img, d, sc, ss), cv2.bilateralFilter(img, d, sc, ss)), (maxv, d, sc, ss)
 
 
 @pytest.mark.parametrize("key", [k for k in GOLD["images"] if k != "a4_p2"])
@@ -246,3 +280,37 @@ def test_native_adaptive_on_an_a4_page(ctx):
     assert np.array_equal(prlib_b200.binarizeNativeAdaptive(page), O.binarizeNativeAdaptive(page))
     assert np.array_equal(prlib_b200.binarizeNativeAdaptive(page, isAdaptiveThresholdCalculatedByGaussian=False, adaptiveThresholdingBlockSize=0),
                           O.binarizeNativeAdaptive(page, isAdaptiveThresholdCalculatedByGaussian=False, adaptiveThresholdingBlockSize=0))
+
+
+@pytest.mark.gpu
+def test_bilateral_filter_equals_cv2(ctx):
+    rng = np.random.default_rng(78)
+    gray = rng.integers(0, 256, (300, 421), dtype=np.uint8)
+    smooth = cv2.GaussianBlur(gray, (0, 0), 2.0)
+    mask = ((rng.random((257, 300)) < 0.3) * 255).astype(np.uint8)
+    with O._single_thread():
+        for d, sc, ss in BILATERAL_CASES + ((31, 90.0, 6.0),):
+            for img in (gray, smooth, mask, gray[:1], gray[:, :1], gray[:3, :2], gray[:40, :33]):
+                assert np.array_equal(ctx.bilateral_filter(img, d, sc, ss), cv2.bilateralFilter(img, d, sc, ss)), (d, sc, ss, img.shape)
+        for maxv in (255, 180, 1):
+            for d, sc, ss in ((5, 150.0, 150.0), (5, 20.0, 1.5), (4, 300.0, 0.8), (0, 75.0, 1.4)):
+                img = _two_level_neighbourhoods(2, maxv, rng)
+                assert np.array_equal(ctx.bilateral_filter(img, d, sc, ss), cv2.bilateralFilter(img, d, sc, ss)), (maxv, d, sc, ss)
+        page = CO.synth_page(1, 900, 700)
+        m = cv2.adaptiveThreshold(page, 255, cv2.ADAPTIVE_THRESH_MEAN_C, cv2.THRESH_BINARY, 19, 9)
+        for d, sc, ss in ((5, 150.0, 150.0), (9, 40.0, 3.0)):
+            assert np.array_equal(ctx.bilateral_filter(m, d, sc, ss), cv2.bilateralFilter(m, d, sc, ss)), (d, sc, ss)
+
+
+@pytest.mark.gpu
+def test_native_adaptive_with_the_bilateral_step_equals_the_reference(ctx):
+    import prlib_b200
+    W = R if R.available() else O
+    for name, img in IMAGES.items():
+        for kw in ({"bilateralFilterBlockSize": 5}, {"bilateralFilterBlockSize": 3, "bilateralFilterColorSigma": 25.0, "bilateralFilterSpaceSigma": 0.9},
+                   {"bilateralFilterBlockSize": 9, "bilateralFilterColorSigma": 40.0, "bilateralFilterSpaceSigma": 3.0, "adaptiveThresholdingMaxValue": 180},
+                   {"bilateralFilterBlockSize": 2, "bilateralFilterColorSigma": 0.0},                    # below 3: the step is skipped, sigmas unchecked
+                   {"bilateralFilterBlockSize": 7, "bilateralFilterColorSigma": 0.0},                    # std::invalid_argument
+                   {"bilateralFilterBlockSize": 7, "bilateralFilterSpaceSigma": -2.0},
+                   {"bilateralFilterBlockSize": 7, "bilateralFilterColorSigma": -1.0, "adaptiveThresholdingBlockSize": 20}):   # cv::Exception comes first
+            assert same_outcome(outcome(lambda: prlib_b200.binarizeNativeAdaptive(img, **kw)), outcome(lambda: W.binarizeNativeAdaptive(img, **kw))), (name, kw)
