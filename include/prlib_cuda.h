@@ -71,7 +71,9 @@ int         prl_cuda_set_workspace_limit(prl_cuda_ctx* ctx, size_t bytes);
  *   "fused_page_cap"  = n  : undecided pixels per page (0..128, default 128) the fused path finishes itself by
  *                            brute force; a page with more is redone by kernel 1 + kernel 2 (test hook: 0);
  *   "fused_no_tier2"  != 0 : the fused path skips its FP64 estimate, so every pixel its FP32 estimate cannot settle
- *                            goes to the brute-force list (test hook for the list and the hand-back). */
+ *                            goes to the brute-force list (test hook for the list and the hand-back);
+ *   "median_legacy"   != 0 : cv::medianBlur with kernel sizes 3 and 5 runs the radix-select kernel of the larger sizes
+ *                            instead of the selection network (same medians; A/B and test hook). */
 int         prl_cuda_set_option(prl_cuda_ctx* ctx, const char* name, long long value);
 
 /* Geometry of the reference's processingRect (binarizeSauvola.cpp:57,66; binarizeWolfJolion.cpp:58,69):
@@ -287,6 +289,12 @@ typedef struct prl_adaptive_params {
 } prl_adaptive_params;
 int prl_cuda_binarize_adaptive(prl_cuda_ctx* ctx, const uint8_t* src, int rows, int cols, size_t step, int channels,
                                const prl_adaptive_params* params, uint8_t* dst, size_t dst_step);
+/* The same over n_pages images of one size resident in HBM (image p at d_src + p * src_page_stride, `channels` interleaved bytes
+ * per pixel; result p at d_dst + p * dst_page_stride, one byte per pixel): the per-page kernel sequences run concurrently on the
+ * context's page lanes.  Synchronous.  Argument errors as prl_cuda_binarize_adaptive. */
+int prl_cuda_binarize_adaptive_batch_dev(prl_cuda_ctx* ctx, const uint8_t* d_src, int n_pages, int rows, int cols, size_t src_step,
+                                         size_t src_page_stride, int channels, const prl_adaptive_params* params, uint8_t* d_dst,
+                                         size_t dst_step, size_t dst_page_stride);
 /* cv::bilateralFilter(src, dst, d, sigmaColor, sigmaSpace) for CV_8UC1, BORDER_DEFAULT -- OpenCV's own C++ arithmetic (float32
  * weights from its SIMD exponential, taps in raster order; csrc/adaptive.cu spells it out).  The reference applies it to the
  * 0 / maxval mask of binarizeNativeAdaptive (binarizeNativeAdaptive.cpp:129-133).  d <= 0 derives the radius from sigmaSpace. */

@@ -364,6 +364,13 @@ class Context:
                                                                    status.ctypes.data))
         return n_rects, status
 
+    def binarize_adaptive_batch_dev(self, d_src, n_pages, rows, cols, src_step, src_page_stride, channels, d_dst, dst_step, dst_page_stride, **kw):
+        """prl_cuda_binarize_adaptive_batch_dev: the adaptive family over pages resident in HBM; keyword arguments = the fields of
+        struct prl_adaptive_params"""
+        p = capi.AdaptiveParams(**kw)
+        self._check(self._L.prl_cuda_binarize_adaptive_batch_dev(self._h, d_src, n_pages, rows, cols, src_step, src_page_stride, channels,
+                                                                 C.byref(p), d_dst, dst_step, dst_page_stride))
+
     def remove_lines_batch_dev(self, d_gray, n_pages, rows, cols, step, page_stride, d_dst, dst_step, dst_page_stride):
         self._check(self._L.prl_cuda_remove_lines_batch_dev(self._h, d_gray, n_pages, rows, cols, step, page_stride, d_dst, dst_step, dst_page_stride))
 

@@ -170,7 +170,7 @@ extern "C" void prl_cuda_destroy(prl_cuda_ctx* c)
     for (auto& ev : c->event_pool) cudaEventDestroy(ev);
     cudaFree(c->sched); cudaFree(c->planes); cudaFree(c->carry); cudaFree(c->colsum); cudaFree(c->scalars); cudaFree(c->fused_ws);
     cudaFree(c->d_redo_total);
-    cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_tmp); cudaFree(c->d_misc); cudaFree(c->d_bgr); cudaFree(c->edges_ws); cudaFree(c->adaptive_ws); cudaFree(c->rects_ws); cudaFree(c->clahe_ws);
+    cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_res); cudaFree(c->d_tmp); cudaFree(c->d_misc); cudaFree(c->d_bgr); cudaFree(c->edges_ws); cudaFree(c->adaptive_ws); cudaFree(c->rects_ws); cudaFree(c->clahe_ws);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -216,6 +216,7 @@ extern "C" int prl_cuda_set_option(prl_cuda_ctx* c, const char* name, long long 
     else if (strcmp(name, "morph_bytes") == 0) c->morph_bytes = value != 0;
     else if (strcmp(name, "thr_rows") == 0) c->thr_rows = value <= 0 ? 0 : ((int)std::min<long long>(std::max<long long>(value, 2), 64) & ~1);
     else if (strcmp(name, "tiles_legacy") == 0) c->tiles_legacy = value != 0;
+    else if (strcmp(name, "median_legacy") == 0) c->median_legacy = value != 0;
     else if (strcmp(name, "otsu_group") == 0) c->otsu_group = (int)std::min<long long>(std::max<long long>(value, -1), 65535);
     else if (strcmp(name, "tile_prefetch") == 0) c->tile_prefetch = (int)std::min<long long>(std::max<long long>(value, 0), 31);
     else if (strcmp(name, "fused_no_tier2") == 0) c->fused_no_tier2 = value != 0;
@@ -1114,15 +1115,10 @@ extern "C" int prl_cuda_adaptive_threshold(prl_cuda_ctx* c, const uint8_t* src, 
     return PRL_OK;
 }
 
-// One call for prl::binarizeNativeAdaptive / binarizeAT / binarizeAGT / binarizePureAdaptiveGaussian: the image crosses
-// PCIe once each way; colour conversion, blur, threshold and the mean test all run on the device.
-extern "C" int prl_cuda_binarize_adaptive(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step, int channels,
-                                          const prl_adaptive_params* p, uint8_t* dst, size_t dst_step)
+// prl_adaptive_params checked the way the reference's functions and cv::adaptiveThreshold / medianBlur / GaussianBlur check their
+// arguments; *bs receives the block size (the automatic one when asked for)
+static int adaptive_check(prl_cuda_ctx* c, int rows, int cols, int channels, const prl_adaptive_params* p, int* bs_out)
 {
-    if (!c) return PRL_E_INVALID;
-    if (!src || !dst || !p || rows <= 0 || cols <= 0 || (channels != 1 && channels != 3 && channels != 4) ||
-        step < (size_t)cols * channels || dst_step < (size_t)cols)
-        return prl_set_err(c, PRL_E_INVALID, "bad argument");
     if (!(p->maxval >= 0 && p->maxval <= 255) && p->check_maxval)
         return prl_set_err(c, PRL_E_INVALID, "Max value must be in range [0; 255]");                // binarizeNativeAdaptive.cpp:53-56
     int bs = p->block_size;
@@ -1140,62 +1136,114 @@ extern "C" int prl_cuda_binarize_adaptive(prl_cuda_ctx* c, const uint8_t* src, i
         if (channels != 1 && !p->gray_first) return prl_set_err(c, PRL_E_UNSUPPORTED, "Gaussian blur of a colour image is not supported");
     }
     if ((p->method != 0 && p->method != 1) || (p->type != 0 && p->type != 1)) return prl_set_err(c, PRL_E_INVALID, "unknown method or threshold type");
-    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    *bs_out = bs;
+    return PRL_OK;
+}
 
+// The kernel sequence of the adaptive family for one image resident in HBM, on c's stream with c's scratch: colour conversion,
+// blur, threshold, the mean test and the optional bilateral filter.  d_src: `channels` interleaved bytes per pixel, pitch
+// src_step; d_dst: one byte per pixel.  Asynchronous.
+static int adaptive_dev(prl_cuda_ctx* c, const uint8_t* d_src, int rows, int cols, size_t src_step, int channels, const prl_adaptive_params* p,
+                        int bs, uint8_t* d_dst, size_t dst_step)
+{
     const size_t g_step = round16((size_t)cols), g_img = g_step * rows;
     const size_t c_step = round16((size_t)cols * channels);
-    int rc = prl_ensure(c, (void**)&c->d_in, &c->d_in_bytes, g_img); if (rc) return rc;
-    rc = prl_ensure(c, (void**)&c->d_tmp, &c->d_tmp_bytes, g_img); if (rc) return rc;
+    const bool bilateral = p->bilateral_d >= 3;
+    int rc = prl_ensure(c, (void**)&c->d_tmp, &c->d_tmp_bytes, g_img); if (rc) return rc;
     rc = prl_ensure(c, &c->adaptive_ws, &c->adaptive_ws_bytes,
-                    prl_adaptive_scratch_bytes(rows, cols) + (p->bilateral_d >= 3 ? prl_bilateral_scratch_bytes(p->bilateral_d, p->bilateral_sigma_space) : 0));
+                    prl_adaptive_scratch_bytes(rows, cols) + (bilateral ? prl_bilateral_scratch_bytes(p->bilateral_d, p->bilateral_sigma_space) : 0));
     if (rc) return rc;
-    const uint8_t* gray = nullptr;          // what adaptiveThreshold reads
-    if (channels == 1) {
-        size_t in_step;
-        rc = stage_in(c, src, rows, cols, step, &in_step); if (rc) return rc;       // -> d_in (pitch g_step)
-        gray = c->d_in;
-    } else {
-        rc = prl_ensure(c, (void**)&c->d_bgr, &c->d_bgr_bytes, c_step * rows); if (rc) return rc;
-        PRL_CUDA_TRY(c, copy2d(c->d_bgr, c_step, src, step, (size_t)cols * channels, rows, cudaMemcpyHostToDevice, c->stream));
-        const uint8_t* colour = c->d_bgr;
+    const uint8_t* gray = d_src;            // what adaptiveThreshold reads
+    size_t gray_step = src_step;
+    if (channels != 1) {
+        rc = prl_ensure(c, (void**)&c->d_in, &c->d_in_bytes, g_img); if (rc) return rc;
+        const uint8_t* colour = d_src;
+        size_t colour_step = src_step;
         if (!p->gray_first && p->blur == 1 && p->blur_ksize > 1) {                  // cv::medianBlur on the colour image (binarizeAT.cpp:53)
             rc = prl_ensure(c, &c->d_misc, &c->d_misc_bytes, c_step * rows); if (rc) return rc;
-            rc = prl_k_median_blur(c, c->d_bgr, rows, cols, c_step, channels, p->blur_ksize, (uint8_t*)c->d_misc, c_step); if (rc) return rc;
-            colour = (const uint8_t*)c->d_misc;
+            rc = prl_k_median_blur(c, d_src, rows, cols, src_step, channels, p->blur_ksize, (uint8_t*)c->d_misc, c_step); if (rc) return rc;
+            colour = (const uint8_t*)c->d_misc; colour_step = c_step;
         }
-        rc = prl_k_bgr2gray(c, colour, rows, cols, c_step, channels, c->d_in, g_step, false); if (rc) return rc;   // COLOR_BGR2GRAY
-        gray = c->d_in;
+        rc = prl_k_bgr2gray(c, colour, rows, cols, colour_step, channels, c->d_in, g_step, false); if (rc) return rc;   // COLOR_BGR2GRAY
+        gray = c->d_in; gray_step = g_step;
     }
     if (p->blur != 0 && (channels == 1 || p->gray_first)) {
         if (p->blur == 1 && p->blur_ksize > 1) {
-            rc = prl_k_median_blur(c, gray, rows, cols, g_step, 1, p->blur_ksize, c->d_tmp, g_step); if (rc) return rc;
-            gray = c->d_tmp;
+            rc = prl_k_median_blur(c, gray, rows, cols, gray_step, 1, p->blur_ksize, c->d_tmp, g_step); if (rc) return rc;
+            gray = c->d_tmp; gray_step = g_step;
         } else if (p->blur == 2) {
             rc = prl_ensure(c, &c->edges_ws, &c->edges_ws_bytes, g_img * 2 + 256); if (rc) return rc;
-            rc = prl_k_gaussian_blur(c, gray, rows, cols, g_step, p->blur_ksize, p->blur_sigma, c->d_tmp, g_step, (uint16_t*)c->edges_ws);
+            rc = prl_k_gaussian_blur(c, gray, rows, cols, gray_step, p->blur_ksize, p->blur_sigma, c->d_tmp, g_step, (uint16_t*)c->edges_ws);
             if (rc) return rc;
-            gray = c->d_tmp;
+            gray = c->d_tmp; gray_step = g_step;
         }
     }
-    const size_t o_step = (dst_step == (size_t)cols) ? (size_t)cols : g_step;
-    rc = prl_ensure(c, (void**)&c->d_out, &c->d_out_bytes, o_step * rows + 16); if (rc) return rc;
-    rc = prl_k_adaptive_threshold(c, gray, rows, cols, g_step, p->maxval, p->method, p->type, bs, p->delta, c->d_out, o_step,
+    uint8_t* thr = d_dst;                   // the threshold writes the result itself unless the bilateral filter follows
+    size_t thr_step = dst_step;
+    if (bilateral) {
+        rc = prl_ensure(c, (void**)&c->d_out, &c->d_out_bytes, g_img + 16); if (rc) return rc;
+        thr = c->d_out; thr_step = g_step;
+    }
+    rc = prl_k_adaptive_threshold(c, gray, rows, cols, gray_step, p->maxval, p->method, p->type, bs, p->delta, thr, thr_step,
                                   c->adaptive_ws, p->invert_if_dark != 0);
     if (rc) return rc;
-    const uint8_t* result = c->d_out;
-    size_t r_step = o_step;
-    if (p->bilateral_d >= 3) {                                                                      // binarizeNativeAdaptive.cpp:116-134
+    if (bilateral) {                                                                                // binarizeNativeAdaptive.cpp:116-134
         // the reference reaches these checks after the threshold, so its cv::Exceptions above come first
         if (p->bilateral_sigma_color <= 0) return prl_set_err(c, PRL_E_INVALID, "Color sigma for bilateral filtration must be greater than 0");
         if (p->bilateral_sigma_space <= 0) return prl_set_err(c, PRL_E_INVALID, "Space sigma for bilateral filtration must be greater than 0");
-        rc = prl_k_bilateral(c, c->d_out, rows, cols, o_step, p->bilateral_d, p->bilateral_sigma_color, p->bilateral_sigma_space,
-                             c->d_tmp, g_step, (char*)c->adaptive_ws + prl_adaptive_scratch_bytes(rows, cols));
+        rc = prl_k_bilateral(c, thr, rows, cols, thr_step, p->bilateral_d, p->bilateral_sigma_color, p->bilateral_sigma_space,
+                             d_dst, dst_step, (char*)c->adaptive_ws + prl_adaptive_scratch_bytes(rows, cols));
         if (rc) return rc;
-        result = c->d_tmp; r_step = g_step;
     }
-    PRL_CUDA_TRY(c, copy2d(dst, dst_step, result, r_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
+    return PRL_OK;
+}
+
+// One call for prl::binarizeNativeAdaptive / binarizeAT / binarizeAGT / binarizePureAdaptiveGaussian: the image crosses
+// PCIe once each way; colour conversion, blur, threshold, the mean test and the bilateral filter all run on the device.
+extern "C" int prl_cuda_binarize_adaptive(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step, int channels,
+                                          const prl_adaptive_params* p, uint8_t* dst, size_t dst_step)
+{
+    if (!c) return PRL_E_INVALID;
+    if (!src || !dst || !p || rows <= 0 || cols <= 0 || (channels != 1 && channels != 3 && channels != 4) ||
+        step < (size_t)cols * channels || dst_step < (size_t)cols)
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    int bs = 0;
+    int rc = adaptive_check(c, rows, cols, channels, p, &bs); if (rc) return rc;
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    const size_t c_step = round16((size_t)cols * channels);
+    rc = prl_ensure(c, (void**)&c->d_bgr, &c->d_bgr_bytes, c_step * rows); if (rc) return rc;
+    PRL_CUDA_TRY(c, copy2d(c->d_bgr, c_step, src, step, (size_t)cols * channels, rows, cudaMemcpyHostToDevice, c->stream));
+    const size_t o_step = (dst_step == (size_t)cols) ? (size_t)cols : round16((size_t)cols);
+    rc = prl_ensure(c, (void**)&c->d_res, &c->d_res_bytes, o_step * rows + 16); if (rc) return rc;  // d_out may hold the mask the bilateral filter reads
+    uint8_t* d_res = c->d_res;
+    rc = adaptive_dev(c, c->d_bgr, rows, cols, c_step, channels, p, bs, d_res, o_step); if (rc) return rc;
+    PRL_CUDA_TRY(c, copy2d(dst, dst_step, d_res, o_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
     PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return PRL_OK;
+}
+
+// The same over n_pages images of one size resident in HBM (page p at d_src + p * src_page_stride): the per-page kernel sequences
+// run on the context's page lanes (own streams and scratch), up to 16 pages at a time.  Synchronous.
+extern "C" int prl_cuda_binarize_adaptive_batch_dev(prl_cuda_ctx* c, const uint8_t* d_src, int n_pages, int rows, int cols, size_t src_step,
+                                                    size_t src_page_stride, int channels, const prl_adaptive_params* p, uint8_t* d_dst,
+                                                    size_t dst_step, size_t dst_page_stride)
+{
+    if (!c) return PRL_E_INVALID;
+    if (!d_src || !d_dst || !p || n_pages <= 0 || rows <= 0 || cols <= 0 || (channels != 1 && channels != 3 && channels != 4) ||
+        src_step < (size_t)cols * channels || dst_step < (size_t)cols)
+        return prl_set_err(c, PRL_E_INVALID, "bad argument");
+    int bs = 0;
+    int rc = adaptive_check(c, rows, cols, channels, p, &bs); if (rc) return rc;
+    PRL_CUDA_TRY(c, cudaSetDevice(c->device));
+    const int nl = std::min(kLanes, n_pages);
+    rc = ensure_lanes(c, nl); if (rc) return rc;
+    PRL_CUDA_TRY(c, cudaStreamSynchronize(c->stream));               // the pages may have been produced on the caller's stream
+    for (int pg = 0; pg < n_pages; ++pg) {
+        prl_cuda_ctx* l = c->lanes[pg % nl];
+        rc = adaptive_dev(l, d_src + (size_t)pg * src_page_stride, rows, cols, src_step, channels, p, bs, d_dst + (size_t)pg * dst_page_stride, dst_step);
+        if (rc) { c->err = l->err; sync_lanes(c, nl); return rc; }
+    }
+    return sync_lanes(c, nl);
 }
 
 extern "C" int prl_cuda_bilateral_filter(prl_cuda_ctx* c, const uint8_t* src, int rows, int cols, size_t step, int d, double sigma_color,

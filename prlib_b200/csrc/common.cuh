@@ -74,11 +74,13 @@ struct prl_cuda_ctx {
     void* d_misc = nullptr;     size_t d_misc_bytes = 0;   // histograms, thresholds, rect lists
     void* clahe_ws = nullptr;   size_t clahe_ws_bytes = 0; // CLAHE: enhanced image, intermediate, LUTs
     void* rects_ws = nullptr;   size_t rects_ws_bytes = 0; // contour rectangles: count, list, thresholds, labels, boxes
+    uint8_t* d_res = nullptr;   size_t d_res_bytes = 0;    // adaptive family, single-image call: the result image
     void* adaptive_ws = nullptr; size_t adaptive_ws_bytes = 0; // adaptive family: pixel counter, float32 rows of the Gaussian mean
     void* edges_ws = nullptr;   size_t edges_ws_bytes = 0; // edge front-end: blurred image, 8.8 rows, class map, labels, flags
     // pinned host staging
 
     bool force_exact = false;   // validation: kernel 2 runs the literal FP64 path for every pixel
+    bool median_legacy = false;  // medianBlur 3 / 5: the radix-select kernel instead of the selection network (A/B and tests)
     bool dbg_skip_exact = false; // DIAGNOSTIC ONLY: kernel 2 (TMA) leaves undecided pixels black; timing experiments, never a result
     int k1_bands = 0;           // kernel 1: row bands per page (0 = automatic)
     int thr_stages = 2;         // kernel 2 (TMA): ring stages per CTA (2: three CTAs per SM -- measured 7 % faster; 3: two CTAs per SM)

@@ -216,10 +216,36 @@ def test_cuda_reproduces_the_reference_digests(ctx, key):
         assert digest_or_class(lambda: getattr(prlib_b200, fn)(img, *args, **kw)) == want, (key, name)
 
 
+def test_median_selection_networks_by_the_zero_one_principle():
+    """the compare-exchange lists csrc/adaptive.cu executes for 3 x 3 and 5 x 5 medians leave the median in wire 4 / 12 for
+    every 0/1 input (all 2^9 / 2^25 of them), hence for every input"""
+    import re
+    text = open(os.path.join(HERE, "..", "prlib_b200", "csrc", "adaptive.cu")).read()
+    for name, n, out in (("PRL_MED9_NETWORK", 9, 4), ("PRL_MED25_NETWORK", 25, 12)):
+        lines = text[text.index("#define " + name):].split("\n")
+        k = next(i for i, ln in enumerate(lines) if not ln.rstrip().endswith("\\"))
+        body = "\n".join(lines[:k + 1])
+        net = [(int(a), int(b)) for a, b in re.findall(r"CE\((\d+), (\d+)\)", body)]
+        assert len(net) == (19 if n == 9 else 99)
+        idx = np.arange(1 << n, dtype=np.uint32)
+        wires = [((idx >> k) & 1).astype(bool) for k in range(n)]
+        ones = sum(w.astype(np.uint8) for w in wires)
+        for a, b in net:
+            wires[a], wires[b] = wires[a] & wires[b], wires[a] | wires[b]
+        assert np.array_equal(wires[out], ones >= n // 2 + 1), name
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("ksize", [3, 5, 7, 9, 15, 31])
 def test_median_blur_equals_cv2(ctx, ksize):
     rng = np.random.default_rng(ksize)
+    if ksize <= 5:                                                   # both kernels: selection network (default) and radix select
+        img = rng.integers(0, 256, (70, 131, 3), dtype=np.uint8)
+        want = cv2.medianBlur(img, ksize)
+        ctx.set_option("median_legacy", 1)
+        assert np.array_equal(ctx.median_blur(img, ksize), want)
+        ctx.set_option("median_legacy", 0)
+        assert np.array_equal(ctx.median_blur(img, ksize), want)
     with O._single_thread():
         for shape in ((97, 131), (33, 70, 3), (64, 12, 4), (5, 3), (1, 40), (300, 257, 3)):
             if ksize > 5 and len(shape) == 3 and shape[0] * shape[1] > 20000:
@@ -314,3 +340,39 @@ def test_native_adaptive_with_the_bilateral_step_equals_the_reference(ctx):
                    {"bilateralFilterBlockSize": 7, "bilateralFilterSpaceSigma": -2.0},
                    {"bilateralFilterBlockSize": 7, "bilateralFilterColorSigma": -1.0, "adaptiveThresholdingBlockSize": 20}):   # cv::Exception comes first
             assert same_outcome(outcome(lambda: prlib_b200.binarizeNativeAdaptive(img, **kw)), outcome(lambda: W.binarizeNativeAdaptive(img, **kw))), (name, kw)
+
+
+@pytest.mark.gpu
+def test_batched_family_equals_the_single_image_calls(ctx):
+    """prl_cuda_binarize_adaptive_batch_dev: pages resident in HBM, per-page kernel sequences on the context's page lanes"""
+    import torch
+    rng = np.random.default_rng(5)
+    n, rows, cols = 19, 211, 307                                     # more pages than lanes; odd sizes
+    for channels, kws in ((1, ({"gray_first": 1, "blur": 1, "blur_ksize": 5, "assert_ksize": 1, "method": 1, "type": 1, "maxval": 255.0, "check_maxval": 1,
+                                 "block_size": 19, "auto_block": 1, "delta": 9.0, "invert_if_dark": 1},
+                                {"gray_first": 1, "blur": 2, "blur_ksize": 7, "blur_sigma": 150.0, "method": 0, "type": 1, "maxval": 200.0, "block_size": 21,
+                                 "auto_block": 1, "delta": 3.0, "invert_if_dark": 1, "bilateral_d": 5, "bilateral_sigma_color": 150.0,
+                                 "bilateral_sigma_space": 150.0})),
+                          (3, ({"gray_first": 0, "blur": 1, "blur_ksize": 5, "method": 0, "type": 0, "maxval": 255.0, "block_size": 19, "delta": 9.0},
+                               {"gray_first": 0, "blur": 0, "method": 1, "type": 0, "maxval": 255.0, "block_size": 15, "delta": 4.0}))):
+        shape = (n, rows, cols) if channels == 1 else (n, rows, cols, channels)
+        pages = rng.integers(0, 256, shape, dtype=np.uint8)
+        pages[3] //= 5                                               # a dark page: the mean test of NativeAdaptive flips it
+        step = (cols * channels + 15) // 16 * 16
+        d_src = torch.zeros((n, rows, step), dtype=torch.uint8, device="cuda")
+        d_src[:, :, :cols * channels] = torch.from_numpy(pages.reshape(n, rows, cols * channels)).cuda()
+        ostep = (cols + 15) // 16 * 16
+        for kw in kws:
+            d_dst = torch.zeros((n, rows, ostep), dtype=torch.uint8, device="cuda")
+            ctx.binarize_adaptive_batch_dev(d_src.data_ptr(), n, rows, cols, step, rows * step, channels, d_dst.data_ptr(), ostep, rows * ostep, **kw)
+            got = d_dst[:, :, :cols].cpu().numpy()
+            for i in range(n):
+                assert np.array_equal(got[i], ctx.binarize_adaptive(pages[i], **kw)), (channels, kw, i)
+    with pytest.raises(prlib_b200_error()):
+        ctx.binarize_adaptive_batch_dev(d_src.data_ptr(), n, rows, cols, step, rows * step, 3, d_dst.data_ptr(), ostep, rows * ostep,
+                                        method=0, type=0, maxval=255.0, block_size=20, delta=1.0)
+
+
+def prlib_b200_error():
+    from prlib_b200 import PrlCudaError
+    return PrlCudaError
