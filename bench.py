@@ -391,9 +391,22 @@ def run_ours(args):
         prlib_b200.binarize_batch(hp, capi.SAUVOLA, WINDOW, (K_COEF,), 0, devices=[local_rank], out=hm)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    unpack_threads = int(capi.load().prl_cuda_batch_unpack_threads())     # > 0: the masks crossed PCIe as bits (library default where the host has the cores)
     # the e2e masks must equal the device-resident ones
     same = bool(torch.equal(host_masks[:2].to(dev), masks[:2, :, :g["out_cols"]])) and \
         bool(torch.equal(host_masks[-1:].to(dev), masks[-1:, :, :g["out_cols"]]))
+    # the same call with the masks crossing PCIe as bytes (round 1's return path; "batch_unpack_threads" = 0)
+    prlib_b200.set_global_option("batch_unpack_threads", 0)
+    host_masks.zero_()
+    prlib_b200.binarize_batch(hp, capi.SAUVOLA, WINDOW, (K_COEF,), 0, devices=[local_rank], out=hm)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        prlib_b200.binarize_batch(hp, capi.SAUVOLA, WINDOW, (K_COEF,), 0, devices=[local_rank], out=hm)
+    torch.cuda.synchronize()
+    bytes_s = time.perf_counter() - t0
+    prlib_b200.set_global_option("batch_unpack_threads", -1)
+    same = same and bool(torch.equal(host_masks[:2].to(dev), masks[:2, :, :g["out_cols"]]))
     # extra: the same call with 1-bit-per-pixel output (prl_cuda_binarize_batch_packed, PIX layout): D2H is 8x smaller
     wpl = (g["out_cols"] + 31) // 32
     host_bits = torch.empty((n_pages, g["out_rows"], wpl), dtype=torch.int32, pin_memory=True)
@@ -488,14 +501,15 @@ def run_ours(args):
                 dispatcher = {"error": f"{type(ex).__name__}: {ex}"}
         host_barrier()
 
-    t_dev = torch.tensor([ms_total, e2e_s * 1e3, packed_s * 1e3, (default_path or {}).get("ms_per_step", 0.0)] + [t * 1e3 for t in pcie_t],
-                         dtype=torch.float64, device=dev)
+    t_dev = torch.tensor([ms_total, e2e_s * 1e3, packed_s * 1e3, (default_path or {}).get("ms_per_step", 0.0)] + [t * 1e3 for t in pcie_t] +
+                         [bytes_s * 1e3], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     ms_total, e2e_ms, packed_ms = float(t_dev[0]), float(t_dev[1]), float(t_dev[2])
     if default_path and "ms_per_step" in default_path:
         default_path["ms_per_step"] = float(t_dev[3])
     pcie_ms = [float(t_dev[4]), float(t_dev[5]), float(t_dev[6])]
+    bytes_ms = float(t_dev[7])
 
     if rank == 0:
         total_pages = n_pages * world
@@ -560,7 +574,9 @@ def run_ours(args):
                 "both_each_way_gbs": world * min(in_bytes, out_bytes) / (pcie_ms[2] / 1e3) / 1e9,
                 "note": f"aggregate over {world} GPU(s), all ranks copying at once: one linear pinned copy of the step's pages in / masks out per "
                         "direction, then both directions together; no kernels running"}
-        pcie["e2e_ceiling_pages_per_sec"] = total_pages / (pcie_ms[2] / 1e3)
+        pcie["e2e_ceiling_pages_per_sec"] = total_pages / (pcie_ms[2] / 1e3)          # masks returned as bytes: both directions loaded alike
+        pcie["e2e_ceiling_bits_return_pages_per_sec"] = total_pages / (pcie_ms[0] / 1e3)   # masks returned as bits: H2D is the loaded direction
+        bits_bytes = n_pages * g["out_rows"] * wpl * 4
         line = {
             "metric": METRIC,
             "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -571,10 +587,18 @@ def run_ours(args):
             "golden_check": {"ok": golden_ok, "pages": golden,
                              "what": "sha1 of masks 0 and 1 of the timed batch == tests/golden/ref_golden.json (outputs of the reference's own C++)"},
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": in_bytes,
-                    "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_ms / e2e_steps,
+                    "d2h_bytes_per_step": bits_bytes if unpack_threads > 0 else out_bytes, "ms_per_step": e2e_ms / e2e_steps,
                     "pages_per_sec": total_pages * e2e_steps / (e2e_ms / 1e3), "masks_match_device_path": same,
-                    "frac_of_pcie_ceiling": (total_pages * e2e_steps / (e2e_ms / 1e3)) / pcie["e2e_ceiling_pages_per_sec"],
-                    "api": "prl_cuda_binarize_batch (pinned host pages -> H2D -> kernels -> D2H -> host masks, 3-slot ring, library defaults)",
+                    "host_result_bytes_per_step": out_bytes,
+                    "frac_of_pcie_ceiling": (total_pages * e2e_steps / (e2e_ms / 1e3)) /
+                    pcie["e2e_ceiling_bits_return_pages_per_sec" if unpack_threads > 0 else "e2e_ceiling_pages_per_sec"],
+                    "mask_return": (f"1 bit per pixel over PCIe, expanded to the caller's 0/255 bytes by {unpack_threads} library host threads per GPU "
+                                    "inside the call") if unpack_threads > 0 else "0/255 bytes over PCIe (too few host cores per GPU for the 1-bit return path)",
+                    "api": "prl_cuda_binarize_batch (pinned host pages -> H2D -> kernels -> D2H -> host masks of 0/255 bytes; 3-slot ring, library defaults)",
+                    "bytes_return": {"value": total_pages * e2e_steps * mp_per_page / (bytes_ms / 1e3), "unit": "MP/s",
+                                     "pages_per_sec": total_pages * e2e_steps / (bytes_ms / 1e3), "d2h_bytes_per_step": out_bytes,
+                                     "frac_of_pcie_ceiling": (total_pages * e2e_steps / (bytes_ms / 1e3)) / pcie["e2e_ceiling_pages_per_sec"],
+                                     "api": "the same call with \"batch_unpack_threads\" = 0: the byte masks themselves cross PCIe (round 1's path)"},
                     "host_affinity": numa_note},
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "pcie": pcie,

@@ -73,7 +73,9 @@ int         prl_cuda_set_workspace_limit(prl_cuda_ctx* ctx, size_t bytes);
  *   "fused_no_tier2"  != 0 : the fused path skips its FP64 estimate, so every pixel its FP32 estimate cannot settle
  *                            goes to the brute-force list (test hook for the list and the hand-back);
  *   "median_legacy"   != 0 : cv::medianBlur with kernel sizes 3 and 5 runs the radix-select kernel of the larger sizes
- *                            instead of the selection network (same medians; A/B and test hook). */
+ *                            instead of the selection network (same medians; A/B and test hook);
+ *   "gauss_legacy"    != 0 : cv::adaptiveThreshold(GAUSSIAN_C) runs its row and column passes as two kernels over a float32
+ *                            plane in HBM for every block size, not only above 63 (same bytes; A/B and test hook). */
 int         prl_cuda_set_option(prl_cuda_ctx* ctx, const char* name, long long value);
 
 /* Geometry of the reference's processingRect (binarizeSauvola.cpp:57,66; binarizeWolfJolion.cpp:58,69):
@@ -189,8 +191,19 @@ int prl_cuda_host_register(void* p, size_t bytes);
 int prl_cuda_host_unregister(void* p);
 /* Process-wide options of the ctx-less entry points: "batch_chunk_pages" (pages per ring slot, 0 = automatic,
  * about 72 MiB of input), "batch_stage_pageable" (1 = bounce pageable memory through pinned buffers, default;
- * 0 = hand it to the driver as it is).  PRL_E_INVALID for an unknown name. */
+ * 0 = hand it to the driver as it is), "batch_unpack_threads" (n > 0: the byte masks of prl_cuda_binarize_batch cross
+ * PCIe as 1 bit per pixel into library-owned pinned buffers and n host threads per device expand them into `masks`
+ * while later chunks are in flight -- the link carries 1.125 instead of 2 bytes per pixel and `masks` need not be
+ * page-locked; 0: the bytes themselves cross; -1, the default: min(8, host cores per GPU - 2) threads where that is at
+ * least 6, else 0 -- [B200 box, 16 cores] 4.8 k A4 pages/s as bytes, 5.9 k as bits with 8 threads, 3.2 k with 4),
+ * "batch_unpack_nt" (1, default: the expansion uses non-temporal stores; 0: ordinary stores -- A/B switch).
+ * PRL_E_INVALID for an unknown name. */
 int prl_cuda_set_global_option(const char* name, long long value);
+/* What "batch_unpack_threads" resolves to right now: host threads per device expanding 1-bit masks, 0 = the bytes cross PCIe. */
+int prl_cuda_batch_unpack_threads(void);
+/* The host half of that return path alone (test hook): PIX words (prl_cuda_pack_mask_dev layout, wpl = (cols + 31) / 32) to a
+ * dense rows x cols 0/255 mask; force_scalar != 0 takes the portable loop instead of the AVX2 one. */
+int prl_cuda_unpack_mask_host(const uint32_t* bits, int rows, int cols, uint8_t* mask, int force_scalar);
 
 /* ---- edge front-end of prl::binarizeLocalOtsu -----------------------
  * prl_cuda_canny_edge_detection = CannyEdgeDetection (src/imageLibCommon.cpp:244-324: GaussianBlur k x k sigma 0,

@@ -103,6 +103,8 @@ SIGNATURES.update({
     "prl_cuda_gauss_kernel_float": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
     "prl_cuda_binarize_adaptive_batch_dev": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_int,
                                                        C.POINTER(AdaptiveParams), C.c_void_p, C.c_size_t, C.c_size_t]),
+    "prl_cuda_batch_unpack_threads": (C.c_int, []),
+    "prl_cuda_unpack_mask_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "prl_cuda_bilateral_filter": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_double, C.c_double, C.c_void_p,
                                             C.c_size_t]),
     "prl_cuda_binarize_adaptive": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.POINTER(AdaptiveParams),

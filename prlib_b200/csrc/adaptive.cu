@@ -271,6 +271,68 @@ gaussf_cols_threshold_kernel(const float* __restrict__ tmp, size_t tstep, const 
     }
 }
 
+// GAUSSIAN_C in one kernel for blocks up to 63 taps: a CTA owns 64 x 32 outputs, keeps the u8 tile and its row-pass results in
+// shared memory and runs the column pass from there -- the float32 plane of the two kernels above (4 B per pixel written, n times
+// that re-read through L2) never exists.  Same operations in the same order per pixel, so the same bits.
+constexpr int kGfTW = 64, kGfTH = 32;
+
+__global__ void __launch_bounds__(256)
+gaussf_fused_kernel(const uint8_t* __restrict__ src, size_t step, int rows, int cols, const __grid_constant__ GaussF K, TabArgs T,
+                    uint8_t* __restrict__ dst, size_t dstep, unsigned long long* __restrict__ nset)
+{
+    extern __shared__ __align__(16) uint8_t gf_sm[];
+    const int n = K.n, h = n / 2;
+    const int tw = kGfTW + n - 1, th = kGfTH + n - 1;
+    float* kk = reinterpret_cast<float*>(gf_sm);                         // 64 coefficients
+    float* rsum = kk + 64;                                               // th x kGfTW row-pass results
+    uint8_t* tile = reinterpret_cast<uint8_t*>(rsum + (size_t)th * kGfTW);   // th x tw pixels, BORDER_REPLICATE
+    const int x0 = blockIdx.x * kGfTW, y0 = blockIdx.y * kGfTH;
+    for (int i = threadIdx.x; i < n; i += 256) kk[i] = K.k[i];
+    for (int i = threadIdx.x; i < tw * th; i += 256) {
+        const int ty = i / tw, tx = i - ty * tw;
+        tile[i] = src[(size_t)min(max(y0 - h + ty, 0), rows - 1) * step + min(max(x0 - h + tx, 0), cols - 1)];
+    }
+    __syncthreads();
+    const int nu = K.n_unfused, cols4 = cols & ~3;
+    for (int i = threadIdx.x; i < th * kGfTW; i += 256) {
+        const int ty = i / kGfTW, tx = i - ty * kGfTW;
+        const uint8_t* p = tile + ty * tw + tx;
+        float s = __fmul_rn((float)p[0], kk[0]);
+        if (x0 + tx < cols4) {
+            for (int k = 1; k < n; ++k) s = __fmaf_rn((float)p[k], kk[k], s);
+        } else {
+            for (int k = 1; k <= nu; ++k) s = __fadd_rn(s, __fmul_rn((float)p[k], kk[k]));
+            for (int k = nu + 1; k < n; ++k) s = __fmaf_rn((float)p[k], kk[k], s);
+        }
+        rsum[i] = s;
+    }
+    __syncthreads();
+    const int lx = threadIdx.x % kGfTW, ly0 = threadIdx.x / kGfTW;       // 4 rows of threads, 8 output rows each
+    const int x = x0 + lx;
+    const bool fused = x < (cols & ~7);
+    unsigned int set = 0;
+    for (int ly = ly0; ly < kGfTH; ly += 256 / kGfTW) {
+        const int y = y0 + ly;
+        if (x < cols && y < rows) {
+            const float* c = rsum + (ly + h) * kGfTW + lx;
+            float s = __fmul_rn(c[0], kk[h]);
+            for (int j = 1; j <= h; ++j) {
+                const float pr = __fadd_rn(c[j * kGfTW], c[-j * kGfTW]);
+                s = fused ? __fmaf_rn(pr, kk[h + j], s) : __fadd_rn(s, __fmul_rn(pr, kk[h + j]));
+            }
+            int mean = __float2int_rn(s);                                // saturate_cast<uchar>(float): cvRound, then clamp
+            mean = min(max(mean, 0), 255);
+            const int v = tab_value(T, tile[(ly + h) * tw + lx + h], mean);
+            dst[(size_t)y * dstep + x] = (uint8_t)v;
+            set += v ? 1u : 0u;
+        }
+    }
+    if (nset != nullptr) {
+        set = __reduce_add_sync(0xffffffffu, set);
+        if ((threadIdx.x & 31) == 0 && set) atomicAdd(nset, (unsigned long long)set);
+    }
+}
+
 // inputImageChannels[c] = 255 - inputImageChannels[c] when cv::mean(...)[0] < 128 (binarizeNativeAdaptive.cpp:108-111)
 __global__ void __launch_bounds__(256)
 invert_if_dark_kernel(uint8_t* __restrict__ img, size_t step, int rows, int cols, int maxv, const unsigned long long* __restrict__ nset)
@@ -450,14 +512,23 @@ int prl_k_adaptive_threshold(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, 
             K1 = K; K1.n = 1; K1.n_unfused = 0; K1.k[0] = 1.f;
             const GaussF& Kx = cols > 1 ? K : K1;
             const GaussF& Ky = rows > 1 ? K : K1;
-            dim3 grid((cols + 255) / 256, rows);
-            {
+            if (block_size <= 63 && rows > 1 && cols > 1 && !ctx->gauss_legacy) {
+                const size_t smem = 64 * sizeof(float) + (size_t)(kGfTH + block_size - 1) * kGfTW * sizeof(float) +
+                                    (size_t)(kGfTH + block_size - 1) * (kGfTW + block_size - 1);
+                dim3 grid((cols + kGfTW - 1) / kGfTW, (rows + kGfTH - 1) / kGfTH);
+                PRL_CUDA_TRY(ctx, cudaFuncSetAttribute(gaussf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 prl_launch_scope ls(ctx, FAM_ADAPTIVE);
-                gaussf_rows_kernel<<<grid, 256, 0, ctx->stream>>>(d_src, step, rows, cols, Kx, tmp, tstep);
-            }
-            {
-                prl_launch_scope ls(ctx, FAM_ADAPTIVE);
-                gaussf_cols_threshold_kernel<<<grid, 256, 0, ctx->stream>>>(tmp, tstep, d_src, step, rows, cols, Ky, T, d_dst, dst_step, nset);
+                gaussf_fused_kernel<<<grid, 256, smem, ctx->stream>>>(d_src, step, rows, cols, K, T, d_dst, dst_step, nset);
+            } else {
+                dim3 grid((cols + 255) / 256, rows);
+                {
+                    prl_launch_scope ls(ctx, FAM_ADAPTIVE);
+                    gaussf_rows_kernel<<<grid, 256, 0, ctx->stream>>>(d_src, step, rows, cols, Kx, tmp, tstep);
+                }
+                {
+                    prl_launch_scope ls(ctx, FAM_ADAPTIVE);
+                    gaussf_cols_threshold_kernel<<<grid, 256, 0, ctx->stream>>>(tmp, tstep, d_src, step, rows, cols, Ky, T, d_dst, dst_step, nset);
+                }
             }
         } else {
             return prl_set_err(ctx, PRL_E_INVALID, "Unknown/unsupported adaptive threshold method");

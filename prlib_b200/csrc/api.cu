@@ -12,11 +12,22 @@
 
 #include <atomic>
 #include <condition_variable>
+#include <deque>
+#if defined(__linux__)
+#include <sched.h>
+#endif
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#endif
 
 static thread_local std::string g_create_err;
 
 // process-wide knobs of the ctx-less batch entry points (prl_cuda_set_global_option)
 static std::atomic<long long> g_batch_chunk_pages{0};     // pages per ring slot, 0 = automatic (~72 MiB of input)
+static std::atomic<long long> g_batch_unpack_threads{-1}; // > 0: byte masks cross PCIe as 1 bit per pixel and this many host threads per
+                                                          //    device expand them into the caller's buffer; 0: the bytes themselves cross;
+                                                          //    -1 (default): decided from the host cores per GPU, see unpack_threads_auto
+static std::atomic<long long> g_batch_unpack_nt{1};       // AVX2 expansion: non-temporal stores (1) or ordinary ones (0)
 static std::atomic<long long> g_batch_pageable{1};        // 1: pageable host buffers are staged through library-owned pinned
                                                           //    bounce buffers (correct overlap, host-memcpy bound); 0: handed to the
                                                           //    driver as they are (synchronous staged copies, no overlap)
@@ -217,6 +228,7 @@ extern "C" int prl_cuda_set_option(prl_cuda_ctx* c, const char* name, long long 
     else if (strcmp(name, "thr_rows") == 0) c->thr_rows = value <= 0 ? 0 : ((int)std::min<long long>(std::max<long long>(value, 2), 64) & ~1);
     else if (strcmp(name, "tiles_legacy") == 0) c->tiles_legacy = value != 0;
     else if (strcmp(name, "median_legacy") == 0) c->median_legacy = value != 0;
+    else if (strcmp(name, "gauss_legacy") == 0) c->gauss_legacy = value != 0;
     else if (strcmp(name, "otsu_group") == 0) c->otsu_group = (int)std::min<long long>(std::max<long long>(value, -1), 65535);
     else if (strcmp(name, "tile_prefetch") == 0) c->tile_prefetch = (int)std::min<long long>(std::max<long long>(value, 0), 31);
     else if (strcmp(name, "fused_no_tier2") == 0) c->fused_no_tier2 = value != 0;
@@ -1354,10 +1366,150 @@ extern "C" int prl_cuda_otsu_tiles(prl_cuda_ctx* c, const uint8_t* src, int rows
 // ------------------------------------------------------------------------------------------------
 // host batch: pinned-memory loader + page dispatcher (one host thread per device, no collective)
 // ------------------------------------------------------------------------------------------------
+
+// ---- masks over PCIe at 1 bit per pixel.  The end-to-end rate of prl_cuda_binarize_batch is the PCIe link's: 8.7 MB in and 8.7 MB
+// out per A4 page, both directions busy ([B200 box] 49.6 GB/s each way together, 55.6 GB/s for H2D alone).  The result is a 0/255
+// mask, so it crosses as PIX words (prl_k_pack_mask: bit 31 - (x & 31) of word x >> 5, 1 = black) into library-owned pinned
+// buffers and a few host threads per device expand it into the caller's buffer while later chunks are in flight: the link then
+// carries 1.125 bytes per pixel instead of 2, and the caller's mask buffer no longer has to be page-locked.
+static void unpack_rows_scalar(const uint32_t* bits, size_t wpl, uint8_t* dst, int rows, int cols)
+{
+    static uint64_t lut[256];
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (int b = 0; b < 256; ++b) {
+            uint64_t v = 0;
+            for (int i = 0; i < 8; ++i) if (!((b >> (7 - i)) & 1)) v |= 0xffull << (8 * i);    // first pixel = top bit; 0 = white = 255
+            lut[b] = v;
+        }
+    });
+    for (int y = 0; y < rows; ++y) {
+        const uint32_t* w = bits + (size_t)y * wpl;
+        uint8_t* o = dst + (size_t)y * cols;
+        int x = 0;
+        for (; x + 32 <= cols; x += 32) {
+            const uint32_t v = w[x >> 5];
+            for (int k = 0; k < 4; ++k) memcpy(o + x + 8 * k, &lut[(v >> (24 - 8 * k)) & 0xffu], 8);
+        }
+        for (; x < cols; ++x) o[x] = ((w[x >> 5] >> (31 - (x & 31))) & 1u) ? 0 : 255;
+    }
+}
+
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("avx2"))) static void unpack_rows_avx2(const uint32_t* bits, size_t wpl, uint8_t* dst, int rows, int cols)
+{
+    // byte j of the vector takes source byte 3 - j / 8 of the word (PIX words are most-significant-bit first), bit 7 - j % 8.
+    // The destination is written once and not read back here: aligned non-temporal stores (no read-for-ownership traffic; an
+    // ordinary store loop tops out near 7 GB/s per thread); rows start at any alignment, so the bit stream is re-cut at the
+    // first 32-byte boundary of each row.
+    const __m256i pick = _mm256_setr_epi8(3, 3, 3, 3, 3, 3, 3, 3, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0);
+    const __m256i bit = _mm256_set1_epi64x((long long)0x0102040810204080ull);
+    const bool nt = g_batch_unpack_nt.load() != 0;
+    for (int y = 0; y < rows; ++y) {
+        const uint32_t* w = bits + (size_t)y * wpl;
+        uint8_t* o = dst + (size_t)y * cols;
+        const int head = std::min(cols, (int)((32 - ((uintptr_t)o & 31)) & 31));
+        int x = 0;
+        for (; x < head; ++x) o[x] = ((w[x >> 5] >> (31 - (x & 31))) & 1u) ? 0 : 255;
+        const int sh = head & 31;
+        for (int i = 0; x + 32 <= cols; x += 32, ++i) {
+            const uint32_t v = sh ? (w[i] << sh) | (w[i + 1] >> (32 - sh)) : w[i];            // pixels x .. x + 31, first pixel in the top bit
+            const __m256i e = _mm256_shuffle_epi8(_mm256_set1_epi32((int)v), pick);
+            const __m256i white = _mm256_cmpeq_epi8(_mm256_and_si256(e, bit), _mm256_setzero_si256());
+            if (nt) _mm256_stream_si256(reinterpret_cast<__m256i*>(o + x), white); else _mm256_store_si256(reinterpret_cast<__m256i*>(o + x), white);
+        }
+        for (; x < cols; ++x) o[x] = ((w[x >> 5] >> (31 - (x & 31))) & 1u) ? 0 : 255;
+    }
+    _mm_sfence();
+}
+static void unpack_rows(const uint32_t* bits, size_t wpl, uint8_t* dst, int rows, int cols)
+{
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) unpack_rows_avx2(bits, wpl, dst, rows, cols); else unpack_rows_scalar(bits, wpl, dst, rows, cols);
+}
+#else
+static void unpack_rows(const uint32_t* bits, size_t wpl, uint8_t* dst, int rows, int cols) { unpack_rows_scalar(bits, wpl, dst, rows, cols); }
+#endif
+
+// How many host threads per device expand masks when the caller did not say.  The expansion writes 8.7 MB per A4 page: on the
+// measured boxes it takes ~8 threads to keep up with the link ([B200 box, 16 cores] 4 threads 3.2 k pages/s, 8 threads 5.9 k,
+// bytes over PCIe 4.8 k), so it only pays where each GPU of the box has that many cores to itself; otherwise the bytes cross.
+static int unpack_threads_auto()
+{
+    static const int n = [] {
+        int cores = (int)std::thread::hardware_concurrency();
+#if defined(__linux__)
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
+#endif
+        const int gpus = std::max(1, prl_cuda_device_count());
+        const int t = std::min(8, cores / gpus - 2);              // leave the submitting thread and the caller some room
+        return t >= 6 ? t : 0;
+    }();
+    return n;
+}
+
+extern "C" int prl_cuda_batch_unpack_threads(void)
+{
+    const long long v = g_batch_unpack_threads.load();
+    return v < 0 ? unpack_threads_auto() : (int)v;
+}
+
+// test hook: the host-side expansion alone
+extern "C" int prl_cuda_unpack_mask_host(const uint32_t* bits, int rows, int cols, uint8_t* mask, int force_scalar)
+{
+    if (!bits || !mask || rows <= 0 || cols <= 0) return PRL_E_INVALID;
+    const size_t wpl = ((size_t)cols + 31) / 32;
+    if (force_scalar) unpack_rows_scalar(bits, wpl, mask, rows, cols); else unpack_rows(bits, wpl, mask, rows, cols);
+    return PRL_OK;
+}
+
 namespace {
+
+// a few threads per device worker that expand packed pages; a job is a band of rows of one page
+struct UnpackPool {
+    struct Job { const uint32_t* bits; size_t wpl; uint8_t* dst; int rows, cols; std::atomic<int>* left; };
+    std::vector<std::thread> threads;
+    std::mutex mu;
+    std::condition_variable cv, cv_done;
+    std::deque<Job> jobs;
+    bool stop = false;
+    void start(int n)
+    {
+        while ((int)threads.size() < n)
+            threads.emplace_back([this] {
+                for (;;) {
+                    Job j;
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [this] { return stop || !jobs.empty(); });
+                        if (jobs.empty()) return;
+                        j = jobs.front(); jobs.pop_front();
+                    }
+                    unpack_rows(j.bits, j.wpl, j.dst, j.rows, j.cols);
+                    if (j.left->fetch_sub(1) == 1) { std::lock_guard<std::mutex> lk(mu); cv_done.notify_all(); }
+                }
+            });
+    }
+    void submit(const Job& j) { { std::lock_guard<std::mutex> lk(mu); jobs.push_back(j); } cv.notify_one(); }
+    void wait(std::atomic<int>& left) { std::unique_lock<std::mutex> lk(mu); cv_done.wait(lk, [&] { return left.load() == 0; }); }
+    ~UnpackPool()
+    {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        for (auto& t : threads) t.join();
+    }
+};
 
 struct DeviceWorker {
     prl_cuda_ctx* ctx = nullptr;
+    static constexpr int HB = 6;                              // host slots of the 1-bit return path (twice the device ring: the
+    uint32_t* h_bits[HB] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // expansion of a chunk trails its D2H)
+    size_t h_bits_bytes = 0;
+    cudaEvent_t ev_hb[HB];
+    int n_hb_events = 0;
+    std::atomic<int> hb_left[HB];
+    UnpackPool pool;
     std::mutex busy;                                          // held for a whole shard: concurrent callers on one device take turns
     cudaStream_t s_in = nullptr, s_out = nullptr;
     static constexpr int NBUF = 3;
@@ -1380,6 +1532,8 @@ struct DeviceWorker {
             if (h_in[i]) cudaFreeHost(h_in[i]);
             if (h_out[i]) cudaFreeHost(h_out[i]);
         }
+        for (int i = 0; i < HB; ++i) if (h_bits[i]) cudaFreeHost(h_bits[i]);
+        for (int i = 0; i < n_hb_events; ++i) cudaEventDestroy(ev_hb[i]);
         for (int i = 0; i < n_events; ++i) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_comp[i]); cudaEventDestroy(ev_out[i]); }
         if (s_in) cudaStreamDestroy(s_in);
         if (s_out) cudaStreamDestroy(s_out);
@@ -1411,6 +1565,11 @@ std::shared_ptr<DeviceWorker> get_worker(int device, std::string* err)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->ev_out[i], cudaEventDisableTiming);
         if (e == cudaSuccess) w->n_events = i + 1;
     }
+    for (int i = 0; e == cudaSuccess && i < DeviceWorker::HB; ++i) {
+        e = cudaEventCreateWithFlags(&w->ev_hb[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) w->n_hb_events = i + 1;
+        w->hb_left[i].store(0);
+    }
     if (e != cudaSuccess) { *err = std::string("batch worker: ") + cudaGetErrorString(e); cudaGetLastError(); return nullptr; }
     g_workers[device] = w;
     return w;
@@ -1432,8 +1591,11 @@ int run_shard_locked(DeviceWorker* w, int method, const uint8_t* pages, int p0, 
     prl_cuda_ctx* c = w->ctx;
 #define SHARD_TRY(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { *err = std::string(#call) + ": " + cudaGetErrorString(_e); return PRL_E_CUDA; } } while (0)
     SHARD_TRY(cudaSetDevice(c->device));
-    // masks dense on the device: linear D2H.  Packed variant: aligned mask rows feed the pack kernel, the bits are dense.
-    const size_t in_step = round16(cols), o_step = packed ? round16((size_t)g.out_cols) : (size_t)g.out_cols;
+    // byte masks returned as bits and expanded on the host (see UnpackPool) unless switched off
+    const int unpack_threads = prl_cuda_batch_unpack_threads();
+    const bool via_bits = !packed && unpack_threads > 0;
+    // masks dense on the device: linear D2H.  Packed variants: aligned mask rows feed the pack kernel, the bits are dense.
+    const size_t in_step = round16(cols), o_step = (packed || via_bits) ? round16((size_t)g.out_cols) : (size_t)g.out_cols;
     const size_t in_page = in_step * rows, out_page = o_step * g.out_rows;
     const size_t wpl = ((size_t)g.out_cols + 31) / 32, bits_page = wpl * g.out_rows * sizeof(uint32_t);
     const size_t host_in_page = (size_t)rows * cols, host_out_page = packed ? bits_page : (size_t)g.out_rows * g.out_cols;
@@ -1454,7 +1616,7 @@ int run_shard_locked(DeviceWorker* w, int method, const uint8_t* pages, int p0, 
         }
         w->in_bytes = in_page * chunk; w->out_bytes = out_page * chunk;
     }
-    if (packed && bits_page * chunk > w->bits_bytes) {
+    if ((packed || via_bits) && bits_page * chunk > w->bits_bytes) {
         SHARD_TRY(cudaDeviceSynchronize());
         for (int i = 0; i < DeviceWorker::NBUF; ++i) { cudaFree(w->d_bits[i]); w->d_bits[i] = nullptr; }
         w->bits_bytes = 0;
@@ -1467,7 +1629,36 @@ int run_shard_locked(DeviceWorker* w, int method, const uint8_t* pages, int p0, 
     // cudaMallocHost) goes to the copy engines directly and is what the quoted end-to-end throughput needs.
     const bool stage_pageable = g_batch_pageable.load() != 0;
     const bool bounce_in = stage_pageable && !host_range_pinned(pages);
-    const bool bounce_out = stage_pageable && !host_range_pinned(packed ? (const void*)packed : (const void*)masks);
+    const bool bounce_out = !via_bits && stage_pageable && !host_range_pinned(packed ? (const void*)packed : (const void*)masks);
+    if (via_bits) {
+        if (bits_page * chunk > w->h_bits_bytes) {
+            SHARD_TRY(cudaDeviceSynchronize());
+            for (int i = 0; i < DeviceWorker::HB; ++i) { if (w->h_bits[i]) cudaFreeHost(w->h_bits[i]); w->h_bits[i] = nullptr; }
+            w->h_bits_bytes = 0;
+            for (int i = 0; i < DeviceWorker::HB; ++i) SHARD_TRY(cudaMallocHost((void**)&w->h_bits[i], bits_page * chunk));
+            w->h_bits_bytes = bits_page * chunk;
+        }
+        w->pool.start(unpack_threads);
+    }
+    // via_bits: chunk j sits in host slot j % HB; its expansion is handed to the pool two iterations after its D2H was queued
+    // and must be over before the slot is reused HB iterations later
+    struct HostChunk { int p, np; };
+    HostChunk hchunk[DeviceWorker::HB] = {};
+    auto expand = [&](int j) -> int {                                         // chunk j arrived: hand its pages to the pool
+        const int hs = j % DeviceWorker::HB;
+        cudaError_t e = cudaEventSynchronize(w->ev_hb[hs]);
+        if (e != cudaSuccess) { *err = std::string("cudaEventSynchronize: ") + cudaGetErrorString(e); return PRL_E_CUDA; }
+        const int bands = std::max(1, std::min(unpack_threads, 4));           // a page in a few bands: short jobs, even load
+        w->hb_left[hs].store(hchunk[hs].np * bands);
+        for (int i = 0; i < hchunk[hs].np; ++i)
+            for (int b = 0; b < bands; ++b) {
+                const int r0 = (int)((long long)g.out_rows * b / bands), r1 = (int)((long long)g.out_rows * (b + 1) / bands);
+                w->pool.submit(UnpackPool::Job{w->h_bits[hs] + ((size_t)i * g.out_rows + r0) * wpl, wpl,
+                                               masks + ((size_t)(hchunk[hs].p + i) * g.out_rows + r0) * g.out_cols, r1 - r0, g.out_cols,
+                                               &w->hb_left[hs]});
+            }
+        return PRL_OK;
+    };
     if (bounce_in && host_in_page * chunk > w->h_in_bytes) {
         SHARD_TRY(cudaDeviceSynchronize());
         for (int i = 0; i < DeviceWorker::NBUF; ++i) { if (w->h_in[i]) cudaFreeHost(w->h_in[i]); w->h_in[i] = nullptr; }
@@ -1499,6 +1690,8 @@ int run_shard_locked(DeviceWorker* w, int method, const uint8_t* pages, int p0, 
             SHARD_TRY(cudaStreamWaitEvent(w->s_in, w->ev_comp[slot], 0));     // d_in[slot] consumed
             SHARD_TRY(cudaStreamWaitEvent(c->stream, w->ev_out[slot], 0));    // d_out[slot] drained
         }
+        const int hs = it % DeviceWorker::HB;
+        if (via_bits && it >= DeviceWorker::HB) w->pool.wait(w->hb_left[hs]);   // the chunk that used this host slot is expanded
         const uint8_t* hsrc = pages + (size_t)p * host_in_page;
         if (bounce_in) { memcpy(w->h_in[slot], hsrc, host_in_page * np); hsrc = w->h_in[slot]; }
         SHARD_TRY(copy2d(w->d_in[slot], in_step, hsrc, cols, cols, (size_t)rows * np, cudaMemcpyHostToDevice, w->s_in));
@@ -1507,19 +1700,28 @@ int run_shard_locked(DeviceWorker* w, int method, const uint8_t* pages, int p0, 
         int rc = prl_cuda_binarize_local_batch_dev(c, method, w->d_in[slot], np, rows, cols, in_step, in_page, window,
                                                    params, morph_iters, w->d_out[slot], o_step, out_page);
         if (rc) { *err = c->err; return rc; }
-        if (packed) {
+        if (packed || via_bits) {
             rc = prl_k_pack_mask(c, w->d_out[slot], np, g.out_rows, g.out_cols, o_step, out_page, w->d_bits[slot]);
             if (rc) { *err = c->err; return rc; }
         }
         SHARD_TRY(cudaEventRecord(w->ev_comp[slot], c->stream));
         SHARD_TRY(cudaStreamWaitEvent(w->s_out, w->ev_comp[slot], 0));
         uint8_t* hdst = bounce_out ? w->h_out[slot] : host_out + (size_t)p * host_out_page;
-        if (packed)
+        if (via_bits) {
+            SHARD_TRY(cudaMemcpyAsync(w->h_bits[hs], w->d_bits[slot], bits_page * np, cudaMemcpyDeviceToHost, w->s_out));
+            SHARD_TRY(cudaEventRecord(w->ev_hb[hs], w->s_out));
+            hchunk[hs] = HostChunk{p, np};
+        } else if (packed)
             SHARD_TRY(cudaMemcpyAsync(hdst, w->d_bits[slot], bits_page * np, cudaMemcpyDeviceToHost, w->s_out));
         else
             SHARD_TRY(copy2d(hdst, g.out_cols, w->d_out[slot], o_step, g.out_cols, (size_t)g.out_rows * np, cudaMemcpyDeviceToHost, w->s_out));
         SHARD_TRY(cudaEventRecord(w->ev_out[slot], w->s_out));
         if (bounce_out) pend[slot] = Pending{p, np};
+        if (via_bits && it >= 2) { rc = expand(it - 2); if (rc) return rc; }
+    }
+    if (via_bits) {
+        for (int j = std::max(0, it - 2); j < it; ++j) { int rc = expand(j); if (rc) return rc; }
+        for (int j = std::max(0, it - DeviceWorker::HB); j < it; ++j) w->pool.wait(w->hb_left[j % DeviceWorker::HB]);
     }
     SHARD_TRY(cudaStreamSynchronize(w->s_out));
     SHARD_TRY(cudaStreamSynchronize(c->stream));
@@ -1541,6 +1743,7 @@ int run_shard(DeviceWorker* w, int method, const uint8_t* pages, int p0, int p1,
     const int rc = run_shard_locked(w, method, pages, p0, p1, rows, cols, window, params, morph_iters, masks, g, err, packed);
     if (rc) {
         cudaSetDevice(w->ctx->device);
+        for (int i = 0; i < DeviceWorker::HB; ++i) w->pool.wait(w->hb_left[i]);      // expansions already handed out write into `masks`
         cudaStreamSynchronize(w->s_in); cudaStreamSynchronize(w->ctx->stream); cudaStreamSynchronize(w->s_out);
         cudaGetLastError();
         w->poisoned = true;
@@ -1641,6 +1844,8 @@ extern "C" int prl_cuda_set_global_option(const char* name, long long value)
     if (!name) return PRL_E_INVALID;
     if (strcmp(name, "batch_chunk_pages") == 0) g_batch_chunk_pages.store(value < 0 ? 0 : value);
     else if (strcmp(name, "batch_stage_pageable") == 0) g_batch_pageable.store(value != 0);
+    else if (strcmp(name, "batch_unpack_nt") == 0) g_batch_unpack_nt.store(value != 0);
+    else if (strcmp(name, "batch_unpack_threads") == 0) g_batch_unpack_threads.store(std::min<long long>(std::max<long long>(value, -1), 64));
     else return prl_set_err(nullptr, PRL_E_INVALID, "unknown global option");
     return PRL_OK;
 }

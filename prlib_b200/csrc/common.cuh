@@ -80,6 +80,7 @@ struct prl_cuda_ctx {
     // pinned host staging
 
     bool force_exact = false;   // validation: kernel 2 runs the literal FP64 path for every pixel
+    bool gauss_legacy = false;   // adaptiveThreshold GAUSSIAN_C: the two-kernel form (float32 plane in HBM) for every block size (A/B and tests)
     bool median_legacy = false;  // medianBlur 3 / 5: the radix-select kernel instead of the selection network (A/B and tests)
     bool dbg_skip_exact = false; // DIAGNOSTIC ONLY: kernel 2 (TMA) leaves undecided pixels black; timing experiments, never a result
     int k1_bands = 0;           // kernel 1: row bands per page (0 = automatic)

@@ -275,6 +275,18 @@ def test_adaptive_threshold_equals_cv2(ctx, method):
 
 
 @pytest.mark.gpu
+def test_gaussian_mean_single_kernel_equals_the_two_kernel_form(ctx):
+    rng = np.random.default_rng(31)
+    for shape in ((97, 131), (33, 64), (200, 257), (40, 9), (3, 300)):
+        g = rng.integers(0, 256, shape, dtype=np.uint8)
+        for bs in (3, 7, 19, 35, 63):
+            ctx.set_option("gauss_legacy", 1)
+            want = ctx.adaptive_threshold(g, 255, 1, 0, bs, 4.0)
+            ctx.set_option("gauss_legacy", 0)
+            assert np.array_equal(ctx.adaptive_threshold(g, 255, 1, 0, bs, 4.0), want), (shape, bs)
+
+
+@pytest.mark.gpu
 def test_family_equals_the_reference(ctx):
     import prlib_b200
     from prlib_b200 import PrlCudaError

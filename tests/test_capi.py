@@ -123,3 +123,20 @@ def test_committed_dram_traffic_agrees_with_the_byte_model():
         model = per_page * t[fam]["pages_per_launch"]
         assert abs(t[fam]["dram_bytes_per_launch"] / model - 1.0) < 0.03, (fam, t[fam]["dram_bytes_per_launch"], model)
     assert t.get("commit")
+
+
+def test_host_side_mask_expansion_equals_the_pix_layout():
+    """prl_cuda_unpack_mask_host, the host half of the batch loader's 1-bit return path (no GPU involved): PIX words
+    (bit 31 - (x & 31) of word x >> 5, 1 = black) to 0/255 bytes, AVX2 and portable loops, widths around the 32-pixel groups"""
+    import numpy as np
+    from prlib_b200 import capi, unpack_lept1
+    L = capi.load()
+    rng = np.random.default_rng(4)
+    for rows, cols in ((1, 1), (3, 31), (5, 32), (4, 33), (7, 64), (9, 100), (37, 421), (11, 2479)):
+        wpl = (cols + 31) // 32
+        bits = rng.integers(0, 1 << 32, (rows, wpl), dtype=np.uint64).astype(np.uint32)
+        want = unpack_lept1(bits, cols)
+        for scalar in (0, 1):
+            got = np.full((rows, cols), 7, np.uint8)
+            assert L.prl_cuda_unpack_mask_host(bits.ctypes.data, rows, cols, got.ctypes.data, scalar) == capi.PRL_OK
+            assert np.array_equal(got, want), (rows, cols, scalar)

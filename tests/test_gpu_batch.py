@@ -366,12 +366,19 @@ def test_batch_loader_pinned_pageable_and_concurrent_callers():
         prlib_b200.set_global_option("batch_stage_pageable", 1)
         for chunk in (1, 2, 100):
             prlib_b200.set_global_option("batch_chunk_pages", chunk)
-            assert np.array_equal(prlib_b200.binarize_batch(pages, 0, 15, (0.2,), 0, devices=[0]), want), chunk
+            # the masks' way back: as bytes, or as bits expanded by 1 / 4 / 7 host threads (9 chunks of one page: every host slot reused)
+            for unpack in (0, 1, 4, 7):
+                prlib_b200.set_global_option("batch_unpack_threads", unpack)
+                assert np.array_equal(prlib_b200.binarize_batch(pages, 0, 15, (0.2,), 0, devices=[0]), want), (chunk, unpack)
+                got = prlib_b200.binarize_batch(pin_in.array, 0, 15, (0.2,), 0, devices=[0], out=pin_out.array)
+                assert np.array_equal(got, want), (chunk, unpack)
+            prlib_b200.set_global_option("batch_unpack_threads", -1)
             assert np.array_equal(prlib_b200.unpack_lept1(
                 prlib_b200.binarize_batch(pages, 0, 15, (0.2,), 0, devices=[0], packed=True), want.shape[2]), want), chunk
     finally:
         prlib_b200.set_global_option("batch_chunk_pages", 0)
         prlib_b200.set_global_option("batch_stage_pageable", 1)
+        prlib_b200.set_global_option("batch_unpack_threads", -1)
     with pytest.raises(ValueError):
         prlib_b200.set_global_option("no_such_option", 1)
     # concurrent callers, same device, different methods and shapes
