@@ -194,8 +194,10 @@ int prl_cuda_host_unregister(void* p);
  * 0 = hand it to the driver as it is), "batch_unpack_threads" (n > 0: the byte masks of prl_cuda_binarize_batch cross
  * PCIe as 1 bit per pixel into library-owned pinned buffers and n host threads per device expand them into `masks`
  * while later chunks are in flight -- the link carries 1.125 instead of 2 bytes per pixel and `masks` need not be
- * page-locked; 0: the bytes themselves cross; -1, the default: min(8, host cores per GPU - 2) threads where that is at
- * least 6, else 0 -- [B200 box, 16 cores] 4.8 k A4 pages/s as bytes, 5.9 k as bits with 8 threads, 3.2 k with 4),
+ * page-locked; 0: the bytes themselves cross; -1, the default: on boxes of 4 or more GPUs always bits with host cores per
+ * GPU - 1 threads (2..8), on 1 or 2 GPUs min(8, cores per GPU - 2) threads where that is at least 6, else bytes --
+ * [1 B200, 16 cores] 4.8 k A4 pages/s as bytes, 5.9 k as bits with 8 threads, 3.2 k with 4; [8 B200, 32 cores] 7.6 k as
+ * bytes, 9.3 k as bits with 3 threads per GPU),
  * "batch_unpack_nt" (1, default: the expansion uses non-temporal stores; 0: ordinary stores -- A/B switch).
  * PRL_E_INVALID for an unknown name. */
 int prl_cuda_set_global_option(const char* name, long long value);

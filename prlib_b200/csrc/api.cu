@@ -1431,9 +1431,14 @@ static void unpack_rows(const uint32_t* bits, size_t wpl, uint8_t* dst, int rows
 static void unpack_rows(const uint32_t* bits, size_t wpl, uint8_t* dst, int rows, int cols) { unpack_rows_scalar(bits, wpl, dst, rows, cols); }
 #endif
 
-// How many host threads per device expand masks when the caller did not say.  The expansion writes 8.7 MB per A4 page: on the
-// measured boxes it takes ~8 threads to keep up with the link ([B200 box, 16 cores] 4 threads 3.2 k pages/s, 8 threads 5.9 k,
-// bytes over PCIe 4.8 k), so it only pays where each GPU of the box has that many cores to itself; otherwise the bytes cross.
+// How many host threads per device expand masks when the caller did not say.  The expansion writes 8.7 MB per A4 page, about
+// 0.75 k pages/s per thread on the measured hosts, and it competes with what the same call achieves sending bytes:
+//   [1 B200, 16 cores]   bytes 4.8 k pages/s; bits with 4 threads 3.2 k, 8 threads 5.9 k, 12 threads 5.8 k
+//   [2 B200]             bytes 9.0 k; bits with 8 threads per GPU 9.3 k
+//   [8 B200, 32 cores]   bytes 7.6 k (D2H into host memory is that box's weak direction: 91 GB/s alone, 63 GB/s beside H2D, against
+//                        187 GB/s for H2D alone); bits with 1 thread per GPU 5.9 k, 2: 8.6 k, 3: 9.3 k, 4: 9.4 k, 6: 9.4 k
+// So: on boxes of four or more GPUs, where the link is shared and bytes are the expensive direction, always bits with
+// cores per GPU - 1 threads (2 to 8); on one or two GPUs only where 6 or more threads can be spared, else bytes.
 static int unpack_threads_auto()
 {
     static const int n = [] {
@@ -1443,7 +1448,9 @@ static int unpack_threads_auto()
         if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
 #endif
         const int gpus = std::max(1, prl_cuda_device_count());
-        const int t = std::min(8, cores / gpus - 2);              // leave the submitting thread and the caller some room
+        const int per_gpu = cores / gpus;
+        if (gpus >= 4) return std::min(8, std::max(2, per_gpu - 1));
+        const int t = std::min(8, per_gpu - 2);                   // leave the submitting thread and the caller some room
         return t >= 6 ? t : 0;
     }();
     return n;
