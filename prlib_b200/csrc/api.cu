@@ -13,6 +13,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #if defined(__linux__)
 #include <sched.h>
 #endif
@@ -120,6 +121,148 @@ static inline size_t round16(size_t v) { return (v + 15) & ~(size_t)15; }
 
 // 2-D copy that degenerates to ONE linear DMA when both pitches equal the row width: the copy
 // engines move 2.4 KB rows at ~15 GB/s but a linear range at ~55 GB/s (measured, PCIe Gen5 x16).
+// ---- masks over PCIe at 1 bit per pixel.  The end-to-end rate of prl_cuda_binarize_batch is the PCIe link's: 8.7 MB in and 8.7 MB
+// out per A4 page, both directions busy ([B200 box] 49.6 GB/s each way together, 55.6 GB/s for H2D alone).  The result is a 0/255
+// mask, so it crosses as PIX words (prl_k_pack_mask: bit 31 - (x & 31) of word x >> 5, 1 = black) into library-owned pinned
+// buffers and a few host threads per device expand it into the caller's buffer while later chunks are in flight: the link then
+// carries 1.125 bytes per pixel instead of 2, and the caller's mask buffer no longer has to be page-locked.
+static void unpack_rows_scalar(const uint32_t* bits, size_t wpl, uint8_t* dst, size_t dpitch, int rows, int cols)
+{
+    static uint64_t lut[256];
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (int b = 0; b < 256; ++b) {
+            uint64_t v = 0;
+            for (int i = 0; i < 8; ++i) if (!((b >> (7 - i)) & 1)) v |= 0xffull << (8 * i);    // first pixel = top bit; 0 = white = 255
+            lut[b] = v;
+        }
+    });
+    for (int y = 0; y < rows; ++y) {
+        const uint32_t* w = bits + (size_t)y * wpl;
+        uint8_t* o = dst + (size_t)y * dpitch;
+        int x = 0;
+        for (; x + 32 <= cols; x += 32) {
+            const uint32_t v = w[x >> 5];
+            for (int k = 0; k < 4; ++k) memcpy(o + x + 8 * k, &lut[(v >> (24 - 8 * k)) & 0xffu], 8);
+        }
+        for (; x < cols; ++x) o[x] = ((w[x >> 5] >> (31 - (x & 31))) & 1u) ? 0 : 255;
+    }
+}
+
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("avx2"))) static void unpack_rows_avx2(const uint32_t* bits, size_t wpl, uint8_t* dst, size_t dpitch, int rows, int cols)
+{
+    // byte j of the vector takes source byte 3 - j / 8 of the word (PIX words are most-significant-bit first), bit 7 - j % 8.
+    // The destination is written once and not read back here: aligned non-temporal stores (no read-for-ownership traffic; an
+    // ordinary store loop tops out near 7 GB/s per thread); rows start at any alignment, so the bit stream is re-cut at the
+    // first 32-byte boundary of each row.
+    const __m256i pick = _mm256_setr_epi8(3, 3, 3, 3, 3, 3, 3, 3, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0);
+    const __m256i bit = _mm256_set1_epi64x((long long)0x0102040810204080ull);
+    const bool nt = g_batch_unpack_nt.load() != 0;
+    for (int y = 0; y < rows; ++y) {
+        const uint32_t* w = bits + (size_t)y * wpl;
+        uint8_t* o = dst + (size_t)y * dpitch;
+        const int head = std::min(cols, (int)((32 - ((uintptr_t)o & 31)) & 31));
+        int x = 0;
+        for (; x < head; ++x) o[x] = ((w[x >> 5] >> (31 - (x & 31))) & 1u) ? 0 : 255;
+        const int sh = head & 31;
+        for (int i = 0; x + 32 <= cols; x += 32, ++i) {
+            const uint32_t v = sh ? (w[i] << sh) | (w[i + 1] >> (32 - sh)) : w[i];            // pixels x .. x + 31, first pixel in the top bit
+            const __m256i e = _mm256_shuffle_epi8(_mm256_set1_epi32((int)v), pick);
+            const __m256i white = _mm256_cmpeq_epi8(_mm256_and_si256(e, bit), _mm256_setzero_si256());
+            if (nt) _mm256_stream_si256(reinterpret_cast<__m256i*>(o + x), white); else _mm256_store_si256(reinterpret_cast<__m256i*>(o + x), white);
+        }
+        for (; x < cols; ++x) o[x] = ((w[x >> 5] >> (31 - (x & 31))) & 1u) ? 0 : 255;
+    }
+    _mm_sfence();
+}
+static void unpack_rows(const uint32_t* bits, size_t wpl, uint8_t* dst, size_t dpitch, int rows, int cols)
+{
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) unpack_rows_avx2(bits, wpl, dst, dpitch, rows, cols); else unpack_rows_scalar(bits, wpl, dst, dpitch, rows, cols);
+}
+#else
+static void unpack_rows(const uint32_t* bits, size_t wpl, uint8_t* dst, size_t dpitch, int rows, int cols) { unpack_rows_scalar(bits, wpl, dst, dpitch, rows, cols); }
+#endif
+
+// How many host threads per device expand masks when the caller did not say.  The expansion writes 8.7 MB per A4 page, about
+// 0.75 k pages/s per thread on the measured hosts, and it competes with what the same call achieves sending bytes:
+//   [1 B200, 16 cores]   bytes 4.8 k pages/s; bits with 4 threads 3.2 k, 8 threads 5.9 k, 12 threads 5.8 k
+//   [2 B200]             bytes 9.0 k; bits with 8 threads per GPU 9.3 k
+//   [8 B200, 32 cores]   bytes 7.6 k (D2H into host memory is that box's weak direction: 91 GB/s alone, 63 GB/s beside H2D, against
+//                        187 GB/s for H2D alone); bits with 1 thread per GPU 5.9 k, 2: 8.6 k, 3: 9.3 k, 4: 9.4 k, 6: 9.4 k
+// So: on boxes of four or more GPUs, where the link is shared and bytes are the expensive direction, always bits with
+// cores per GPU - 1 threads (2 to 8); on one or two GPUs only where 6 or more threads can be spared, else bytes.
+static int unpack_threads_auto()
+{
+    static const int n = [] {
+        int cores = (int)std::thread::hardware_concurrency();
+#if defined(__linux__)
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
+#endif
+        const int gpus = std::max(1, prl_cuda_device_count());
+        const int per_gpu = cores / gpus;
+        if (gpus >= 4) return std::min(8, std::max(2, per_gpu - 1));
+        const int t = std::min(8, per_gpu - 2);                   // leave the submitting thread and the caller some room
+        return t >= 6 ? t : 0;
+    }();
+    return n;
+}
+
+extern "C" int prl_cuda_batch_unpack_threads(void)
+{
+    const long long v = g_batch_unpack_threads.load();
+    return v < 0 ? unpack_threads_auto() : (int)v;
+}
+
+// test hook: the host-side expansion alone
+extern "C" int prl_cuda_unpack_mask_host(const uint32_t* bits, int rows, int cols, uint8_t* mask, int force_scalar)
+{
+    if (!bits || !mask || rows <= 0 || cols <= 0) return PRL_E_INVALID;
+    const size_t wpl = ((size_t)cols + 31) / 32;
+    if (force_scalar) unpack_rows_scalar(bits, wpl, mask, (size_t)cols, rows, cols); else unpack_rows(bits, wpl, mask, (size_t)cols, rows, cols);
+    return PRL_OK;
+}
+
+namespace {
+// a few host threads that expand packed masks (and stage pageable images); a job is a band of rows
+struct UnpackPool {
+    struct Job { std::function<void()> fn; std::atomic<int>* left; };
+    std::vector<std::thread> threads;
+    std::mutex mu;
+    std::condition_variable cv, cv_done;
+    std::deque<Job> jobs;
+    bool stop = false;
+    void start(int n)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        while ((int)threads.size() < n)
+            threads.emplace_back([this] {
+                for (;;) {
+                    Job j;
+                    {
+                        std::unique_lock<std::mutex> lk2(mu);
+                        cv.wait(lk2, [this] { return stop || !jobs.empty(); });
+                        if (jobs.empty()) return;
+                        j = std::move(jobs.front()); jobs.pop_front();
+                    }
+                    j.fn();
+                    if (j.left->fetch_sub(1) == 1) { std::lock_guard<std::mutex> lk2(mu); cv_done.notify_all(); }
+                }
+            });
+    }
+    void submit(std::function<void()> fn, std::atomic<int>* left) { { std::lock_guard<std::mutex> lk(mu); jobs.push_back(Job{std::move(fn), left}); } cv.notify_one(); }
+    void wait(std::atomic<int>& left) { std::unique_lock<std::mutex> lk(mu); cv_done.wait(lk, [&] { return left.load() == 0; }); }
+    ~UnpackPool()
+    {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        for (auto& t : threads) t.join();
+    }
+};
+}  // namespace
+
 static cudaError_t copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
                           cudaMemcpyKind kind, cudaStream_t s)
 {
@@ -590,6 +733,9 @@ static int local_host(prl_cuda_ctx* c, int method, int mode, const uint8_t* src,
     if (gray_out)
         PRL_CUDA_TRY(c, copy2d(gray_out, gray_step, c->d_in, in_step, cols, rows, cudaMemcpyDeviceToHost, c->stream));
     // dense device mask when the caller's rows are dense too (a continuous cv::Mat): one linear D2H
+    // (library-side staging -- the image copied into pinned memory in bands by a pool of host threads, the mask back as bits and
+    // expanded by them -- was measured for this call and is slower than the driver's own staged copies at every thread count:
+    // A4 gray 0.99 ms with the driver, 1.24 ms with 8 threads, 2.1 ms with 2; the pool's wake-ups cost more than they save)
     const size_t o_step = (dst_step == (size_t)g.out_cols) ? (size_t)g.out_cols : round16(g.out_cols);
     rc = prl_ensure(c, (void**)&c->d_out, &c->d_out_bytes, o_step * g.out_rows + 16); if (rc) return rc;
     rc = local_batch_dev(c, method, mode, c->d_in, 1, rows, cols, in_step, in_step * rows, window, params, morph_iters,
@@ -1367,146 +1513,7 @@ extern "C" int prl_cuda_otsu_tiles(prl_cuda_ctx* c, const uint8_t* src, int rows
 // host batch: pinned-memory loader + page dispatcher (one host thread per device, no collective)
 // ------------------------------------------------------------------------------------------------
 
-// ---- masks over PCIe at 1 bit per pixel.  The end-to-end rate of prl_cuda_binarize_batch is the PCIe link's: 8.7 MB in and 8.7 MB
-// out per A4 page, both directions busy ([B200 box] 49.6 GB/s each way together, 55.6 GB/s for H2D alone).  The result is a 0/255
-// mask, so it crosses as PIX words (prl_k_pack_mask: bit 31 - (x & 31) of word x >> 5, 1 = black) into library-owned pinned
-// buffers and a few host threads per device expand it into the caller's buffer while later chunks are in flight: the link then
-// carries 1.125 bytes per pixel instead of 2, and the caller's mask buffer no longer has to be page-locked.
-static void unpack_rows_scalar(const uint32_t* bits, size_t wpl, uint8_t* dst, int rows, int cols)
-{
-    static uint64_t lut[256];
-    static std::once_flag once;
-    std::call_once(once, [] {
-        for (int b = 0; b < 256; ++b) {
-            uint64_t v = 0;
-            for (int i = 0; i < 8; ++i) if (!((b >> (7 - i)) & 1)) v |= 0xffull << (8 * i);    // first pixel = top bit; 0 = white = 255
-            lut[b] = v;
-        }
-    });
-    for (int y = 0; y < rows; ++y) {
-        const uint32_t* w = bits + (size_t)y * wpl;
-        uint8_t* o = dst + (size_t)y * cols;
-        int x = 0;
-        for (; x + 32 <= cols; x += 32) {
-            const uint32_t v = w[x >> 5];
-            for (int k = 0; k < 4; ++k) memcpy(o + x + 8 * k, &lut[(v >> (24 - 8 * k)) & 0xffu], 8);
-        }
-        for (; x < cols; ++x) o[x] = ((w[x >> 5] >> (31 - (x & 31))) & 1u) ? 0 : 255;
-    }
-}
-
-#if defined(__x86_64__) && defined(__GNUC__)
-__attribute__((target("avx2"))) static void unpack_rows_avx2(const uint32_t* bits, size_t wpl, uint8_t* dst, int rows, int cols)
-{
-    // byte j of the vector takes source byte 3 - j / 8 of the word (PIX words are most-significant-bit first), bit 7 - j % 8.
-    // The destination is written once and not read back here: aligned non-temporal stores (no read-for-ownership traffic; an
-    // ordinary store loop tops out near 7 GB/s per thread); rows start at any alignment, so the bit stream is re-cut at the
-    // first 32-byte boundary of each row.
-    const __m256i pick = _mm256_setr_epi8(3, 3, 3, 3, 3, 3, 3, 3, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0);
-    const __m256i bit = _mm256_set1_epi64x((long long)0x0102040810204080ull);
-    const bool nt = g_batch_unpack_nt.load() != 0;
-    for (int y = 0; y < rows; ++y) {
-        const uint32_t* w = bits + (size_t)y * wpl;
-        uint8_t* o = dst + (size_t)y * cols;
-        const int head = std::min(cols, (int)((32 - ((uintptr_t)o & 31)) & 31));
-        int x = 0;
-        for (; x < head; ++x) o[x] = ((w[x >> 5] >> (31 - (x & 31))) & 1u) ? 0 : 255;
-        const int sh = head & 31;
-        for (int i = 0; x + 32 <= cols; x += 32, ++i) {
-            const uint32_t v = sh ? (w[i] << sh) | (w[i + 1] >> (32 - sh)) : w[i];            // pixels x .. x + 31, first pixel in the top bit
-            const __m256i e = _mm256_shuffle_epi8(_mm256_set1_epi32((int)v), pick);
-            const __m256i white = _mm256_cmpeq_epi8(_mm256_and_si256(e, bit), _mm256_setzero_si256());
-            if (nt) _mm256_stream_si256(reinterpret_cast<__m256i*>(o + x), white); else _mm256_store_si256(reinterpret_cast<__m256i*>(o + x), white);
-        }
-        for (; x < cols; ++x) o[x] = ((w[x >> 5] >> (31 - (x & 31))) & 1u) ? 0 : 255;
-    }
-    _mm_sfence();
-}
-static void unpack_rows(const uint32_t* bits, size_t wpl, uint8_t* dst, int rows, int cols)
-{
-    static const bool avx2 = __builtin_cpu_supports("avx2");
-    if (avx2) unpack_rows_avx2(bits, wpl, dst, rows, cols); else unpack_rows_scalar(bits, wpl, dst, rows, cols);
-}
-#else
-static void unpack_rows(const uint32_t* bits, size_t wpl, uint8_t* dst, int rows, int cols) { unpack_rows_scalar(bits, wpl, dst, rows, cols); }
-#endif
-
-// How many host threads per device expand masks when the caller did not say.  The expansion writes 8.7 MB per A4 page, about
-// 0.75 k pages/s per thread on the measured hosts, and it competes with what the same call achieves sending bytes:
-//   [1 B200, 16 cores]   bytes 4.8 k pages/s; bits with 4 threads 3.2 k, 8 threads 5.9 k, 12 threads 5.8 k
-//   [2 B200]             bytes 9.0 k; bits with 8 threads per GPU 9.3 k
-//   [8 B200, 32 cores]   bytes 7.6 k (D2H into host memory is that box's weak direction: 91 GB/s alone, 63 GB/s beside H2D, against
-//                        187 GB/s for H2D alone); bits with 1 thread per GPU 5.9 k, 2: 8.6 k, 3: 9.3 k, 4: 9.4 k, 6: 9.4 k
-// So: on boxes of four or more GPUs, where the link is shared and bytes are the expensive direction, always bits with
-// cores per GPU - 1 threads (2 to 8); on one or two GPUs only where 6 or more threads can be spared, else bytes.
-static int unpack_threads_auto()
-{
-    static const int n = [] {
-        int cores = (int)std::thread::hardware_concurrency();
-#if defined(__linux__)
-        cpu_set_t set;
-        if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
-#endif
-        const int gpus = std::max(1, prl_cuda_device_count());
-        const int per_gpu = cores / gpus;
-        if (gpus >= 4) return std::min(8, std::max(2, per_gpu - 1));
-        const int t = std::min(8, per_gpu - 2);                   // leave the submitting thread and the caller some room
-        return t >= 6 ? t : 0;
-    }();
-    return n;
-}
-
-extern "C" int prl_cuda_batch_unpack_threads(void)
-{
-    const long long v = g_batch_unpack_threads.load();
-    return v < 0 ? unpack_threads_auto() : (int)v;
-}
-
-// test hook: the host-side expansion alone
-extern "C" int prl_cuda_unpack_mask_host(const uint32_t* bits, int rows, int cols, uint8_t* mask, int force_scalar)
-{
-    if (!bits || !mask || rows <= 0 || cols <= 0) return PRL_E_INVALID;
-    const size_t wpl = ((size_t)cols + 31) / 32;
-    if (force_scalar) unpack_rows_scalar(bits, wpl, mask, rows, cols); else unpack_rows(bits, wpl, mask, rows, cols);
-    return PRL_OK;
-}
-
 namespace {
-
-// a few threads per device worker that expand packed pages; a job is a band of rows of one page
-struct UnpackPool {
-    struct Job { const uint32_t* bits; size_t wpl; uint8_t* dst; int rows, cols; std::atomic<int>* left; };
-    std::vector<std::thread> threads;
-    std::mutex mu;
-    std::condition_variable cv, cv_done;
-    std::deque<Job> jobs;
-    bool stop = false;
-    void start(int n)
-    {
-        while ((int)threads.size() < n)
-            threads.emplace_back([this] {
-                for (;;) {
-                    Job j;
-                    {
-                        std::unique_lock<std::mutex> lk(mu);
-                        cv.wait(lk, [this] { return stop || !jobs.empty(); });
-                        if (jobs.empty()) return;
-                        j = jobs.front(); jobs.pop_front();
-                    }
-                    unpack_rows(j.bits, j.wpl, j.dst, j.rows, j.cols);
-                    if (j.left->fetch_sub(1) == 1) { std::lock_guard<std::mutex> lk(mu); cv_done.notify_all(); }
-                }
-            });
-    }
-    void submit(const Job& j) { { std::lock_guard<std::mutex> lk(mu); jobs.push_back(j); } cv.notify_one(); }
-    void wait(std::atomic<int>& left) { std::unique_lock<std::mutex> lk(mu); cv_done.wait(lk, [&] { return left.load() == 0; }); }
-    ~UnpackPool()
-    {
-        { std::lock_guard<std::mutex> lk(mu); stop = true; }
-        cv.notify_all();
-        for (auto& t : threads) t.join();
-    }
-};
 
 struct DeviceWorker {
     prl_cuda_ctx* ctx = nullptr;
@@ -1660,9 +1667,10 @@ int run_shard_locked(DeviceWorker* w, int method, const uint8_t* pages, int p0, 
         for (int i = 0; i < hchunk[hs].np; ++i)
             for (int b = 0; b < bands; ++b) {
                 const int r0 = (int)((long long)g.out_rows * b / bands), r1 = (int)((long long)g.out_rows * (b + 1) / bands);
-                w->pool.submit(UnpackPool::Job{w->h_bits[hs] + ((size_t)i * g.out_rows + r0) * wpl, wpl,
-                                               masks + ((size_t)(hchunk[hs].p + i) * g.out_rows + r0) * g.out_cols, r1 - r0, g.out_cols,
-                                               &w->hb_left[hs]});
+                const uint32_t* jb = w->h_bits[hs] + ((size_t)i * g.out_rows + r0) * wpl;
+                uint8_t* jd = masks + ((size_t)(hchunk[hs].p + i) * g.out_rows + r0) * g.out_cols;
+                const int jr = r1 - r0, jc = g.out_cols;
+                w->pool.submit([jb, wpl, jd, jr, jc] { unpack_rows(jb, wpl, jd, (size_t)jc, jr, jc); }, &w->hb_left[hs]);
             }
         return PRL_OK;
     };
