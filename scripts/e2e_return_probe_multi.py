@@ -18,8 +18,11 @@ hm = torch.empty((n, rows - 1, cols - 1), dtype=torch.uint8, pin_memory=True)
 if rank == 0:
     print(json.dumps({"host_cores": len(os.sched_getaffinity(0)), "gpus": world, "auto_threads": int(capi.load().prl_cuda_batch_unpack_threads())}), flush=True)
 ref = None
-for threads in (0, 1, 2, 3, 4, 6):
-    prlib_b200.set_global_option("batch_unpack_threads", threads)
+cases = [(0, 1), (1, 1), (2, 1), (3, 1), (4, 1), (6, 1)]
+if os.environ.get("PROBE_CASES"):
+    cases = [tuple(int(v) for v in c.split(":")) for c in os.environ["PROBE_CASES"].split(",")]
+for threads, nt in cases:
+    prlib_b200.set_global_option("batch_unpack_threads", threads); prlib_b200.set_global_option("batch_unpack_nt", nt)
     f = lambda: prlib_b200.binarize_batch(hp.numpy(), capi.SAUVOLA, 15, (0.2,), 0, devices=[local], out=hm.numpy())
     f()
     if world > 1: dist.barrier()
@@ -30,4 +33,4 @@ for threads in (0, 1, 2, 3, 4, 6):
     if ref is None: ref = hm.numpy()[::41].copy()
     same = bool(np.array_equal(hm.numpy()[::41], ref))
     if rank == 0:
-        print(json.dumps({"unpack_threads_per_gpu": threads, "pages_per_sec_all_gpus": round(n * world / float(dt[0]), 1), "same": same}), flush=True)
+        print(json.dumps({"unpack_threads_per_gpu": threads, "non_temporal": nt, "pages_per_sec_all_gpus": round(n * world / float(dt[0]), 1), "same": same}), flush=True)
