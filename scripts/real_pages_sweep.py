@@ -32,7 +32,12 @@ CASES = [
     ("NativeAdaptiveMeanGauss", lambda m, im: m.binarizeNativeAdaptive(im, True, 5, 7, 150.0, False)),
     ("AT", lambda m, im: m.binarizeAT(im, 5, 255, 19, 9)), ("AGT", lambda m, im: m.binarizeAGT(im, 5, 255, 19, 9)),
     ("PureAdaptiveGaussian", lambda m, im: m.binarizePureAdaptiveGaussian(im, 255, 15, 4)),
+    ("NativeAdaptiveBilateral5", lambda m, im: m.binarizeNativeAdaptive(im, bilateralFilterBlockSize=5)),
+    ("NativeAdaptiveBilateral9", lambda m, im: m.binarizeNativeAdaptive(im, bilateralFilterBlockSize=9, bilateralFilterColorSigma=40.0,
+                                                                         bilateralFilterSpaceSigma=3.0)),
 ]
+if len(sys.argv) > 2:                         # optional: only the named cases
+    CASES = [c for c in CASES if c[0] in sys.argv[2].split(",")]
 bad = 0; n = 0; exc = 0
 for f in sorted(glob.glob(os.path.join(sys.argv[1], "*.png"))):
     img = cv2.imread(f)                      # BGR, as the samples read it
