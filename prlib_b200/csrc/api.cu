@@ -28,6 +28,7 @@ static std::atomic<long long> g_batch_chunk_pages{0};     // pages per ring slot
 static std::atomic<long long> g_batch_unpack_threads{-1}; // > 0: byte masks cross PCIe as 1 bit per pixel and this many host threads per
                                                           //    device expand them into the caller's buffer; 0: the bytes themselves cross;
                                                           //    -1 (default): decided from the host cores per GPU, see unpack_threads_auto
+static std::atomic<long long> g_batch_unpack_lag{0};      // 0: the expansion jobs wait for their chunk's D2H themselves; 1: the submitting thread does
 static std::atomic<long long> g_batch_unpack_nt{1};       // AVX2 expansion: non-temporal stores (1) or ordinary ones (0)
 static std::atomic<long long> g_batch_pageable{1};        // 1: pageable host buffers are staged through library-owned pinned
                                                           //    bounce buffers (correct overlap, host-memcpy bound); 0: handed to the
@@ -1658,10 +1659,14 @@ int run_shard_locked(DeviceWorker* w, int method, const uint8_t* pages, int p0, 
     // and must be over before the slot is reused HB iterations later
     struct HostChunk { int p, np; };
     HostChunk hchunk[DeviceWorker::HB] = {};
-    auto expand = [&](int j) -> int {                                         // chunk j arrived: hand its pages to the pool
+    const bool pool_waits = g_batch_unpack_lag.load() == 0;                   // the pool's threads wait for the chunk themselves
+    auto expand = [&](int j) -> int {                                         // chunk j is on its way: hand its pages to the pool
         const int hs = j % DeviceWorker::HB;
-        cudaError_t e = cudaEventSynchronize(w->ev_hb[hs]);
-        if (e != cudaSuccess) { *err = std::string("cudaEventSynchronize: ") + cudaGetErrorString(e); return PRL_E_CUDA; }
+        cudaEvent_t arrived = pool_waits ? w->ev_hb[hs] : nullptr;
+        if (!pool_waits) {
+            cudaError_t e = cudaEventSynchronize(w->ev_hb[hs]);
+            if (e != cudaSuccess) { *err = std::string("cudaEventSynchronize: ") + cudaGetErrorString(e); return PRL_E_CUDA; }
+        }
         const int bands = std::max(1, std::min(unpack_threads, 4));           // a page in a few bands: short jobs, even load
         w->hb_left[hs].store(hchunk[hs].np * bands);
         for (int i = 0; i < hchunk[hs].np; ++i)
@@ -1670,7 +1675,10 @@ int run_shard_locked(DeviceWorker* w, int method, const uint8_t* pages, int p0, 
                 const uint32_t* jb = w->h_bits[hs] + ((size_t)i * g.out_rows + r0) * wpl;
                 uint8_t* jd = masks + ((size_t)(hchunk[hs].p + i) * g.out_rows + r0) * g.out_cols;
                 const int jr = r1 - r0, jc = g.out_cols;
-                w->pool.submit([jb, wpl, jd, jr, jc] { unpack_rows(jb, wpl, jd, (size_t)jc, jr, jc); }, &w->hb_left[hs]);
+                w->pool.submit([arrived, jb, wpl, jd, jr, jc] {
+                    if (arrived) cudaEventSynchronize(arrived);                   // a failed copy surfaces at the stream synchronisation below
+                    unpack_rows(jb, wpl, jd, (size_t)jc, jr, jc);
+                }, &w->hb_left[hs]);
             }
         return PRL_OK;
     };
@@ -1732,10 +1740,11 @@ int run_shard_locked(DeviceWorker* w, int method, const uint8_t* pages, int p0, 
             SHARD_TRY(copy2d(hdst, g.out_cols, w->d_out[slot], o_step, g.out_cols, (size_t)g.out_rows * np, cudaMemcpyDeviceToHost, w->s_out));
         SHARD_TRY(cudaEventRecord(w->ev_out[slot], w->s_out));
         if (bounce_out) pend[slot] = Pending{p, np};
-        if (via_bits && it >= 2) { rc = expand(it - 2); if (rc) return rc; }
+        if (via_bits && pool_waits) { rc = expand(it); if (rc) return rc; }
+        else if (via_bits && it >= 2) { rc = expand(it - 2); if (rc) return rc; }
     }
     if (via_bits) {
-        for (int j = std::max(0, it - 2); j < it; ++j) { int rc = expand(j); if (rc) return rc; }
+        if (!pool_waits) for (int j = std::max(0, it - 2); j < it; ++j) { int rc = expand(j); if (rc) return rc; }
         for (int j = std::max(0, it - DeviceWorker::HB); j < it; ++j) w->pool.wait(w->hb_left[j % DeviceWorker::HB]);
     }
     SHARD_TRY(cudaStreamSynchronize(w->s_out));
@@ -1860,6 +1869,7 @@ extern "C" int prl_cuda_set_global_option(const char* name, long long value)
     if (strcmp(name, "batch_chunk_pages") == 0) g_batch_chunk_pages.store(value < 0 ? 0 : value);
     else if (strcmp(name, "batch_stage_pageable") == 0) g_batch_pageable.store(value != 0);
     else if (strcmp(name, "batch_unpack_nt") == 0) g_batch_unpack_nt.store(value != 0);
+    else if (strcmp(name, "batch_unpack_lag") == 0) g_batch_unpack_lag.store(value != 0);
     else if (strcmp(name, "batch_unpack_threads") == 0) g_batch_unpack_threads.store(std::min<long long>(std::max<long long>(value, -1), 64));
     else return prl_set_err(nullptr, PRL_E_INVALID, "unknown global option");
     return PRL_OK;
