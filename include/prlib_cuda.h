@@ -198,7 +198,9 @@ int prl_cuda_host_unregister(void* p);
  * GPU - 1 threads (2..8), on 1 or 2 GPUs min(8, cores per GPU - 2) threads where that is at least 6, else bytes --
  * [1 B200, 16 cores] 4.8 k A4 pages/s as bytes, 5.9 k as bits with 8 threads, 3.2 k with 4; [8 B200, 32 cores] 7.6 k as
  * bytes, 9.3 k as bits with 3 threads per GPU),
- * "batch_unpack_nt" (1, default: the expansion uses non-temporal stores; 0: ordinary stores -- A/B switch).
+ * "batch_unpack_nt" (1, default: the expansion uses non-temporal stores; 0: ordinary stores -- A/B switch),
+ * "batch_unpack_lag" (0, default: the expansion jobs wait for their chunk's copy themselves; 1: the submitting thread
+ * waits and hands them out two chunks later -- A/B switch).
  * PRL_E_INVALID for an unknown name. */
 int prl_cuda_set_global_option(const char* name, long long value);
 /* What "batch_unpack_threads" resolves to right now: host threads per device expanding 1-bit masks, 0 = the bytes cross PCIe. */

@@ -420,7 +420,7 @@ class PinnedArray:
 
 
 def set_global_option(name: str, value: int):
-    """prl_cuda_set_global_option: "batch_chunk_pages", "batch_stage_pageable", "batch_unpack_threads" (-1 = automatic), "batch_unpack_nt"."""
+    """prl_cuda_set_global_option: "batch_chunk_pages", "batch_stage_pageable", "batch_unpack_threads" (-1 = automatic), "batch_unpack_nt", "batch_unpack_lag"."""
     rc = capi.load().prl_cuda_set_global_option(name.encode(), int(value))
     if rc != capi.PRL_OK:
         raise ValueError(f"unknown global option {name!r}")

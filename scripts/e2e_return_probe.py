@@ -13,8 +13,10 @@ hm = torch.empty((n, rows - 1, cols - 1), dtype=torch.uint8, pin_memory=True)
 pageable = np.empty((n, rows - 1, cols - 1), np.uint8)
 print(json.dumps({"host_cores": len(os.sched_getaffinity(0))}))
 ref = None
-for threads, nt, out, tag in ((0, 1, hm.numpy(), "bytes over PCIe, pinned"), (4, 1, hm.numpy(), "bits"), (4, 0, hm.numpy(), "bits"), (8, 1, hm.numpy(), "bits"), (8, 0, hm.numpy(), "bits"),
-                              (12, 1, hm.numpy(), "bits"), (12, 0, hm.numpy(), "bits"), (16, 0, hm.numpy(), "bits"), (0, 1, pageable, "bytes over PCIe, pageable masks"), (8, 0, pageable, "bits, pageable masks")):
+for threads, nt, lag, out, tag in ((0, 1, 0, hm.numpy(), "bytes over PCIe, pinned"), (8, 1, 1, hm.numpy(), "bits"), (8, 1, 0, hm.numpy(), "bits"), (8, 1, 1, hm.numpy(), "bits"),
+                                   (8, 1, 0, hm.numpy(), "bits"), (6, 1, 0, hm.numpy(), "bits"), (10, 1, 0, hm.numpy(), "bits"), (8, 0, 0, hm.numpy(), "bits"),
+                                   (8, 1, 0, pageable, "bits, pageable masks")):
+    prlib_b200.set_global_option("batch_unpack_lag", lag)
     prlib_b200.set_global_option("batch_unpack_threads", threads); prlib_b200.set_global_option("batch_unpack_nt", nt)
     f = lambda: prlib_b200.binarize_batch(hp.numpy(), capi.SAUVOLA, 15, (0.2,), 0, devices=[0], out=out)
     f(); f()
@@ -22,4 +24,4 @@ for threads, nt, out, tag in ((0, 1, hm.numpy(), "bytes over PCIe, pinned"), (4,
     for _ in range(4): f()
     dt = (time.perf_counter() - t0) / 4
     if ref is None: ref = out[::37].copy()
-    print(json.dumps({"return": tag, "unpack_threads": threads, "non_temporal": nt, "pages_per_sec": round(n / dt, 1), "same": bool(np.array_equal(out[::37], ref))}), flush=True)
+    print(json.dumps({"return": tag, "unpack_threads": threads, "non_temporal": nt, "submitter_waits": lag, "pages_per_sec": round(n / dt, 1), "same": bool(np.array_equal(out[::37], ref))}), flush=True)
