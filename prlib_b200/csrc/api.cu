@@ -1675,8 +1675,10 @@ int run_shard_locked(DeviceWorker* w, int method, const uint8_t* pages, int p0, 
                 const uint32_t* jb = w->h_bits[hs] + ((size_t)i * g.out_rows + r0) * wpl;
                 uint8_t* jd = masks + ((size_t)(hchunk[hs].p + i) * g.out_rows + r0) * g.out_cols;
                 const int jr = r1 - r0, jc = g.out_cols;
-                w->pool.submit([arrived, jb, wpl, jd, jr, jc] {
-                    if (arrived) cudaEventSynchronize(arrived);                   // a failed copy surfaces at the stream synchronisation below
+                const int dev = c->device;
+                w->pool.submit([arrived, dev, jb, wpl, jd, jr, jc] {
+                    // (the pool's threads start on device 0: waiting there would open a context on it from every process of a box)
+                    if (arrived) { cudaSetDevice(dev); cudaEventSynchronize(arrived); }   // a failed copy surfaces at the stream synchronisation below
                     unpack_rows(jb, wpl, jd, (size_t)jc, jr, jc);
                 }, &w->hb_left[hs]);
             }
