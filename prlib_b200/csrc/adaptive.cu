@@ -285,24 +285,25 @@ gaussf_fused_kernel(const uint8_t* __restrict__ src, size_t step, int rows, int 
     const int tw = kGfTW + n - 1, th = kGfTH + n - 1;
     float* kk = reinterpret_cast<float*>(gf_sm);                         // 64 coefficients
     float* rsum = kk + 64;                                               // th x kGfTW row-pass results
-    uint8_t* tile = reinterpret_cast<uint8_t*>(rsum + (size_t)th * kGfTW);   // th x tw pixels, BORDER_REPLICATE
+    float* tile = rsum + (size_t)th * kGfTW;                             // th x tw pixels as floats (converted once, not per tap), BORDER_REPLICATE
     const int x0 = blockIdx.x * kGfTW, y0 = blockIdx.y * kGfTH;
     for (int i = threadIdx.x; i < n; i += 256) kk[i] = K.k[i];
     for (int i = threadIdx.x; i < tw * th; i += 256) {
         const int ty = i / tw, tx = i - ty * tw;
-        tile[i] = src[(size_t)min(max(y0 - h + ty, 0), rows - 1) * step + min(max(x0 - h + tx, 0), cols - 1)];
+        tile[i] = (float)src[(size_t)min(max(y0 - h + ty, 0), rows - 1) * step + min(max(x0 - h + tx, 0), cols - 1)];
     }
     __syncthreads();
     const int nu = K.n_unfused, cols4 = cols & ~3;
     for (int i = threadIdx.x; i < th * kGfTW; i += 256) {
         const int ty = i / kGfTW, tx = i - ty * kGfTW;
-        const uint8_t* p = tile + ty * tw + tx;
-        float s = __fmul_rn((float)p[0], kk[0]);
+        const float* p = tile + ty * tw + tx;
+        float s = __fmul_rn(p[0], kk[0]);
         if (x0 + tx < cols4) {
-            for (int k = 1; k < n; ++k) s = __fmaf_rn((float)p[k], kk[k], s);
+#pragma unroll 6
+            for (int k = 1; k < n; ++k) s = __fmaf_rn(p[k], kk[k], s);
         } else {
-            for (int k = 1; k <= nu; ++k) s = __fadd_rn(s, __fmul_rn((float)p[k], kk[k]));
-            for (int k = nu + 1; k < n; ++k) s = __fmaf_rn((float)p[k], kk[k], s);
+            for (int k = 1; k <= nu; ++k) s = __fadd_rn(s, __fmul_rn(p[k], kk[k]));
+            for (int k = nu + 1; k < n; ++k) s = __fmaf_rn(p[k], kk[k], s);
         }
         rsum[i] = s;
     }
@@ -316,13 +317,15 @@ gaussf_fused_kernel(const uint8_t* __restrict__ src, size_t step, int rows, int 
         if (x < cols && y < rows) {
             const float* c = rsum + (ly + h) * kGfTW + lx;
             float s = __fmul_rn(c[0], kk[h]);
-            for (int j = 1; j <= h; ++j) {
-                const float pr = __fadd_rn(c[j * kGfTW], c[-j * kGfTW]);
-                s = fused ? __fmaf_rn(pr, kk[h + j], s) : __fadd_rn(s, __fmul_rn(pr, kk[h + j]));
+            if (fused) {
+#pragma unroll 3
+                for (int j = 1; j <= h; ++j) s = __fmaf_rn(__fadd_rn(c[j * kGfTW], c[-j * kGfTW]), kk[h + j], s);
+            } else {
+                for (int j = 1; j <= h; ++j) s = __fadd_rn(s, __fmul_rn(__fadd_rn(c[j * kGfTW], c[-j * kGfTW]), kk[h + j]));
             }
             int mean = __float2int_rn(s);                                // saturate_cast<uchar>(float): cvRound, then clamp
             mean = min(max(mean, 0), 255);
-            const int v = tab_value(T, tile[(ly + h) * tw + lx + h], mean);
+            const int v = tab_value(T, (int)tile[(ly + h) * tw + lx + h], mean);
             dst[(size_t)y * dstep + x] = (uint8_t)v;
             set += v ? 1u : 0u;
         }
@@ -339,8 +342,21 @@ invert_if_dark_kernel(uint8_t* __restrict__ img, size_t step, int rows, int cols
 {
     // mean = maxv * nset / (rows * cols) < 128  <=>  maxv * nset < 128 * rows * cols   (exact in 64-bit integers)
     if ((unsigned long long)maxv * *nset >= 128ull * (unsigned long long)rows * (unsigned long long)cols) return;
-    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
-    if (x < cols) img[(size_t)y * step + x] = (uint8_t)(255 - img[(size_t)y * step + x]);
+    // 16 pixels per thread where the rows are 16-byte aligned
+    const int y = blockIdx.y;
+    uint8_t* row = img + (size_t)y * step;
+    if (((((uintptr_t)img) | step) & 15u) == 0) {
+        const int x = (blockIdx.x * 256 + threadIdx.x) * 16;
+        if (x + 16 <= cols) {
+            uint4 v = *reinterpret_cast<uint4*>(row + x);
+            v.x = ~v.x; v.y = ~v.y; v.z = ~v.z; v.w = ~v.w;              // 255 - b == ~b for bytes
+            *reinterpret_cast<uint4*>(row + x) = v;
+        } else {
+            for (int i = x; i < cols; ++i) row[i] = (uint8_t)(255 - row[i]);
+        }
+    } else {
+        for (int x = (blockIdx.x * 256 + threadIdx.x) * 16, e = min(x + 16, cols); x < e; ++x) row[x] = (uint8_t)(255 - row[x]);
+    }
 }
 
 
@@ -514,7 +530,7 @@ int prl_k_adaptive_threshold(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, 
             const GaussF& Ky = rows > 1 ? K : K1;
             if (block_size <= 63 && rows > 1 && cols > 1 && !ctx->gauss_legacy) {
                 const size_t smem = 64 * sizeof(float) + (size_t)(kGfTH + block_size - 1) * kGfTW * sizeof(float) +
-                                    (size_t)(kGfTH + block_size - 1) * (kGfTW + block_size - 1);
+                                    (size_t)(kGfTH + block_size - 1) * (kGfTW + block_size - 1) * sizeof(float);
                 dim3 grid((cols + kGfTW - 1) / kGfTW, (rows + kGfTH - 1) / kGfTH);
                 PRL_CUDA_TRY(ctx, cudaFuncSetAttribute(gaussf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 prl_launch_scope ls(ctx, FAM_ADAPTIVE);
@@ -536,7 +552,7 @@ int prl_k_adaptive_threshold(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, 
     }
     if (invert_if_dark) {
         prl_launch_scope ls(ctx, FAM_ADAPTIVE);
-        invert_if_dark_kernel<<<dim3((cols + 255) / 256, rows), 256, 0, ctx->stream>>>(d_dst, dst_step, rows, cols, T.maxv, nset);
+        invert_if_dark_kernel<<<dim3((cols + 4095) / 4096, rows), 256, 0, ctx->stream>>>(d_dst, dst_step, rows, cols, T.maxv, nset);
     }
     PRL_CUDA_TRY(ctx, cudaGetLastError());
     return PRL_OK;

@@ -1,5 +1,5 @@
 """Runs every secondary kernel family once or twice on a small batch (for ncu captures).
-usage: profile_ops.py [pages] [what ...]   what in {tiles, otsu, morph, fused, a3, wj}"""
+usage: profile_ops.py [pages] [what ...]   what in {tiles, otsu, morph, fused, a3, wj, adaptive}"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -50,4 +50,13 @@ if "wj" in what:
     local(capi.WOLFJOLION, (0.5,), 15, n, rows, cols)
 if "a3" in what:
     local(capi.NICK, (-0.1,), 101, max(n // 8, 2), 9921, 7016)
+if "adaptive" in what:
+    buf, step = pages(n, rows, cols)
+    out = torch.empty_like(buf)
+    native = dict(gray_first=1, blur=1, blur_ksize=5, assert_ksize=1, method=1, type=1, maxval=255.0, check_maxval=1, block_size=19, auto_block=1,
+                  delta=9.0, invert_if_dark=1)
+    for kw in (native, dict(native, method=0, bilateral_d=5, bilateral_sigma_color=150.0, bilateral_sigma_space=150.0)):
+        for _ in range(2):
+            ctx.binarize_adaptive_batch_dev(buf.data_ptr(), n, rows, cols, step, rows * step, 1, out.data_ptr(), step, rows * step, **kw)
+    torch.cuda.synchronize()
 print("done")
