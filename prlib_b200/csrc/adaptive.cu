@@ -271,10 +271,10 @@ gaussf_cols_threshold_kernel(const float* __restrict__ tmp, size_t tstep, const 
     }
 }
 
-// GAUSSIAN_C in one kernel for blocks up to 63 taps: a CTA owns 64 x 32 outputs, keeps the u8 tile and its row-pass results in
+// GAUSSIAN_C in one kernel for blocks up to 63 taps: a CTA owns 64 x 64 outputs, keeps the u8 tile and its row-pass results in
 // shared memory and runs the column pass from there -- the float32 plane of the two kernels above (4 B per pixel written, n times
 // that re-read through L2) never exists.  Same operations in the same order per pixel, so the same bits.
-constexpr int kGfTW = 64, kGfTH = 32;
+constexpr int kGfTW = 64, kGfTH = 64;
 
 __global__ void __launch_bounds__(256)
 gaussf_fused_kernel(const uint8_t* __restrict__ src, size_t step, int rows, int cols, const __grid_constant__ GaussF K, TabArgs T,
@@ -293,22 +293,33 @@ gaussf_fused_kernel(const uint8_t* __restrict__ src, size_t step, int rows, int 
         tile[i] = (float)src[(size_t)min(max(y0 - h + ty, 0), rows - 1) * step + min(max(x0 - h + tx, 0), cols - 1)];
     }
     __syncthreads();
+    // row pass, four adjacent outputs per thread: one pixel load feeds four running sums, the coefficient window slides through
+    // registers.  Output j meets tap i = k - j at step k; outside [0, n) its coefficient is 0 and fma(v, 0, s) == s exactly, and the
+    // first real step fma(v, k0, 0) is the rounded product OpenCV starts from -- the same bits as one output per thread.
     const int nu = K.n_unfused, cols4 = cols & ~3;
-    for (int i = threadIdx.x; i < th * kGfTW; i += 256) {
-        const int ty = i / kGfTW, tx = i - ty * kGfTW;
+    for (int i = threadIdx.x; i < th * (kGfTW / 4); i += 256) {
+        const int ty = i / (kGfTW / 4), tx = (i - ty * (kGfTW / 4)) * 4;
         const float* p = tile + ty * tw + tx;
-        float s = __fmul_rn(p[0], kk[0]);
-        if (x0 + tx < cols4) {
-#pragma unroll 6
-            for (int k = 1; k < n; ++k) s = __fmaf_rn(p[k], kk[k], s);
+        float* out = rsum + ty * kGfTW + tx;
+        if (x0 + tx < cols4) {                               // cols4 and tx are multiples of 4: all four columns are on this side
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+            for (int k = 0; k < n + 3; ++k) {
+                const float v = p[k], c0 = k < n ? kk[k] : 0.f;
+                s0 = __fmaf_rn(v, c0, s0); s1 = __fmaf_rn(v, c1, s1); s2 = __fmaf_rn(v, c2, s2); s3 = __fmaf_rn(v, c3, s3);
+                c3 = c2; c2 = c1; c1 = c0;
+            }
+            *reinterpret_cast<float4*>(out) = make_float4(s0, s1, s2, s3);
         } else {
-            for (int k = 1; k <= nu; ++k) s = __fadd_rn(s, __fmul_rn(p[k], kk[k]));
-            for (int k = nu + 1; k < n; ++k) s = __fmaf_rn(p[k], kk[k], s);
+            for (int j = 0; j < 4; ++j) {                    // the scalar tail of OpenCV's row filter (and columns past the image)
+                float s = __fmul_rn(p[j], kk[0]);
+                for (int k = 1; k <= nu; ++k) s = __fadd_rn(s, __fmul_rn(p[j + k], kk[k]));
+                for (int k = nu + 1; k < n; ++k) s = __fmaf_rn(p[j + k], kk[k], s);
+                out[j] = s;
+            }
         }
-        rsum[i] = s;
     }
     __syncthreads();
-    const int lx = threadIdx.x % kGfTW, ly0 = threadIdx.x / kGfTW;       // 4 rows of threads, 8 output rows each
+    const int lx = threadIdx.x % kGfTW, ly0 = threadIdx.x / kGfTW;       // 4 rows of threads, 16 output rows each
     const int x = x0 + lx;
     const bool fused = x < (cols & ~7);
     unsigned int set = 0;
@@ -379,11 +390,13 @@ bilateral_kernel(const uint8_t* __restrict__ src, size_t step, int rows, int col
 {
     extern __shared__ __align__(16) uint8_t bil_sm[];
     float* cw = reinterpret_cast<float*>(bil_sm);                       // 256 colour weights
-    uint8_t* tile = bil_sm + 256 * sizeof(float);                       // (kBilTH + 2 radius) x (kBilTW + 2 radius) pixels
+    BilTap* stap = reinterpret_cast<BilTap*>(bil_sm + 256 * sizeof(float));   // the taps (every thread walks the same list)
+    uint8_t* tile = bil_sm + 256 * sizeof(float) + (size_t)n_taps * sizeof(BilTap);   // (kBilTH + 2 radius) x (kBilTW + 2 radius) pixels
     const int tw = kBilTW + 2 * radius, th = kBilTH + 2 * radius;
     const int tid = threadIdx.y * kBilTW + threadIdx.x;
     const int x0 = blockIdx.x * kBilTW - radius, y0 = blockIdx.y * kBilTH - radius;
     for (int i = tid; i < 256; i += kBilTW * kBilTH) cw[i] = color_weight[i];
+    for (int i = tid; i < n_taps; i += kBilTW * kBilTH) stap[i] = taps[i];
     for (int i = tid; i < tw * th; i += kBilTW * kBilTH) {
         const int ty = i / tw, tx = i - ty * tw;
         tile[i] = src[(size_t)reflect101(y0 + ty, rows) * step + reflect101(x0 + tx, cols)];
@@ -394,8 +407,9 @@ bilateral_kernel(const uint8_t* __restrict__ src, size_t step, int rows, int col
     const uint8_t* c = tile + (threadIdx.y + radius) * tw + threadIdx.x + radius;
     const int v0 = *c;
     float sum = 0.f, wsum = 0.f;
+#pragma unroll 4
     for (int k = 0; k < n_taps; ++k) {
-        const BilTap t = taps[k];
+        const BilTap t = stap[k];
         const int v = c[t.dy * tw + t.dx];
         const float w = __fmul_rn(t.sw, cw[abs(v - v0)]);
         wsum = __fadd_rn(wsum, w);
@@ -591,7 +605,8 @@ int prl_k_bilateral(prl_cuda_ctx* ctx, const uint8_t* d_src, int rows, int cols,
     // the tables are a few KB of pageable memory: the copies return once staged, so the locals may go out of scope
     PRL_CUDA_TRY(ctx, cudaMemcpyAsync(d_cw, cw, sizeof(cw), cudaMemcpyHostToDevice, ctx->stream));
     PRL_CUDA_TRY(ctx, cudaMemcpyAsync(d_taps, taps.data(), taps.size() * sizeof(BilTap), cudaMemcpyHostToDevice, ctx->stream));
-    const size_t smem = 256 * sizeof(float) + (size_t)(kBilTW + 2 * radius) * (kBilTH + 2 * radius);
+    const size_t smem = 256 * sizeof(float) + taps.size() * sizeof(BilTap) + (size_t)(kBilTW + 2 * radius) * (kBilTH + 2 * radius);
+    PRL_CUDA_TRY(ctx, cudaFuncSetAttribute(bilateral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
     prl_launch_scope ls(ctx, FAM_ADAPTIVE);
     bilateral_kernel<<<dim3((cols + kBilTW - 1) / kBilTW, (rows + kBilTH - 1) / kBilTH), dim3(kBilTW, kBilTH), smem, ctx->stream>>>(
         d_src, step, rows, cols, radius, d_taps, (int)taps.size(), d_cw, d_dst, dst_step);
