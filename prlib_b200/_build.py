@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libprlib_cuda.so")
-SOURCES = ["api.cu", "integral.cu", "integral_sq.cu", "threshold.cu", "fused.cu", "morph.cu", "misc.cu", "otsu.cu", "edges.cu", "lines.cu", "adaptive.cu"]
+SOURCES = ["api.cu", "batch.cu", "integral.cu", "integral_sq.cu", "threshold.cu", "fused.cu", "morph.cu", "misc.cu", "otsu.cu", "edges.cu", "lines.cu", "adaptive.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-Wall", "-cudart", "static"]
 

@@ -121,6 +121,17 @@ int  prl_ensure(prl_cuda_ctx* ctx, void** ptr, size_t* have, size_t need);      
 void prl_launch_begin(prl_cuda_ctx* ctx, int family);
 void prl_launch_end(prl_cuda_ctx* ctx);
 
+inline size_t round16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+// 2-D copy that degenerates to ONE linear DMA when both pitches equal the row width: the copy
+// engines move 2.4 KB rows at ~15 GB/s but a linear range at ~55 GB/s (measured, PCIe Gen5 x16).
+inline cudaError_t copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
+                          cudaMemcpyKind kind, cudaStream_t s)
+{
+    if (dpitch == width && spitch == width) return cudaMemcpyAsync(dst, src, width * height, kind, s);
+    return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, s);
+}
+
 #define PRL_CUDA_TRY(ctx, call)                                                        \
     do { cudaError_t _e = (call);                                                      \
          if (_e != cudaSuccess) return prl_set_err((ctx), PRL_E_CUDA, #call, _e); } while (0)
