@@ -288,9 +288,10 @@ gaussf_fused_kernel(const uint8_t* __restrict__ src, size_t step, int rows, int 
     float* tile = rsum + (size_t)th * kGfTW;                             // th x tw pixels as floats (converted once, not per tap), BORDER_REPLICATE
     const int x0 = blockIdx.x * kGfTW, y0 = blockIdx.y * kGfTH;
     for (int i = threadIdx.x; i < n; i += 256) kk[i] = K.k[i];
-    for (int i = threadIdx.x; i < tw * th; i += 256) {
-        const int ty = i / tw, tx = i - ty * tw;
-        tile[i] = (float)src[(size_t)min(max(y0 - h + ty, 0), rows - 1) * step + min(max(x0 - h + tx, 0), cols - 1)];
+    for (int ty = threadIdx.x >> 5; ty < th; ty += 8) {                 // a warp per tile row: no division by the run-time tile width
+        const uint8_t* srow = src + (size_t)min(max(y0 - h + ty, 0), rows - 1) * step;
+        float* trow = tile + ty * tw;
+        for (int tx = threadIdx.x & 31; tx < tw; tx += 32) trow[tx] = (float)srow[min(max(x0 - h + tx, 0), cols - 1)];
     }
     __syncthreads();
     // row pass, four adjacent outputs per thread: one pixel load feeds four running sums, the coefficient window slides through
@@ -397,9 +398,9 @@ bilateral_kernel(const uint8_t* __restrict__ src, size_t step, int rows, int col
     const int x0 = blockIdx.x * kBilTW - radius, y0 = blockIdx.y * kBilTH - radius;
     for (int i = tid; i < 256; i += kBilTW * kBilTH) cw[i] = color_weight[i];
     for (int i = tid; i < n_taps; i += kBilTW * kBilTH) stap[i] = taps[i];
-    for (int i = tid; i < tw * th; i += kBilTW * kBilTH) {
-        const int ty = i / tw, tx = i - ty * tw;
-        tile[i] = src[(size_t)reflect101(y0 + ty, rows) * step + reflect101(x0 + tx, cols)];
+    for (int ty = tid >> 5; ty < th; ty += kBilTW * kBilTH / 32) {      // a warp per tile row
+        const uint8_t* srow = src + (size_t)reflect101(y0 + ty, rows) * step;
+        for (int tx = tid & 31; tx < tw; tx += 32) tile[ty * tw + tx] = srow[reflect101(x0 + tx, cols)];
     }
     __syncthreads();
     const int x = blockIdx.x * kBilTW + threadIdx.x, y = blockIdx.y * kBilTH + threadIdx.y;
