@@ -398,3 +398,26 @@ def test_batch_loader_pinned_pageable_and_concurrent_callers():
         for p in range(pg.shape[0]):
             assert np.array_equal(results[i][p], CO.binarize_local(pg[p], m, w, prm, mo)), (i, p)
     pin_in.close(); pin_out.close()
+
+
+@pytest.mark.gpu
+def test_batch_return_paths_on_odd_shapes():
+    """prl_cuda_binarize_batch with the masks back as bits (forced: 3 expansion threads) and as bytes: page shapes around the
+    32-pixel word and 16-byte alignment boundaries, more chunks than host slots, every method that has a morphology tail"""
+    rng = np.random.default_rng(21)
+    try:
+        for (n, rows, cols), method, window, params, morph in (((37, 97, 61), 1, 15, (-0.2,), 0), ((13, 130, 33), 0, 15, (0.2,), 1),
+                                                               ((20, 64, 97), 3, 21, (-0.1,), 0), ((7, 211, 128), 4, 21, (0.12, 0.25, 0.04, 2.0), 2),
+                                                               ((5, 300, 421), 2, 15, (0.5,), 0)):
+            pages = rng.integers(0, 256, (n, rows, cols), dtype=np.uint8)
+            pages[n // 2] = CO.synth_page(3, rows, cols)
+            want = np.stack([CO.binarize_local(pages[p], method, window, params, morph) for p in range(n)])
+            for chunk in (1, 4):
+                prlib_b200.set_global_option("batch_chunk_pages", chunk)
+                for unpack in (3, 0):
+                    prlib_b200.set_global_option("batch_unpack_threads", unpack)
+                    got = prlib_b200.binarize_batch(pages, method, window, params, morph, devices=[0])
+                    assert np.array_equal(got, want), ((n, rows, cols), method, chunk, unpack)
+    finally:
+        prlib_b200.set_global_option("batch_chunk_pages", 0)
+        prlib_b200.set_global_option("batch_unpack_threads", -1)
