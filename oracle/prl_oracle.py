@@ -17,6 +17,11 @@ OpenCV primitives the C++ reference links against), of
   src/binarizations/binarizeLocalOtsu.cpp:138-162   (per-rectangle Otsu loop)
   cv::threshold(..., THRESH_BINARY|THRESH_OTSU) call sites (src/deskew/deskew.cpp:224,
   src/removeLines.cpp:45, src/imageLibCommon.cpp:295-296)          ("Global Otsu")
+  src/binarizations/binarizeLocalOtsu.cpp:38-163, src/removeLines.cpp:30-77 (the "next" rows F3 / F4)
+  src/binarizations/binarizeNativeAdaptive.cpp:34-135 (bilateral step included), binarizeAT / AGT / GAT / PureAdaptive /
+  PureAdaptiveGaussian.cpp                                          (the adaptive-mean family, F4)
+plus first-principles numpy models of the OpenCV primitives whose arithmetic csrc/ restates (box and Gaussian means of
+cv::adaptiveThreshold, cv::bilateralFilter), each checked against the real cv2 call in tests/test_adaptive.py.
 
 Every arithmetic primitive the reference calls (copyMakeBorder, integral, filter2D, mul,
 subtract, sqrt, convertTo, compare, minMaxLoc, addWeighted, divide, pow, threshold, dilate,
