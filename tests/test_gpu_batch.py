@@ -414,10 +414,14 @@ def test_batch_return_paths_on_odd_shapes():
             want = np.stack([CO.binarize_local(pages[p], method, window, params, morph) for p in range(n)])
             for chunk in (1, 4):
                 prlib_b200.set_global_option("batch_chunk_pages", chunk)
-                for unpack in (3, 0):
+                for unpack, lag, nt in ((3, 0, 1), (3, 1, 1), (2, 0, 0), (0, 0, 1)):      # bits (both hand-over schemes, both store kinds), bytes
                     prlib_b200.set_global_option("batch_unpack_threads", unpack)
+                    prlib_b200.set_global_option("batch_unpack_lag", lag)
+                    prlib_b200.set_global_option("batch_unpack_nt", nt)
                     got = prlib_b200.binarize_batch(pages, method, window, params, morph, devices=[0])
-                    assert np.array_equal(got, want), ((n, rows, cols), method, chunk, unpack)
+                    assert np.array_equal(got, want), ((n, rows, cols), method, chunk, unpack, lag, nt)
     finally:
         prlib_b200.set_global_option("batch_chunk_pages", 0)
         prlib_b200.set_global_option("batch_unpack_threads", -1)
+        prlib_b200.set_global_option("batch_unpack_lag", 0)
+        prlib_b200.set_global_option("batch_unpack_nt", 1)
