@@ -256,6 +256,31 @@ def test_tile_otsu_lane_kernel_equals_batched_kernel_and_oracle(ctx, tw, th):
     ctx.set_stream(None)
 
 
+@pytest.mark.parametrize("rows,cols,tw,th,n", [(70, 16, 16, 16, 3), (130, 64, 64, 64, 5), (65, 80, 64, 64, 40), (1, 4096, 64, 64, 2),
+                                              (200, 48, 32, 7, 33), (64, 2048, 64, 64, 1)])
+def test_tile_otsu_ring_kernel_run_shapes(ctx, rows, cols, tw, th, n):
+    """The ring-fed kernel moves whole runs of tiles adjacent in x with one bulk copy per pixel row: pages one tile wide (every
+    lane heads a run), two tiles wide with a narrow second tile, one pixel row high, exactly 32 tiles wide (one run per warp),
+    more pages than a warp has lanes -- against the warp-batched kernel and the oracle."""
+    rng = np.random.default_rng(rows * cols + tw)
+    host = rng.integers(0, 256, (n, rows, cols), dtype=np.uint8)
+    host[0] = CO.synth_page(7, rows, cols)
+    buf = torch.from_numpy(host).to("cuda:0")
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    outs = []
+    for legacy in (0, 1):
+        ctx.set_option("tiles_legacy", legacy)
+        out = torch.zeros((n, rows, cols), dtype=torch.uint8, device="cuda:0")
+        ctx.otsu_tiles_batch_dev(buf.data_ptr(), n, rows, cols, cols, rows * cols, tw, th, 255.0, out.data_ptr(), cols, rows * cols)
+        torch.cuda.synchronize()
+        outs.append(out.cpu().numpy())
+    ctx.set_option("tiles_legacy", 0)
+    ctx.set_stream(None)
+    assert np.array_equal(outs[0], outs[1])
+    for p in (0, n - 1):
+        assert np.array_equal(outs[0][p], O.otsu_tiles(host[p], tw, th, 255.0)), p
+
+
 def test_host_batch_dispatcher(golden):
     n, rows, cols = 10, 1200, 1600
     pages = np.stack([CO.synth_page(p, rows, cols) for p in range(n)])
