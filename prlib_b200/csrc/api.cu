@@ -194,7 +194,7 @@ extern "C" int prl_cuda_set_option(prl_cuda_ctx* c, const char* name, long long 
     else if (strcmp(name, "enable_fused") == 0) c->use_fused = value != 0;
     else if (strcmp(name, "morph_bytes") == 0) c->morph_bytes = value != 0;
     else if (strcmp(name, "thr_rows") == 0) c->thr_rows = value <= 0 ? 0 : ((int)std::min<long long>(std::max<long long>(value, 2), 64) & ~1);
-    else if (strcmp(name, "tiles_legacy") == 0) c->tiles_legacy = value == 2 ? 2 : (value != 0);
+    else if (strcmp(name, "tiles_legacy") == 0) c->tiles_legacy = (value == 2 || value == 3) ? (int)value : (value != 0);
     else if (strcmp(name, "median_legacy") == 0) c->median_legacy = value != 0;
     else if (strcmp(name, "gauss_legacy") == 0) c->gauss_legacy = value != 0;
     else if (strcmp(name, "otsu_group") == 0) c->otsu_group = (int)std::min<long long>(std::max<long long>(value, -1), 65535);

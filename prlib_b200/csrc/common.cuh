@@ -91,7 +91,8 @@ struct prl_cuda_ctx {
     bool no_tma = false;        // validation: kernel 1 uses the generic (non-TMA) kernel
     int thr_rows = 0;           // kernel 2: output rows per CTA (0 = automatic: 4, or 8 when the tap distance exceeds 64)
     int tiles_legacy = 0;       // validation: tile Otsu runs 1 = the round-1 warp-batched kernel, 2 = the lane-per-tile kernel with register-staged
-                                // global loads, instead of the lane-per-tile kernel fed by the bulk-copy ring
+                                // global loads, 3 = the ring-fed lane-per-tile kernel for every tile width up to 64 (0: the ring-fed kernel for
+                                // 64-wide tiles at least 48 high, kernel 2 for the other aligned shapes up to 128 wide, kernel 1 for the rest)
     int tile_prefetch = 0;      // tile Otsu: how many tiles ahead a warp pulls into L2 (0 = off)
     bool morph_bytes = false;   // validation: the morphology tail runs the byte kernels even on binary masks
     bool use_fused = true;      // windows <= 31 take the fused small-window strip kernel (integral planes never reach HBM);

@@ -1,5 +1,5 @@
-"""64x64-tile Otsu timing: the three kernels (set_option("tiles_legacy", v): 0 = bulk-copy ring, 2 = lane-per-tile with
-register-staged loads, 1 = round-1 warp-batched kernel) on the same pages, outputs compared.  usage: tile_bench.py [pages] [tw th]"""
+"""64x64-tile Otsu timing: the three kernels (set_option("tiles_legacy", v): 3 = bulk-copy ring, 2 = lane-per-tile with
+register-staged loads, 1 = round-1 warp-batched kernel, 0 = the library's choice) on the same pages, outputs compared.  usage: tile_bench.py [pages] [tw th]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -13,7 +13,7 @@ step = (cols + 15) // 16 * 16
 buf = torch.empty((n, rows, step), dtype=torch.uint8, device="cuda")
 ctx.synth_pages_dev(buf.data_ptr(), n, rows, cols, step, rows * step, 2024, 0)
 ref = None
-for variant in (1, 2, 0, 2, 0):
+for variant in (1, 2, 3, 2, 3, 0):
     ctx.set_option("tiles_legacy", variant)
     out = torch.zeros_like(buf)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -230,8 +230,8 @@ def test_otsu_batch_dev(ctx, golden):
 @pytest.mark.parametrize("tw,th", [(16, 16), (32, 64), (48, 52), (64, 64), (128, 40), (112, 300), (64, 1000)])
 def test_tile_otsu_lane_kernel_equals_batched_kernel_and_oracle(ctx, tw, th):
     """16-byte aligned pages with a width that is a multiple of 16 take a lane-per-tile kernel (per-lane histograms in
-    shared memory; tiles up to 64 wide are fed by the bulk-copy ring, "tiles_legacy" = 2 forces register-staged loads);
-    "tiles_legacy" = 1 forces the round-1 warp-batched kernel.  Edge tiles (partial width and height), several
+    shared memory; 64-wide tiles at least 48 high are fed by the bulk-copy ring, "tiles_legacy" = 3 forces that kernel for every
+    width up to 64, "tiles_legacy" = 2 forces register-staged loads); "tiles_legacy" = 1 forces the round-1 warp-batched kernel.  Edge tiles (partial width and height), several
     pages per warp batch, maxValue below 255."""
     n, rows, cols = 7, 333, 1200
     host = np.stack([CO.synth_page(40 + p, rows, cols) for p in range(n)])
@@ -242,7 +242,7 @@ def test_tile_otsu_lane_kernel_equals_batched_kernel_and_oracle(ctx, tw, th):
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     outs = {}
     for mv in (255.0, 200.0):
-        for legacy in (0, 1, 2):
+        for legacy in (0, 1, 2, 3):
             ctx.set_option("tiles_legacy", legacy)
             out = torch.zeros((n, rows, cols), dtype=torch.uint8, device="cuda:0")
             ctx.otsu_tiles_batch_dev(buf.data_ptr(), n, rows, cols, cols, rows * cols, tw, th, mv, out.data_ptr(), cols, rows * cols)
@@ -251,6 +251,7 @@ def test_tile_otsu_lane_kernel_equals_batched_kernel_and_oracle(ctx, tw, th):
         ctx.set_option("tiles_legacy", 0)
         assert np.array_equal(outs[(mv, 0)], outs[(mv, 1)]), (tw, th, mv)
         assert np.array_equal(outs[(mv, 0)], outs[(mv, 2)]), (tw, th, mv)
+        assert np.array_equal(outs[(mv, 0)], outs[(mv, 3)]), (tw, th, mv)
         for p in range(n):
             assert np.array_equal(outs[(mv, 0)][p], O.otsu_tiles(host[p], tw, th, mv)), (tw, th, mv, p)
     ctx.set_stream(None)
@@ -268,7 +269,7 @@ def test_tile_otsu_ring_kernel_run_shapes(ctx, rows, cols, tw, th, n):
     buf = torch.from_numpy(host).to("cuda:0")
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     outs = []
-    for legacy in (0, 1):
+    for legacy in (3, 1):
         ctx.set_option("tiles_legacy", legacy)
         out = torch.zeros((n, rows, cols), dtype=torch.uint8, device="cuda:0")
         ctx.otsu_tiles_batch_dev(buf.data_ptr(), n, rows, cols, cols, rows * cols, tw, th, 255.0, out.data_ptr(), cols, rows * cols)
